@@ -1,0 +1,60 @@
+"""Build libemoport.so (all sm_100a kernels + the C-ABI) in-tree with nvcc.
+
+    python -m emoportraits_b200.csrc.build [--force]
+
+The library is built next to the sources so that it travels with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import pathlib
+import shutil
+import subprocess
+import sys
+
+HERE = pathlib.Path(__file__).resolve().parent
+LIB = HERE / "libemoport.so"
+SOURCES = ["conv_igemm.cu", "grid_sample.cu", "norm.cu", "misc.cu"]
+HEADERS = ["common.cuh", "../../include/emoportraits_b200.h"]
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _nvcc() -> str:
+    for cand in [os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"]:
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS + ["build.py"]:
+        h.update((HERE / f).read_bytes())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    stamp = HERE / ".build_stamp"
+    dig = _digest()
+    if LIB.exists() and not force and stamp.exists() and stamp.read_text() == dig:
+        return LIB
+    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false"]
+    cmd = [c for c in cmd if c != "--use_fast_math=false"]
+    cmd += ["-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", str(LIB)] + [str(HERE / s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed building libemoport.so")
+    if verbose:
+        sys.stderr.write(r.stdout + r.stderr)
+    stamp.write_text(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print(p)

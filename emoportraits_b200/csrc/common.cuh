@@ -1,0 +1,72 @@
+// Shared device/host helpers for the emoportraits_b200 sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/emoportraits_b200.h"
+
+namespace emo {
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing (thread-local last-error string, see emo_last_error in the C-ABI)
+// ------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define EMO_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::emo::set_error(__VA_ARGS__);           \
+      return EMO_ERR_INVALID;                  \
+    }                                          \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> (bf16 hi, bf16 lo) split.  x ~= hi + lo with |x - hi - lo| <= 2^-17 |x|.
+// The three-product expansion hi*hi' + hi*lo' + lo*hi' then carries ~16 mantissa bits.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// split 4 floats -> 2x uint2 (4 bf16 hi, 4 bf16 lo)
+__device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  split_bf16(v.x, h0, l0);
+  split_bf16(v.y, h1, l1);
+  split_bf16(v.z, h2, l2);
+  split_bf16(v.w, h3, l3);
+  hi.x = pack_bf16x2(h0, h1);
+  hi.y = pack_bf16x2(h2, h3);
+  lo.x = pack_bf16x2(l0, l1);
+  lo.y = pack_bf16x2(l2, l3);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  switch (act) {
+    case EMO_ACT_RELU: return fmaxf(v, 0.f);
+    case EMO_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    case EMO_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+}  // namespace emo

@@ -1,0 +1,586 @@
+// Implicit-GEMM convolution (2-D / 3-D) for sm_100a: TMA-fed, tcgen05.mma with TMEM accumulators.
+//
+// Replaces the F.conv2d / F.conv3d call sites of the reference hot path
+// (networks/volumetric_avatar/utils.py:661-788 ResBlock, :894-915 Conv2d_ws/Conv3d_ws,
+//  decoder.py:77-81,349-356, local_encoder.py:104-108, warp_generator_resnet.py:99-106).
+//
+// GEMM view:   D[pixel][cout] = sum_{tap, cin} A[pixel + tap][cin] * W[tap][cout][cin]
+//   M = 128 output pixels of one (td x th x tw) box of one sample,
+//   N = BN output channels, K = taps * Cin walked in chunks of KC channels.
+// im2col-free: for every (tap, k-chunk) the A tile is ONE TMA box load of the channels-last activation
+//   tensor at the tap-shifted coordinate; out-of-bounds rows/columns are zero-filled by TMA, which is
+//   exactly the conv zero padding.  The box lands in shared memory as [pixel][KC] rows with the
+//   128B/64B hardware swizzle = the canonical K-major UMMA operand layout.
+// Precision: fp32 activations/weights are pre-split into bf16 (hi, lo) planes; each K step issues
+//   hi*hi + hi*lo + lo*hi (3 x tcgen05.mma kind::f16, fp32 accumulate) => ~2^-16 relative error,
+//   which is what the 1e-3 max-abs parity budget of BASELINE.json needs (plain bf16/tf32 does not hold it).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+//   warps 2..5 = epilogue (TMEM -> registers -> bias/residual/activation -> global, GN statistics).
+// Persistent CTAs walk tiles round-robin; two TMEM accumulator stages overlap epilogue and MMA.
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace emo {
+
+static constexpr int kThreads = 192;
+static constexpr int kMaxStages = 8;
+static constexpr int kTileM = 128;
+
+struct ConvKParams {
+  int N, Dout, Hout, Wout, Cout;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int kchunks;
+  int tw, th, td;
+  int tiles_w, tiles_h, tiles_d;
+  int m_tiles, n_tiles;
+  int BN;
+  int stages;
+  const float* bias;
+  const float* residual;
+  int res_shift;
+  int rD, rH, rW;
+  int act;
+  const float* post_add;
+  float* out;
+  int out_nchw;
+  double* stats;
+  int G, cpg;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+template <int KC>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+  constexpr uint64_t row_bytes = KC * 2;          // 128 or 64
+  constexpr uint64_t sbo = (8 * row_bytes) >> 4;  // 8-row swizzle atom pitch
+  constexpr uint64_t layout = (KC == 64) ? 2ull : 4ull;
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  const __grid_constant__ ConvKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16B-aligned by the API; realign to 1024 for the swizzle atoms.
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  const int BN = p.BN;
+  const uint32_t a_bytes = kTileM * KC * 2;
+  const uint32_t b_bytes = (uint32_t)BN * KC * 2;
+  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const int S = p.stages;
+
+  uint8_t* tail = smem + (size_t)S * stage_bytes;
+  uint64_t* full_bar = (uint64_t*)tail;
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  float* col_sum = (float*)(tmem_slot + 4);  // [2][256]
+  float* col_sq = col_sum + 2 * 256;         // [2][256]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 4 * 256; i += kThreads) col_sum[i] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = p.kd * p.kh * p.kw;
+  const int ksteps = taps * p.kchunks;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int rows_a = p.tw * p.th * p.td;
+  const uint32_t tx_bytes = 2u * (uint32_t)rows_a * KC * 2 + 2u * b_bytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile / p.m_tiles;
+        int mt = tile - nt * p.m_tiles;
+        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+        const int thi = mt % p.tiles_h; mt /= p.tiles_h;
+        const int tdi = mt % p.tiles_d; mt /= p.tiles_d;
+        const int n = mt;
+        const int x0 = twi * p.tw * p.sw - p.pw;
+        const int y0 = thi * p.th * p.sh - p.ph;
+        const int z0 = tdi * p.td * p.sd - p.pd;
+        const int n0 = nt * BN;
+        for (int a = 0; a < p.kd; ++a)
+          for (int b = 0; b < p.kh; ++b)
+            for (int c = 0; c < p.kw; ++c) {
+              const int tap = (a * p.kh + b) * p.kw + c;
+              for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                mbar_expect_tx(&full_bar[stage], tx_bytes);
+                tma_load_5d(&tmA_hi, &full_bar[stage], st, kc * KC, x0 + c, y0 + b, z0 + a, n);
+                tma_load_5d(&tmA_lo, &full_bar[stage], st + a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
+                tma_load_3d(&tmB_hi, &full_bar[stage], st + 2 * a_bytes, kc * KC, n0, tap);
+                tma_load_3d(&tmB_lo, &full_bar[stage], st + 2 * a_bytes + b_bytes, kc * KC, n0, tap);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+              }
+            }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1,
+    // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t dAh = make_kmajor_desc<KC>(sa);
+          const uint64_t dAl = make_kmajor_desc<KC>(sa + a_bytes);
+          const uint64_t dBh = make_kmajor_desc<KC>(sa + 2 * a_bytes);
+          const uint64_t dBl = make_kmajor_desc<KC>(sa + 2 * a_bytes + b_bytes);
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);  // 16 bf16 = 32 B = 2 x 16B units
+            umma_bf16(tmem_d, dAl + adv, dBh + adv, idesc, (ks | kk) != 0);
+            umma_bf16(tmem_d, dAh + adv, dBl + adv, idesc, 1);
+            umma_bf16(tmem_d, dAh + adv, dBh + adv, idesc, 1);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;   // accumulator row == pixel index inside the tile box
+    const int et = threadIdx.x - 64;    // 0..127 among the epilogue threads
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1;
+      const int nt = tile / p.m_tiles;
+      int mt = tile - nt * p.m_tiles;
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
+      const int tdi = mt % p.tiles_d; mt /= p.tiles_d;
+      const int n = mt;
+      const int n0 = nt * BN;
+      const int wl = row % p.tw;
+      const int hl = (row / p.tw) % p.th;
+      const int dl = row / (p.tw * p.th);
+      const int ow = twi * p.tw + wl, oh = thi * p.th + hl, od = tdi * p.td + dl;
+      const bool valid = (row < rows_a) && ow < p.Wout && oh < p.Hout && od < p.Dout;
+      const long long pix = (((long long)n * p.Dout + od) * p.Hout + oh) * p.Wout + ow;
+      long long rpix = 0;
+      if (p.residual) {
+        const int rw = ow >> p.res_shift, rh = oh >> p.res_shift;
+        rpix = (((long long)n * p.rD + od) * p.rH + rh) * p.rW + rw;
+      }
+      const long long ppix = (((long long)od) * p.Hout + oh) * p.Wout + ow;
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+      float* cs = col_sum + as * 256;
+      float* cq = col_sq + as * 256;
+
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t raw[16];
+        tmem_ld16(taddr + (uint32_t)c0, raw);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        const int cbase = n0 + c0;
+        const bool cfull = (cbase + 16 <= p.Cout);
+        if (valid && cbase < p.Cout) {
+          if (cfull) {
+            if (p.bias) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 b4 = __ldg((const float4*)(p.bias + cbase) + q);
+                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+              }
+            }
+            if (p.residual) {
+              const float4* r4 = (const float4*)(p.residual + rpix * p.Cout + cbase);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 b4 = __ldg(r4 + q);
+                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+              }
+            }
+            if (p.act != EMO_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
+            }
+            if (p.post_add) {
+              const float4* r4 = (const float4*)(p.post_add + ppix * p.Cout + cbase);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 b4 = __ldg(r4 + q);
+                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+              }
+            }
+            if (!p.out_nchw) {
+              float4* o4 = (float4*)(p.out + pix * p.Cout + cbase);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            } else {
+              const long long sp = (long long)p.Dout * p.Hout * p.Wout;
+              const long long spi = ((long long)od * p.Hout + oh) * p.Wout + ow;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) p.out[((long long)n * p.Cout + cbase + j) * sp + spi] = v[j];
+            }
+          } else {
+            // ragged channel tail (e.g. Cout = 3): scalar path
+            const long long sp = (long long)p.Dout * p.Hout * p.Wout;
+            const long long spi = ((long long)od * p.Hout + oh) * p.Wout + ow;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = cbase + j;
+              if (c < p.Cout) {
+                float x = v[j];
+                if (p.bias) x += __ldg(p.bias + c);
+                if (p.residual) x += __ldg(p.residual + rpix * p.Cout + c);
+                x = act_apply(x, p.act);
+                if (p.post_add) x += __ldg(p.post_add + ppix * p.Cout + c);
+                v[j] = x;
+                if (!p.out_nchw) p.out[pix * p.Cout + c] = x;
+                else p.out[((long long)n * p.Cout + c) * sp + spi] = x;
+              } else {
+                v[j] = 0.f;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        }
+        if (p.stats) {
+          // column sums over the warp's 32 pixels by a butterfly transpose-reduce (15 + 15 shuffles):
+          // after the 4 halving steps lane l holds columns (l & 15) partial over lanes {l, l^16}... see below.
+          float s[16], q[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { s[j] = v[j]; q[j] = v[j] * v[j]; }
+          // first fold the two half-warps together so that 16 columns map onto 16 lane pairs
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
+            q[j] += __shfl_xor_sync(0xffffffffu, q[j], 16);
+          }
+#pragma unroll
+          for (int off = 8; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int j = 0; j < off; ++j) {
+              const float send_s = upper ? s[j] : s[j + off];
+              const float send_q = upper ? q[j] : q[j + off];
+              const float keep_s = upper ? s[j + off] : s[j];
+              const float keep_q = upper ? q[j + off] : q[j];
+              s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
+              q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
+            }
+          }
+          // lane l (and l^16, identical) now holds the sum of column (l & 15)
+          if (lane < 16) {
+            atomicAdd(&cs[c0 + lane], s[0]);
+            atomicAdd(&cq[c0 + lane], q[0]);
+          }
+        }
+      }
+      // release the accumulator stage back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+
+      if (p.stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // one double RED per (group, quantity): thread g sums the cpg columns of its group
+        const int cpg = p.cpg;
+        if (BN % cpg == 0 && (n0 % cpg) == 0) {
+          const int ng = BN / cpg;
+          if (et < ng) {
+            float a = 0.f, b = 0.f;
+            for (int j = 0; j < cpg; ++j) {
+              a += cs[et * cpg + j]; b += cq[et * cpg + j];
+              cs[et * cpg + j] = 0.f; cq[et * cpg + j] = 0.f;
+            }
+            const int g = (n0 / cpg) + et;
+            if (g < p.G) {
+              atomicAdd(&p.stats[((long long)n * p.G + g) * 2], (double)a);
+              atomicAdd(&p.stats[((long long)n * p.G + g) * 2 + 1], (double)b);
+            }
+          }
+        } else {
+          for (int j = et; j < BN; j += 128) {
+            const int c = n0 + j;
+            if (c < p.Cout) {
+              const int g = c / cpg;
+              atomicAdd(&p.stats[((long long)n * p.G + g) * 2], (double)cs[j]);
+              atomicAdd(&p.stats[((long long)n * p.G + g) * 2 + 1], (double)cq[j]);
+            }
+            cs[j] = 0.f; cq[j] = 0.f;
+          }
+        }
+      }
+    }
+  }
+
+  // teardown
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled get_encode() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = (PFN_cuTensorMapEncodeTiled)p;
+  }
+  return fn;
+}
+
+static int pick_box(int dim, int want) {
+  int b = want;
+  while (b > dim) b >>= 1;
+  return b < 1 ? 1 : b;
+}
+
+}  // namespace emo
+
+using namespace emo;
+
+extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->a_hi && d->a_lo && d->w_hi && d->w_lo && d->out, "emo_conv_igemm: null pointer");
+  EMO_REQUIRE(d->Cin % 32 == 0, "emo_conv_igemm: Cin=%d must be a multiple of 32 (use emo_conv_direct)", d->Cin);
+  EMO_REQUIRE(d->Cout_pad % 16 == 0 && d->Cout <= d->Cout_pad, "emo_conv_igemm: Cout_pad=%d must be a multiple of 16 >= Cout", d->Cout_pad);
+  EMO_REQUIRE(d->sd >= 1 && d->sh >= 1 && d->sw >= 1 && d->sd <= 2 && d->sh <= 2 && d->sw <= 2, "emo_conv_igemm: stride must be 1 or 2");
+  EMO_REQUIRE(((uintptr_t)d->a_hi % 16) == 0 && ((uintptr_t)d->a_lo % 16) == 0 && ((uintptr_t)d->w_hi % 16) == 0 &&
+                  ((uintptr_t)d->w_lo % 16) == 0 && ((uintptr_t)d->out % 16) == 0,
+              "emo_conv_igemm: pointers must be 16-byte aligned");
+  if (d->stats) EMO_REQUIRE(d->G > 0 && d->Cout % d->G == 0, "emo_conv_igemm: Cout=%d not divisible by G=%d", d->Cout, d->G);
+  const bool vec_ok = (d->Cout % 4 == 0);
+  EMO_REQUIRE(vec_ok || d->Cout < 16, "emo_conv_igemm: Cout=%d must be a multiple of 4 (or < 16)", d->Cout);
+
+  PFN_cuTensorMapEncodeTiled encode = get_encode();
+  if (!encode) { set_error("emo_conv_igemm: cuTensorMapEncodeTiled entry point unavailable"); return EMO_ERR_CUDA; }
+
+  const int KC = (d->Cin % 64 == 0) ? 64 : 32;
+  // N tile: largest divisor-friendly width <= 256 (multiple of 16)
+  int BN = d->Cout_pad;
+  if (BN > 256) {
+    BN = 0;
+    for (int cand = 256; cand >= 16; cand -= 16)
+      if (d->Cout_pad % cand == 0) { BN = cand; break; }
+  }
+  // prefer 128-wide tiles when that fills the machine better (more tiles than SMs matters more than tile width)
+  int sm_count = 148;
+  {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+
+  ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = d->N; p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+  p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+  p.kchunks = d->Cin / KC;
+  // pixel box: 128 pixels, widest along W first
+  p.tw = pick_box(d->Wout, 16);
+  p.th = pick_box(d->Hout, kTileM / p.tw > 0 ? kTileM / p.tw : 1);
+  p.td = pick_box(d->Dout, kTileM / (p.tw * p.th) > 0 ? kTileM / (p.tw * p.th) : 1);
+  if (p.tw * p.th * p.td < kTileM && p.tw < d->Wout) {  // shallow/short tensor: widen along W
+    int tw = p.tw;
+    while (tw * 2 <= d->Wout && tw * 2 * p.th * p.td <= kTileM && tw * 2 * d->sw <= 256) tw *= 2;
+    p.tw = tw;
+  }
+  EMO_REQUIRE(p.tw * d->sw <= 256 && p.th * d->sh <= 256 && p.td * d->sd <= 256, "emo_conv_igemm: TMA box too large");
+  p.tiles_w = cdiv(d->Wout, p.tw); p.tiles_h = cdiv(d->Hout, p.th); p.tiles_d = cdiv(d->Dout, p.td);
+  p.m_tiles = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
+  if (BN > 128 && (BN / 2) % 16 == 0 && (long long)p.m_tiles * (d->Cout_pad / BN) < sm_count) BN /= 2;
+  p.BN = BN;
+  p.n_tiles = d->Cout_pad / BN;
+  p.bias = d->bias; p.residual = d->residual; p.res_shift = d->res_shift; p.act = d->act;
+  p.rD = d->Dout; p.rH = d->Hout >> d->res_shift; p.rW = d->Wout >> d->res_shift;
+  p.post_add = d->post_add; p.out = d->out; p.out_nchw = d->out_nchw;
+  p.stats = d->stats; p.G = d->G; p.cpg = d->G > 0 ? d->Cout / d->G : 1;
+  EMO_REQUIRE(!d->residual || ((d->Hout % (1 << d->res_shift)) == 0 && (d->Wout % (1 << d->res_shift)) == 0),
+              "emo_conv_igemm: residual shift does not divide the output size");
+
+  const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)BN * KC * 2;
+  const size_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const size_t tail_bytes = (2 * kMaxStages + 4) * 8 + 16 + 4 * 256 * sizeof(float);
+  const size_t smem_limit = 227 * 1024;
+  int stages = (int)((smem_limit - tail_bytes - 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  EMO_REQUIRE(stages >= 2, "emo_conv_igemm: tile does not fit shared memory (BN=%d KC=%d)", BN, KC);
+  p.stages = stages;
+  const size_t smem_bytes = stages * stage_bytes + tail_bytes + 1024;
+
+  // ---- tensor maps ----
+  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  {
+    cuuint64_t gdim[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->Din, (cuuint64_t)d->N};
+    cuuint64_t gstr[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2,
+                          (cuuint64_t)d->Din * d->Hin * d->Win * d->Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(p.tw * d->sw), (cuuint32_t)(p.th * d->sh), (cuuint32_t)(p.td * d->sd), 1};
+    cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->sd, 1};
+    const CUtensorMapSwizzle sw = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r1 = encode(&tmAh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)d->a_hi, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tmAl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)d->a_lo, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+      set_error("emo_conv_igemm: cuTensorMapEncodeTiled(A) failed: %d %d (Cin=%d W=%d H=%d D=%d N=%d box=%d,%d,%d)", (int)r1, (int)r2,
+                d->Cin, d->Win, d->Hin, d->Din, d->N, p.tw, p.th, p.td);
+      return EMO_ERR_CUDA;
+    }
+    const int taps = d->kd * d->kh * d->kw;
+    cuuint64_t wdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout_pad, (cuuint64_t)taps};
+    cuuint64_t wstr[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout_pad * d->Cin * 2};
+    cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
+    cuuint32_t wes[3] = {1, 1, 1};
+    CUresult r3 = encode(&tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->w_hi, wdim, wstr, wbox, wes,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r4 = encode(&tmBl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->w_lo, wdim, wstr, wbox, wes,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r3 != CUDA_SUCCESS || r4 != CUDA_SUCCESS) {
+      set_error("emo_conv_igemm: cuTensorMapEncodeTiled(W) failed: %d %d", (int)r3, (int)r4);
+      return EMO_ERR_CUDA;
+    }
+  }
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int grid = total_tiles < sm_count ? total_tiles : sm_count;
+  cudaError_t e;
+  if (KC == 64) {
+    e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }
+    conv_igemm_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(tmAh, tmAl, tmBh, tmBl, p);
+  } else {
+    e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }
+    conv_igemm_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(tmAh, tmAl, tmBh, tmBl, p);
+  }
+  return check_launch("emo_conv_igemm");
+}

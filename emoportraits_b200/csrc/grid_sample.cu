@@ -1,0 +1,336 @@
+// grid_sample kernels (HBM-bound; see DESIGN.md "grid_sample_3d").
+//
+//  emo_grid_sample3d        trilinear, zeros padding, align_corners=False
+//     replaces models/stage_1/volumetric_avatar/va.py:261-265 (F.grid_sample on a 5-D volume) and, with
+//     `theta`, also the affine lattice build notebooks/infer.py:441-444 / :583-588
+//     (identity_grid_3d (va.py:101-105: linspace(-1,1,n) per axis, [x,y,z,1]) . theta[:, :3]^T), so the
+//     (N,D,H,W,3) grid tensor never exists in HBM.
+//  emo_grid_sample2d_affine bilinear face alignment of expression_embedder.py:224-231.
+//  emo_resize_bilinear      F.interpolate(mode='bilinear') of head_pose_regressor.py:24-25.
+//
+// Un-normalisation (align_corners=False): ix = ((x + 1) * W - 1) / 2  (utils.py:24-27 restates it).
+#include "common.cuh"
+
+namespace emo {
+
+struct GS3Params {
+  const float* in;
+  const float* grid;
+  const float* theta;
+  int N, C, Din, Hin, Win, Dout, Hout, Wout;
+  float* out;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long os_n, os_c, os_d, os_h, os_w;
+  // brick decomposition of the output lattice (channels-last kernel)
+  int bw, bh, bd, bricks_w, bricks_h, bricks_d;
+};
+
+// linspace(-1, 1, n)[i] exactly as torch computes it (start + i*step for the first half,
+// end - (n-1-i)*step for the second half; step = 2/(n-1) in fp32).
+__device__ __forceinline__ float lin_m1_p1(int i, int n) {
+  if (n == 1) return -1.f;
+  const float step = 2.0f / (float)(n - 1);
+  return (i < n / 2) ? (-1.f + step * (float)i) : (1.f - step * (float)(n - 1 - i));
+}
+
+__device__ __forceinline__ void sample_coord(const GS3Params& p, int n, int od, int oh, int ow, float& gx, float& gy, float& gz) {
+  if (p.theta) {
+    const float* t = p.theta + n * 12;
+    const float u = lin_m1_p1(ow, p.Wout), v = lin_m1_p1(oh, p.Hout), w = lin_m1_p1(od, p.Dout);
+    // bmm row . column in the order torch accumulates a 4-term dot: ((u*t0 + v*t1) + w*t2) + 1*t3
+    gx = fmaf(w, t[2], fmaf(v, t[1], u * t[0])) + t[3];
+    gy = fmaf(w, t[6], fmaf(v, t[5], u * t[4])) + t[7];
+    gz = fmaf(w, t[10], fmaf(v, t[9], u * t[8])) + t[11];
+  } else {
+    const float* g = p.grid + ((((long long)n * p.Dout + od) * p.Hout + oh) * p.Wout + ow) * 3;
+    gx = __ldg(g); gy = __ldg(g + 1); gz = __ldg(g + 2);
+  }
+}
+
+struct Corner8 {
+  int x0, y0, z0;
+  float fx, fy, fz;
+};
+
+__device__ __forceinline__ Corner8 corners(const GS3Params& p, float gx, float gy, float gz) {
+  const float ix = ((gx + 1.f) * (float)p.Win - 1.f) * 0.5f;
+  const float iy = ((gy + 1.f) * (float)p.Hin - 1.f) * 0.5f;
+  const float iz = ((gz + 1.f) * (float)p.Din - 1.f) * 0.5f;
+  const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+  Corner8 c;
+  // clamp before the int conversion so that wild coordinates stay out of range instead of overflowing
+  c.x0 = (int)fminf(fmaxf(x0, -2.f), (float)p.Win + 1.f);
+  c.y0 = (int)fminf(fmaxf(y0, -2.f), (float)p.Hin + 1.f);
+  c.z0 = (int)fminf(fmaxf(z0, -2.f), (float)p.Din + 1.f);
+  c.fx = ix - x0; c.fy = iy - y0; c.fz = iz - z0;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// channels-last kernel: one thread = one float4 of channels of one output voxel.  A CTA walks a compact
+// (bd x bh x bw) brick of the output lattice so the 8-corner footprints of neighbouring voxels overlap in L1.
+// Every corner fetch is a 16-byte load inside a contiguous C*4-byte run.
+// ------------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
+  const int c4n = p.C >> 2;
+  int b = blockIdx.x;
+  const int bwi = b % p.bricks_w; b /= p.bricks_w;
+  const int bhi = b % p.bricks_h; b /= p.bricks_h;
+  const int bdi = b % p.bricks_d; b /= p.bricks_d;
+  const int n = b;
+  const int brick_vox = p.bw * p.bh * p.bd;
+  const int work = brick_vox * c4n;
+  const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
+  for (int t = threadIdx.x; t < work; t += blockDim.x) {
+    const int vox = t / c4n, c4 = t - vox * c4n;
+    const int lw = vox % p.bw, lh = (vox / p.bw) % p.bh, ld = vox / (p.bw * p.bh);
+    const int ow = bwi * p.bw + lw, oh = bhi * p.bh + lh, od = bdi * p.bd + ld;
+    if (ow >= p.Wout || oh >= p.Hout || od >= p.Dout) continue;
+    float gx, gy, gz;
+    sample_coord(p, n, od, oh, ow, gx, gy, gz);
+    const Corner8 k = corners(p, gx, gy, gz);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz) {
+      const int z = k.z0 + dz;
+      const float wz = dz ? k.fz : 1.f - k.fz;
+      if (z < 0 || z >= p.Din) continue;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = k.y0 + dy;
+        const float wy = dy ? k.fy : 1.f - k.fy;
+        if (y < 0 || y >= p.Hin) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int x = k.x0 + dx;
+          const float wx = dx ? k.fx : 1.f - k.fx;
+          if (x < 0 || x >= p.Win) continue;
+          const float wgt = wx * wy * wz;
+          const float4 v = __ldg(in4 + (((long long)z * p.Hin + y) * p.Win + x) * c4n + c4);
+          acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y);
+          acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
+        }
+      }
+    }
+    const long long o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w + (long long)(c4 * 4) * p.os_c;
+    if (p.os_c == 1) {
+      if (p.out) *(float4*)(p.out + o) = acc;
+      if (SPLIT) {
+        uint2 hi, lo;
+        split4(acc, hi, lo);
+        *(uint2*)(p.out_hi + o) = hi;
+        *(uint2*)(p.out_lo + o) = lo;
+      }
+    } else {
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.out) p.out[o + j * p.os_c] = a[j];
+        if (SPLIT) {
+          __nv_bfloat16 h, l;
+          split_bf16(a[j], h, l);
+          p.out_hi[o + j * p.os_c] = h;
+          p.out_lo[o + j * p.os_c] = l;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCDHW kernel (drop-in layout of F.grid_sample): one thread = one output voxel, loops over channels with the
+// corner offsets/weights held in registers; lanes run along W so both the gathers and the stores coalesce.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gs3_nc_kernel(const GS3Params p) {
+  const long long total = (long long)p.N * p.Dout * p.Hout * p.Wout;
+  const long long plane_in = (long long)p.Din * p.Hin * p.Win;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int ow = (int)(r % p.Wout); r /= p.Wout;
+    const int oh = (int)(r % p.Hout); r /= p.Hout;
+    const int od = (int)(r % p.Dout); r /= p.Dout;
+    const int n = (int)r;
+    float gx, gy, gz;
+    sample_coord(p, n, od, oh, ow, gx, gy, gz);
+    const Corner8 k = corners(p, gx, gy, gz);
+    int off[8];
+    float wgt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+      const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+      const bool ok = x >= 0 && x < p.Win && y >= 0 && y < p.Hin && z >= 0 && z < p.Din;
+      off[j] = ok ? ((z * p.Hin + y) * p.Win + x) : 0;
+      wgt[j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+    }
+    const float* src = p.in + (long long)n * p.C * plane_in;
+    const long long o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
+    for (int c = 0; c < p.C; ++c) {
+      const float* s = src + (long long)c * plane_in;
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(__ldg(s + off[j]), wgt[j], acc);
+      if (p.out) p.out[o + (long long)c * p.os_c] = acc;
+      if (p.out_hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(acc, h, l);
+        p.out_hi[o + (long long)c * p.os_c] = h;
+        p.out_lo[o + (long long)c * p.os_c] = l;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2-D affine bilinear sampler, NCHW in -> channels-last (padded) out, optional normalisation
+// ------------------------------------------------------------------------------------------------
+struct GS2Params {
+  const float* in;
+  int N, C, Hin, Win, Hout, Wout, C_pad;
+  const float* theta;
+  const float* mean;
+  const float* std;
+  float* out;
+  float* out_nchw;
+};
+
+__global__ void gs2_affine_kernel(const GS2Params p) {
+  const long long total = (long long)p.N * p.Hout * p.Wout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int ow = (int)(r % p.Wout); r /= p.Wout;
+    const int oh = (int)(r % p.Hout); r /= p.Hout;
+    const int n = (int)r;
+    const float* t = p.theta + n * 6;
+    const float u = lin_m1_p1(ow, p.Wout), v = lin_m1_p1(oh, p.Hout);
+    const float gx = fmaf(v, t[1], u * t[0]) + t[2];
+    const float gy = fmaf(v, t[4], u * t[3]) + t[5];
+    const float ix = ((gx + 1.f) * (float)p.Win - 1.f) * 0.5f;
+    const float iy = ((gy + 1.f) * (float)p.Hin - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fminf(fmaxf(fx0, -2.f), (float)p.Win + 1.f);
+    const int y0 = (int)fminf(fmaxf(fy0, -2.f), (float)p.Hin + 1.f);
+    const float fx = ix - fx0, fy = iy - fy0;
+    float w[4];
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int dx = j & 1, dy = j >> 1;
+      const int x = x0 + dx, y = y0 + dy;
+      const bool ok = x >= 0 && x < p.Win && y >= 0 && y < p.Hin;
+      off[j] = ok ? y * p.Win + x : 0;
+      w[j] = ok ? (dx ? fx : 1.f - fx) * (dy ? fy : 1.f - fy) : 0.f;
+    }
+    for (int c = 0; c < p.C_pad; ++c) {
+      float acc = 0.f;
+      if (c < p.C) {
+        const float* s = p.in + ((long long)n * p.C + c) * p.Hin * p.Win;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fmaf(__ldg(s + off[j]), w[j], acc);
+        if (p.out_nchw) p.out_nchw[(((long long)n * p.C + c) * p.Hout + oh) * p.Wout + ow] = acc;
+        if (p.mean) acc = (acc - __ldg(p.mean + c)) / __ldg(p.std + c);
+      }
+      p.out[idx * p.C_pad + c] = acc;
+    }
+  }
+}
+
+// F.interpolate bilinear, align_corners=False, no antialias: src = (dst + 0.5) * scale - 0.5 clamped at 0
+struct ResizeParams {
+  const float* in;
+  int N, C, Hin, Win, Hout, Wout, C_pad;
+  const float* mean;
+  const float* std;
+  float* out;
+};
+
+__global__ void resize_bilinear_kernel(const ResizeParams p) {
+  const long long total = (long long)p.N * p.Hout * p.Wout;
+  const float sh = (float)p.Hin / (float)p.Hout, sw = (float)p.Win / (float)p.Wout;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int ow = (int)(r % p.Wout); r /= p.Wout;
+    const int oh = (int)(r % p.Hout); r /= p.Hout;
+    const int n = (int)r;
+    float sy = fmaxf(((float)oh + 0.5f) * sh - 0.5f, 0.f);
+    float sx = fmaxf(((float)ow + 0.5f) * sw - 0.5f, 0.f);
+    const int y0 = (int)sy, x0 = (int)sx;
+    const int y1 = y0 + (y0 < p.Hin - 1 ? 1 : 0), x1 = x0 + (x0 < p.Win - 1 ? 1 : 0);
+    const float ly = sy - (float)y0, lx = sx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    for (int c = 0; c < p.C_pad; ++c) {
+      float acc = 0.f;
+      if (c < p.C) {
+        const float* s = p.in + ((long long)n * p.C + c) * p.Hin * p.Win;
+        acc = hy * (hx * __ldg(s + y0 * p.Win + x0) + lx * __ldg(s + y0 * p.Win + x1)) +
+              ly * (hx * __ldg(s + y1 * p.Win + x0) + lx * __ldg(s + y1 * p.Win + x1));
+        if (p.mean) acc = (acc - __ldg(p.mean + c)) / __ldg(p.std + c);
+      }
+      p.out[idx * p.C_pad + c] = acc;
+    }
+  }
+}
+
+}  // namespace emo
+
+using namespace emo;
+
+extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->in, "emo_grid_sample3d: null input");
+  EMO_REQUIRE((d->grid != nullptr) != (d->theta != nullptr), "emo_grid_sample3d: exactly one of grid/theta must be given");
+  EMO_REQUIRE(d->out || (d->out_hi && d->out_lo), "emo_grid_sample3d: no output");
+  EMO_REQUIRE(d->N > 0 && d->C > 0 && d->Din > 0 && d->Hin > 0 && d->Win > 0 && d->Dout > 0 && d->Hout > 0 && d->Wout > 0,
+              "emo_grid_sample3d: bad shape");
+  GS3Params p;
+  p.in = d->in; p.grid = d->grid; p.theta = d->theta;
+  p.N = d->N; p.C = d->C; p.Din = d->Din; p.Hin = d->Hin; p.Win = d->Win;
+  p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout;
+  p.out = d->out; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
+  p.os_n = d->os_n; p.os_c = d->os_c; p.os_d = d->os_d; p.os_h = d->os_h; p.os_w = d->os_w;
+  if (d->in_layout == 1) {
+    EMO_REQUIRE(d->C % 4 == 0, "emo_grid_sample3d: channels-last path needs C %% 4 == 0 (C=%d)", d->C);
+    EMO_REQUIRE(((uintptr_t)d->in % 16) == 0, "emo_grid_sample3d: input must be 16-byte aligned");
+    if (d->os_c == 1)
+      EMO_REQUIRE(d->os_n % 4 == 0 && d->os_d % 4 == 0 && d->os_h % 4 == 0 && d->os_w % 4 == 0,
+                  "emo_grid_sample3d: vectorised output needs strides that are multiples of 4");
+    // brick: 8 x 4 x 2 voxels (w,h,d) -> 64 voxels * C/4 float4s per CTA pass
+    p.bw = d->Wout >= 8 ? 8 : d->Wout;
+    p.bh = d->Hout >= 4 ? 4 : d->Hout;
+    p.bd = d->Dout >= 2 ? 2 : d->Dout;
+    p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
+    const long long blocks = (long long)d->N * p.bricks_d * p.bricks_h * p.bricks_w;
+    EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");
+    if (d->out_hi) gs3_cl_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    else gs3_cl_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+  } else {
+    p.bw = p.bh = p.bd = p.bricks_w = p.bricks_h = p.bricks_d = 1;
+    const long long total = (long long)d->N * d->Dout * d->Hout * d->Wout;
+    long long blocks = cdivll(total, 256);
+    if (blocks > 148ll * 64) blocks = 148ll * 64;
+    gs3_nc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+  }
+  return check_launch("emo_grid_sample3d");
+}
+
+extern "C" int emo_grid_sample2d_affine(const emo_grid_sample2d_affine_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->in && d->theta && d->out, "emo_grid_sample2d_affine: null pointer");
+  EMO_REQUIRE(d->C_pad >= d->C, "emo_grid_sample2d_affine: C_pad < C");
+  GS2Params p{d->in, d->N, d->C, d->Hin, d->Win, d->Hout, d->Wout, d->C_pad, d->theta, d->mean, d->std, d->out, d->out_nchw};
+  const long long total = (long long)d->N * d->Hout * d->Wout;
+  gs2_affine_kernel<<<(unsigned)cdivll(total, 128), 128, 0, stream>>>(p);
+  return check_launch("emo_grid_sample2d_affine");
+}
+
+extern "C" int emo_resize_bilinear(const emo_resize_bilinear_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->in && d->out, "emo_resize_bilinear: null pointer");
+  EMO_REQUIRE(d->C_pad >= d->C, "emo_resize_bilinear: C_pad < C");
+  ResizeParams p{d->in, d->N, d->C, d->Hin, d->Win, d->Hout, d->Wout, d->C_pad, d->mean, d->std, d->out};
+  const long long total = (long long)d->N * d->Hout * d->Wout;
+  resize_bilinear_kernel<<<(unsigned)cdivll(total, 128), 128, 0, stream>>>(p);
+  return check_launch("emo_resize_bilinear");
+}

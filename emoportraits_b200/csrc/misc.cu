@@ -1,0 +1,516 @@
+// Small dense ops (fp32 SIMT, exact): linear layers, the RGB stem convolutions, resampling, pose algebra.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace emo {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return EMO_ERR_CUDA;
+  }
+  return EMO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear: one warp per output element (m, n), lanes stride over K.  Sizes are tiny (<= 20 MFLOP).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) linear_kernel(const emo_linear_desc d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= d.M * d.N) return;
+  const int m = warp / d.N, n = warp % d.N;
+  const float* xr = d.x + (long long)m * d.xs_m;
+  const float* wr = d.w + (long long)n * d.K;
+  float acc = 0.f;
+  for (int k = lane; k < d.K; k += 32) acc = fmaf(__ldg(xr + (long long)k * d.xs_k), __ldg(wr + k), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const long long o = (long long)m * d.os_m + (long long)n * d.os_n;
+    if (d.bias) acc += d.bias[n];
+    if (d.add) acc += d.add[o];
+    d.out[o] = act_apply(acc * d.scale, d.act);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct conv, channels-last, tiny Cin (RGB stems).  Thread = (pixel, 4 output channels).
+// weights [kh][kw][Cin_pad][Cout]: the co-vector load is coalesced across the co-threads of a pixel,
+// the activation load is a warp broadcast.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_direct_kernel(const emo_conv_direct_desc d) {
+  const int co4n = d.Cout >> 2;
+  const long long total = (long long)d.N * d.Hout * d.Wout * co4n;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ float sstat[];  // [2][G] when stats requested
+  if (d.stats) {
+    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int co4 = 0, n = 0;
+  const bool active = t < total;
+  if (active) {
+    co4 = (int)(t % co4n);
+    long long pix = t / co4n;
+    const int ow = (int)(pix % d.Wout); pix /= d.Wout;
+    const int oh = (int)(pix % d.Hout); pix /= d.Hout;
+    n = (int)pix;
+    if (d.bias) acc = __ldg((const float4*)d.bias + co4);
+    for (int ky = 0; ky < d.kh; ++ky) {
+      const int iy = oh * d.stride + ky - d.pad;
+      if (iy < 0 || iy >= d.Hin) continue;
+      for (int kx = 0; kx < d.kw; ++kx) {
+        const int ix = ow * d.stride + kx - d.pad;
+        if (ix < 0 || ix >= d.Win) continue;
+        const float* xp = d.x + (((long long)n * d.Hin + iy) * d.Win + ix) * d.Cin_pad;
+        const float4* wp = (const float4*)(d.w + ((long long)(ky * d.kw + kx) * d.Cin_pad) * d.Cout) + co4;
+        for (int ci = 0; ci < d.Cin_pad; ++ci) {
+          const float xv = __ldg(xp + ci);
+          const float4 wv = __ldg(wp + (long long)ci * co4n);
+          acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y);
+          acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+        }
+      }
+    }
+    ((float4*)d.out)[t] = acc;
+  }
+  if (d.stats) {
+    // a CTA may straddle two samples only if Hout*Wout*co4n < blockDim; host guarantees divisibility instead
+    if (active) {
+      const int cpg = d.Cout / d.G;
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (co4 * 4 + j) / cpg;
+        atomicAdd(&sstat[g], a[j]);
+        atomicAdd(&sstat[d.G + g], a[j] * a[j]);
+      }
+    }
+    __syncthreads();
+    const long long first = (long long)blockIdx.x * blockDim.x;
+    const int nb = (int)(first / ((long long)d.Hout * d.Wout * co4n));
+    for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
+      atomicAdd(&d.stats[((long long)nb * d.G + g) * 2], (double)sstat[g]);
+      atomicAdd(&d.stats[((long long)nb * d.G + g) * 2 + 1], (double)sstat[d.G + g]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// trilinear upsample (align_corners=False), factors in {1,2} per axis, channels-last, optional add + GN stats
+//   src = max((dst + 0.5)/f - 0.5, 0); i0 = floor(src); i1 = min(i0+1, n-1); l = src - i0
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up_coord(int o, int f, int n_in, int& i0, int& i1, float& l) {
+  if (f == 1) { i0 = o; i1 = o; l = 0.f; return; }
+  float s = ((float)o + 0.5f) * 0.5f - 0.5f;
+  s = fmaxf(s, 0.f);
+  i0 = (int)s;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resample_desc d) {
+  const int c4n = d.C >> 2;
+  const int Do = d.D * d.fd, Ho = d.H * d.fh, Wo = d.W * d.fw;
+  const long long So = (long long)Do * Ho * Wo;
+  const long long per_n = So * c4n;
+  // grid.y = sample index so that a CTA never straddles samples (needed for the stats reduction)
+  const int n = blockIdx.y;
+  extern __shared__ float sstat[];
+  if (d.stats) {
+    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+  }
+  const float4* x4 = (const float4*)d.x + (long long)n * d.D * d.H * d.W * c4n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per_n; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % c4n);
+    long long s = t / c4n;
+    const int ow = (int)(s % Wo); s /= Wo;
+    const int oh = (int)(s % Ho); s /= Ho;
+    const int od = (int)s;
+    int z0, z1, y0, y1, x0, x1;
+    float lz, ly, lx;
+    up_coord(od, d.fd, d.D, z0, z1, lz);
+    up_coord(oh, d.fh, d.H, y0, y1, ly);
+    up_coord(ow, d.fw, d.W, x0, x1, lx);
+    auto ld = [&](int z, int y, int x) { return __ldg(x4 + (((long long)z * d.H + y) * d.W + x) * c4n + c4); };
+    const float hz = 1.f - lz, hy = 1.f - ly, hx = 1.f - lx;
+    float4 acc;
+    {
+      const float4 a000 = ld(z0, y0, x0), a001 = ld(z0, y0, x1), a010 = ld(z0, y1, x0), a011 = ld(z0, y1, x1);
+      const float4 a100 = ld(z1, y0, x0), a101 = ld(z1, y0, x1), a110 = ld(z1, y1, x0), a111 = ld(z1, y1, x1);
+#define EMO_TRI(f) \
+  (hz * (hy * (hx * a000.f + lx * a001.f) + ly * (hx * a010.f + lx * a011.f)) + \
+   lz * (hy * (hx * a100.f + lx * a101.f) + ly * (hx * a110.f + lx * a111.f)))
+      acc.x = EMO_TRI(x); acc.y = EMO_TRI(y); acc.z = EMO_TRI(z); acc.w = EMO_TRI(w);
+#undef EMO_TRI
+    }
+    const long long o = (long long)n * per_n + t;
+    if (d.add) {
+      const float4 a = __ldg((const float4*)d.add + o);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    ((float4*)d.out)[o] = acc;
+    if (d.stats) {
+      const int cpg = d.C / d.G;
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c4 * 4 + j) / cpg;
+        atomicAdd(&sstat[g], a[j]);
+        atomicAdd(&sstat[d.G + g], a[j] * a[j]);
+      }
+    }
+  }
+  if (d.stats) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2], (double)sstat[g]);
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2 + 1], (double)sstat[d.G + g]);
+    }
+  }
+}
+
+// avgpool with kernel == stride == (fd, fh, fw), channels-last; optional add + stats of the result
+__global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d) {
+  const int c4n = d.C >> 2;
+  const int Do = d.D / d.fd, Ho = d.H / d.fh, Wo = d.W / d.fw;
+  const long long per_n = (long long)Do * Ho * Wo * c4n;
+  const int n = blockIdx.y;
+  extern __shared__ float sstat[];
+  if (d.stats) {
+    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+  }
+  const float4* x4 = (const float4*)d.x + (long long)n * d.D * d.H * d.W * c4n;
+  const float inv = 1.f / (float)(d.fd * d.fh * d.fw);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per_n; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % c4n);
+    long long s = t / c4n;
+    const int ow = (int)(s % Wo); s /= Wo;
+    const int oh = (int)(s % Ho); s /= Ho;
+    const int od = (int)s;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int a = 0; a < d.fd; ++a)
+      for (int b = 0; b < d.fh; ++b)
+        for (int c = 0; c < d.fw; ++c) {
+          const float4 v = __ldg(x4 + (((long long)(od * d.fd + a) * d.H + (oh * d.fh + b)) * d.W + (ow * d.fw + c)) * c4n + c4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+    const long long o = (long long)n * per_n + t;
+    if (d.add) {
+      const float4 a = __ldg((const float4*)d.add + o);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    ((float4*)d.out)[o] = acc;
+    if (d.stats) {
+      const int cpg = d.C / d.G;
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c4 * 4 + j) / cpg;
+        atomicAdd(&sstat[g], a[j]);
+        atomicAdd(&sstat[d.G + g], a[j] * a[j]);
+      }
+    }
+  }
+  if (d.stats) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2], (double)sstat[g]);
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2 + 1], (double)sstat[d.G + g]);
+    }
+  }
+}
+
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int N, int H, int W, int C, float* __restrict__ out) {
+  const int c4n = C >> 2;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * c4n;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % c4n);
+    long long s = t / c4n;
+    const int ow = (int)(s % Wo); s /= Wo;
+    const int oh = (int)(s % Ho); s /= Ho;
+    const int n = (int)s;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oh * 2 + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ow * 2 + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = __ldg((const float4*)x + (((long long)n * H + iy) * W + ix) * c4n + c4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    ((float4*)out)[t] = m;
+  }
+}
+
+__global__ void global_avgpool_kernel(const float* __restrict__ x, int N, long long S, int C, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * C) return;
+  const int n = idx / C, c = idx % C;
+  float acc = 0.f;
+  for (long long s = 0; s < S; ++s) acc += x[((long long)n * S + s) * C + c];
+  out[idx] = acc / (float)S;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pose algebra (single thread per sample; a few hundred flops)
+// ------------------------------------------------------------------------------------------------
+__device__ void mat4_mul(const float* a, const float* b, float* c) {
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
+      c[i * 4 + j] = s;
+    }
+}
+
+// general 4x4 inverse by Gauss-Jordan with partial pivoting, fp32 in/out, fp64 inside
+// (torch.inverse is LU in fp32; the fp64 inside only makes us closer to the exact inverse)
+__device__ void mat4_inv(const float* a, float* out) {
+  double m[4][8];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) { m[i][j] = a[i * 4 + j]; m[i][4 + j] = (i == j) ? 1.0 : 0.0; }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    double best = fabs(m[c][c]);
+    for (int r = c + 1; r < 4; ++r)
+      if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
+    if (piv != c)
+      for (int j = 0; j < 8; ++j) { double t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+    const double inv = 1.0 / m[c][c];
+    for (int j = 0; j < 8; ++j) m[c][j] *= inv;
+    for (int r = 0; r < 4; ++r)
+      if (r != c) {
+        const double f = m[r][c];
+        for (int j = 0; j < 8; ++j) m[r][j] -= f * m[c][j];
+      }
+  }
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) out[i * 4 + j] = (float)m[i][4 + j];
+}
+
+// polar decomposition A = U P of a 3x3 matrix in fp64 (Newton iteration on the orthogonal factor,
+// quadratically convergent; scipy.linalg.polar gets the same U, P via SVD)
+__device__ void polar3(const double* A, double* U, double* P) {
+  double X[9];
+  for (int i = 0; i < 9; ++i) X[i] = A[i];
+  for (int it = 0; it < 60; ++it) {
+    // inverse transpose of X via cofactors
+    double c[9];
+    c[0] = X[4] * X[8] - X[5] * X[7]; c[1] = X[5] * X[6] - X[3] * X[8]; c[2] = X[3] * X[7] - X[4] * X[6];
+    c[3] = X[2] * X[7] - X[1] * X[8]; c[4] = X[0] * X[8] - X[2] * X[6]; c[5] = X[1] * X[6] - X[0] * X[7];
+    c[6] = X[1] * X[5] - X[2] * X[4]; c[7] = X[2] * X[3] - X[0] * X[5]; c[8] = X[0] * X[4] - X[1] * X[3];
+    const double det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
+    double diff = 0.0;
+    for (int i = 0; i < 9; ++i) {
+      const double nx = 0.5 * (X[i] + c[i] / det);  // c/det = X^{-T}
+      diff += fabs(nx - X[i]);
+      X[i] = nx;
+    }
+    if (diff < 1e-15) break;
+  }
+  for (int i = 0; i < 9; ++i) U[i] = X[i];
+  // P = U^T A
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += U[k * 3 + i] * A[k * 3 + j];
+      P[i * 3 + j] = s;
+    }
+  // symmetrise (exact P is symmetric)
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j) { const double s = 0.5 * (P[i * 3 + j] + P[j * 3 + i]); P[i * 3 + j] = s; P[j * 3 + i] = s; }
+}
+
+__global__ void pose_theta_kernel(const emo_pose_desc d) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= d.N) return;
+  const float* q = d.srt + n * 9;
+  // utils/point_transforms.py:187-240
+  float S[16] = {q[0], 0, 0, 0, 0, q[1], 0, 0, 0, 0, q[2], 0, 0, 0, 0, 1};
+  const float pi = 3.14159265358979323846f;
+  const float yaw = fminf(fmaxf(q[3], -pi / 2), pi), pitch = fminf(fmaxf(q[4], -pi / 2), pi), roll = fminf(fmaxf(q[5], -pi / 2), pi);
+  const float cy = cosf(yaw), sy = sinf(yaw), cp = cosf(pitch), sp = sinf(pitch), cr = cosf(roll), sr = sinf(roll);
+  float R[16] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr, 0,
+                 sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr, 0,
+                 -sp,     cp * sr,                cp * cr,                0,
+                 0, 0, 0, 1};
+  float T[16] = {1, 0, 0, q[6], 0, 1, 0, q[7], 0, 0, 1, q[8], 0, 0, 0, 1};
+  float SR[16], th[16];
+  mat4_mul(S, R, SR);
+  mat4_mul(SR, T, th);
+
+  if (d.mix) {
+    // notebooks/infer.py:686-736 with mix_old=False, B=T=1:
+    //   source_rotation, source_stretch = polar(source_linear); target_rotation, target_stretch = polar(target_linear)
+    //   theta = (source_stretch * target_stretch.mean() / source_stretch.mean()) @ target_rotation @ target_translation
+    // all on 4x4 float64 matrices whose last row/col is that of the identity.
+    double As[9], At[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { As[i * 3 + j] = d.source_theta[i * 4 + j]; At[i * 3 + j] = th[i * 4 + j]; }
+    double Us[9], Ps[9], Ut[9], Pt[9];
+    polar3(As, Us, Ps);
+    polar3(At, Ut, Pt);
+    // .mean() over the 4x4 matrices (15 zeros + the trailing 1 included)
+    double ms = 1.0, mt = 1.0;
+    for (int i = 0; i < 9; ++i) { ms += Ps[i]; mt += Pt[i]; }
+    ms /= 16.0; mt /= 16.0;
+    const double k = mt / ms;
+    double M1[16] = {0}, M2[16] = {0}, M3[16] = {0}, Tm[16] = {0}, Rt[16] = {0};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) { M1[i * 4 + j] = Ps[i * 3 + j] * k; Rt[i * 4 + j] = Ut[i * 3 + j]; }
+    M1[15] = 1.0 * k; Rt[15] = 1.0;
+    for (int i = 0; i < 4; ++i) Tm[i * 4 + i] = 1.0;
+    Tm[3] = th[3]; Tm[7] = th[7]; Tm[11] = th[11];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double s = 0.0;
+        for (int kk = 0; kk < 4; ++kk) s += M1[i * 4 + kk] * Rt[kk * 4 + j];
+        M2[i * 4 + j] = s;
+      }
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double s = 0.0;
+        for (int kk = 0; kk < 4; ++kk) s += M2[i * 4 + kk] * Tm[kk * 4 + j];
+        M3[i * 4 + j] = s;
+      }
+    // the reference keeps rows [:3] only; the 4th row used downstream is [0,0,0,1] (expression_embedder.py:163-168)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j) th[i * 4 + j] = (float)M3[i * 4 + j];
+    th[12] = 0.f; th[13] = 0.f; th[14] = 0.f; th[15] = 1.f;
+  }
+  if (d.theta_out)
+    for (int i = 0; i < 16; ++i) d.theta_out[n * 16 + i] = th[i];
+  float inv[16];
+  if (d.invert_warp || d.align2d) mat4_inv(th, inv);
+  if (d.theta_warp) {
+    const float* src = d.invert_warp ? inv : th;
+    for (int i = 0; i < 12; ++i) d.theta_warp[n * 12 + i] = src[i];
+  }
+  if (d.align2d) {
+    // inverse()[:, :, [0,1,3]][:, [0,1,3]] then @ diag(0.5, 0.5, 1), rows [:2]
+    const int idx[3] = {0, 1, 3};
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const float v = inv[idx[i] * 4 + idx[j]];
+        d.align2d[n * 6 + i * 3 + j] = (j < 2) ? v * 0.5f : v;
+      }
+  }
+}
+
+}  // namespace emo
+
+using namespace emo;
+
+extern "C" const char* emo_last_error(void) { return emo::g_err; }
+extern "C" int emo_version(void) { return 100; }
+
+extern "C" int emo_device_info(int* sm_count, int* cc) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("emo_device_info: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }
+  int sms = 0, major = 0, minor = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (sm_count) *sm_count = sms;
+  if (cc) *cc = major * 10 + minor;
+  return EMO_OK;
+}
+
+extern "C" int emo_linear(const emo_linear_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->x && d->w && d->out, "emo_linear: null pointer");
+  EMO_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "emo_linear: bad shape");
+  const long long warps = (long long)d->M * d->N;
+  linear_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, stream>>>(*d);
+  return check_launch("emo_linear");
+}
+
+extern "C" int emo_conv_direct(const emo_conv_direct_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->x && d->w && d->out, "emo_conv_direct: null pointer");
+  EMO_REQUIRE(d->Cout % 4 == 0, "emo_conv_direct: Cout must be a multiple of 4");
+  const long long per_n = (long long)d->Hout * d->Wout * (d->Cout / 4);
+  if (d->stats) EMO_REQUIRE(per_n % 256 == 0 && d->G > 0 && d->Cout % d->G == 0, "emo_conv_direct: stats need Hout*Wout*Cout/4 %% 256 == 0");
+  const long long total = per_n * d->N;
+  conv_direct_kernel<<<(unsigned)cdivll(total, 256), 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(*d);
+  return check_launch("emo_conv_direct");
+}
+
+static int resample_check(const emo_resample_desc* d, const char* who) {
+  EMO_REQUIRE(d && d->x && d->out, "%s: null pointer", who);
+  EMO_REQUIRE(d->C % 4 == 0, "%s: C must be a multiple of 4", who);
+  EMO_REQUIRE((d->fd == 1 || d->fd == 2) && (d->fh == 1 || d->fh == 2) && (d->fw == 1 || d->fw == 2), "%s: factors must be 1 or 2", who);
+  if (d->stats) EMO_REQUIRE(d->G > 0 && d->C % d->G == 0, "%s: C not divisible by G", who);
+  return EMO_OK;
+}
+
+extern "C" int emo_upsample_trilinear(const emo_resample_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = resample_check(d, "emo_upsample_trilinear");
+  if (rc) return rc;
+  const long long per_n = (long long)d->D * d->fd * d->H * d->fh * d->W * d->fw * (d->C / 4);
+  long long bx = cdivll(per_n, 256 * 4);
+  if (bx > 148 * 16) bx = 148 * 16;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)d->N);
+  upsample_trilinear_kernel<<<grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(*d);
+  return check_launch("emo_upsample_trilinear");
+}
+
+extern "C" int emo_avgpool(const emo_resample_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = resample_check(d, "emo_avgpool");
+  if (rc) return rc;
+  EMO_REQUIRE(d->D % d->fd == 0 && d->H % d->fh == 0 && d->W % d->fw == 0, "emo_avgpool: size not divisible by the kernel");
+  const long long per_n = (long long)(d->D / d->fd) * (d->H / d->fh) * (d->W / d->fw) * (d->C / 4);
+  long long bx = cdivll(per_n, 256 * 4);
+  if (bx > 148 * 16) bx = 148 * 16;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)d->N);
+  avgpool_kernel<<<grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(*d);
+  return check_launch("emo_avgpool");
+}
+
+extern "C" int emo_maxpool2d_3x3s2(const float* x, int N, int H, int W, int C, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(x && out && C % 4 == 0, "emo_maxpool2d_3x3s2: bad arguments");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 4);
+  maxpool3x3s2_kernel<<<(unsigned)cdivll(total, 256), 256, 0, stream>>>(x, N, H, W, C, out);
+  return check_launch("emo_maxpool2d_3x3s2");
+}
+
+extern "C" int emo_global_avgpool(const float* x, int N, long long S, int C, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(x && out, "emo_global_avgpool: null pointer");
+  global_avgpool_kernel<<<cdiv(N * C, 128), 128, 0, stream>>>(x, N, S, C, out);
+  return check_launch("emo_global_avgpool");
+}
+
+extern "C" int emo_pose_theta(const emo_pose_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->srt, "emo_pose_theta: null pointer");
+  EMO_REQUIRE(!d->mix || d->source_theta, "emo_pose_theta: mix needs source_theta");
+  pose_theta_kernel<<<cdiv(d->N, 32), 32, 0, stream>>>(*d);
+  return check_launch("emo_pose_theta");
+}

@@ -1,0 +1,207 @@
+// GroupNorm statistics / affine finalisation / fused apply (HBM-bound elementwise passes).
+//
+// nn.GroupNorm(32, C, eps=1e-5)  networks/volumetric_avatar/utils.py:953,957
+// AdaptiveGroupNorm              utils.py:302-325 (+ assign_adaptive_norm_params :983-995):
+//     y = (GN(x)*w + b) * (w + dw) + (b + db)
+// ResBlock pre-activation order  utils.py:761-788: [nearest up] -> norm -> ReLU -> conv
+// The apply pass writes what the next tensor-core conv consumes: bf16 (hi, lo) planes, channels-last.
+#include "common.cuh"
+
+namespace emo {
+
+// ---- statistics: x [N][S][C] fp32, per (n, g) sum and sum of squares, double accumulation across CTAs ----
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int N, long long S, int C, int G,
+                                                       double* __restrict__ stats, int chunks) {
+  // grid = N * chunks; each CTA reduces a slab of spatial positions for all channels
+  const int n = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  const long long s_per = (S + chunks - 1) / chunks;
+  const long long s0 = (long long)ch * s_per;
+  const long long s1 = (s0 + s_per < S) ? s0 + s_per : S;
+  const int cpg = C / G;
+  extern __shared__ float sh[];  // [2][G]
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int c4n = C >> 2;
+  const float4* x4 = (const float4*)(x + (long long)n * S * C);
+  // each thread owns one float4 channel slot (c4) and a row slot; accumulates in registers, flushes once
+  const int L = c4n < (int)blockDim.x ? c4n : (int)blockDim.x;
+  const int rpi = blockDim.x / L;  // rows handled per pass
+  const int rslot = threadIdx.x / L;
+  if (rslot < rpi) {
+    for (int c4 = threadIdx.x % L; c4 < c4n; c4 += L) {
+      float acc_s[4] = {0, 0, 0, 0}, acc_q[4] = {0, 0, 0, 0};
+      for (long long s = s0 + rslot; s < s1; s += rpi) {
+        const float4 v = __ldg(x4 + s * c4n + c4);
+        acc_s[0] += v.x; acc_q[0] = fmaf(v.x, v.x, acc_q[0]);
+        acc_s[1] += v.y; acc_q[1] = fmaf(v.y, v.y, acc_q[1]);
+        acc_s[2] += v.z; acc_q[2] = fmaf(v.z, v.z, acc_q[2]);
+        acc_s[3] += v.w; acc_q[3] = fmaf(v.w, v.w, acc_q[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c4 * 4 + j) / cpg;
+        atomicAdd(&sh[g], acc_s[j]);
+        atomicAdd(&sh[G + g], acc_q[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    atomicAdd(&stats[((long long)n * G + g) * 2], (double)sh[g]);
+    atomicAdd(&stats[((long long)n * G + g) * 2 + 1], (double)sh[G + g]);
+  }
+}
+
+// ---- finalize: stats -> per-(n,c) scale/shift ----
+__global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d.N * d.C) return;
+  const int n = idx / d.C, c = idx % d.C;
+  const int g = c / (d.C / d.G);
+  const double s = d.stats[((long long)n * d.G + g) * 2], q = d.stats[((long long)n * d.G + g) * 2 + 1];
+  const double mean = s / d.count;
+  double var = q / d.count - mean * mean;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+  float gam = d.gamma ? d.gamma[c] : 1.f, bet = d.beta ? d.beta[c] : 0.f;
+  if (d.ada_w) {
+    const float aw = d.ada_w[idx], ab = d.ada_b[idx];
+    bet = bet * aw + ab;
+    gam = gam * aw;
+  }
+  const float A = rstd * gam;
+  d.A[idx] = A;
+  d.B[idx] = bet - (float)mean * A;
+}
+
+// ---- apply: y = act(x*A + B [+ res*A2 + B2]) -> fp32 / bf16 hi,lo, optional nearest x2 on H,W ----
+template <int UP>
+__global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
+  const int c4n = d.C >> 2;
+  const long long S = (long long)d.D * d.H * d.W;
+  const long long total = (long long)d.N * S * c4n;
+  const float4* x4 = (const float4*)d.x;
+  const float4* r4 = (const float4*)d.res;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(t % c4n);
+    const long long sp = t / c4n;  // n*S + s
+    const int n = (int)(sp / S);
+    float4 v = __ldg(x4 + t);
+    if (d.A) {
+      const float4 a = __ldg((const float4*)(d.A + (d.ab_per_sample ? (long long)n * d.C : 0)) + c4);
+      const float4 b = __ldg((const float4*)(d.B + (d.ab_per_sample ? (long long)n * d.C : 0)) + c4);
+      v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+    }
+    if (r4) {
+      float4 r = __ldg(r4 + t);
+      if (d.A2) {
+        const float4 a = __ldg((const float4*)d.A2 + c4);
+        const float4 b = __ldg((const float4*)d.B2 + c4);
+        r.x = fmaf(r.x, a.x, b.x); r.y = fmaf(r.y, a.y, b.y); r.z = fmaf(r.z, a.z, b.z); r.w = fmaf(r.w, a.w, b.w);
+      }
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    v.x = act_apply(v.x, d.act); v.y = act_apply(v.y, d.act); v.z = act_apply(v.z, d.act); v.w = act_apply(v.w, d.act);
+    uint2 hi, lo;
+    if (d.out_hi) split4(v, hi, lo);
+    if (UP == 1) {
+      if (d.out) ((float4*)d.out)[t] = v;
+      if (d.out_hi) {
+        ((uint2*)d.out_hi)[t] = hi;
+        ((uint2*)d.out_lo)[t] = lo;
+      }
+    } else {
+      const long long s = sp - (long long)n * S;
+      const int w = (int)(s % d.W);
+      const int h = (int)((s / d.W) % d.H);
+      const int dd = (int)(s / ((long long)d.W * d.H));
+      const int H2 = d.H * UP, W2 = d.W * UP;
+#pragma unroll
+      for (int uy = 0; uy < UP; ++uy)
+#pragma unroll
+        for (int ux = 0; ux < UP; ++ux) {
+          const long long o = ((((long long)n * d.D + dd) * H2 + (h * UP + uy)) * W2 + (w * UP + ux)) * c4n + c4;
+          if (d.out) ((float4*)d.out)[o] = v;
+          if (d.out_hi) {
+            ((uint2*)d.out_hi)[o] = hi;
+            ((uint2*)d.out_lo)[o] = lo;
+          }
+        }
+    }
+  }
+}
+
+__global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    uint2 h, l;
+    split4(__ldg((const float4*)x + t), h, l);
+    hi[t] = h; lo[t] = l;
+  }
+}
+
+__global__ void flush_kernel(float4* buf, long long n4) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
+    buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace emo
+
+using namespace emo;
+
+extern "C" int emo_gn_stats(const float* x, int N, long long spatial, int C, int G, double* stats, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(x && stats, "emo_gn_stats: null pointer");
+  EMO_REQUIRE(C % 4 == 0 && G > 0 && C % G == 0, "emo_gn_stats: C=%d must be a multiple of 4 and of G=%d", C, G);
+  EMO_REQUIRE(((uintptr_t)x % 16) == 0, "emo_gn_stats: x must be 16-byte aligned");
+  long long work = spatial * (C / 4);
+  int chunks = (int)(work / (256 * 16));
+  if (chunks < 1) chunks = 1;
+  const int max_chunks = (148 * 8) / (N > 0 ? N : 1) > 0 ? (148 * 8) / N : 1;
+  if (chunks > max_chunks) chunks = max_chunks;
+  gn_stats_kernel<<<N * chunks, 256, 2 * G * sizeof(float), stream>>>(x, N, spatial, C, G, stats, chunks);
+  return check_launch("emo_gn_stats");
+}
+
+extern "C" int emo_gn_finalize(const emo_gn_finalize_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->stats && d->A && d->B, "emo_gn_finalize: null pointer");
+  EMO_REQUIRE(d->G > 0 && d->C % d->G == 0, "emo_gn_finalize: C=%d not divisible by G=%d", d->C, d->G);
+  EMO_REQUIRE((d->ada_w == nullptr) == (d->ada_b == nullptr), "emo_gn_finalize: ada_w/ada_b must come together");
+  const int total = d->N * d->C;
+  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, stream>>>(*d);
+  return check_launch("emo_gn_finalize");
+}
+
+extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->x, "emo_apply: null input");
+  EMO_REQUIRE(d->out || (d->out_hi && d->out_lo), "emo_apply: no output");
+  EMO_REQUIRE(d->C % 4 == 0, "emo_apply: C=%d must be a multiple of 4", d->C);
+  EMO_REQUIRE(d->up == 1 || d->up == 2, "emo_apply: up must be 1 or 2");
+  EMO_REQUIRE((d->A == nullptr) == (d->B == nullptr) && (d->A2 == nullptr) == (d->B2 == nullptr), "emo_apply: A/B must come in pairs");
+  const long long total = (long long)d->N * d->D * d->H * d->W * (d->C / 4);
+  long long blocks = cdivll(total, 256);
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  if (blocks < 1) blocks = 1;
+  if (d->up == 1) apply_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(*d);
+  else apply_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(*d);
+  return check_launch("emo_apply");
+}
+
+extern "C" int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(x && hi && lo, "emo_split_bf16: null pointer");
+  EMO_REQUIRE(n % 4 == 0, "emo_split_bf16: n must be a multiple of 4");
+  long long blocks = cdivll(n / 4, 256);
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  if (blocks < 1) blocks = 1;
+  split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, (uint2*)hi, (uint2*)lo);
+  return check_launch("emo_split_bf16");
+}
+
+extern "C" int emo_l2_flush(void* buf, long long bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(buf && bytes >= 16, "emo_l2_flush: bad buffer");
+  flush_kernel<<<148 * 8, 256, 0, stream>>>((float4*)buf, bytes / 16);
+  return check_launch("emo_l2_flush");
+}

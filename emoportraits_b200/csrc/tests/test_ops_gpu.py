@@ -1,0 +1,267 @@
+"""GPU unit tests of every C-ABI op against a plain PyTorch fp32 CPU reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def cl(x):  # NCDHW/NCHW -> channels-last (N,D,H,W,C)
+    if x.dim() == 4:
+        x = x[:, :, None]
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def uncl(x):  # (N,D,H,W,C) -> NCDHW
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from emoportraits_b200 import ops as o
+    return o
+
+
+def _grid(N, D, H, W, seed, jitter=0.1, rot=False):
+    g = torch.Generator().manual_seed(seed)
+    zs, ys, xs = torch.linspace(-1, 1, D), torch.linspace(-1, 1, H), torch.linspace(-1, 1, W)
+    w, v, u = torch.meshgrid(zs, ys, xs, indexing="ij")
+    base = torch.stack([u, v, w], -1)[None].repeat(N, 1, 1, 1, 1)
+    grid = base + jitter * torch.randn(base.shape, generator=g)
+    if rot:
+        a = math.radians(30)
+        R = torch.tensor([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1.0]])
+        grid = grid @ R.T + 0.2
+    return grid.contiguous()
+
+
+@pytest.mark.parametrize("shape", [(1, 96, 16, 64, 64), (2, 8, 5, 7, 9), (1, 96, 64, 64, 64)])
+@pytest.mark.parametrize("rot", [False, True])
+def test_grid_sample3d_ncdhw(ops, shape, rot):
+    N, C, D, H, W = shape
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(0))
+    grid = _grid(N, D, H, W, 1, rot=rot)
+    ref = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    out = ops.grid_sample3d(x.cuda(), grid=grid.cuda(), in_layout="ncdhw").cpu()
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("shape", [(1, 96, 16, 64, 64), (2, 8, 5, 7, 9)])
+@pytest.mark.parametrize("out_layout", ["cl", "hwdc", "ncdhw"])
+def test_grid_sample3d_channels_last(ops, shape, out_layout):
+    N, C, D, H, W = shape
+    x = torch.randn(shape, generator=torch.Generator().manual_seed(0))
+    grid = _grid(N, D, H, W, 2, rot=True)
+    ref = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    out, sp = ops.grid_sample3d(cl(x).cuda(), grid=grid.cuda(), in_layout="cl", out_layout=out_layout, want_split=True)
+    out, rec = out.cpu(), sp.float().cpu()
+    if out_layout == "cl":
+        out, rec = uncl(out), uncl(rec)
+    elif out_layout == "hwdc":
+        out, rec = out.permute(0, 4, 3, 1, 2), rec.permute(0, 4, 3, 1, 2)
+    assert (out - ref).abs().max().item() < 2e-5
+    assert (rec - ref).abs().max().item() < 2e-5 + ref.abs().max().item() * 2 ** -16
+
+
+def test_grid_sample3d_affine_matches_bmm_grid(ops):
+    """theta variant == identity_grid_3d.bmm(theta[:, :3]^T) then F.grid_sample (infer.py:441-444, 583-588)."""
+    N, C, D, S = 2, 96, 16, 64
+    x = torch.randn(N, C, D, S, S, generator=torch.Generator().manual_seed(3))
+    a, b = math.radians(12), math.radians(-7)
+    th = torch.tensor([[[math.cos(a), -math.sin(a), 0.05, 0.03], [math.sin(a), math.cos(a), -0.02, -0.04], [0.01, 0.03, 1.1, 0.02]],
+                       [[0.9 * math.cos(b), -math.sin(b), 0.0, 0.4], [math.sin(b), 0.9 * math.cos(b), 0.1, -0.3], [0.0, -0.1, 0.8, 0.1]]])
+    gs, gz = torch.linspace(-1, 1, S), torch.linspace(-1, 1, D)
+    w, v, u = torch.meshgrid(gz, gs, gs, indexing="ij")
+    idg = torch.stack([u, v, w, torch.ones_like(u)], 3).view(1, -1, 4).repeat(N, 1, 1)
+    grid = idg.bmm(th.transpose(1, 2)).view(N, D, S, S, 3)
+    ref = F.grid_sample(x, grid, padding_mode="zeros", align_corners=False)
+    out = ops.grid_sample3d(x.cuda(), theta=th.cuda(), out_size=(D, S, S), in_layout="ncdhw").cpu()
+    assert (out - ref).abs().max().item() < 1e-4
+    out2 = uncl(ops.grid_sample3d(cl(x).cuda(), theta=th.cuda(), out_size=(D, S, S), in_layout="cl").cpu())
+    assert (out2 - ref).abs().max().item() < 1e-4
+
+
+def test_grid_sample2d_affine_and_resize(ops):
+    img = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    th = torch.tensor([[[0.5, 0.05, 0.1], [-0.04, 0.55, -0.05]], [[0.45, 0.0, 0.0], [0.0, 0.45, 0.2]]])
+    g = torch.linspace(-1, 1, 32)
+    v, u = torch.meshgrid(g, g, indexing="ij")
+    idg = torch.stack([u, v, torch.ones_like(u)], 2).view(1, -1, 3).repeat(2, 1, 1)
+    grid = idg.bmm(th.transpose(1, 2)).view(2, 32, 32, 2)
+    ref = F.grid_sample(img, grid, align_corners=False)
+    mean, std = torch.tensor([0.485, 0.456, 0.406]), torch.tensor([0.229, 0.224, 0.225])
+    out, nchw = ops.grid_sample2d_affine(img.cuda(), th.cuda(), (32, 32), mean.cuda(), std.cuda(), want_nchw=True)
+    assert (nchw.cpu() - ref).abs().max().item() < 1e-5
+    refn = (ref - mean[None, :, None, None]) / std[None, :, None, None]
+    got = out.cpu()[:, 0].permute(0, 3, 1, 2)
+    assert (got[:, :3] - refn).abs().max().item() < 1e-5 and got[:, 3].abs().max().item() == 0
+    ref2 = F.interpolate(img, size=(16, 16), mode="bilinear")
+    got2 = ops.resize_bilinear(img.cuda(), (16, 16)).cpu()[:, 0].permute(0, 3, 1, 2)[:, :3]
+    assert (got2 - ref2).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("C,shape", [(512, (1, 64, 64)), (96, (16, 16, 16)), (320, (1, 32, 32)), (32, (4, 8, 8))])
+def test_groupnorm_relu_apply(ops, C, shape):
+    N = 2
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, C, *shape, generator=g) * 2 + 0.5
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    ref = F.relu(F.group_norm(x, 32, gamma, beta, 1e-5))
+    xc = cl(x).cuda()
+    st = ops.gn_stats(xc, 32)
+    A, B = ops.gn_finalize(st, x[0].numel() / 32, gamma.cuda(), beta.cuda())
+    out, sp = ops.apply(xc, A, B, act=ops.ACT_RELU, want_f32=True, want_split=True)
+    assert (uncl(out.cpu()) - ref).abs().max().item() < 2e-5
+    assert (uncl(sp.float().cpu()) - ref).abs().max().item() < 2e-5 + ref.abs().max().item() * 2 ** -16
+
+
+def test_apply_upsample_and_residual(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 64, 8, 8, generator=g)
+    r = torch.randn(1, 64, 8, 8, generator=g)
+    A, B = torch.randn(1, 64, generator=g), torch.randn(1, 64, generator=g)
+    ref = F.interpolate(F.relu(x * A[0][None, :, None, None] + B[0][None, :, None, None] + r), scale_factor=2, mode="nearest")
+    out = ops.apply(cl(x).cuda(), A.cuda(), B.cuda(), act=ops.ACT_RELU, res=cl(r).cuda(), up=2, want_f32=True, want_split=False)
+    assert (uncl(out.cpu())[:, :, 0] - ref).abs().max().item() < 1e-6
+
+
+def _conv_case(ops, N, Cin, Cout, sp, k, stride=1, bias=True, residual=False, act=0, stats=False, out_nchw=False, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    three_d = len(sp) == 3
+    x = torch.randn(N, Cin, *sp, generator=g)
+    w = torch.randn(Cout, Cin, *([k] * len(sp)), generator=g) / math.sqrt(Cin * k ** len(sp))
+    b = torch.randn(Cout, generator=g) if bias else None
+    conv = F.conv3d if three_d else F.conv2d
+    ref = conv(x.double(), w.double(), b.double() if bias else None, stride=stride, padding=k // 2)
+    res = None
+    if residual:
+        res = torch.randn(ref.shape, generator=g)
+        ref = ref + res.double()
+    if act == 2:
+        ref = torch.sigmoid(ref)
+    elif act == 3:
+        ref = torch.tanh(ref)
+    pw = ops.pack_conv_weight(w)
+    a = ops.split_bf16(cl(x).cuda())
+    st = ops.new_stats(N, 32, "cuda") if stats else None
+    s3 = (stride,) * 3 if three_d else (1, stride, stride)
+    out = ops.conv_igemm(a, pw, stride=s3, bias=b.cuda() if bias else None, residual=cl(res).cuda() if residual else None,
+                         act=act, stats=st, out_nchw=out_nchw)
+    torch.cuda.synchronize()
+    got = out.cpu() if out_nchw else uncl(out.cpu())
+    if not three_d:
+        got = got[:, :, 0]
+    scale = ref.abs().max().item()
+    err = (got.double() - ref).abs().max().item()
+    assert err < 1e-4 * max(scale, 1.0), (err, scale)
+    if stats:
+        r = ref.float().reshape(N, 32, -1)
+        s_ref = torch.stack([r.double().sum(-1), (r.double() ** 2).sum(-1)], -1)
+        assert torch.allclose(st.cpu(), s_ref, rtol=1e-4, atol=1e-2), (st.cpu() - s_ref).abs().max()
+    return err
+
+
+@pytest.mark.parametrize("Cin,Cout,sp,k", [
+    (64, 64, (16, 16), 3),        # one k-chunk of 64, single tile
+    (128, 128, (32, 32), 3),      # multiple tiles
+    (512, 512, (64, 64), 3),      # decoder res block shape
+    (512, 320, (32, 32), 3),      # N tile 160
+    (192, 128, (32, 32), 3),
+    (96, 96, (16, 16), 3),        # KC = 32 path (SWIZZLE_64B)
+    (1536, 512, (64, 64), 1),     # decoder input 1x1
+    (128, 3, (32, 32), 1),        # ragged Cout head
+    (32, 32, (8, 8), 3),
+])
+def test_conv2d_igemm(ops, Cin, Cout, sp, k):
+    _conv_case(ops, 1, Cin, Cout, sp, k, bias=True, residual=(Cout % 4 == 0), stats=(Cout % 32 == 0))
+
+
+def test_conv2d_igemm_batch_and_act(ops):
+    _conv_case(ops, 2, 128, 3, (32, 32), 1, act=2, out_nchw=True)
+    _conv_case(ops, 2, 64, 64, (16, 16), 3, act=3)
+
+
+@pytest.mark.parametrize("Cin,Cout,sp,k", [
+    (64, 32, (4, 16, 16), 3),
+    (96, 96, (4, 16, 16), 3),
+    (512, 256, (8, 8, 8), 3),
+    (32, 3, (4, 16, 16), 3),
+    (64, 128, (4, 8, 8), 1),
+])
+def test_conv3d_igemm(ops, Cin, Cout, sp, k):
+    _conv_case(ops, 1, Cin, Cout, sp, k, bias=True, residual=(Cout % 4 == 0), stats=(Cout % 32 == 0))
+
+
+@pytest.mark.parametrize("sp", [(32, 32), (8, 8)])
+def test_conv2d_igemm_stride2(ops, sp):
+    _conv_case(ops, 1, 64, 128, sp, 3, stride=2, bias=False)
+    _conv_case(ops, 1, 64, 128, sp, 1, stride=2, bias=False)
+
+
+def test_conv_direct_stem(ops):
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(1, 3, 64, 64, generator=g)
+    w = torch.randn(128, 3, 7, 7, generator=g) * 0.1
+    b = torch.randn(128, generator=g)
+    ref = F.conv2d(x, w, b, padding=3)
+    xc = torch.zeros(1, 1, 64, 64, 4)
+    xc[..., :3] = cl(x)
+    wc = torch.zeros(7, 7, 4, 128)
+    wc[:, :, :3] = w.permute(2, 3, 1, 0)
+    st = ops.new_stats(1, 32, "cuda")
+    out = ops.conv_direct(xc.cuda(), wc.cuda(), 1, 3, b.cuda(), stats=st)
+    assert (uncl(out.cpu())[:, :, 0] - ref).abs().max().item() < 1e-4
+    r = ref.reshape(1, 32, -1).double()
+    assert torch.allclose(st.cpu(), torch.stack([r.sum(-1), (r ** 2).sum(-1)], -1), rtol=1e-4, atol=1e-2)
+    ref2 = F.conv2d(x, w[:64], None, stride=2, padding=3)
+    out2 = ops.conv_direct(xc.cuda(), wc[..., :64].contiguous().cuda(), 2, 3)
+    assert (uncl(out2.cpu())[:, :, 0] - ref2).abs().max().item() < 1e-4
+
+
+def test_linear(ops):
+    g = torch.Generator().manual_seed(0)
+    x, w, b = torch.randn(3, 128, generator=g), torch.randn(70, 128, generator=g), torch.randn(70, generator=g)
+    add = torch.randn(3, 70, generator=g)
+    ref = (x @ w.T + b + add) * 0.5
+    out = ops.linear(x.cuda(), w.cuda(), b.cuda(), add.cuda(), scale=0.5).cpu()
+    assert (out - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("f", [(2, 2, 2), (1, 2, 2), (2, 1, 1)])
+def test_resamples(ops, f):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 64, 4, 6, 8, generator=g)
+    ref = F.interpolate(x, scale_factor=f, mode="trilinear")
+    st = ops.new_stats(2, 32, "cuda")
+    out = ops.upsample_trilinear(cl(x).cuda(), f, stats=st)
+    assert (uncl(out.cpu()) - ref).abs().max().item() < 1e-5
+    r = ref.reshape(2, 32, -1).double()
+    assert torch.allclose(st.cpu(), torch.stack([r.sum(-1), (r ** 2).sum(-1)], -1), rtol=1e-4, atol=1e-2)
+    ref2 = F.avg_pool3d(x, kernel_size=f, stride=f)
+    out2 = ops.avgpool(cl(x).cuda(), f)
+    assert (uncl(out2.cpu()) - ref2).abs().max().item() < 1e-5
+
+
+def test_maxpool_and_global_avgpool(ops):
+    x = torch.randn(2, 64, 16, 16, generator=torch.Generator().manual_seed(0))
+    ref = F.max_pool2d(x, 3, 2, 1)
+    out = ops.maxpool2d_3x3s2(cl(x).cuda())
+    assert (uncl(out.cpu())[:, :, 0] - ref).abs().max().item() == 0
+    assert (ops.global_avgpool(cl(x).cuda()).cpu() - x.mean((2, 3))).abs().max().item() < 1e-5
+
+
+def test_pose_theta(ops):
+    from oracle import restatement as R
+    srt = torch.tensor([[1.0, 1.1, 0.9, 0.15, -0.1, 0.05, 0.03, -0.02, 0.01], [0.8, 0.9, 1.0, -0.3, 0.2, 0.1, -0.1, 0.05, 0.0]])
+    th_ref = R.get_transform_matrix(srt[:, :3], srt[:, 3:6], srt[:, 6:])
+    th, warp, align = ops.pose_theta(srt.cuda(), invert_warp=True)
+    assert (th.cpu() - th_ref).abs().max().item() < 1e-6
+    assert (warp.cpu() - th_ref.inverse()[:, :3]).abs().max().item() < 1e-5
+    src = th_ref[0]
+    mixed_ref = R.get_mixing_theta(src[None], th_ref[1:2])
+    th2, warp2, align2 = ops.pose_theta(srt[1:2].cuda(), source_theta=src.cuda().contiguous(), mix=True)
+    assert (th2.cpu()[:, :3] - mixed_ref).abs().max().item() < 1e-5
+    assert (align2.cpu() - R.align_theta_2d(mixed_ref)).abs().max().item() < 1e-5

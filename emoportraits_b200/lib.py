@@ -1,0 +1,146 @@
+"""ctypes binding of libemoport.so (the C-ABI declared in include/emoportraits_b200.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing the ops raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+_HERE = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _HERE / "csrc" / "libemoport.so"
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+
+c_void_p, c_int, c_ll, c_float, c_double = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double
+
+
+class GridSample3dDesc(C.Structure):
+    _fields_ = [("in_", c_void_p), ("in_layout", c_int), ("N", c_int), ("C", c_int), ("Din", c_int), ("Hin", c_int),
+                ("Win", c_int), ("grid", c_void_p), ("theta", c_void_p), ("Dout", c_int), ("Hout", c_int),
+                ("Wout", c_int), ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p), ("os_n", c_ll),
+                ("os_c", c_ll), ("os_d", c_ll), ("os_h", c_ll), ("os_w", c_ll)]
+
+
+class GridSample2dAffineDesc(C.Structure):
+    _fields_ = [("in_", c_void_p), ("N", c_int), ("C", c_int), ("Hin", c_int), ("Win", c_int), ("theta", c_void_p),
+                ("Hout", c_int), ("Wout", c_int), ("mean", c_void_p), ("std", c_void_p), ("out", c_void_p),
+                ("C_pad", c_int), ("out_nchw", c_void_p)]
+
+
+class ResizeBilinearDesc(C.Structure):
+    _fields_ = [("in_", c_void_p), ("N", c_int), ("C", c_int), ("Hin", c_int), ("Win", c_int), ("Hout", c_int),
+                ("Wout", c_int), ("mean", c_void_p), ("std", c_void_p), ("out", c_void_p), ("C_pad", c_int)]
+
+
+class GnFinalizeDesc(C.Structure):
+    _fields_ = [("stats", c_void_p), ("N", c_int), ("C", c_int), ("G", c_int), ("count", c_double), ("eps", c_float),
+                ("gamma", c_void_p), ("beta", c_void_p), ("ada_w", c_void_p), ("ada_b", c_void_p), ("A", c_void_p),
+                ("B", c_void_p)]
+
+
+class ApplyDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
+                ("A", c_void_p), ("B", c_void_p), ("ab_per_sample", c_int), ("res", c_void_p), ("A2", c_void_p),
+                ("B2", c_void_p), ("act", c_int), ("up", c_int), ("out", c_void_p), ("out_hi", c_void_p),
+                ("out_lo", c_void_p)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("a_hi", c_void_p), ("a_lo", c_void_p), ("N", c_int), ("Din", c_int), ("Hin", c_int), ("Win", c_int),
+                ("Cin", c_int), ("w_hi", c_void_p), ("w_lo", c_void_p), ("Cout", c_int), ("Cout_pad", c_int),
+                ("kd", c_int), ("kh", c_int), ("kw", c_int), ("sd", c_int), ("sh", c_int), ("sw", c_int),
+                ("pd", c_int), ("ph", c_int), ("pw", c_int), ("Dout", c_int), ("Hout", c_int), ("Wout", c_int),
+                ("bias", c_void_p), ("residual", c_void_p), ("res_shift", c_int), ("act", c_int),
+                ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int)]
+
+
+class ConvDirectDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("N", c_int), ("Hin", c_int), ("Win", c_int), ("Cin_pad", c_int), ("w", c_void_p),
+                ("Cout", c_int), ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int), ("Hout", c_int),
+                ("Wout", c_int), ("bias", c_void_p), ("out", c_void_p), ("stats", c_void_p), ("G", c_int)]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("xs_m", c_ll), ("xs_k", c_ll), ("w", c_void_p), ("bias", c_void_p),
+                ("add", c_void_p), ("scale", c_float), ("act", c_int), ("M", c_int), ("N", c_int), ("K", c_int),
+                ("out", c_void_p), ("os_m", c_ll), ("os_n", c_ll)]
+
+
+class ResampleDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("N", c_int), ("D", c_int), ("H", c_int), ("W", c_int), ("C", c_int), ("fd", c_int),
+                ("fh", c_int), ("fw", c_int), ("add", c_void_p), ("out", c_void_p), ("stats", c_void_p), ("G", c_int)]
+
+
+class PoseDesc(C.Structure):
+    _fields_ = [("srt", c_void_p), ("source_theta", c_void_p), ("N", c_int), ("mix", c_int), ("invert_warp", c_int),
+                ("theta_out", c_void_p), ("theta_warp", c_void_p), ("align2d", c_void_p)]
+
+
+# every symbol include/emoportraits_b200.h declares, with its prototype
+SYMBOLS = {
+    "emo_last_error": (C.c_char_p, []),
+    "emo_version": (c_int, []),
+    "emo_device_info": (c_int, [C.POINTER(c_int), C.POINTER(c_int)]),
+    "emo_grid_sample3d": (c_int, [C.POINTER(GridSample3dDesc), c_void_p]),
+    "emo_grid_sample2d_affine": (c_int, [C.POINTER(GridSample2dAffineDesc), c_void_p]),
+    "emo_resize_bilinear": (c_int, [C.POINTER(ResizeBilinearDesc), c_void_p]),
+    "emo_gn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "emo_gn_finalize": (c_int, [C.POINTER(GnFinalizeDesc), c_void_p]),
+    "emo_apply": (c_int, [C.POINTER(ApplyDesc), c_void_p]),
+    "emo_conv_igemm": (c_int, [C.POINTER(ConvDesc), c_void_p]),
+    "emo_conv_direct": (c_int, [C.POINTER(ConvDirectDesc), c_void_p]),
+    "emo_linear": (c_int, [C.POINTER(LinearDesc), c_void_p]),
+    "emo_upsample_trilinear": (c_int, [C.POINTER(ResampleDesc), c_void_p]),
+    "emo_avgpool": (c_int, [C.POINTER(ResampleDesc), c_void_p]),
+    "emo_maxpool2d_3x3s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "emo_global_avgpool": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
+    "emo_pose_theta": (c_int, [C.POINTER(PoseDesc), c_void_p]),
+    "emo_split_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
+    "emo_l2_flush": (c_int, [c_void_p, c_ll, c_void_p]),
+}
+
+_lib = None
+launch_count = 0  # number of kernel-launching C-ABI calls made through call() (bench.py's gpu_launches)
+
+
+class EmoError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the native library.  Fails loudly: there is no CPU or torch fallback for the hot path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EmoError(f"{LIB_PATH} is missing: build it with `python -m emoportraits_b200.csrc.build` "
+                       "(or __graft_entry__.build()). The hot path has no fallback.")
+    import torch  # noqa: F401  (makes libcudart.so.12 resident before our library is resolved)
+
+    try:
+        lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    except OSError:
+        # CPU-only box without a resident cudart: preload the toolkit's runtime, then retry
+        for cand in ("libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so"):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                break
+            except OSError:
+                continue
+        lib = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args) -> None:
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise EmoError(f"{name} failed ({rc}): {lib.emo_last_error().decode()}")
+    launch_count += 1

@@ -1,0 +1,324 @@
+"""Tensor-in / tensor-out wrappers over the C-ABI (PyTorch is only the owner of device memory and streams).
+
+Layout vocabulary
+  "cl"    channels-last activation, fp32, shape (N, D, H, W, C) (D == 1 for 2-D maps)
+  Split   the same tensor as two bf16 planes (hi, lo) — the tensor-core operand format
+  NCDHW   torch-contiguous layout of the reference (only at the API boundary)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda, "emoportraits_b200 ops need CUDA tensors (there is no CPU path)"
+    return t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+    return t
+
+
+@dataclass
+class Split:
+    """bf16 (hi, lo) planes of a channels-last activation (N, D, H, W, C)."""
+    hi: torch.Tensor
+    lo: torch.Tensor
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @staticmethod
+    def empty(shape, device) -> "Split":
+        buf = torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=device)
+        return Split(buf[0], buf[1])
+
+    def float(self) -> torch.Tensor:
+        return self.hi.float() + self.lo.float()
+
+
+@dataclass
+class PackedConvWeight:
+    """Conv weight in the kernel-native layout: bf16 planes [taps][Cout_pad][Cin] (taps = kd*kh*kw)."""
+    hi: torch.Tensor
+    lo: torch.Tensor
+    cout: int
+    cout_pad: int
+    cin: int
+    k: tuple  # (kd, kh, kw)
+
+
+def split_host(w: torch.Tensor):
+    """fp32 -> (bf16 hi, bf16 lo) with torch ops (load-time weight preparation only)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tensor] = None) -> PackedConvWeight:
+    """OIHW / OIDHW fp32 (already SN/WS-folded) -> PackedConvWeight. `in_perm` optionally re-orders input channels."""
+    w = w.detach().float()
+    if w.dim() == 4:
+        w = w[:, :, None]
+    co, ci, kd, kh, kw = w.shape
+    if in_perm is not None:
+        w = w[:, in_perm]
+    co_pad = ((co + 15) // 16) * 16
+    wp = torch.zeros(kd * kh * kw, co_pad, ci, dtype=torch.float32)
+    wp[:, :co] = w.permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci).cpu()
+    hi, lo = split_host(wp)
+    dev = device or "cuda"
+    return PackedConvWeight(hi.contiguous().to(dev), lo.contiguous().to(dev), co, co_pad, ci, (kd, kh, kw))
+
+
+# ------------------------------------------------------------------------------------------------
+# grid_sample
+# ------------------------------------------------------------------------------------------------
+def grid_sample3d(inp: torch.Tensor, grid: Optional[torch.Tensor] = None, theta: Optional[torch.Tensor] = None,
+                  out_size=None, in_layout: str = "ncdhw", out_layout: Optional[str] = None, want_f32: bool = True,
+                  want_split: bool = False):
+    """Trilinear, zeros padding, align_corners=False (va.py:261-265).
+
+    in_layout  'ncdhw' (N,C,D,H,W)  or 'cl' (N,D,H,W,C)
+    out_layout 'ncdhw' | 'cl' | 'hwdc' ((N,H,W,D,C): the decoder's flattened-2D layout); default = in_layout
+    grid (N,Do,Ho,Wo,3) xyz, or theta (N,3,4) with out_size=(Do,Ho,Wo) for the fused affine lattice.
+    """
+    _chk(inp)
+    if in_layout == "ncdhw":
+        N, Cc, Di, Hi, Wi = inp.shape
+    else:
+        N, Di, Hi, Wi, Cc = inp.shape
+    if grid is not None:
+        _chk(grid)
+        assert grid.shape[0] == N and grid.shape[-1] == 3
+        Do, Ho, Wo = grid.shape[1:4]
+    else:
+        _chk(theta)
+        assert theta.shape == (N, 3, 4) and out_size is not None
+        Do, Ho, Wo = out_size
+    out_layout = out_layout or in_layout
+    if out_layout == "ncdhw":
+        shape = (N, Cc, Do, Ho, Wo)
+        os_ = dict(n=Cc * Do * Ho * Wo, c=Do * Ho * Wo, d=Ho * Wo, h=Wo, w=1)
+    elif out_layout == "cl":
+        shape = (N, Do, Ho, Wo, Cc)
+        os_ = dict(n=Do * Ho * Wo * Cc, c=1, d=Ho * Wo * Cc, h=Wo * Cc, w=Cc)
+    elif out_layout == "hwdc":
+        shape = (N, Ho, Wo, Do, Cc)
+        os_ = dict(n=Do * Ho * Wo * Cc, c=1, d=Cc, h=Wo * Do * Cc, w=Do * Cc)
+    else:
+        raise ValueError(out_layout)
+    out = torch.empty(shape, dtype=torch.float32, device=inp.device) if want_f32 else None
+    sp = Split.empty(shape, inp.device) if want_split else None
+    d = L.GridSample3dDesc(_p(inp), 1 if in_layout == "cl" else 0, N, Cc, Di, Hi, Wi, _p(grid), _p(theta), Do, Ho, Wo,
+                           _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, os_["n"], os_["c"],
+                           os_["d"], os_["h"], os_["w"])
+    L.call("emo_grid_sample3d", C.byref(d), _stream())
+    if want_f32 and want_split:
+        return out, sp
+    return out if want_f32 else sp
+
+
+def grid_sample2d_affine(img: torch.Tensor, theta: torch.Tensor, out_hw, mean=None, std=None, c_pad: int = 4,
+                         want_nchw: bool = False):
+    _chk(img); _chk(theta)
+    N, Cc, Hi, Wi = img.shape
+    Ho, Wo = out_hw
+    out = torch.empty((N, 1, Ho, Wo, c_pad), dtype=torch.float32, device=img.device)
+    nchw = torch.empty((N, Cc, Ho, Wo), dtype=torch.float32, device=img.device) if want_nchw else None
+    d = L.GridSample2dAffineDesc(_p(img), N, Cc, Hi, Wi, _p(theta), Ho, Wo, _p(mean), _p(std), _p(out), c_pad, _p(nchw))
+    L.call("emo_grid_sample2d_affine", C.byref(d), _stream())
+    return (out, nchw) if want_nchw else out
+
+
+def resize_bilinear(img: torch.Tensor, out_hw, mean=None, std=None, c_pad: int = 4):
+    _chk(img)
+    N, Cc, Hi, Wi = img.shape
+    Ho, Wo = out_hw
+    out = torch.empty((N, 1, Ho, Wo, c_pad), dtype=torch.float32, device=img.device)
+    d = L.ResizeBilinearDesc(_p(img), N, Cc, Hi, Wi, Ho, Wo, _p(mean), _p(std), _p(out), c_pad)
+    L.call("emo_resize_bilinear", C.byref(d), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm pieces
+# ------------------------------------------------------------------------------------------------
+def new_stats(N: int, G: int, device) -> torch.Tensor:
+    return torch.zeros((N, G, 2), dtype=torch.float64, device=device)
+
+
+def gn_stats(x: torch.Tensor, G: int = 32, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _chk(x)
+    N, Cc = x.shape[0], x.shape[-1]
+    S = x.numel() // (N * Cc)
+    if stats is None:
+        stats = new_stats(N, G, x.device)
+    L.call("emo_gn_stats", _p(x), N, S, Cc, G, _p(stats), _stream())
+    return stats
+
+
+def gn_finalize(stats: torch.Tensor, count: float, gamma, beta, eps: float = 1e-5, ada_w=None, ada_b=None):
+    N, G, _ = stats.shape
+    Cc = gamma.numel()
+    A = torch.empty((N, Cc), dtype=torch.float32, device=stats.device)
+    B = torch.empty_like(A)
+    d = L.GnFinalizeDesc(_p(stats), N, Cc, G, float(count), float(eps), _p(gamma), _p(beta), _p(ada_w), _p(ada_b),
+                         _p(A), _p(B))
+    L.call("emo_gn_finalize", C.byref(d), _stream())
+    return A, B
+
+
+def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
+          want_f32: bool = False, want_split: bool = True, per_sample: bool = True):
+    """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W)."""
+    _chk(x)
+    N, D, H, W, Cc = x.shape
+    shape = (N, D, H * up, W * up, Cc)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device) if want_f32 else None
+    sp = Split.empty(shape, x.device) if want_split else None
+    d = L.ApplyDesc(_p(x), N, Cc, D, H, W, _p(A), _p(B), 1 if per_sample else 0, _p(res), _p(A2), _p(B2), act, up,
+                    _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None)
+    L.call("emo_apply", C.byref(d), _stream())
+    if want_f32 and want_split:
+        return out, sp
+    return out if want_f32 else sp
+
+
+def split_bf16(x: torch.Tensor) -> Split:
+    _chk(x)
+    sp = Split.empty(x.shape, x.device)
+    L.call("emo_split_bf16", _p(x), x.numel(), _p(sp.hi), _p(sp.lo), _stream())
+    return sp
+
+
+# ------------------------------------------------------------------------------------------------
+# convolutions
+# ------------------------------------------------------------------------------------------------
+def _out_dim(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
+def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=None, residual=None, res_shift: int = 0,
+               act: int = ACT_NONE, post_add=None, out_nchw: bool = False, stats: Optional[torch.Tensor] = None,
+               G: int = 32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    N, Di, Hi, Wi, Ci = a.shape
+    assert Ci == w.cin, (Ci, w.cin)
+    kd, kh, kw = w.k
+    if pad is None:
+        pad = (kd // 2, kh // 2, kw // 2)
+    Do, Ho, Wo = _out_dim(Di, kd, stride[0], pad[0]), _out_dim(Hi, kh, stride[1], pad[1]), _out_dim(Wi, kw, stride[2], pad[2])
+    if out is None:
+        shape = (N, w.cout, Do, Ho, Wo) if out_nchw else (N, Do, Ho, Wo, w.cout)
+        out = torch.empty(shape, dtype=torch.float32, device=a.hi.device)
+    d = L.ConvDesc(_p(a.hi), _p(a.lo), N, Di, Hi, Wi, Ci, _p(w.hi), _p(w.lo), w.cout, w.cout_pad, kd, kh, kw,
+                   stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
+                   res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
+                   G if stats is not None else 0)
+    L.call("emo_conv_igemm", C.byref(d), _stream())
+    return out
+
+
+def conv_direct(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, bias=None, stats=None, G: int = 32):
+    """x (N,1,H,W,Cin_pad) fp32 channels-last; w (kh,kw,Cin_pad,Cout) fp32."""
+    _chk(x); _chk(w)
+    N, _, Hi, Wi, Cp = x.shape
+    kh, kw, Cp2, Co = w.shape
+    assert Cp == Cp2
+    Ho, Wo = _out_dim(Hi, kh, stride, pad), _out_dim(Wi, kw, stride, pad)
+    out = torch.empty((N, 1, Ho, Wo, Co), dtype=torch.float32, device=x.device)
+    d = L.ConvDirectDesc(_p(x), N, Hi, Wi, Cp, _p(w), Co, kh, kw, stride, pad, Ho, Wo, _p(bias), _p(out), _p(stats),
+                         G if stats is not None else 0)
+    L.call("emo_conv_direct", C.byref(d), _stream())
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias=None, add=None, scale: float = 1.0, act: int = ACT_NONE,
+           x_strides=None, out: Optional[torch.Tensor] = None, out_strides=None, M=None, K=None):
+    """out[m, n] = act((sum_k x[m,k] w[n,k] + bias[n] + add[m,n]) * scale); strides in elements."""
+    _chk(w)
+    Nn, Kk = w.shape
+    if x_strides is None:
+        assert x.dim() == 2 and x.is_contiguous()
+        M, K = x.shape
+        x_strides = (K, 1)
+    assert K == Kk, (K, Kk)
+    if out is None:
+        out = torch.empty((M, Nn), dtype=torch.float32, device=w.device)
+        out_strides = (Nn, 1)
+    d = L.LinearDesc(_p(x), x_strides[0], x_strides[1], _p(w), _p(bias), _p(add), float(scale), act, M, Nn, Kk, _p(out),
+                     out_strides[0], out_strides[1])
+    L.call("emo_linear", C.byref(d), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# resampling
+# ------------------------------------------------------------------------------------------------
+def upsample_trilinear(x: torch.Tensor, f=(2, 2, 2), add=None, stats=None, G: int = 32):
+    _chk(x)
+    N, D, H, W, Cc = x.shape
+    out = torch.empty((N, D * f[0], H * f[1], W * f[2], Cc), dtype=torch.float32, device=x.device)
+    d = L.ResampleDesc(_p(x), N, D, H, W, Cc, f[0], f[1], f[2], _p(add), _p(out), _p(stats), G if stats is not None else 0)
+    L.call("emo_upsample_trilinear", C.byref(d), _stream())
+    return out
+
+
+def avgpool(x: torch.Tensor, f=(1, 2, 2), add=None, stats=None, G: int = 32):
+    _chk(x)
+    N, D, H, W, Cc = x.shape
+    out = torch.empty((N, D // f[0], H // f[1], W // f[2], Cc), dtype=torch.float32, device=x.device)
+    d = L.ResampleDesc(_p(x), N, D, H, W, Cc, f[0], f[1], f[2], _p(add), _p(out), _p(stats), G if stats is not None else 0)
+    L.call("emo_avgpool", C.byref(d), _stream())
+    return out
+
+
+def maxpool2d_3x3s2(x: torch.Tensor):
+    _chk(x)
+    N, _, H, W, Cc = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((N, 1, Ho, Wo, Cc), dtype=torch.float32, device=x.device)
+    L.call("emo_maxpool2d_3x3s2", _p(x), N, H, W, Cc, _p(out), _stream())
+    return out
+
+
+def global_avgpool(x: torch.Tensor):
+    _chk(x)
+    N, Cc = x.shape[0], x.shape[-1]
+    S = x.numel() // (N * Cc)
+    out = torch.empty((N, Cc), dtype=torch.float32, device=x.device)
+    L.call("emo_global_avgpool", _p(x), N, S, Cc, _p(out), _stream())
+    return out
+
+
+def pose_theta(srt: torch.Tensor, source_theta: Optional[torch.Tensor] = None, mix: bool = False,
+               invert_warp: bool = False):
+    """srt (N,9) -> theta (N,4,4), theta_warp (N,3,4), align2d (N,2,3). See emo_pose_theta."""
+    _chk(srt)
+    N = srt.shape[0]
+    dev = srt.device
+    theta = torch.empty((N, 4, 4), dtype=torch.float32, device=dev)
+    warp = torch.empty((N, 3, 4), dtype=torch.float32, device=dev)
+    align = torch.empty((N, 2, 3), dtype=torch.float32, device=dev)
+    d = L.PoseDesc(_p(srt), _p(source_theta), N, 1 if mix else 0, 1 if invert_warp else 0, _p(theta), _p(warp), _p(align))
+    L.call("emo_pose_theta", C.byref(d), _stream())
+    return theta, warp, align
+
+
+def l2_flush(buf: torch.Tensor):
+    L.call("emo_l2_flush", _p(buf), buf.numel() * buf.element_size(), _stream())

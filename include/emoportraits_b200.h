@@ -1,0 +1,256 @@
+/*
+ * emoportraits_b200 — C-ABI of the B200-native volumetric-avatar inference hot path.
+ *
+ * Drop-in boundary: the reference has no FFI; its hot path is torch library
+ * calls made from `notebooks/infer.py:355-647` (InferenceWrapper.forward) into
+ * `networks/volumetric_avatar/*`.  Each entry point below replaces one family of those torch
+ * call sites; the reference line it replaces is cited next to it.  A maintainer binds these
+ * with ctypes exactly as emoportraits_b200/lib.py does.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *  - `stream` is a cudaStream_t passed as void*;
+ *  - activations are fp32, channels-last ([N][D][H][W][C], D==1 for 2-D), unless a field says
+ *    otherwise; tensor-core operands are the same tensors split into two bf16 planes
+ *    (hi = bf16(x), lo = bf16(x - hi)) so that three bf16 MMAs reproduce an fp32 product to
+ *    ~2^-16 relative (see DESIGN.md "precision");
+ *  - every function returns EMO_OK (0) or a negative error code; emo_last_error() returns the
+ *    message of the last failure on the calling thread;
+ *  - no function allocates device memory; workspaces are passed in.
+ */
+#ifndef EMOPORTRAITS_B200_H
+#define EMOPORTRAITS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMO_OK 0
+#define EMO_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define EMO_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define EMO_ERR_ARCH (-3)    /* not running on sm_100 */
+
+enum { EMO_ACT_NONE = 0, EMO_ACT_RELU = 1, EMO_ACT_SIGMOID = 2, EMO_ACT_TANH = 3 };
+
+const char* emo_last_error(void);
+int emo_version(void);
+/* sm count, and cc major*10+minor of the current device */
+int emo_device_info(int* sm_count, int* cc);
+
+/* ------------------------------------------------------------------------------------------------
+ * grid_sample 3-D: trilinear, padding_mode='zeros', align_corners=False.
+ * Replaces: models/stage_1/volumetric_avatar/va.py:261-265 (Model.grid_sample -> F.grid_sample 5-D)
+ *           and the affine grid build notebooks/infer.py:441-444, 583-588 (identity_grid_3d.bmm(theta^T))
+ * when `theta` is given instead of `grid`.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* in; /* input volume */
+  int in_layout;   /* 0: NCDHW (torch-contiguous, drop-in for F.grid_sample), 1: channels-last NDHWC */
+  int N, C, Din, Hin, Win;
+  const float* grid;  /* [N][Do][Ho][Wo][3] (x,y,z) or NULL */
+  const float* theta; /* [N][3][4] row-major or NULL: grid = lattice(linspace(-1,1)) . theta^T (va.py:101-105) */
+  int Dout, Hout, Wout;
+  float* out;             /* fp32 output or NULL */
+  void* out_hi;           /* optional bf16 split planes (same indexing as out) */
+  void* out_lo;
+  /* output element strides (in elements) for n, c, d, h, w. */
+  long long os_n, os_c, os_d, os_h, os_w;
+} emo_grid_sample3d_desc;
+int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream);
+
+/* grid_sample 2-D, bilinear, zeros, align_corners=False, affine grid from theta [N][2][3]
+ * over an identity lattice linspace(-1,1,Hout/Wout).
+ * Replaces: networks/volumetric_avatar/expression_embedder.py:224-231 (align_warp + F.grid_sample).
+ * in: NCHW fp32; out: channels-last [N][Hout][Wout][C_pad] fp32 with per-channel (x-mean)/std
+ * (expression_embedder.py:441-445, ResNetWrapper.forward normalisation) when mean/std non-NULL.
+ * Channels c >= C of the output are zero-filled. */
+typedef struct {
+  const float* in;
+  int N, C, Hin, Win;
+  const float* theta; /* [N][2][3] */
+  int Hout, Wout;
+  const float* mean; /* [C] or NULL */
+  const float* std;  /* [C] or NULL */
+  float* out;        /* [N][Hout][Wout][C_pad] */
+  int C_pad;
+  float* out_nchw;   /* optional un-normalised NCHW copy (source_img_align), or NULL */
+} emo_grid_sample2d_affine_desc;
+int emo_grid_sample2d_affine(const emo_grid_sample2d_affine_desc* d, void* stream);
+
+/* F.interpolate(mode='bilinear', align_corners=False) NCHW -> channels-last [N][Ho][Wo][C_pad]
+ * with optional per-channel normalisation.
+ * Replaces: head_pose_regressor.py:24-25, identity_embedder.py:82-86. */
+typedef struct {
+  const float* in;
+  int N, C, Hin, Win, Hout, Wout;
+  const float* mean;
+  const float* std;
+  float* out;
+  int C_pad;
+} emo_resize_bilinear_desc;
+int emo_resize_bilinear(const emo_resize_bilinear_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm pieces.  nn.GroupNorm(32, C, eps=1e-5) (networks/volumetric_avatar/utils.py:953,957),
+ * AdaptiveGroupNorm (utils.py:302-325), eval-mode BatchNorm folded to the same affine form.
+ *   stats:    double [N][G][2] = (sum, sum of squares) over (C/G) x spatial
+ *   finalize: A[n][c] = rstd*gamma', B[n][c] = beta' - mean*rstd*gamma'
+ *             gamma' = gamma (plain)  or gamma*(ada_w)  with beta' = beta*ada_w + ada_b (adaptive,
+ *             ada_w = gamma+dw, ada_b = beta+db per sample: utils.py:994-995)
+ *   apply:    y = act(x*A + B [+ res*A2 + B2]) -> fp32 and/or bf16 hi/lo planes, optional
+ *             nearest x2 upsample on write (utils.py:685 F.interpolate(scale_factor=stride)).
+ * ------------------------------------------------------------------------------------------------ */
+int emo_gn_stats(const float* x, int N, long long spatial, int C, int G, double* stats, void* stream);
+
+typedef struct {
+  const double* stats; /* [N][G][2] */
+  int N, C, G;
+  double count;       /* elements per (n, group) */
+  float eps;
+  const float* gamma; /* [C] */
+  const float* beta;  /* [C] */
+  const float* ada_w; /* [N][C] or NULL */
+  const float* ada_b; /* [N][C] or NULL */
+  float* A;           /* [N][C] */
+  float* B;           /* [N][C] */
+} emo_gn_finalize_desc;
+int emo_gn_finalize(const emo_gn_finalize_desc* d, void* stream);
+
+typedef struct {
+  const float* x; /* [N][S][C] fp32 channels-last, S = D*H*W */
+  int N, C;
+  int D, H, W;
+  const float* A; /* [N][C] or NULL (identity) */
+  const float* B;
+  int ab_per_sample; /* 1: A,B are [N][C]; 0: [C] shared by all samples */
+  const float* res;  /* optional residual, same shape as x */
+  const float* A2;   /* optional affine on the residual [C] */
+  const float* B2;
+  int act;
+  int up; /* 1 or 2: nearest upsample factor applied on H,W (D untouched) when writing */
+  float* out;   /* optional fp32 [N][D][H*up][W*up][C] */
+  void* out_hi; /* optional bf16 planes, same shape as out */
+  void* out_lo;
+} emo_apply_desc;
+int emo_apply(const emo_apply_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 (2-D and 3-D, kernel 1 or 3 per dim, stride 1 or 2,
+ * zero padding), bf16x2-split operands, fp32 accumulation in TMEM.
+ * Replaces: F.conv2d / F.conv3d call sites of utils.py:661-788 (ResBlock), :894-915 (Conv*_ws),
+ *           decoder.py:77-81,349-356, local_encoder.py:104-108, warp_generator_resnet.py:99-106.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* a_hi; /* activations, bf16 channels-last [N][Din][Hin][Win][Cin] */
+  const void* a_lo;
+  int N, Din, Hin, Win, Cin;
+  const void* w_hi; /* weights, bf16 [taps][Cout_pad][Cin], taps ordered (kd,kh,kw) */
+  const void* w_lo;
+  int Cout, Cout_pad;
+  int kd, kh, kw;
+  int sd, sh, sw;    /* strides */
+  int pd, ph, pw;    /* paddings */
+  int Dout, Hout, Wout;
+  const float* bias;     /* [Cout] or NULL */
+  const float* residual; /* fp32 channels-last [N][Dout>>rs_d][Hout>>rs][Wout>>rs][Cout] or NULL */
+  int res_shift;         /* residual is read at (h>>res_shift, w>>res_shift) (nearest-upsampled skip) */
+  int act;               /* applied after bias+residual */
+  const float* post_add; /* added after the activation, [Dout][Hout][Wout][Cout] (shared by all n) or NULL */
+  float* out;            /* fp32 */
+  int out_nchw;          /* 0: channels-last; 1: [N][Cout][Dout][Hout][Wout] */
+  double* stats;         /* optional GN statistics of the output: [N][G][2] accumulated (+=) */
+  int G;
+} emo_conv_desc;
+int emo_conv_igemm(const emo_conv_desc* d, void* stream);
+
+/* Direct fp32 SIMT convolution for the layers the tensor-core path does not take (Cin not a
+ * multiple of 32: the RGB stems local_encoder.py:66-74 7x7 and torchvision resnet conv1).
+ * x: fp32 channels-last [N][Hin][Win][Cin_pad]; w: fp32 [kh][kw][Cin_pad][Cout]. */
+typedef struct {
+  const float* x;
+  int N, Hin, Win, Cin_pad;
+  const float* w;
+  int Cout, kh, kw, stride, pad;
+  int Hout, Wout;
+  const float* bias;
+  float* out; /* fp32 channels-last */
+  double* stats;
+  int G;
+} emo_conv_direct_desc;
+int emo_conv_direct(const emo_conv_direct_desc* d, void* stream);
+
+/* y[m][n] = act((sum_k x[m][k] * w[n][k] + bias[n] + add[m][n]) * scale), fp32 SIMT.
+ * Replaces: va.py:820-823 (pose_unsqueeze_nw), :855 (warp_embed_head_orig_nw on a 4x4 map),
+ *           utils.py:1146 (ProjectorNorm u.E.v), warp_generator_resnet.py:138 (first_conv),
+ *           expression_embedder.py:455-460 (pose_head), resnet fc layers.
+ * Output element (m, n) is written at out[m*os_m + n*os_n]. */
+typedef struct {
+  const float* x;
+  long long xs_m, xs_k; /* element strides of x */
+  const float* w;       /* [N][K] row-major */
+  const float* bias;    /* [N] or NULL */
+  const float* add;     /* same indexing as out, or NULL */
+  float scale;
+  int act;
+  int M, N, K;
+  float* out;
+  long long os_m, os_n;
+} emo_linear_desc;
+int emo_linear(const emo_linear_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Resampling on channels-last fp32 tensors.
+ * trilinear: F.interpolate(mode='trilinear', scale_factor=(fd,fh,fw)), align_corners=False
+ *            (unet_3d.py:224,273-275, warp_generator_resnet.py:160-163); optional `add` tensor of
+ *            the output shape (unet_3d.py:286 `outputs + outputs_skip`); optional GN stats of the result.
+ * avgpool:   AvgPool2d/3d with kernel == stride (utils.py:964-969, unet_3d.py:87-90,193, warp_generator_resnet.py:115)
+ * maxpool:   torchvision resnet maxpool 3x3 s2 p1.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* x;
+  int N, D, H, W, C;
+  int fd, fh, fw; /* 1 or 2 */
+  const float* add;
+  float* out;
+  double* stats;
+  int G;
+} emo_resample_desc;
+int emo_upsample_trilinear(const emo_resample_desc* d, void* stream);
+int emo_avgpool(const emo_resample_desc* d, void* stream);
+int emo_maxpool2d_3x3s2(const float* x, int N, int H, int W, int C, float* out, void* stream);
+/* mean over spatial positions: [N][S][C] -> [N][C] */
+int emo_global_avgpool(const float* x, int N, long long S, int C, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pose algebra on device (removes the per-frame host sync of infer.py:568-569, 699-736).
+ *   srt [N][9] = (scale xyz, yaw pitch roll, translation xyz) from the head-pose regressor
+ *   theta = S.R.T (utils/point_transforms.py:187-240)
+ *   mix != 0: get_mixing_theta(source_theta, theta) with mix_old=False (infer.py:686-736):
+ *             polar decompositions in fp64 (scipy.linalg.polar), result rows [:3]
+ *   outputs: theta_out [N][4][4]; theta_warp [N][3][4] = (invert ? inverse(theta) : theta)[:3]
+ *            (infer.py:443 / :586); align2d [N][2][3] = (inverse(theta4)[[0,1,3]][:, [0,1,3]] . diag(.5,.5,1))[:2]
+ *            (expression_embedder.py:176-203).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* srt;          /* [N][9] */
+  const float* source_theta; /* [4][4] or NULL (required when mix) */
+  int N;
+  int mix;
+  int invert_warp;
+  float* theta_out;  /* [N][4][4] */
+  float* theta_warp; /* [N][3][4] */
+  float* align2d;    /* [N][2][3] */
+} emo_pose_desc;
+int emo_pose_theta(const emo_pose_desc* d, void* stream);
+
+/* fp32 -> bf16 hi/lo planes (n elements). */
+int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream);
+/* L2 flush helper for benchmarks: writes `bytes` of `buf`. */
+int emo_l2_flush(void* buf, long long bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMOPORTRAITS_B200_H */
