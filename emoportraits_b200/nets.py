@@ -1,0 +1,475 @@
+"""Network assembly of the volumetric-avatar hot path on top of the C-ABI ops.
+
+Each class mirrors one reference module (same name, same checkpoint prefix, same call order) but holds
+pre-folded, kernel-native weights and launches only emoportraits_b200 kernels:
+
+    LocalEncoder      networks/volumetric_avatar/local_encoder.py:26-125
+    ResNet (18/50)    torchvision resnet as wrapped by identity_embedder.py:12-89, expression_embedder.py:343-478,
+                      head_pose_regressor.py:11-31
+    WarpGenerator     networks/volumetric_avatar/warp_generator_resnet.py:11-181
+    VolumeSource      vpn_resblocks.py:22-49 -> resblocks_3d.py:9-62
+    Unet3D            networks/volumetric_avatar/unet_3d.py:18-290
+    Decoder           networks/volumetric_avatar/decoder.py:20-410
+    ResBlock          networks/volumetric_avatar/utils.py:661-788
+
+Data flowing between layers is a channels-last fp32 tensor (N, D, H, W, C) plus the GroupNorm statistics of that
+tensor (double (N,32,2)), produced by the epilogue of whichever kernel wrote it.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import ops
+from .checkpoint import fold_conv
+from .config import HotPathConfig
+
+G = 32
+
+
+class ConvW:
+    """Packed conv weight (+ bias) resident on the device."""
+
+    def __init__(self, sd, p, dev, ws=False, in_perm=None, out_perm=None):
+        w, b = fold_conv(sd, p, ws=ws)
+        if out_perm is not None:
+            w = w[out_perm]
+            b = b[out_perm] if b is not None else None
+        self.w = ops.pack_conv_weight(w, device=dev, in_perm=in_perm)
+        self.b = b.to(dev).contiguous() if b is not None else None
+        self.cout = w.shape[0]
+
+
+class Norm:
+    def __init__(self, sd, p, dev):
+        self.gamma = sd[p + ".weight"].detach().float().to(dev).contiguous()
+        self.beta = sd[p + ".bias"].detach().float().to(dev).contiguous()
+        self.C = self.gamma.numel()
+        self.gb = torch.stack([self.gamma, self.beta]).contiguous()  # (2, C): `add` operand of the projector GEMM
+
+    def affine(self, stats, count, ada=None):
+        if ada is None:
+            return ops.gn_finalize(stats, count, self.gamma, self.beta)
+        return ops.gn_finalize(stats, count, self.gamma, self.beta, ada_w=ada[0], ada_b=ada[1])
+
+
+def _count(x):
+    """elements per (sample, group) of a channels-last tensor"""
+    return x.numel() / x.shape[0] / G
+
+
+class ResBlock:
+    """utils.py:661-788: [nearest up] -> norm -> relu -> conv -> norm -> relu -> conv [-> avgpool]; skip = [up] -> [1x1] -> [pool]."""
+
+    def __init__(self, sd, p, dev, ws_first=True):
+        self.n1 = Norm(sd, p + ".block_feats.0", dev)
+        self.c1 = ConvW(sd, p + ".block_feats.2", dev, ws=ws_first)
+        self.n2 = Norm(sd, p + ".block_feats.3", dev)
+        self.c2 = ConvW(sd, p + ".block.0", dev)
+        self.skip = ConvW(sd, p + ".skip.0", dev) if (p + ".skip.0.weight_orig") in sd else None
+
+    def __call__(self, x, sx, up=1, down=None, ada=None, want_stats=True):
+        dev = x.device
+        N = x.shape[0]
+        A, B = self.n1.affine(sx, _count(x), ada[0] if ada else None)
+        a = ops.apply(x, A, B, act=ops.ACT_RELU, up=up)
+        st1 = ops.new_stats(N, G, dev)
+        y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1)
+        A, B = self.n2.affine(st1, _count(y), ada[1] if ada else None)
+        b = ops.apply(y, A, B, act=ops.ACT_RELU)
+        # skip path: the 1x1 conv commutes with nearest-upsampling and with average pooling, so it runs at the smaller size
+        s = ops.avgpool(x, down) if down else x
+        if self.skip is not None:
+            s = ops.conv_igemm(ops.split_bf16(s), self.skip.w, bias=self.skip.b)
+        st2 = ops.new_stats(N, G, dev) if want_stats else None
+        if down:
+            full = ops.conv_igemm(b, self.c2.w, bias=self.c2.b)
+            out = ops.avgpool(full, down, add=s, stats=st2)
+        else:
+            out = ops.conv_igemm(b, self.c2.w, bias=self.c2.b, residual=s, res_shift=1 if up == 2 else 0, stats=st2)
+        return out, st2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class LocalEncoder:
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        p = "local_encoder_nw"
+        s = cfg.image_size
+        w, b = fold_conv(sd, f"{p}.from_rgb_{s}px")
+        wc = torch.zeros(7, 7, 4, w.shape[0])
+        wc[:, :, :3] = w.permute(2, 3, 1, 0)
+        self.stem_w, self.stem_b = wc.to(dev).contiguous(), b.to(dev).contiguous()
+        self.blocks = []
+        for i in range(len(cfg.enc_channels) - 1):
+            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev))
+            s //= 2
+        self.fin_norm = Norm(sd, p + ".finale_layers.0", dev)
+        # output channel o = c*D + d in the reference (infer.py:485 view(1,c,d,s,s)); emit d*C + c so the map is (h,w,d,c)
+        C, D = cfg.C, cfg.D
+        operm = torch.tensor([(k % C) * D + (k // C) for k in range(C * D)])
+        self.fin = ConvW(sd, p + ".finale_layers.2", dev, ws=True, out_perm=operm)
+        self.cfg = cfg
+
+    def __call__(self, img_nchw):
+        """img (1,3,H,W) fp32 -> latent volume channels-last (1,D,S,S,C) fp32 + its GN stats."""
+        cfg = self.cfg
+        x4 = ops.resize_bilinear(img_nchw, img_nchw.shape[-2:])  # same-size bilinear == exact NCHW -> NHWC4 repack
+        st = ops.new_stats(1, G, x4.device)
+        x = ops.conv_direct(x4, self.stem_w, 1, 3, self.stem_b, stats=st)
+        for blk in self.blocks:
+            x, st = blk(x, st, down=(1, 2, 2))
+        A, B = self.fin_norm.affine(st, _count(x))
+        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        y = ops.conv_igemm(a, self.fin.w, bias=self.fin.b)  # (1,1,S,S,D*C) == (h,w,d,c)
+        vol = y.view(1, cfg.S, cfg.S, cfg.D, cfg.C).permute(0, 3, 1, 2, 4).contiguous()  # -> (1,D,S,S,C)
+        return vol
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class _RNNorm:
+    """ResNet norm: GroupNorm(32) (replace_bn_to_gn, utils.py:1020) or eval-mode BatchNorm folded to an affine."""
+
+    def __init__(self, sd, p, dev):
+        self.is_bn = (p + ".running_mean") in sd
+        if self.is_bn:
+            g, b = sd[p + ".weight"].float(), sd[p + ".bias"].float()
+            m, v = sd[p + ".running_mean"].float(), sd[p + ".running_var"].float()
+            A = g / torch.sqrt(v + 1e-5)
+            self.A = A[None].to(dev).contiguous()
+            self.B = (b - m * A)[None].to(dev).contiguous()
+        else:
+            self.n = Norm(sd, p, dev)
+
+    def affine(self, stats, count):
+        if self.is_bn:
+            return self.A, self.B
+        return self.n.affine(stats, count)
+
+
+class ResNet:
+    """torchvision resnet18 / resnet50 trunk (conv1..layer4) on channels-last tensors."""
+
+    def __init__(self, sd, p, dev, gn: bool):
+        self.gn = gn
+        w, b = fold_conv(sd, p + ".conv1")
+        wc = torch.zeros(7, 7, 4, w.shape[0])
+        wc[:, :, :3] = w.permute(2, 3, 1, 0)
+        self.stem_w = wc.to(dev).contiguous()
+        self.stem_b = b.to(dev).contiguous() if b is not None else None
+        self.bn1 = _RNNorm(sd, p + ".bn1", dev)
+        self.blocks = []
+        for li in range(1, 5):
+            bi = 0
+            while f"{p}.layer{li}.{bi}.bn1.weight" in sd:
+                q = f"{p}.layer{li}.{bi}"
+                blk = dict(stride=2 if (li > 1 and bi == 0) else 1, bottleneck=(q + ".bn3.weight") in sd)
+                blk["c1"] = ConvW(sd, q + ".conv1", dev)
+                blk["n1"] = _RNNorm(sd, q + ".bn1", dev)
+                blk["c2"] = ConvW(sd, q + ".conv2", dev, ws=gn)
+                blk["n2"] = _RNNorm(sd, q + ".bn2", dev)
+                if blk["bottleneck"]:
+                    blk["c3"] = ConvW(sd, q + ".conv3", dev, ws=gn)
+                    blk["n3"] = _RNNorm(sd, q + ".bn3", dev)
+                if (q + ".downsample.1.weight") in sd:
+                    blk["cd"] = ConvW(sd, q + ".downsample.0", dev)
+                    blk["nd"] = _RNNorm(sd, q + ".downsample.1", dev)
+                self.blocks.append(blk)
+                bi += 1
+
+    def _conv(self, a, cw, stride=1):
+        st = ops.new_stats(a.shape[0], G, a.hi.device) if self.gn else None
+        y = ops.conv_igemm(a, cw.w, stride=(1, stride, stride), bias=cw.b, stats=st)
+        return y, st
+
+    def __call__(self, x4):
+        """x4 (N,1,H,W,4) normalised image, channels-last padded -> (N,1,H/32,W/32,C) fp32."""
+        N, dev = x4.shape[0], x4.device
+        st = ops.new_stats(N, G, dev) if self.gn else None
+        y = ops.conv_direct(x4, self.stem_w, 2, 3, self.stem_b, stats=st)
+        A, B = self.bn1.affine(st, _count(y))
+        y = ops.apply(y, A, B, act=ops.ACT_RELU, want_f32=True, want_split=False, per_sample=not self.bn1.is_bn)
+        x = ops.maxpool2d_3x3s2(y)
+        xs = ops.split_bf16(x)
+        for blk in self.blocks:
+            s = blk["stride"]
+            if blk["bottleneck"]:
+                y, st = self._conv(xs, blk["c1"])
+                A, B = blk["n1"].affine(st, _count(y))
+                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn)
+                y, st = self._conv(a, blk["c2"], s)
+                A, B = blk["n2"].affine(st, _count(y))
+                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n2"].is_bn)
+                y, st = self._conv(a, blk["c3"])
+                A, B = blk["n3"].affine(st, _count(y))
+                last_bn = blk["n3"].is_bn
+            else:
+                y, st = self._conv(xs, blk["c1"], s)
+                A, B = blk["n1"].affine(st, _count(y))
+                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn)
+                y, st = self._conv(a, blk["c2"])
+                A, B = blk["n2"].affine(st, _count(y))
+                last_bn = blk["n2"].is_bn
+            if "cd" in blk:
+                r, std = self._conv(xs, blk["cd"], s)
+                A2, B2 = blk["nd"].affine(std, _count(r))
+                # residual affine is per-channel in the kernel; with GN and N == 1 the per-sample row is that vector
+                assert last_bn or N == 1, "GN ResNet path runs one image at a time"
+                x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=r, A2=A2, B2=B2, want_f32=True, want_split=True,
+                                  per_sample=not last_bn)
+            else:
+                x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=x, want_f32=True, want_split=True, per_sample=not last_bn)
+        return x, xs
+
+
+class HeadPoseRegressor:
+    """head_pose_regressor.py:11-31 — resnet18(num_classes=9), BatchNorm, its own checkpoint."""
+
+    def __init__(self, hsd, dev):
+        sd = {"r." + k: v for k, v in hsd.items()}
+        self.net = ResNet(sd, "r", dev, gn=False)
+        self.fc_w = sd["r.fc.weight"].float().to(dev).contiguous()
+        self.fc_b = sd["r.fc.bias"].float().to(dev).contiguous()
+
+    def __call__(self, img_nchw):
+        x4 = ops.resize_bilinear(img_nchw, (128, 128))
+        f, _ = self.net(x4)
+        return ops.linear(ops.global_avgpool(f), self.fc_w, self.fc_b)  # (N, 9) = scale, rotation, translation
+
+
+class ExpressionEmbed:
+    """expression_embedder.py:132-253 (inference branch) + ResNetWrapper :441-478."""
+
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        p = "expression_embedder_nw.net_face"
+        self.net = ResNet(sd, p + ".net", dev, gn=True)
+        self.fc = ConvW(sd, p + ".net.fc", dev)
+        w, _ = fold_conv(sd, p + ".pose_head")  # (E, E*16), input index c*16 + s (torch.flatten of NCHW)
+        E = cfg.expr_channels
+        self.head_w = w.view(E, E, 16).permute(0, 2, 1).reshape(E, 16 * E).to(dev).contiguous()  # -> index s*E + c
+        self.mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
+        self.std = torch.tensor([0.229, 0.224, 0.225], device=dev)
+        self.grid = cfg.exp_image_size // 2
+
+    def __call__(self, img_nchw, align2d, want_aligned=False):
+        res = ops.grid_sample2d_affine(img_nchw, align2d, (self.grid, self.grid), self.mean, self.std, want_nchw=want_aligned)
+        x4, aligned = (res if want_aligned else (res, None))
+        _, fs = self.net(x4)
+        y = ops.conv_igemm(fs, self.fc.w, bias=self.fc.b)  # (N,1,4,4,E); AdaptiveAvgPool2d(4) is the identity here
+        N = y.shape[0]
+        assert y.shape[2] == 4 and y.shape[3] == 4, "exp_image_size other than 256 needs a real adaptive pool"
+        emb = ops.linear(y.view(N, -1), self.head_w)
+        return emb, aligned
+
+
+class IdtEmbed:
+    """identity_embedder.py:59-89: bilinear -> 256, normalise, resnet50 (GN), fc 1x1 conv, AdaptiveAvgPool2d(4)."""
+
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        p = "idt_embedder_nw"
+        self.net = ResNet(sd, p + ".net", dev, gn=True)
+        self.fc = ConvW(sd, p + ".net.fc", dev)
+        self.mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
+        self.std = torch.tensor([0.229, 0.224, 0.225], device=dev)
+        self.size = cfg.idt_image_size
+
+    def __call__(self, img_nchw):
+        x4 = ops.resize_bilinear(img_nchw, (self.size, self.size), self.mean, self.std)
+        _, fs = self.net(x4)
+        y = ops.conv_igemm(fs, self.fc.w, bias=self.fc.b)  # (1,1,8,8,512)
+        y = ops.avgpool(y, (1, y.shape[2] // 4, y.shape[3] // 4)) if y.shape[2] != 4 else y
+        # reference layout of idt_embed is NCHW (1,512,4,4); keep that for the wrapper API and predict_embed
+        return y[:, 0].permute(0, 3, 1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class PredictEmbed:
+    """va.py:813-885 (gen_pred_mixing True, cat_em False): 'orig' = conv1x1((pose_unsqueeze(pose) + idt) * 0.5)."""
+
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        self.w_unsq = sd["pose_unsqueeze_nw.weight"].detach().float().to(dev).contiguous()
+        w, _ = fold_conv(sd, "warp_embed_head_orig_nw")
+        self.w_head = w.reshape(w.shape[0], w.shape[1]).to(dev).contiguous()
+        self.Cm = cfg.gen_max_channels
+        self.es2 = cfg.embed_size ** 2
+
+    def __call__(self, pose_embed, idt_nchw):
+        """pose (1,E), idt (1,512,4,4) NCHW -> E 'orig' (1,512,16) [c][s] contiguous."""
+        h = ops.linear(pose_embed, self.w_unsq, add=idt_nchw.reshape(1, -1), scale=0.5)  # (1, 512*16) index c*16+s
+        E = torch.empty((1, self.Cm, self.es2), dtype=torch.float32, device=h.device)
+        ops.linear(h, self.w_head, x_strides=(1, self.es2), M=self.es2, K=self.Cm, out=E, out_strides=(1, self.es2))
+        return E
+
+
+class WarpGenerator:
+    def __init__(self, sd, p, cfg: HotPathConfig, dev):
+        self.cfg = cfg
+        ch = cfg.warp_channels
+        self.ch = ch
+        isz = cfg.embed_size
+        w, _ = fold_conv(sd, p + ".first_conv")
+        w = w.reshape(w.shape[0], w.shape[1])  # (ch0*isz, 512); out index o = c*isz + d (view(b,-1,isz,isz,isz))
+        self.first_w = [w[d::isz].to(dev).contiguous() for d in range(isz)]  # per depth slice: rows c -> o = c*isz+d
+        self.blocks = [ResBlock(sd, f"{p}.blocks_3d.{i}", dev, ws_first=True) for i in range(len(ch) - 1)]
+        self.pu, self.pvT = [], []
+        j = 0
+        while f"{p}.projector.u.{j}" in sd:
+            self.pu.append(sd[f"{p}.projector.u.{j}"].detach().float().to(dev).contiguous())
+            self.pvT.append(sd[f"{p}.projector.v.{j}"].detach().float().t().to(dev).contiguous())  # (2,16)
+            j += 1
+        self.pre_head = Norm(sd, p + ".pre_head.0", dev)
+        self.head = ConvW(sd, p + ".head.0.0", dev)
+        idg = sd[p + ".identity_grid"].detach().float()  # (1,3,D,S,S) -> (D,S,S,3)
+        self.idg = idg[0].permute(1, 2, 3, 0).contiguous().to(dev)
+
+    def _ada(self, E, j, norm: Norm):
+        """ProjectorNorm utils.py:1140-1151 + assign_adaptive_norm_params :994-995 for one AdaptiveGroupNorm:
+        (gamma + (u.E.v)[:,0], beta + (u.E.v)[:,1]) as a (2, C) tensor."""
+        u, vT = self.pu[j], self.pvT[j]
+        Cc = u.shape[0]
+        T = torch.empty((Cc, 16), dtype=torch.float32, device=E.device)
+        ops.linear(E, u, x_strides=(1, 16), M=16, K=u.shape[1], out=T, out_strides=(1, 16))  # T[c][s] = sum_k u[c][k] E[k][s]
+        out = torch.empty((2, Cc), dtype=torch.float32, device=E.device)
+        ops.linear(T, vT, add=norm.gb, x_strides=(16, 1), M=Cc, K=16, out=out, out_strides=(1, Cc))
+        return out[0:1], out[1:2]
+
+    def __call__(self, E):
+        """E (1,512,16) -> warp (1,D,S,S,3) fp32 channels-last == the (b,D,H,W,3) grid of the reference."""
+        cfg = self.cfg
+        assert E.shape[0] == 1, "per-frame call (batch the frames over ranks/streams, not here)"
+        dev = E.device
+        isz = cfg.embed_size
+        Em = E[0]
+        x = torch.empty((1, isz, isz, isz, self.ch[0]), dtype=torch.float32, device=dev)
+        for d in range(isz):  # first_conv 1x1 on the 4x4 map, written straight into the (d,h,w,c) volume
+            ops.linear(Em, self.first_w[d], x_strides=(1, isz * isz), M=isz * isz, K=Em.shape[0], out=x[0, d],
+                       out_strides=(self.ch[0], 1))
+        size = [isz, isz, isz]
+        ndr = int(math.log2(cfg.S // isz))
+        nblk = len(self.blocks)
+        st = None
+        for i in range(1, nblk + 1):
+            size[1] *= 2
+            size[2] *= 2
+            depth_new = min(cfg.D * 2 ** (ndr - i), size[1]) if i < ndr else cfg.D
+            up_depth, down_depth = depth_new > size[0], depth_new < size[0]
+            size[0] = depth_new
+            st = ops.new_stats(1, G, dev)
+            x = ops.upsample_trilinear(x, (2, 2, 2) if up_depth else (1, 2, 2), stats=st)
+            blk = self.blocks[i - 1]
+            ada = (self._ada(Em, 2 * (i - 1), blk.n1), self._ada(Em, 2 * (i - 1) + 1, blk.n2))
+            x, st = blk(x, st, ada=ada, want_stats=not down_depth)
+            if down_depth:
+                st = ops.new_stats(1, G, dev)
+                x = ops.avgpool(x, (2, 1, 1), stats=st)
+        A, B = self.pre_head.affine(st, _count(x))
+        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        return ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_TANH, post_add=self.idg)
+
+
+class VolumeSource:
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        self.blocks = [ResBlock(sd, f"volume_source_nw.net.net.{i}", dev, ws_first=False)
+                       for i in range(cfg.source_volume_num_blocks)]
+
+    def __call__(self, vol):
+        st = ops.gn_stats(vol, G)
+        for i, blk in enumerate(self.blocks):
+            vol, st = blk(vol, st, want_stats=i < len(self.blocks) - 1)
+        return vol
+
+
+class Unet3D:
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        p = "volume_process_nw"
+        self.cfg = cfg
+        nb = len(cfg.unet_channels) - 1
+        self.nb = nb
+        self.down = [ResBlock(sd, f"{p}.blocks_3d_down.{i}", dev, ws_first=False) for i in range(nb)]
+        self.up = [ResBlock(sd, f"{p}.blocks_3d_up.{i}", dev, ws_first=False) for i in range(nb)]
+        self.skipb = [ResBlock(sd, f"{p}.skip_blocks_3d_up.{i}", dev, ws_first=False) for i in range(nb)]
+        it = sd[p + ".input_tensor"].detach().float()  # (1,C,8,8,8)
+        self.seed = it.permute(0, 2, 3, 4, 1).contiguous().to(dev)
+        self.head_norm = Norm(sd, p + ".head.0", dev)
+        self.head = ConvW(sd, p + ".head.2", dev)
+
+    def __call__(self, vol):
+        cfg, dev, nb = self.cfg, vol.device, self.nb
+        x = vol
+        feats = []
+        size = [cfg.D, vol.shape[2], vol.shape[3]]
+        st = None
+        for i in range(nb):
+            kind = "none"
+            if i < nb - 1:
+                size[1] //= 2
+                size[2] //= 2
+                depth_new = min(size[0] * 2, size[1])
+                kind = "up" if depth_new > size[0] else ("down" if depth_new < size[0] else "none")
+                size[0] = depth_new
+            if kind == "up":
+                st = ops.new_stats(1, G, dev)
+                x = ops.upsample_trilinear(x, (2, 1, 1), stats=st)
+            elif st is None:
+                st = ops.gn_stats(x, G)
+            x, st_out = self.down[i](x, st)
+            feats.append((x, st_out))
+            if i < nb - 1:
+                st = ops.new_stats(1, G, dev)
+                x = ops.avgpool(x, (2, 2, 2) if kind == "down" else (1, 2, 2), stats=st)
+        feats = feats[::-1]
+        x = self.seed
+        size = [x.shape[1], x.shape[2], x.shape[3]]
+        st = None
+        for i in range(1, nb + 1):
+            size[1] *= 2
+            size[2] *= 2
+            depth_new = min(cfg.D * 2 ** (nb - i), size[1])
+            kind = "up" if depth_new > size[0] else ("down" if depth_new < size[0] else "none")
+            size[0] = depth_new
+            f, fst = feats[i - 1]
+            skip, _ = self.skipb[i - 1](f, fst, want_stats=False)
+            st = ops.new_stats(1, G, dev)
+            x = ops.upsample_trilinear(x, (2, 2, 2) if kind == "up" else (1, 2, 2), add=skip, stats=st)
+            x, st = self.up[i - 1](x, st, want_stats=kind != "down")
+            if kind == "down":
+                st = ops.new_stats(1, G, dev)
+                x = ops.avgpool(x, (2, 1, 1), stats=st)
+        A, B = self.head_norm.affine(st, _count(x))
+        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        return ops.conv_igemm(a, self.head.w, bias=self.head.b)
+
+
+class Decoder:
+    def __init__(self, sd, cfg: HotPathConfig, dev):
+        p = "decoder_nw"
+        C, D = cfg.C, cfg.D
+        # the warped volume arrives as (h, w, d, c): channel k' = d*C + c  <->  reference channel c*D + d (infer.py:627)
+        iperm = torch.tensor([(k % C) * D + (k // C) for k in range(C * D)])
+        self.inp = ConvW(sd, p + ".res_decoder.0", dev, in_perm=iperm)
+        self.res = [ResBlock(sd, f"{p}.res_decoder.{i + 1}", dev) for i in range(cfg.dec_num_blocks)]
+        self.img = []
+        j = 0
+        while f"{p}.img_decoder.dec_img_blocks.{j}.block.0.weight_orig" in sd:
+            self.img.append(ResBlock(sd, f"{p}.img_decoder.dec_img_blocks.{j}", dev))
+            j += 1
+        self.lrs = cfg.im_dec_lrs
+        self.head_norm = Norm(sd, p + ".img_decoder.dec_img_head.0", dev)
+        self.head = ConvW(sd, p + ".img_decoder.dec_img_head.2", dev, ws=True)
+
+    def __call__(self, feat: "ops.Split", want_logits: bool = False):
+        """feat: Split (N,1,S,S,C*D) in (h,w,d,c) order -> img (N,3,H,W) fp32 NCHW, feat_2d, img_feat."""
+        N, dev = feat.shape[0], feat.hi.device
+        st = ops.new_stats(N, G, dev)
+        x = ops.conv_igemm(feat, self.inp.w, stats=st)
+        for blk in self.res:
+            x, st = blk(x, st)
+        feat2d = x
+        for j, blk in enumerate(self.img):
+            x, st = blk(x, st, up=2 if (j % self.lrs == 0) else 1)
+        A, B = self.head_norm.affine(st, _count(x))
+        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        img = ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_NONE if want_logits else ops.ACT_SIGMOID,
+                             out_nchw=True)
+        return img[:, :, 0], feat2d, x
