@@ -1,0 +1,230 @@
+"""Drop-in for the reference's stage-1 inference API: `notebooks/infer.py:62-647` InferenceWrapper.
+
+Same constructor and `forward` signature, same `args.txt` / checkpoint layout (`project_dir/folder/experiment_name/
+{args.txt, checkpoints/<model_file_name>}`), same cached source state on `self`, same return value
+`(list[PIL.Image], img Tensor (B,3,H,W) fp32 on device)`.  The hot path underneath is emoportraits_b200's sm_100a
+kernels; there is no torch/CPU fallback — without a B200 and the built libemoport.so this module raises.
+
+Out of scope here: the external face detector (crop=True), MODNet and BiSeNet mask
+networks.  `crop=True`/`modnet_mask=True` raise NotImplementedError; when `source_mask` is not given the mask is all
+ones (what the stubbed reference oracle uses too).
+"""
+from __future__ import annotations
+
+import pathlib
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import nets, ops
+from .config import HotPathConfig, hot_path_config, parse_args
+
+
+class Model:
+    """Inference-only counterpart of models/stage_1/volumetric_avatar/va.py:39 Model (attribute names kept)."""
+
+    def __init__(self, cfg: HotPathConfig, state_dict, head_pose_state_dict, device="cuda"):
+        self.cfg = cfg
+        dev = torch.device(device)
+        sd = state_dict
+        self.local_encoder_nw = nets.LocalEncoder(sd, cfg, dev)
+        self.idt_embedder_nw = nets.IdtEmbed(sd, cfg, dev)
+        self.expression_embedder_nw = nets.ExpressionEmbed(sd, cfg, dev)
+        self.predict_embed = nets.PredictEmbed(sd, cfg, dev)
+        self.xy_generator_nw = nets.WarpGenerator(sd, "xy_generator_nw", cfg, dev)
+        self.uv_generator_nw = nets.WarpGenerator(sd, "uv_generator_nw", cfg, dev)
+        self.volume_source_nw = nets.VolumeSource(sd, cfg, dev) if cfg.source_volume_num_blocks > 0 else None
+        self.volume_process_nw = nets.Unet3D(sd, cfg, dev)
+        self.decoder_nw = nets.Decoder(sd, cfg, dev)
+        self.head_pose_regressor = nets.HeadPoseRegressor(head_pose_state_dict, dev)
+        self.device = dev
+
+    # ---- notebooks/infer.py:374-507 ----
+    @torch.no_grad()
+    def source_pass(self, src: torch.Tensor, taps: Optional[dict] = None):
+        """src (1,3,H,W) fp32 in [0,1] on device, already masked.  Returns the cached source state."""
+        cfg = self.cfg
+        st = SimpleNamespace()
+        st.idt_embed = self.idt_embedder_nw(src)                       # (1,512,4,4) NCHW
+        vol = self.local_encoder_nw(src)                               # (1,D,S,S,C)
+        srt = self.head_pose_regressor(src)
+        st.pred_source_theta, inv_warp, align = ops.pose_theta(srt, invert_warp=True)
+        st.source_theta_dev = st.pred_source_theta[0].contiguous()
+        pose_embed, _ = self.expression_embedder_nw(src, align)
+        st.pred_source_pose_embed = pose_embed
+        E = self.predict_embed(pose_embed, st.idt_embed)
+        xy_warp = self.xy_generator_nw(E)                              # (1,D,S,S,3)
+        if self.volume_source_nw is not None:
+            vol = self.volume_source_nw(vol)
+        st.source_latent_volume = vol
+        st.source_rotation_warp_theta = inv_warp
+        st.source_xy_warp_resize = xy_warp
+        v = ops.grid_sample3d(vol, theta=inv_warp, out_size=(cfg.D, cfg.S, cfg.S), in_layout="cl")
+        v = ops.grid_sample3d(v, grid=xy_warp, in_layout="cl")
+        st.target_latent_volume_1 = v
+        st.target_latent_volume = self.volume_process_nw(v)           # (1,D,S,S,C) channels-last
+        if taps is not None:
+            taps.update(srt_source=srt, source_pose_embed=pose_embed, source_embed=E, xy_warp=xy_warp)
+        return st
+
+    # ---- notebooks/infer.py:511-644 ----
+    @torch.no_grad()
+    def driver_pass(self, st, drv: torch.Tensor, mix: bool = True, target_theta: bool = True, taps: Optional[dict] = None,
+                    want_logits: bool = False):
+        """drv (1,3,H,W) fp32 on device -> (img (1,3,H,W), feat_2d, img_feat)."""
+        cfg = self.cfg
+        srt = self.head_pose_regressor(drv)
+        theta, warp, align = ops.pose_theta(srt, source_theta=st.source_theta_dev if mix else None, mix=mix)
+        if not target_theta:
+            warp = st.pred_source_theta[:, :3].contiguous()
+        pose_embed, aligned = self.expression_embedder_nw(drv, align, want_aligned=taps is not None)
+        E = self.predict_embed(pose_embed, st.idt_embed)
+        uv_warp = self.uv_generator_nw(E)
+        v = ops.grid_sample3d(st.target_latent_volume, grid=uv_warp, in_layout="cl")
+        feat = ops.grid_sample3d(v, theta=warp, out_size=(cfg.D, cfg.S, cfg.S), in_layout="cl", out_layout="hwdc",
+                                 want_f32=taps is not None, want_split=True)
+        if taps is not None:
+            aligned_vol, feat = feat
+            taps.update(srt=srt, theta=warp, pose_embed=pose_embed, embed=E, uv_warp=uv_warp, aligned_face=aligned,
+                        aligned_volume_hwdc=aligned_vol)
+        feat2d = ops.Split(feat.hi.view(1, 1, cfg.S, cfg.S, cfg.D * cfg.C), feat.lo.view(1, 1, cfg.S, cfg.S, cfg.D * cfg.C))
+        img, deep_f, img_f = self.decoder_nw(feat2d, want_logits=want_logits)
+        st_out = SimpleNamespace(pred_target_theta=theta, target_pose_embed=pose_embed, srt=srt)
+        return img, deep_f, img_f, st_out
+
+
+class InferenceWrapper(torch.nn.Module):
+    def __init__(self, experiment_name, which_epoch='latest', model_file_name='', use_gpu=True, num_gpus=1,
+                 fixed_bounding_box=False, project_dir='./', folder='mp_logs', model_='va',
+                 torch_home='', debug=False, print_model=False, print_params=True, args_overwrite={}, state_dict=None,
+                 pose_momentum=0.5, rank=0, args_path=None, head_pose_state_dict=None):
+        super().__init__()
+        if not use_gpu or not torch.cuda.is_available():
+            raise RuntimeError("emoportraits_b200.InferenceWrapper needs a CUDA device (B200); there is no CPU path")
+        if model_ != 'va':
+            raise NotImplementedError(f"model_={model_!r}: only the stage-1 'va' model is implemented")
+        self.use_gpu, self.debug, self.num_gpus, self.rank = use_gpu, debug, num_gpus, rank
+        args_path = pathlib.Path(project_dir) / folder / experiment_name / 'args.txt' if args_path is None else args_path
+        self.args = parse_args(args_path)
+        self.args.project_dir = project_dir
+        for k, v in (args_overwrite or {}).items():
+            setattr(self.args, k, v)
+        self.cfg = hot_path_config(self.args)
+        self.device = torch.device('cuda', torch.cuda.current_device())
+
+        self.model_checkpoint = pathlib.Path(project_dir) / folder / experiment_name / 'checkpoints' / model_file_name
+        if state_dict is None:
+            state_dict = torch.load(self.model_checkpoint, map_location='cpu')
+        self.model_dict = state_dict
+        if head_pose_state_dict is None:
+            hp = getattr(self.args, 'head_pose_regressor_path', None)
+            if not hp or not pathlib.Path(str(hp)).exists():
+                raise FileNotFoundError(f"head pose regressor checkpoint not found ({hp}); pass head_pose_state_dict=")
+            head_pose_state_dict = torch.load(hp, map_location='cpu')
+        self.model = Model(self.cfg, state_dict, head_pose_state_dict, self.device)
+        if rank == 0 and print_params:
+            n = sum(v.numel() for v in state_dict.values())
+            print(f'Number of parameters/buffers in checkpoint: {n}')
+
+        # face tracking / smoothing state kept for API parity (notebooks/infer.py:159-177)
+        self.fixed_bounding_box = fixed_bounding_box
+        self.momentum = 0.01
+        self.center = None
+        self.size = None
+        self.pose_momentum = pose_momentum
+        self.theta = None
+        self.norm_momentum = 0.1
+        self.delta_yaw = None
+        self.delta_pitch = None
+        self.resize_warp = False
+        self.use_seg = getattr(self.args, 'use_seg', True)
+        self._state = None
+
+    # -- notebooks/infer.py:229-243
+    def convert_to_tensor(self, image):
+        def one(img):
+            a = np.asarray(img)
+            if a.ndim == 2:
+                a = a[:, :, None]
+            t = torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1)
+            return t.float().div(255) if t.dtype == torch.uint8 else t.float()
+
+        if isinstance(image, torch.Tensor):
+            t = image
+        elif isinstance(image, list):
+            t = torch.stack([one(i) for i in image])
+        else:
+            t = one(image)
+        if t.dim() == 3:
+            t = t[None]
+        return t.to(self.device)
+
+    def _prep(self, image):
+        t = self.convert_to_tensor(image)[:, :3]
+        s = self.cfg.image_size
+        if t.shape[-2:] != (s, s):
+            t = F.interpolate(t, size=(s, s), mode='bicubic')  # pre-processing resize, infer.py:401-402 / :554-555
+        return t.contiguous().float()
+
+    def forward(self, source_image=None, driver_image=None, source_mask=None, source_mask_add=0, driver_mask=None,
+                crop=True, reset_tracking=False, smooth_pose=False, hard_normalize=False, soft_normalize=False,
+                delta_yaw=None, delta_pitch=None, cloth=False, thetas_pass='', theta_n=0, target_theta=True, mix=False,
+                mix_old=True, c_source_latent_volume=None, c_target_latent_volume=None, custome_target_pose_embed=None,
+                custome_target_theta_embed=None, no_grad_infer=True, modnet_mask=False):
+        if crop:
+            raise NotImplementedError("crop=True needs the external mediapipe face detector (out of scope); pass crop=False "
+                                      "with pre-cropped images, as notebooks/E_emo_infer_video.ipynb does")
+        if modnet_mask:
+            raise NotImplementedError("modnet_mask=True needs the external MODNet (out of scope)")
+        if mix and mix_old:
+            raise NotImplementedError("mix_old=True pose mixing is not implemented (the notebook uses mix_old=False)")
+        if smooth_pose or custome_target_pose_embed is not None or custome_target_theta_embed is not None or \
+                c_source_latent_volume is not None or c_target_latent_volume is not None:
+            raise NotImplementedError("smooth_pose / custom embeddings / custom volumes are not implemented")
+        self.target_theta, self.mix, self.mix_old = target_theta, mix, mix_old
+        if reset_tracking:
+            self.center = self.size = self.theta = self.delta_yaw = self.delta_pitch = None
+
+        if source_image is not None:
+            src = self._prep(source_image)
+            self.source_image = src
+            if source_mask is None:
+                source_mask = torch.ones_like(src[:, :1])
+            source_mask = source_mask.to(self.device).float()
+            if source_mask_add:
+                source_mask = source_mask.clamp_(max=1, min=0)
+            self.source_img_mask = source_mask
+            masked = (src * source_mask).contiguous()
+            self.source_img = src
+            st = self.model.source_pass(masked)
+            self._state = st
+            # cached attributes of the reference wrapper (infer.py:405-507)
+            self.idt_embed = st.idt_embed
+            self.pred_source_theta = st.pred_source_theta
+            self.pred_source_pose_embed = st.pred_source_pose_embed
+            self.source_latent_volume = st.source_latent_volume.permute(0, 4, 1, 2, 3)       # NCDHW views
+            self.source_xy_warp_resize = st.source_xy_warp_resize
+            self.target_latent_volume_1 = st.target_latent_volume_1.permute(0, 4, 1, 2, 3)
+            self.target_latent_volume = st.target_latent_volume.permute(0, 4, 1, 2, 3)
+
+        if driver_image is None:
+            return None
+        if self._state is None:
+            raise RuntimeError("forward(driver_image=...) called before a source image was given")
+        drv = self._prep(driver_image)
+        imgs = []
+        for i in range(drv.shape[0]):
+            img, deep_f, img_f, so = self.model.driver_pass(self._state, drv[i:i + 1].contiguous(), mix=mix,
+                                                            target_theta=target_theta)
+            imgs.append(img)
+            self.pred_target_theta = so.pred_target_theta
+            self.target_pose_embed = so.target_pose_embed
+        img = torch.cat(imgs)
+        from PIL import Image
+
+        host = (img.detach().clamp(0, 1) * 255).byte().permute(0, 2, 3, 1).cpu().numpy()  # ToPILImage: mul(255).byte()
+        pred_target_img = [Image.fromarray(h) for h in host]
+        return pred_target_img, img

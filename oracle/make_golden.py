@@ -1,0 +1,115 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, through oracle/ref_harness.py) in this container.  /root/reference cannot travel to the GPU box,
+so the fixtures are committed together with this script:
+
+    python -m oracle.make_golden            # writes tests/golden/*.pt and the checkpoint-layout manifests
+
+What is recorded, for image_size 256 and 512 (shipped config, experiments/args.txt):
+  * the checkpoint layout (key -> shape) of va.Model.state_dict() and of the head-pose resnet18;
+  * the reference InferenceWrapper's outputs for seeded synthetic frames with the seeded synthetic checkpoint of
+    emoportraits_b200.checkpoint.synthetic_state_dict (loaded with load_state_dict(strict=True) into the reference
+    model, which is itself the proof that our structural layout spec equals the reference's):
+    final image, pre-sigmoid logits, and stage-boundary taps (large tensors strided down to keep fixtures small).
+"""
+from __future__ import annotations
+
+import pathlib
+import sys
+
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+GOLD = ROOT / "tests" / "golden"
+
+SRC_SEED, DRV_SEEDS = 0, (1, 2)
+
+
+def sub(t: torch.Tensor, max_elems: int = 40000):
+    """deterministic strided subsample of a large tensor: returns (flat_values, stride)"""
+    f = t.detach().float().reshape(-1)
+    stride = max(1, (f.numel() + max_elems - 1) // max_elems)
+    return f[::stride].clone(), stride
+
+
+def run(image_size: int):
+    import oracle.ref_harness as H
+    from emoportraits_b200.checkpoint import (state_dict_spec, head_pose_spec, synthetic_state_dict,
+                                              synthetic_head_pose_state_dict)
+    from emoportraits_b200.config import shipped_config
+
+    w, msd, hsd, lines = H.build_reference_wrapper(image_size, 0)
+    cfg = shipped_config(image_size)
+
+    # ---- layout manifests (from the REFERENCE objects) ----
+    (GOLD / f"state_dict_manifest_{image_size}.txt").write_text(
+        "".join(f"{k} {tuple(v.shape)}\n" for k, v in msd.items()))
+    (GOLD / "head_pose_manifest.txt").write_text("".join(f"{k} {tuple(v.shape)}\n" for k, v in hsd.items()))
+    (GOLD / f"args_{image_size}.txt").write_text("".join(lines))
+    spec = state_dict_spec(cfg)
+    assert {k: tuple(v.shape) for k, v in msd.items()} == {k: tuple(v) for k, v in spec.items()}, "layout spec mismatch"
+    assert {k: tuple(v.shape) for k, v in hsd.items()} == {k: tuple(v) for k, v in head_pose_spec().items()}
+
+    # ---- seeded synthetic checkpoint into the reference model ----
+    sd = synthetic_state_dict(cfg, seed=0)
+    hp = synthetic_head_pose_state_dict(seed=0)
+    # aligned_keypoints is a buffer read from data/aligned_keypoints_3d.npy; keep the reference's own values
+    sd["expression_embedder_nw.aligned_keypoints"] = msd["expression_embedder_nw.aligned_keypoints"]
+    missing = w.model.load_state_dict(sd, strict=True)
+    w.model.head_pose_regressor.net.load_state_dict(hp, strict=True)
+    w.model.eval()
+    w.model.head_pose_regressor.net.eval()
+
+    taps = {}
+    hooks = []
+    hooks.append(w.model.decoder_nw.img_decoder.dec_img_head[2].register_forward_hook(
+        lambda m, i, o: taps.__setitem__("logits", o.detach().clone())))
+    hooks.append(w.model.uv_generator_nw.register_forward_hook(
+        lambda m, i, o: taps.__setitem__("uv_warp", o[0].detach().clone())))
+    hooks.append(w.model.decoder_nw.register_forward_pre_hook(
+        lambda m, i: taps.__setitem__("aligned_feat2d", i[2].detach().clone())))
+    hooks.append(w.model.decoder_nw.res_decoder.register_forward_hook(
+        lambda m, i, o: taps.__setitem__("dec_feat", o.detach().clone())))
+
+    out = {"image_size": image_size, "src_seed": SRC_SEED, "drv_seeds": list(DRV_SEEDS), "frames": []}
+    src = H.synthetic_frame(image_size, SRC_SEED)
+    first = True
+    for ds in DRV_SEEDS:
+        drv = H.synthetic_frame(image_size, ds)
+        with torch.no_grad():
+            res = w.forward(src if first else None, drv, crop=False, mix=True, mix_old=False)
+        if first:
+            out["source"] = {
+                "idt_embed": w.idt_embed.clone(),
+                "pred_source_theta": w.pred_source_theta.clone(),
+                "pred_source_pose_embed": w.pred_source_pose_embed.clone(),
+                "xy_warp": sub(w.source_xy_warp_resize),
+                "source_latent_volume": sub(w.source_latent_volume),
+                "target_latent_volume_1": sub(w.target_latent_volume_1),
+                "target_latent_volume": sub(w.target_latent_volume),
+            }
+            first = False
+        out["frames"].append({
+            "seed": ds,
+            # full tensors at 256; strided subsamples at 512 to keep the committed fixture small
+            "img": res[1].detach().clone() if image_size <= 256 else sub(res[1], 250000),
+            "logits": taps["logits"] if image_size <= 256 else sub(taps["logits"], 250000),
+            "pred_target_theta": w.pred_target_theta.clone(),
+            "target_pose_embed": w.target_pose_embed.clone(),
+            "uv_warp": sub(taps["uv_warp"]),
+            "aligned_feat2d": sub(taps["aligned_feat2d"]),
+            "dec_feat": sub(taps["dec_feat"]),
+        })
+        print(f"[golden {image_size}] frame seed {ds}: img mean {res[1].mean().item():.4f} "
+              f"logits [{taps['logits'].min().item():.2f}, {taps['logits'].max().item():.2f}]")
+    for h in hooks:
+        h.remove()
+    torch.save(out, GOLD / f"va{image_size}_seed0.pt")
+    return out
+
+
+if __name__ == "__main__":
+    GOLD.mkdir(parents=True, exist_ok=True)
+    sizes = [int(a) for a in sys.argv[1:]] or [256, 512]
+    for s in sizes:
+        run(s)
