@@ -47,6 +47,7 @@ class Model:
     def source_pass(self, src: torch.Tensor, taps: Optional[dict] = None):
         """src (1,3,H,W) fp32 in [0,1] on device, already masked.  Returns the cached source state."""
         cfg = self.cfg
+        src = src.contiguous().float()
         st = SimpleNamespace()
         st.idt_embed = self.idt_embedder_nw(src)                       # (1,512,4,4) NCHW
         vol = self.local_encoder_nw(src)                               # (1,D,S,S,C)
@@ -76,6 +77,7 @@ class Model:
                     want_logits: bool = False):
         """drv (1,3,H,W) fp32 on device -> (img (1,3,H,W), feat_2d, img_feat)."""
         cfg = self.cfg
+        drv = drv.contiguous().float()
         srt = self.head_pose_regressor(drv)
         theta, warp, align = ops.pose_theta(srt, source_theta=st.source_theta_dev if mix else None, mix=mix)
         if not target_theta:
@@ -94,6 +96,31 @@ class Model:
         img, deep_f, img_f = self.decoder_nw(feat2d, want_logits=want_logits)
         st_out = SimpleNamespace(pred_target_theta=theta, target_pose_embed=pose_embed, srt=srt)
         return img, deep_f, img_f, st_out
+
+
+    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True):
+        """Capture one driver frame (all ~350 kernel launches) into a CUDA graph: removes the Python/ctypes launch
+        overhead from the per-frame loop.  Returns replay(drv (1,3,H,W) on device) -> img (1,3,H,W) (static buffer)."""
+        s = self.cfg.image_size
+        static_in = torch.zeros((1, 3, s, s), dtype=torch.float32, device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.driver_pass(st, static_in, mix=mix, target_theta=target_theta)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self.driver_pass(st, static_in, mix=mix, target_theta=target_theta)[0]
+
+        def replay(drv: torch.Tensor) -> torch.Tensor:
+            static_in.copy_(drv, non_blocking=True)
+            graph.replay()
+            return static_out
+
+        replay.graph = graph
+        return replay
 
 
 class InferenceWrapper(torch.nn.Module):

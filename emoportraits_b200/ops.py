@@ -18,18 +18,20 @@ from .lib import ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH  # noqa: F401
 
 
 def _stream() -> int:
+    if L.DRY_RUN:
+        return 0
     return torch.cuda.current_stream().cuda_stream
 
 
 def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     if t is None:
         return None
-    assert t.is_cuda, "emoportraits_b200 ops need CUDA tensors (there is no CPU path)"
+    assert t.is_cuda or L.DRY_RUN, "emoportraits_b200 ops need CUDA tensors (there is no CPU path)"
     return t.data_ptr()
 
 
 def _chk(t: torch.Tensor, dtype=torch.float32):
-    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
+    assert (t.is_cuda or L.DRY_RUN) and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype, t.is_contiguous())
     return t
 
 
@@ -214,6 +216,26 @@ def _out_dim(i, k, s, p):
     return (i + 2 * p - k) // s + 1
 
 
+class ConvProfiler:
+    """CUDA-event bracket around every tensor-core conv launch (bench.py roofline evidence; off by default)."""
+
+    def __init__(self):
+        self.rec = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.rec)
+        return ms, sum(f for _, _, f in self.rec), len(self.rec)
+
+
+_conv_profiler: Optional[ConvProfiler] = None
+
+
+def set_conv_profiler(p: Optional[ConvProfiler]):
+    global _conv_profiler
+    _conv_profiler = p
+
+
 def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=None, residual=None, res_shift: int = 0,
                act: int = ACT_NONE, post_add=None, out_nchw: bool = False, stats: Optional[torch.Tensor] = None,
                G: int = 32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -230,7 +252,14 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
                    G if stats is not None else 0)
-    L.call("emo_conv_igemm", C.byref(d), _stream())
+    if _conv_profiler is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.call("emo_conv_igemm", C.byref(d), _stream())
+        e1.record()
+        _conv_profiler.rec.append((e0, e1, 2.0 * N * Do * Ho * Wo * w.cout * Ci * kd * kh * kw))
+    else:
+        L.call("emo_conv_igemm", C.byref(d), _stream())
     return out
 
 
