@@ -92,7 +92,22 @@ def cpu_port_fps(steps, warmup, threads=None):
     from emoportraits_b200.config import shipped_config
     from oracle import restatement as R
 
-    threads = threads or os.cpu_count() or 1
+    if threads is None:
+        # "all the host threads it can use": pick the thread count that is fastest for a representative conv
+        # (oversubscribed or quota-limited boxes get slower past a point)
+        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        x, w = torch.randn(1, 128, 256, 256), torch.randn(128, 128, 3, 3)
+        best = (1e9, 1)
+        for t in sorted({min(avail, c) for c in (8, 16, 32, 64, avail)}):
+            torch.set_num_threads(t)
+            torch.nn.functional.conv2d(x, w, padding=1)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                torch.nn.functional.conv2d(x, w, padding=1)
+            dt = time.perf_counter() - t0
+            if dt < best[0]:
+                best = (dt, t)
+        threads = best[1]
     torch.set_num_threads(threads)
     cfg = shipped_config(SIZE)
     sd, hsd = synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0)
@@ -269,6 +284,14 @@ def run_ours(args):
     launches_per_step = (L.launch_count - l0) // 3
     ops.set_conv_profiler(None)
     conv_ms, conv_flops, n_conv = prof.summary()
+    try:
+        (ROOT / "gpurun_out").mkdir(exist_ok=True)
+        with open(ROOT / "gpurun_out" / "conv_layers.csv", "w") as f:
+            f.write("shape,launches(3 frames),ms_total,algorithmic_TFLOPs,mma_TFLOPs\n")
+            for r in prof.table():
+                f.write(f"{r[0]},{r[1]},{r[2]:.4f},{r[3]:.1f},{r[4]:.1f}\n")
+    except OSError:
+        pass
     conv_tflops = conv_flops / conv_ms / 1e9 if conv_ms > 0 else 0.0
     frame_ms = ms_max / K
     gs = grid_sample_roofline(peaks)
@@ -299,7 +322,8 @@ def run_ours(args):
                      "achieved": conv_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                      "frac": conv_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
                      "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                     "mma_passes": 3, "tensor_pipe_frac_est": 3 * conv_tflops / peaks["bf16_tflops_sustained"],
+                     "mma_passes": "3 per product (decoder) / 6 (embedding+warp nets)",
+                     "tensor_pipe_frac_est": (prof.mma_flops / conv_ms / 1e9) / peaks["bf16_tflops_sustained"],
                      "algorithmic_flops_per_step": conv_flops / 3, "kernel_ms_per_step": conv_ms / 3, "launches_per_step": n_conv // 3,
                      "share_of_step": (conv_ms / 3) / frame_ms},
         "roofline_grid_sample3d": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],

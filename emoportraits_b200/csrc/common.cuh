@@ -54,6 +54,25 @@ __device__ __forceinline__ void split4(const float4& v, uint2& hi, uint2& lo) {
   lo.y = pack_bf16x2(l2, l3);
 }
 
+// three-plane split: x ~= hi + lo + lo2 to ~2^-26 |x| (each residual is exact in fp32)
+__device__ __forceinline__ void split_bf16x3(float x, __nv_bfloat16& hi, __nv_bfloat16& lo, __nv_bfloat16& lo2) {
+  hi = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(hi);
+  lo = __float2bfloat16_rn(r1);
+  lo2 = __float2bfloat16_rn(r1 - __bfloat162float(lo));
+}
+
+__device__ __forceinline__ void split4x3(const float4& v, uint2& hi, uint2& lo, uint2& lo2) {
+  __nv_bfloat16 h[4], l[4], m[4];
+  split_bf16x3(v.x, h[0], l[0], m[0]);
+  split_bf16x3(v.y, h[1], l[1], m[1]);
+  split_bf16x3(v.z, h[2], l[2], m[2]);
+  split_bf16x3(v.w, h[3], l[3], m[3]);
+  hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
+  lo.x = pack_bf16x2(l[0], l[1]); lo.y = pack_bf16x2(l[2], l[3]);
+  lo2.x = pack_bf16x2(m[0], m[1]); lo2.y = pack_bf16x2(m[2], m[3]);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -129,11 +129,15 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <int KC>
+struct TMaps {
+  CUtensorMap a[3];  // activation planes: hi, lo, lo2
+  CUtensorMap b[3];  // weight planes
+};
+
+// NP = number of bf16 planes per operand: 2 -> 3 products (~2^-16 relative), 3 -> 6 products (~2^-24, fp32-faithful)
+template <int KC, int NP>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                  const __grid_constant__ ConvKParams p) {
+conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16B-aligned by the API; realign to 1024 for the swizzle atoms.
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -141,7 +145,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int BN = p.BN;
   const uint32_t a_bytes = kTileM * KC * 2;
   const uint32_t b_bytes = (uint32_t)BN * KC * 2;
-  const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const uint32_t stage_bytes = NP * a_bytes + NP * b_bytes;
   const int S = p.stages;
 
   uint8_t* tail = smem + (size_t)S * stage_bytes;
@@ -157,10 +161,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB_lo) : "memory");
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b[i]) : "memory");
+    }
     for (int i = 0; i < S; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -186,7 +191,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   const int ksteps = taps * p.kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int rows_a = p.tw * p.th * p.td;
-  const uint32_t tx_bytes = 2u * (uint32_t)rows_a * KC * 2 + 2u * b_bytes;
+  const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -212,10 +217,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&full_bar[stage], tx_bytes);
-                tma_load_5d(&tmA_hi, &full_bar[stage], st, kc * KC, x0 + c, y0 + b, z0 + a, n);
-                tma_load_5d(&tmA_lo, &full_bar[stage], st + a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
-                tma_load_3d(&tmB_hi, &full_bar[stage], st + 2 * a_bytes, kc * KC, n0, tap);
-                tma_load_3d(&tmB_lo, &full_bar[stage], st + 2 * a_bytes + b_bytes, kc * KC, n0, tap);
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl) {
+                  tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
+                  tma_load_3d(&tm.b[pl], &full_bar[stage], st + NP * a_bytes + pl * b_bytes, kc * KC, n0, tap);
+                }
                 if (++stage == S) { stage = 0; phase ^= 1; }
               }
             }
@@ -240,16 +246,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         tcgen05_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t dAh = make_kmajor_desc<KC>(sa);
-          const uint64_t dAl = make_kmajor_desc<KC>(sa + a_bytes);
-          const uint64_t dBh = make_kmajor_desc<KC>(sa + 2 * a_bytes);
-          const uint64_t dBl = make_kmajor_desc<KC>(sa + 2 * a_bytes + b_bytes);
+          uint64_t dA[NP], dB[NP];
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl) {
+            dA[pl] = make_kmajor_desc<KC>(sa + pl * a_bytes);
+            dB[pl] = make_kmajor_desc<KC>(sa + NP * a_bytes + pl * b_bytes);
+          }
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);  // 16 bf16 = 32 B = 2 x 16B units
-            umma_bf16(tmem_d, dAl + adv, dBh + adv, idesc, (ks | kk) != 0);
-            umma_bf16(tmem_d, dAh + adv, dBl + adv, idesc, 1);
-            umma_bf16(tmem_d, dAh + adv, dBh + adv, idesc, 1);
+            const uint32_t first = (ks | kk) != 0;
+            if (NP == 2) {
+              umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, first);
+              umma_bf16(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
+              umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
+            } else {
+              // smallest terms first: lo2*hi, hi*lo2, lo*lo, lo*hi, hi*lo, hi*hi
+              umma_bf16(tmem_d, dA[NP - 1] + adv, dB[0] + adv, idesc, first);
+              umma_bf16(tmem_d, dA[0] + adv, dB[NP - 1] + adv, idesc, 1);
+              umma_bf16(tmem_d, dA[1] + adv, dB[1] + adv, idesc, 1);
+              umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, 1);
+              umma_bf16(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
+              umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
@@ -484,7 +503,9 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   PFN_cuTensorMapEncodeTiled encode = get_encode();
   if (!encode) { set_error("emo_conv_igemm: cuTensorMapEncodeTiled entry point unavailable"); return EMO_ERR_CUDA; }
 
-  const int KC = (d->Cin % 64 == 0) ? 64 : 32;
+  const int NP = d->a_lo2 ? 3 : 2;
+  EMO_REQUIRE((d->a_lo2 == nullptr) == (d->w_lo2 == nullptr), "emo_conv_igemm: a_lo2 and w_lo2 must be given together");
+  const int KC = (NP == 3) ? 32 : ((d->Cin % 64 == 0) ? 64 : 32);
   // N tile: largest divisor-friendly width <= 256 (multiple of 16)
   int BN = d->Cout_pad;
   if (BN > 256) {
@@ -528,7 +549,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
               "emo_conv_igemm: residual shift does not divide the output size");
 
   const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)BN * KC * 2;
-  const size_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+  const size_t stage_bytes = NP * (a_bytes + b_bytes);
   const size_t tail_bytes = (2 * kMaxStages + 4) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
   int stages = (int)((smem_limit - tail_bytes - 1024) / stage_bytes);
@@ -538,7 +559,8 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   const size_t smem_bytes = stages * stage_bytes + tail_bytes + 1024;
 
   // ---- tensor maps ----
-  CUtensorMap tmAh, tmAl, tmBh, tmBl;
+  TMaps tm;
+  memset(&tm, 0, sizeof(tm));
   {
     cuuint64_t gdim[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->Din, (cuuint64_t)d->N};
     cuuint64_t gstr[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2,
@@ -546,41 +568,39 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(p.tw * d->sw), (cuuint32_t)(p.th * d->sh), (cuuint32_t)(p.td * d->sd), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->sd, 1};
     const CUtensorMapSwizzle sw = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    CUresult r1 = encode(&tmAh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)d->a_hi, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = encode(&tmAl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)d->a_lo, gdim, gstr, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-      set_error("emo_conv_igemm: cuTensorMapEncodeTiled(A) failed: %d %d (Cin=%d W=%d H=%d D=%d N=%d box=%d,%d,%d)", (int)r1, (int)r2,
-                d->Cin, d->Win, d->Hin, d->Din, d->N, p.tw, p.th, p.td);
-      return EMO_ERR_CUDA;
-    }
     const int taps = d->kd * d->kh * d->kw;
     cuuint64_t wdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout_pad, (cuuint64_t)taps};
     cuuint64_t wstr[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout_pad * d->Cin * 2};
     cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
     cuuint32_t wes[3] = {1, 1, 1};
-    CUresult r3 = encode(&tmBh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->w_hi, wdim, wstr, wbox, wes,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r4 = encode(&tmBl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)d->w_lo, wdim, wstr, wbox, wes,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r3 != CUDA_SUCCESS || r4 != CUDA_SUCCESS) {
-      set_error("emo_conv_igemm: cuTensorMapEncodeTiled(W) failed: %d %d", (int)r3, (int)r4);
-      return EMO_ERR_CUDA;
+    const void* ap[3] = {d->a_hi, d->a_lo, d->a_lo2};
+    const void* wp[3] = {d->w_hi, d->w_lo, d->w_lo2};
+    for (int pl = 0; pl < NP; ++pl) {
+      EMO_REQUIRE(((uintptr_t)ap[pl] % 16) == 0 && ((uintptr_t)wp[pl] % 16) == 0, "emo_conv_igemm: planes must be 16-byte aligned");
+      CUresult r1 = encode(&tm.a[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ap[pl], gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      CUresult r2 = encode(&tm.b[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wp[pl], wdim, wstr, wbox, wes,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+        set_error("emo_conv_igemm: cuTensorMapEncodeTiled failed: A %d W %d (Cin=%d W=%d H=%d D=%d N=%d box=%d,%d,%d BN=%d)", (int)r1,
+                  (int)r2, d->Cin, d->Win, d->Hin, d->Din, d->N, p.tw, p.th, p.td, BN);
+        return EMO_ERR_CUDA;
+      }
     }
   }
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < sm_count ? total_tiles : sm_count;
   cudaError_t e;
-  if (KC == 64) {
-    e = cudaFuncSetAttribute(conv_igemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }
-    conv_igemm_kernel<64><<<grid, kThreads, smem_bytes, stream>>>(tmAh, tmAl, tmBh, tmBl, p);
-  } else {
-    e = cudaFuncSetAttribute(conv_igemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }
-    conv_igemm_kernel<32><<<grid, kThreads, smem_bytes, stream>>>(tmAh, tmAl, tmBh, tmBl, p);
-  }
+#define EMO_LAUNCH_CONV(KC_, NP_)                                                                                         \
+  do {                                                                                                                    \
+    e = cudaFuncSetAttribute(conv_igemm_kernel<KC_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);   \
+    if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; } \
+    conv_igemm_kernel<KC_, NP_><<<grid, kThreads, smem_bytes, stream>>>(tm, p);                                            \
+  } while (0)
+  if (NP == 3) EMO_LAUNCH_CONV(32, 3);
+  else if (KC == 64) EMO_LAUNCH_CONV(64, 2);
+  else EMO_LAUNCH_CONV(32, 2);
+#undef EMO_LAUNCH_CONV
   return check_launch("emo_conv_igemm");
 }

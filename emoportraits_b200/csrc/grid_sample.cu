@@ -21,6 +21,7 @@ struct GS3Params {
   float* out;
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  __nv_bfloat16* out_lo2;
   long long os_n, os_c, os_d, os_h, os_w;
   // brick decomposition of the output lattice (channels-last kernel)
   int bw, bh, bd, bricks_w, bricks_h, bricks_d;
@@ -118,8 +119,13 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
     if (p.os_c == 1) {
       if (p.out) *(float4*)(p.out + o) = acc;
       if (SPLIT) {
-        uint2 hi, lo;
-        split4(acc, hi, lo);
+        uint2 hi, lo, lo2;
+        if (p.out_lo2) {
+          split4x3(acc, hi, lo, lo2);
+          *(uint2*)(p.out_lo2 + o) = lo2;
+        } else {
+          split4(acc, hi, lo);
+        }
         *(uint2*)(p.out_hi + o) = hi;
         *(uint2*)(p.out_lo + o) = lo;
       }
@@ -129,10 +135,12 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
       for (int j = 0; j < 4; ++j) {
         if (p.out) p.out[o + j * p.os_c] = a[j];
         if (SPLIT) {
-          __nv_bfloat16 h, l;
-          split_bf16(a[j], h, l);
+          __nv_bfloat16 h, l, l2;
+          split_bf16x3(a[j], h, l, l2);
+          if (!p.out_lo2) split_bf16(a[j], h, l);
           p.out_hi[o + j * p.os_c] = h;
           p.out_lo[o + j * p.os_c] = l;
+          if (p.out_lo2) p.out_lo2[o + j * p.os_c] = l2;
         }
       }
     }
@@ -174,10 +182,12 @@ __global__ void __launch_bounds__(256) gs3_nc_kernel(const GS3Params p) {
       for (int j = 0; j < 8; ++j) acc = fmaf(__ldg(s + off[j]), wgt[j], acc);
       if (p.out) p.out[o + (long long)c * p.os_c] = acc;
       if (p.out_hi) {
-        __nv_bfloat16 h, l;
-        split_bf16(acc, h, l);
+        __nv_bfloat16 h, l, l2;
+        split_bf16x3(acc, h, l, l2);
+        if (!p.out_lo2) split_bf16(acc, h, l);
         p.out_hi[o + (long long)c * p.os_c] = h;
         p.out_lo[o + (long long)c * p.os_c] = l;
+        if (p.out_lo2) p.out_lo2[o + (long long)c * p.os_c] = l2;
       }
     }
   }
@@ -289,6 +299,7 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
   p.N = d->N; p.C = d->C; p.Din = d->Din; p.Hin = d->Hin; p.Win = d->Win;
   p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout;
   p.out = d->out; p.out_hi = (__nv_bfloat16*)d->out_hi; p.out_lo = (__nv_bfloat16*)d->out_lo;
+  p.out_lo2 = (__nv_bfloat16*)d->out_lo2;
   p.os_n = d->os_n; p.os_c = d->os_c; p.os_d = d->os_d; p.os_h = d->os_h; p.os_w = d->os_w;
   if (d->in_layout == 1) {
     EMO_REQUIRE(d->C % 4 == 0, "emo_grid_sample3d: channels-last path needs C %% 4 == 0 (C=%d)", d->C);

@@ -102,13 +102,17 @@ __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
       v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     v.x = act_apply(v.x, d.act); v.y = act_apply(v.y, d.act); v.z = act_apply(v.z, d.act); v.w = act_apply(v.w, d.act);
-    uint2 hi, lo;
-    if (d.out_hi) split4(v, hi, lo);
+    uint2 hi, lo, lo2;
+    if (d.out_hi) {
+      if (d.out_lo2) split4x3(v, hi, lo, lo2);
+      else split4(v, hi, lo);
+    }
     if (UP == 1) {
       if (d.out) ((float4*)d.out)[t] = v;
       if (d.out_hi) {
         ((uint2*)d.out_hi)[t] = hi;
         ((uint2*)d.out_lo)[t] = lo;
+        if (d.out_lo2) ((uint2*)d.out_lo2)[t] = lo2;
       }
     } else {
       const long long s = sp - (long long)n * S;
@@ -125,16 +129,23 @@ __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
           if (d.out_hi) {
             ((uint2*)d.out_hi)[o] = hi;
             ((uint2*)d.out_lo)[o] = lo;
+            if (d.out_lo2) ((uint2*)d.out_lo2)[o] = lo2;
           }
         }
     }
   }
 }
 
-__global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+__global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                             uint2* __restrict__ lo2) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
-    uint2 h, l;
-    split4(__ldg((const float4*)x + t), h, l);
+    uint2 h, l, l2;
+    if (lo2) {
+      split4x3(__ldg((const float4*)x + t), h, l, l2);
+      lo2[t] = l2;
+    } else {
+      split4(__ldg((const float4*)x + t), h, l);
+    }
     hi[t] = h; lo[t] = l;
   }
 }
@@ -188,14 +199,14 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   return check_launch("emo_apply");
 }
 
-extern "C" int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream_) {
+extern "C" int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* lo2, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EMO_REQUIRE(x && hi && lo, "emo_split_bf16: null pointer");
   EMO_REQUIRE(n % 4 == 0, "emo_split_bf16: n must be a multiple of 4");
   long long blocks = cdivll(n / 4, 256);
   if (blocks > 148ll * 32) blocks = 148ll * 32;
   if (blocks < 1) blocks = 1;
-  split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, (uint2*)hi, (uint2*)lo);
+  split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, (uint2*)hi, (uint2*)lo, (uint2*)lo2);
   return check_launch("emo_split_bf16");
 }
 

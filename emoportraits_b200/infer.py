@@ -11,6 +11,7 @@ ones (what the stubbed reference oracle uses too).
 """
 from __future__ import annotations
 
+import os
 import pathlib
 from types import SimpleNamespace
 from typing import Optional
@@ -26,20 +27,31 @@ from .config import HotPathConfig, hot_path_config, parse_args
 class Model:
     """Inference-only counterpart of models/stage_1/volumetric_avatar/va.py:39 Model (attribute names kept)."""
 
-    def __init__(self, cfg: HotPathConfig, state_dict, head_pose_state_dict, device="cuda"):
+    # bf16 planes per tensor-core operand, per network: 2 -> 3 MMAs/product (~2^-16 relative), 3 -> 6 MMAs/product
+    # (~2^-24, fp32-faithful).  The embedding / warp networks are tiny but the warp they produce is differentiated by
+    # the sampler (an error of 1e-4 in the embedding moves the image by 1e-2), so they run fp32-faithful; measured
+    # stage by stage in tests/test_stage_parity_gpu.py.  EMO_PLANES=<n> overrides every entry (experiments only).
+    PRECISION = dict(head_pose=3, expression=3, idt=3, warp=3, local_encoder=3, volume_source=3, unet3d=3, decoder=2)
+
+    def __init__(self, cfg: HotPathConfig, state_dict, head_pose_state_dict, device="cuda", precision: Optional[dict] = None):
         self.cfg = cfg
         dev = torch.device(device)
         sd = state_dict
-        self.local_encoder_nw = nets.LocalEncoder(sd, cfg, dev)
-        self.idt_embedder_nw = nets.IdtEmbed(sd, cfg, dev)
-        self.expression_embedder_nw = nets.ExpressionEmbed(sd, cfg, dev)
+        pr = dict(self.PRECISION)
+        pr.update(precision or {})
+        if os.environ.get("EMO_PLANES"):
+            pr = {k: int(os.environ["EMO_PLANES"]) for k in pr}
+        self.precision = pr
+        self.local_encoder_nw = nets.LocalEncoder(sd, cfg, dev, planes=pr["local_encoder"])
+        self.idt_embedder_nw = nets.IdtEmbed(sd, cfg, dev, planes=pr["idt"])
+        self.expression_embedder_nw = nets.ExpressionEmbed(sd, cfg, dev, planes=pr["expression"])
         self.predict_embed = nets.PredictEmbed(sd, cfg, dev)
-        self.xy_generator_nw = nets.WarpGenerator(sd, "xy_generator_nw", cfg, dev)
-        self.uv_generator_nw = nets.WarpGenerator(sd, "uv_generator_nw", cfg, dev)
-        self.volume_source_nw = nets.VolumeSource(sd, cfg, dev) if cfg.source_volume_num_blocks > 0 else None
-        self.volume_process_nw = nets.Unet3D(sd, cfg, dev)
-        self.decoder_nw = nets.Decoder(sd, cfg, dev)
-        self.head_pose_regressor = nets.HeadPoseRegressor(head_pose_state_dict, dev)
+        self.xy_generator_nw = nets.WarpGenerator(sd, "xy_generator_nw", cfg, dev, planes=pr["warp"])
+        self.uv_generator_nw = nets.WarpGenerator(sd, "uv_generator_nw", cfg, dev, planes=pr["warp"])
+        self.volume_source_nw = nets.VolumeSource(sd, cfg, dev, planes=pr["volume_source"]) if cfg.source_volume_num_blocks > 0 else None
+        self.volume_process_nw = nets.Unet3D(sd, cfg, dev, planes=pr["unet3d"])
+        self.decoder_nw = nets.Decoder(sd, cfg, dev, planes=pr["decoder"])
+        self.head_pose_regressor = nets.HeadPoseRegressor(head_pose_state_dict, dev, planes=pr["head_pose"])
         self.device = dev
 
     # ---- notebooks/infer.py:374-507 ----
@@ -87,12 +99,12 @@ class Model:
         uv_warp = self.uv_generator_nw(E)
         v = ops.grid_sample3d(st.target_latent_volume, grid=uv_warp, in_layout="cl")
         feat = ops.grid_sample3d(v, theta=warp, out_size=(cfg.D, cfg.S, cfg.S), in_layout="cl", out_layout="hwdc",
-                                 want_f32=taps is not None, want_split=True)
+                                 want_f32=taps is not None, want_split=True, planes=self.decoder_nw.planes)
         if taps is not None:
             aligned_vol, feat = feat
             taps.update(srt=srt, theta=warp, pose_embed=pose_embed, embed=E, uv_warp=uv_warp, aligned_face=aligned,
                         aligned_volume_hwdc=aligned_vol)
-        feat2d = ops.Split(feat.hi.view(1, 1, cfg.S, cfg.S, cfg.D * cfg.C), feat.lo.view(1, 1, cfg.S, cfg.S, cfg.D * cfg.C))
+        feat2d = feat.view(1, 1, cfg.S, cfg.S, cfg.D * cfg.C)
         img, deep_f, img_f = self.decoder_nw(feat2d, want_logits=want_logits)
         st_out = SimpleNamespace(pred_target_theta=theta, target_pose_embed=pose_embed, srt=srt)
         return img, deep_f, img_f, st_out

@@ -20,7 +20,7 @@ class GridSample3dDesc(C.Structure):
     _fields_ = [("in_", c_void_p), ("in_layout", c_int), ("N", c_int), ("C", c_int), ("Din", c_int), ("Hin", c_int),
                 ("Win", c_int), ("grid", c_void_p), ("theta", c_void_p), ("Dout", c_int), ("Hout", c_int),
                 ("Wout", c_int), ("out", c_void_p), ("out_hi", c_void_p), ("out_lo", c_void_p), ("os_n", c_ll),
-                ("os_c", c_ll), ("os_d", c_ll), ("os_h", c_ll), ("os_w", c_ll)]
+                ("os_c", c_ll), ("os_d", c_ll), ("os_h", c_ll), ("os_w", c_ll), ("out_lo2", c_void_p)]
 
 
 class GridSample2dAffineDesc(C.Structure):
@@ -44,7 +44,7 @@ class ApplyDesc(C.Structure):
     _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
                 ("A", c_void_p), ("B", c_void_p), ("ab_per_sample", c_int), ("res", c_void_p), ("A2", c_void_p),
                 ("B2", c_void_p), ("act", c_int), ("up", c_int), ("out", c_void_p), ("out_hi", c_void_p),
-                ("out_lo", c_void_p)]
+                ("out_lo", c_void_p), ("out_lo2", c_void_p)]
 
 
 class ConvDesc(C.Structure):
@@ -53,7 +53,8 @@ class ConvDesc(C.Structure):
                 ("kd", c_int), ("kh", c_int), ("kw", c_int), ("sd", c_int), ("sh", c_int), ("sw", c_int),
                 ("pd", c_int), ("ph", c_int), ("pw", c_int), ("Dout", c_int), ("Hout", c_int), ("Wout", c_int),
                 ("bias", c_void_p), ("residual", c_void_p), ("res_shift", c_int), ("act", c_int),
-                ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int)]
+                ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int),
+                ("a_lo2", c_void_p), ("w_lo2", c_void_p)]
 
 
 class ConvDirectDesc(C.Structure):
@@ -97,7 +98,7 @@ SYMBOLS = {
     "emo_maxpool2d_3x3s2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "emo_global_avgpool": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
     "emo_pose_theta": (c_int, [C.POINTER(PoseDesc), c_void_p]),
-    "emo_split_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p]),
+    "emo_split_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emo_l2_flush": (c_int, [c_void_p, c_ll, c_void_p]),
 }
 

@@ -32,12 +32,12 @@ G = 32
 class ConvW:
     """Packed conv weight (+ bias) resident on the device."""
 
-    def __init__(self, sd, p, dev, ws=False, in_perm=None, out_perm=None):
+    def __init__(self, sd, p, dev, ws=False, in_perm=None, out_perm=None, planes=2):
         w, b = fold_conv(sd, p, ws=ws)
         if out_perm is not None:
             w = w[out_perm]
             b = b[out_perm] if b is not None else None
-        self.w = ops.pack_conv_weight(w, device=dev, in_perm=in_perm)
+        self.w = ops.pack_conv_weight(w, device=dev, in_perm=in_perm, planes=planes)
         self.b = b.to(dev).contiguous() if b is not None else None
         self.cout = w.shape[0]
 
@@ -63,26 +63,27 @@ def _count(x):
 class ResBlock:
     """utils.py:661-788: [nearest up] -> norm -> relu -> conv -> norm -> relu -> conv [-> avgpool]; skip = [up] -> [1x1] -> [pool]."""
 
-    def __init__(self, sd, p, dev, ws_first=True):
+    def __init__(self, sd, p, dev, ws_first=True, planes=2):
+        self.planes = planes
         self.n1 = Norm(sd, p + ".block_feats.0", dev)
-        self.c1 = ConvW(sd, p + ".block_feats.2", dev, ws=ws_first)
+        self.c1 = ConvW(sd, p + ".block_feats.2", dev, ws=ws_first, planes=planes)
         self.n2 = Norm(sd, p + ".block_feats.3", dev)
-        self.c2 = ConvW(sd, p + ".block.0", dev)
-        self.skip = ConvW(sd, p + ".skip.0", dev) if (p + ".skip.0.weight_orig") in sd else None
+        self.c2 = ConvW(sd, p + ".block.0", dev, planes=planes)
+        self.skip = ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
 
     def __call__(self, x, sx, up=1, down=None, ada=None, want_stats=True):
         dev = x.device
         N = x.shape[0]
         A, B = self.n1.affine(sx, _count(x), ada[0] if ada else None)
-        a = ops.apply(x, A, B, act=ops.ACT_RELU, up=up)
+        a = ops.apply(x, A, B, act=ops.ACT_RELU, up=up, planes=self.planes)
         st1 = ops.new_stats(N, G, dev)
         y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1)
         A, B = self.n2.affine(st1, _count(y), ada[1] if ada else None)
-        b = ops.apply(y, A, B, act=ops.ACT_RELU)
+        b = ops.apply(y, A, B, act=ops.ACT_RELU, planes=self.planes)
         # skip path: the 1x1 conv commutes with nearest-upsampling and with average pooling, so it runs at the smaller size
         s = ops.avgpool(x, down) if down else x
         if self.skip is not None:
-            s = ops.conv_igemm(ops.split_bf16(s), self.skip.w, bias=self.skip.b)
+            s = ops.conv_igemm(ops.split_bf16(s, self.planes), self.skip.w, bias=self.skip.b)
         st2 = ops.new_stats(N, G, dev) if want_stats else None
         if down:
             full = ops.conv_igemm(b, self.c2.w, bias=self.c2.b)
@@ -94,7 +95,8 @@ class ResBlock:
 
 # ------------------------------------------------------------------------------------------------------------------
 class LocalEncoder:
-    def __init__(self, sd, cfg: HotPathConfig, dev):
+    def __init__(self, sd, cfg: HotPathConfig, dev, planes=2):
+        self.planes = planes
         p = "local_encoder_nw"
         s = cfg.image_size
         w, b = fold_conv(sd, f"{p}.from_rgb_{s}px")
@@ -103,13 +105,13 @@ class LocalEncoder:
         self.stem_w, self.stem_b = wc.to(dev).contiguous(), b.to(dev).contiguous()
         self.blocks = []
         for i in range(len(cfg.enc_channels) - 1):
-            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev))
+            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev, planes=planes))
             s //= 2
         self.fin_norm = Norm(sd, p + ".finale_layers.0", dev)
         # output channel o = c*D + d in the reference (infer.py:485 view(1,c,d,s,s)); emit d*C + c so the map is (h,w,d,c)
         C, D = cfg.C, cfg.D
         operm = torch.tensor([(k % C) * D + (k // C) for k in range(C * D)])
-        self.fin = ConvW(sd, p + ".finale_layers.2", dev, ws=True, out_perm=operm)
+        self.fin = ConvW(sd, p + ".finale_layers.2", dev, ws=True, out_perm=operm, planes=planes)
         self.cfg = cfg
 
     def __call__(self, img_nchw):
@@ -121,7 +123,7 @@ class LocalEncoder:
         for blk in self.blocks:
             x, st = blk(x, st, down=(1, 2, 2))
         A, B = self.fin_norm.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
         y = ops.conv_igemm(a, self.fin.w, bias=self.fin.b)  # (1,1,S,S,D*C) == (h,w,d,c)
         vol = y.view(1, cfg.S, cfg.S, cfg.D, cfg.C).permute(0, 3, 1, 2, 4).contiguous()  # -> (1,D,S,S,C)
         return vol
@@ -151,8 +153,9 @@ class _RNNorm:
 class ResNet:
     """torchvision resnet18 / resnet50 trunk (conv1..layer4) on channels-last tensors."""
 
-    def __init__(self, sd, p, dev, gn: bool):
+    def __init__(self, sd, p, dev, gn: bool, planes=2):
         self.gn = gn
+        self.planes = planes
         w, b = fold_conv(sd, p + ".conv1")
         wc = torch.zeros(7, 7, 4, w.shape[0])
         wc[:, :, :3] = w.permute(2, 3, 1, 0)
@@ -165,15 +168,15 @@ class ResNet:
             while f"{p}.layer{li}.{bi}.bn1.weight" in sd:
                 q = f"{p}.layer{li}.{bi}"
                 blk = dict(stride=2 if (li > 1 and bi == 0) else 1, bottleneck=(q + ".bn3.weight") in sd)
-                blk["c1"] = ConvW(sd, q + ".conv1", dev)
+                blk["c1"] = ConvW(sd, q + ".conv1", dev, planes=planes)
                 blk["n1"] = _RNNorm(sd, q + ".bn1", dev)
-                blk["c2"] = ConvW(sd, q + ".conv2", dev, ws=gn)
+                blk["c2"] = ConvW(sd, q + ".conv2", dev, ws=gn, planes=planes)
                 blk["n2"] = _RNNorm(sd, q + ".bn2", dev)
                 if blk["bottleneck"]:
-                    blk["c3"] = ConvW(sd, q + ".conv3", dev, ws=gn)
+                    blk["c3"] = ConvW(sd, q + ".conv3", dev, ws=gn, planes=planes)
                     blk["n3"] = _RNNorm(sd, q + ".bn3", dev)
                 if (q + ".downsample.1.weight") in sd:
-                    blk["cd"] = ConvW(sd, q + ".downsample.0", dev)
+                    blk["cd"] = ConvW(sd, q + ".downsample.0", dev, planes=planes)
                     blk["nd"] = _RNNorm(sd, q + ".downsample.1", dev)
                 self.blocks.append(blk)
                 bi += 1
@@ -191,23 +194,24 @@ class ResNet:
         A, B = self.bn1.affine(st, _count(y))
         y = ops.apply(y, A, B, act=ops.ACT_RELU, want_f32=True, want_split=False, per_sample=not self.bn1.is_bn)
         x = ops.maxpool2d_3x3s2(y)
-        xs = ops.split_bf16(x)
+        xs = ops.split_bf16(x, self.planes)
+        P = self.planes
         for blk in self.blocks:
             s = blk["stride"]
             if blk["bottleneck"]:
                 y, st = self._conv(xs, blk["c1"])
                 A, B = blk["n1"].affine(st, _count(y))
-                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn)
+                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn, planes=P)
                 y, st = self._conv(a, blk["c2"], s)
                 A, B = blk["n2"].affine(st, _count(y))
-                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n2"].is_bn)
+                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n2"].is_bn, planes=P)
                 y, st = self._conv(a, blk["c3"])
                 A, B = blk["n3"].affine(st, _count(y))
                 last_bn = blk["n3"].is_bn
             else:
                 y, st = self._conv(xs, blk["c1"], s)
                 A, B = blk["n1"].affine(st, _count(y))
-                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn)
+                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn, planes=P)
                 y, st = self._conv(a, blk["c2"])
                 A, B = blk["n2"].affine(st, _count(y))
                 last_bn = blk["n2"].is_bn
@@ -217,18 +221,19 @@ class ResNet:
                 # residual affine is per-channel in the kernel; with GN and N == 1 the per-sample row is that vector
                 assert last_bn or N == 1, "GN ResNet path runs one image at a time"
                 x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=r, A2=A2, B2=B2, want_f32=True, want_split=True,
-                                  per_sample=not last_bn)
+                                  per_sample=not last_bn, planes=P)
             else:
-                x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=x, want_f32=True, want_split=True, per_sample=not last_bn)
+                x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=x, want_f32=True, want_split=True, per_sample=not last_bn,
+                                  planes=P)
         return x, xs
 
 
 class HeadPoseRegressor:
     """head_pose_regressor.py:11-31 — resnet18(num_classes=9), BatchNorm, its own checkpoint."""
 
-    def __init__(self, hsd, dev):
+    def __init__(self, hsd, dev, planes=2):
         sd = {"r." + k: v for k, v in hsd.items()}
-        self.net = ResNet(sd, "r", dev, gn=False)
+        self.net = ResNet(sd, "r", dev, gn=False, planes=planes)
         self.fc_w = sd["r.fc.weight"].float().to(dev).contiguous()
         self.fc_b = sd["r.fc.bias"].float().to(dev).contiguous()
 
@@ -241,10 +246,10 @@ class HeadPoseRegressor:
 class ExpressionEmbed:
     """expression_embedder.py:132-253 (inference branch) + ResNetWrapper :441-478."""
 
-    def __init__(self, sd, cfg: HotPathConfig, dev):
+    def __init__(self, sd, cfg: HotPathConfig, dev, planes=2):
         p = "expression_embedder_nw.net_face"
-        self.net = ResNet(sd, p + ".net", dev, gn=True)
-        self.fc = ConvW(sd, p + ".net.fc", dev)
+        self.net = ResNet(sd, p + ".net", dev, gn=True, planes=planes)
+        self.fc = ConvW(sd, p + ".net.fc", dev, planes=planes)
         w, _ = fold_conv(sd, p + ".pose_head")  # (E, E*16), input index c*16 + s (torch.flatten of NCHW)
         E = cfg.expr_channels
         self.head_w = w.view(E, E, 16).permute(0, 2, 1).reshape(E, 16 * E).to(dev).contiguous()  # -> index s*E + c
@@ -266,10 +271,10 @@ class ExpressionEmbed:
 class IdtEmbed:
     """identity_embedder.py:59-89: bilinear -> 256, normalise, resnet50 (GN), fc 1x1 conv, AdaptiveAvgPool2d(4)."""
 
-    def __init__(self, sd, cfg: HotPathConfig, dev):
+    def __init__(self, sd, cfg: HotPathConfig, dev, planes=2):
         p = "idt_embedder_nw"
-        self.net = ResNet(sd, p + ".net", dev, gn=True)
-        self.fc = ConvW(sd, p + ".net.fc", dev)
+        self.net = ResNet(sd, p + ".net", dev, gn=True, planes=planes)
+        self.fc = ConvW(sd, p + ".net.fc", dev, planes=planes)
         self.mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
         self.std = torch.tensor([0.229, 0.224, 0.225], device=dev)
         self.size = cfg.idt_image_size
@@ -303,15 +308,16 @@ class PredictEmbed:
 
 
 class WarpGenerator:
-    def __init__(self, sd, p, cfg: HotPathConfig, dev):
+    def __init__(self, sd, p, cfg: HotPathConfig, dev, planes=2):
         self.cfg = cfg
+        self.planes = planes
         ch = cfg.warp_channels
         self.ch = ch
         isz = cfg.embed_size
         w, _ = fold_conv(sd, p + ".first_conv")
         w = w.reshape(w.shape[0], w.shape[1])  # (ch0*isz, 512); out index o = c*isz + d (view(b,-1,isz,isz,isz))
         self.first_w = [w[d::isz].to(dev).contiguous() for d in range(isz)]  # per depth slice: rows c -> o = c*isz+d
-        self.blocks = [ResBlock(sd, f"{p}.blocks_3d.{i}", dev, ws_first=True) for i in range(len(ch) - 1)]
+        self.blocks = [ResBlock(sd, f"{p}.blocks_3d.{i}", dev, ws_first=True, planes=planes) for i in range(len(ch) - 1)]
         self.pu, self.pvT = [], []
         j = 0
         while f"{p}.projector.u.{j}" in sd:
@@ -319,7 +325,7 @@ class WarpGenerator:
             self.pvT.append(sd[f"{p}.projector.v.{j}"].detach().float().t().to(dev).contiguous())  # (2,16)
             j += 1
         self.pre_head = Norm(sd, p + ".pre_head.0", dev)
-        self.head = ConvW(sd, p + ".head.0.0", dev)
+        self.head = ConvW(sd, p + ".head.0.0", dev, planes=planes)
         idg = sd[p + ".identity_grid"].detach().float()  # (1,3,D,S,S) -> (D,S,S,3)
         self.idg = idg[0].permute(1, 2, 3, 0).contiguous().to(dev)
 
@@ -364,13 +370,13 @@ class WarpGenerator:
                 st = ops.new_stats(1, G, dev)
                 x = ops.avgpool(x, (2, 1, 1), stats=st)
         A, B = self.pre_head.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
         return ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_TANH, post_add=self.idg)
 
 
 class VolumeSource:
-    def __init__(self, sd, cfg: HotPathConfig, dev):
-        self.blocks = [ResBlock(sd, f"volume_source_nw.net.net.{i}", dev, ws_first=False)
+    def __init__(self, sd, cfg: HotPathConfig, dev, planes=2):
+        self.blocks = [ResBlock(sd, f"volume_source_nw.net.net.{i}", dev, ws_first=False, planes=planes)
                        for i in range(cfg.source_volume_num_blocks)]
 
     def __call__(self, vol):
@@ -381,18 +387,19 @@ class VolumeSource:
 
 
 class Unet3D:
-    def __init__(self, sd, cfg: HotPathConfig, dev):
+    def __init__(self, sd, cfg: HotPathConfig, dev, planes=2):
         p = "volume_process_nw"
         self.cfg = cfg
+        self.planes = planes
         nb = len(cfg.unet_channels) - 1
         self.nb = nb
-        self.down = [ResBlock(sd, f"{p}.blocks_3d_down.{i}", dev, ws_first=False) for i in range(nb)]
-        self.up = [ResBlock(sd, f"{p}.blocks_3d_up.{i}", dev, ws_first=False) for i in range(nb)]
-        self.skipb = [ResBlock(sd, f"{p}.skip_blocks_3d_up.{i}", dev, ws_first=False) for i in range(nb)]
+        self.down = [ResBlock(sd, f"{p}.blocks_3d_down.{i}", dev, ws_first=False, planes=planes) for i in range(nb)]
+        self.up = [ResBlock(sd, f"{p}.blocks_3d_up.{i}", dev, ws_first=False, planes=planes) for i in range(nb)]
+        self.skipb = [ResBlock(sd, f"{p}.skip_blocks_3d_up.{i}", dev, ws_first=False, planes=planes) for i in range(nb)]
         it = sd[p + ".input_tensor"].detach().float()  # (1,C,8,8,8)
         self.seed = it.permute(0, 2, 3, 4, 1).contiguous().to(dev)
         self.head_norm = Norm(sd, p + ".head.0", dev)
-        self.head = ConvW(sd, p + ".head.2", dev)
+        self.head = ConvW(sd, p + ".head.2", dev, planes=planes)
 
     def __call__(self, vol):
         cfg, dev, nb = self.cfg, vol.device, self.nb
@@ -437,26 +444,27 @@ class Unet3D:
                 st = ops.new_stats(1, G, dev)
                 x = ops.avgpool(x, (2, 1, 1), stats=st)
         A, B = self.head_norm.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
         return ops.conv_igemm(a, self.head.w, bias=self.head.b)
 
 
 class Decoder:
-    def __init__(self, sd, cfg: HotPathConfig, dev):
+    def __init__(self, sd, cfg: HotPathConfig, dev, planes=2):
+        self.planes = planes
         p = "decoder_nw"
         C, D = cfg.C, cfg.D
         # the warped volume arrives as (h, w, d, c): channel k' = d*C + c  <->  reference channel c*D + d (infer.py:627)
         iperm = torch.tensor([(k % C) * D + (k // C) for k in range(C * D)])
-        self.inp = ConvW(sd, p + ".res_decoder.0", dev, in_perm=iperm)
-        self.res = [ResBlock(sd, f"{p}.res_decoder.{i + 1}", dev) for i in range(cfg.dec_num_blocks)]
+        self.inp = ConvW(sd, p + ".res_decoder.0", dev, in_perm=iperm, planes=planes)
+        self.res = [ResBlock(sd, f"{p}.res_decoder.{i + 1}", dev, planes=planes) for i in range(cfg.dec_num_blocks)]
         self.img = []
         j = 0
         while f"{p}.img_decoder.dec_img_blocks.{j}.block.0.weight_orig" in sd:
-            self.img.append(ResBlock(sd, f"{p}.img_decoder.dec_img_blocks.{j}", dev))
+            self.img.append(ResBlock(sd, f"{p}.img_decoder.dec_img_blocks.{j}", dev, planes=planes))
             j += 1
         self.lrs = cfg.im_dec_lrs
         self.head_norm = Norm(sd, p + ".img_decoder.dec_img_head.0", dev)
-        self.head = ConvW(sd, p + ".img_decoder.dec_img_head.2", dev, ws=True)
+        self.head = ConvW(sd, p + ".img_decoder.dec_img_head.2", dev, ws=True, planes=planes)
 
     def __call__(self, feat: "ops.Split", want_logits: bool = False):
         """feat: Split (N,1,S,S,C*D) in (h,w,d,c) order -> img (N,3,H,W) fp32 NCHW, feat_2d, img_feat."""
@@ -469,7 +477,7 @@ class Decoder:
         for j, blk in enumerate(self.img):
             x, st = blk(x, st, up=2 if (j % self.lrs == 0) else 1)
         A, B = self.head_norm.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU)
+        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
         img = ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_NONE if want_logits else ops.ACT_SIGMOID,
                              out_nchw=True)
         return img[:, :, 0], feat2d, x

@@ -37,21 +37,31 @@ def _chk(t: torch.Tensor, dtype=torch.float32):
 
 @dataclass
 class Split:
-    """bf16 (hi, lo) planes of a channels-last activation (N, D, H, W, C)."""
+    """bf16 planes of a channels-last activation (N, D, H, W, C): (hi, lo) — or (hi, lo, lo2) in the fp32-faithful
+    three-plane mode used by the numerically sensitive networks."""
     hi: torch.Tensor
     lo: torch.Tensor
+    lo2: Optional[torch.Tensor] = None
 
     @property
     def shape(self):
         return self.hi.shape
 
+    @property
+    def planes(self) -> int:
+        return 3 if self.lo2 is not None else 2
+
     @staticmethod
-    def empty(shape, device) -> "Split":
-        buf = torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=device)
-        return Split(buf[0], buf[1])
+    def empty(shape, device, planes: int = 2) -> "Split":
+        buf = torch.empty((planes,) + tuple(shape), dtype=torch.bfloat16, device=device)
+        return Split(buf[0], buf[1], buf[2] if planes == 3 else None)
+
+    def view(self, *shape) -> "Split":
+        return Split(self.hi.view(*shape), self.lo.view(*shape), self.lo2.view(*shape) if self.lo2 is not None else None)
 
     def float(self) -> torch.Tensor:
-        return self.hi.float() + self.lo.float()
+        f = self.hi.float() + self.lo.float()
+        return f + self.lo2.float() if self.lo2 is not None else f
 
 
 @dataclass
@@ -63,16 +73,21 @@ class PackedConvWeight:
     cout_pad: int
     cin: int
     k: tuple  # (kd, kh, kw)
+    lo2: Optional[torch.Tensor] = None
 
 
-def split_host(w: torch.Tensor):
-    """fp32 -> (bf16 hi, bf16 lo) with torch ops (load-time weight preparation only)."""
+def split_host(w: torch.Tensor, planes: int = 2):
+    """fp32 -> bf16 planes with torch ops (load-time weight preparation only)."""
     hi = w.to(torch.bfloat16)
-    lo = (w - hi.float()).to(torch.bfloat16)
-    return hi, lo
+    r = w - hi.float()
+    lo = r.to(torch.bfloat16)
+    if planes == 2:
+        return hi, lo
+    lo2 = (r - lo.float()).to(torch.bfloat16)
+    return hi, lo, lo2
 
 
-def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tensor] = None) -> PackedConvWeight:
+def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tensor] = None, planes: int = 2) -> PackedConvWeight:
     """OIHW / OIDHW fp32 (already SN/WS-folded) -> PackedConvWeight. `in_perm` optionally re-orders input channels."""
     w = w.detach().float()
     if w.dim() == 4:
@@ -83,9 +98,10 @@ def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tenso
     co_pad = ((co + 15) // 16) * 16
     wp = torch.zeros(kd * kh * kw, co_pad, ci, dtype=torch.float32)
     wp[:, :co] = w.permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci).cpu()
-    hi, lo = split_host(wp)
+    pl = split_host(wp, planes)
     dev = device or "cuda"
-    return PackedConvWeight(hi.contiguous().to(dev), lo.contiguous().to(dev), co, co_pad, ci, (kd, kh, kw))
+    return PackedConvWeight(pl[0].contiguous().to(dev), pl[1].contiguous().to(dev), co, co_pad, ci, (kd, kh, kw),
+                            pl[2].contiguous().to(dev) if planes == 3 else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,7 +109,7 @@ def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tenso
 # ------------------------------------------------------------------------------------------------
 def grid_sample3d(inp: torch.Tensor, grid: Optional[torch.Tensor] = None, theta: Optional[torch.Tensor] = None,
                   out_size=None, in_layout: str = "ncdhw", out_layout: Optional[str] = None, want_f32: bool = True,
-                  want_split: bool = False):
+                  want_split: bool = False, planes: int = 2):
     """Trilinear, zeros padding, align_corners=False (va.py:261-265).
 
     in_layout  'ncdhw' (N,C,D,H,W)  or 'cl' (N,D,H,W,C)
@@ -126,10 +142,10 @@ def grid_sample3d(inp: torch.Tensor, grid: Optional[torch.Tensor] = None, theta:
     else:
         raise ValueError(out_layout)
     out = torch.empty(shape, dtype=torch.float32, device=inp.device) if want_f32 else None
-    sp = Split.empty(shape, inp.device) if want_split else None
+    sp = Split.empty(shape, inp.device, planes) if want_split else None
     d = L.GridSample3dDesc(_p(inp), 1 if in_layout == "cl" else 0, N, Cc, Di, Hi, Wi, _p(grid), _p(theta), Do, Ho, Wo,
                            _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, os_["n"], os_["c"],
-                           os_["d"], os_["h"], os_["w"])
+                           os_["d"], os_["h"], os_["w"], _p(sp.lo2) if sp else None)
     L.call("emo_grid_sample3d", C.byref(d), _stream())
     if want_f32 and want_split:
         return out, sp
@@ -187,25 +203,25 @@ def gn_finalize(stats: torch.Tensor, count: float, gamma, beta, eps: float = 1e-
 
 
 def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
-          want_f32: bool = False, want_split: bool = True, per_sample: bool = True):
+          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes: int = 2):
     """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W)."""
     _chk(x)
     N, D, H, W, Cc = x.shape
     shape = (N, D, H * up, W * up, Cc)
     out = torch.empty(shape, dtype=torch.float32, device=x.device) if want_f32 else None
-    sp = Split.empty(shape, x.device) if want_split else None
+    sp = Split.empty(shape, x.device, planes) if want_split else None
     d = L.ApplyDesc(_p(x), N, Cc, D, H, W, _p(A), _p(B), 1 if per_sample else 0, _p(res), _p(A2), _p(B2), act, up,
-                    _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None)
+                    _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, _p(sp.lo2) if sp else None)
     L.call("emo_apply", C.byref(d), _stream())
     if want_f32 and want_split:
         return out, sp
     return out if want_f32 else sp
 
 
-def split_bf16(x: torch.Tensor) -> Split:
+def split_bf16(x: torch.Tensor, planes: int = 2) -> Split:
     _chk(x)
-    sp = Split.empty(x.shape, x.device)
-    L.call("emo_split_bf16", _p(x), x.numel(), _p(sp.hi), _p(sp.lo), _stream())
+    sp = Split.empty(x.shape, x.device, planes)
+    L.call("emo_split_bf16", _p(x), x.numel(), _p(sp.hi), _p(sp.lo), _p(sp.lo2), _stream())
     return sp
 
 
@@ -224,8 +240,19 @@ class ConvProfiler:
 
     def summary(self):
         torch.cuda.synchronize()
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in self.rec)
-        return ms, sum(f for _, _, f in self.rec), len(self.rec)
+        ms = sum(r[0].elapsed_time(r[1]) for r in self.rec)
+        self.mma_flops = sum(r[2] * r[3] for r in self.rec)  # bf16 MMA flops actually issued (3 or 6 per product)
+        return ms, sum(r[2] for r in self.rec), len(self.rec)
+
+    def table(self):
+        """per-shape aggregate: (shape, launches, total ms, algorithmic TFLOP/s, MMA TFLOP/s)"""
+        torch.cuda.synchronize()
+        agg = {}
+        for e0, e1, fl, passes, name in self.rec:
+            a = agg.setdefault(name, [0, 0.0, 0.0, passes])
+            a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += fl
+        rows = [(k, v[0], v[1], v[2] / v[1] / 1e9, v[2] * v[3] / v[1] / 1e9) for k, v in agg.items()]
+        return sorted(rows, key=lambda r: -r[2])
 
 
 _conv_profiler: Optional[ConvProfiler] = None
@@ -241,6 +268,8 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                G: int = 32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     N, Di, Hi, Wi, Ci = a.shape
     assert Ci == w.cin, (Ci, w.cin)
+    three = a.lo2 is not None
+    assert not three or w.lo2 is not None, "3-plane activations need 3-plane weights (pack_conv_weight(planes=3))"
     kd, kh, kw = w.k
     if pad is None:
         pad = (kd // 2, kh // 2, kw // 2)
@@ -251,13 +280,14 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
     d = L.ConvDesc(_p(a.hi), _p(a.lo), N, Di, Hi, Wi, Ci, _p(w.hi), _p(w.lo), w.cout, w.cout_pad, kd, kh, kw,
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
-                   G if stats is not None else 0)
+                   G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         L.call("emo_conv_igemm", C.byref(d), _stream())
         e1.record()
-        _conv_profiler.rec.append((e0, e1, 2.0 * N * Do * Ho * Wo * w.cout * Ci * kd * kh * kw))
+        _conv_profiler.rec.append((e0, e1, 2.0 * N * Do * Ho * Wo * w.cout * Ci * kd * kh * kw, 6 if three else 3,
+                                   f"{N}x{Di}x{Hi}x{Wi}x{Ci}->{w.cout} k{kd}{kh}{kw} s{stride[1]} p{3 if three else 2}"))
     else:
         L.call("emo_conv_igemm", C.byref(d), _stream())
     return out

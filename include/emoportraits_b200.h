@@ -57,6 +57,7 @@ typedef struct {
   void* out_lo;
   /* output element strides (in elements) for n, c, d, h, w. */
   long long os_n, os_c, os_d, os_h, os_w;
+  void* out_lo2;          /* optional third bf16 plane (with out_hi/out_lo) */
 } emo_grid_sample3d_desc;
 int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream);
 
@@ -133,6 +134,7 @@ typedef struct {
   float* out;   /* optional fp32 [N][D][H*up][W*up][C] */
   void* out_hi; /* optional bf16 planes, same shape as out */
   void* out_lo;
+  void* out_lo2; /* optional third plane (needs out_hi/out_lo) */
 } emo_apply_desc;
 int emo_apply(const emo_apply_desc* d, void* stream);
 
@@ -162,6 +164,10 @@ typedef struct {
   int out_nchw;          /* 0: channels-last; 1: [N][Cout][Dout][Hout][Wout] */
   double* stats;         /* optional GN statistics of the output: [N][G][2] accumulated (+=) */
   int G;
+  /* optional third bf16 plane of both operands (lo2 = bf16(x - hi - lo)): six MMAs per product, ~2^-24 relative
+   * (fp32-faithful) for the numerically sensitive embedding / warp networks.  Both or neither. */
+  const void* a_lo2;
+  const void* w_lo2;
 } emo_conv_desc;
 int emo_conv_igemm(const emo_conv_desc* d, void* stream);
 
@@ -245,8 +251,8 @@ typedef struct {
 } emo_pose_desc;
 int emo_pose_theta(const emo_pose_desc* d, void* stream);
 
-/* fp32 -> bf16 hi/lo planes (n elements). */
-int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* stream);
+/* fp32 -> bf16 hi/lo(/lo2) planes (n elements); lo2 may be NULL. */
+int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* lo2, void* stream);
 /* L2 flush helper for benchmarks: writes `bytes` of `buf`. */
 int emo_l2_flush(void* buf, long long bytes, void* stream);
 
