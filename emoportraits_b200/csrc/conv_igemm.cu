@@ -26,6 +26,7 @@ namespace emo {
 static constexpr int kThreads = 192;
 static constexpr int kMaxStages = 8;
 static constexpr int kTileM = 128;
+static constexpr int kMaxBN = 128;  // N tile cap: the epilogue threads keep the whole row of accumulators in registers
 
 struct ConvKParams {
   int N, Dout, Hout, Wout, Cout;
@@ -36,6 +37,7 @@ struct ConvKParams {
   int m_tiles, n_tiles;
   int BN;
   int stages;
+  int flush;  // k-steps per TMEM accumulation chunk
   const float* bias;
   const float* residual;
   int res_shift;
@@ -234,14 +236,22 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1;
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
-      tcgen05_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+    uint32_t g = 0;  // running accumulation-chunk counter (continues across tiles)
+    const int F = p.flush;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      uint32_t tmem_d = 0;
+      int as = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
+        const bool chunk_first = (ks % F) == 0;
+        const bool chunk_last = ((ks + 1) % F) == 0 || ks == ksteps - 1;
+        if (chunk_first) {
+          // the tensor core accumulates with truncation (measured: tools/accum_probe.py), so an accumulator only ever
+          // takes a short chunk of MMAs; the epilogue warps add the chunks in fp32 registers (round-to-nearest).
+          as = (int)(g & 1);
+          mbar_wait(&tempty_bar[as], ((g >> 1) & 1) ^ 1);
+          tcgen05_fence_after();
+          tmem_d = tmem_base + (uint32_t)(as * BN);
+        }
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (lane == 0) {
@@ -255,14 +265,14 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);  // 16 bf16 = 32 B = 2 x 16B units
-            const uint32_t first = (ks | kk) != 0;
+            const uint32_t acc0 = (chunk_first && kk == 0) ? 0u : 1u;
             if (NP == 2) {
-              umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, first);
+              umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, acc0);
               umma_bf16(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
               umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
             } else {
               // smallest terms first: lo2*hi, hi*lo2, lo*lo, lo*hi, hi*lo, hi*hi
-              umma_bf16(tmem_d, dA[NP - 1] + adv, dB[0] + adv, idesc, first);
+              umma_bf16(tmem_d, dA[NP - 1] + adv, dB[0] + adv, idesc, acc0);
               umma_bf16(tmem_d, dA[0] + adv, dB[NP - 1] + adv, idesc, 1);
               umma_bf16(tmem_d, dA[1] + adv, dB[1] + adv, idesc, 1);
               umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, 1);
@@ -271,9 +281,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (ks == ksteps - 1) umma_commit(&tfull_bar[as]);
+          if (chunk_last) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
+        if (chunk_last) ++g;
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
@@ -282,10 +293,11 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;   // accumulator row == pixel index inside the tile box
     const int et = threadIdx.x - 64;    // 0..127 among the epilogue threads
+    const int F = p.flush;
+    const int nchunks = (ksteps + F - 1) / F;
+    uint32_t g = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1;
       const int nt = tile / p.m_tiles;
       int mt = tile - nt * p.m_tiles;
       const int twi = mt % p.tiles_w; mt /= p.tiles_w;
@@ -306,19 +318,43 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
       }
       const long long ppix = (((long long)od) * p.Hout + oh) * p.Wout + ow;
 
-      mbar_wait(&tfull_bar[as], aphase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-      float* cs = col_sum + as * 256;
-      float* cq = col_sq + as * 256;
+      // ---- fp32 register accumulation of the short TMEM chunks ----
+      float acc[kMaxBN];
+#pragma unroll
+      for (int j = 0; j < kMaxBN; ++j) acc[j] = 0.f;
+      for (int ch = 0; ch < nchunks; ++ch, ++g) {
+        const int as = (int)(g & 1);
+        mbar_wait(&tfull_bar[as], (g >> 1) & 1);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll
+        for (int c0 = 0; c0 < kMaxBN; c0 += 32) {
+          if (c0 < BN) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr + (uint32_t)c0, r0);
+            if (c0 + 16 < BN) tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
+            if (c0 + 16 < BN) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[c0 + 16 + j] += __uint_as_float(r1[j]);
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
 
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(taddr + (uint32_t)c0, raw);
-        tmem_ld_wait();
+      float* cs = col_sum + (it & 1) * 256;
+      float* cq = col_sq + (it & 1) * 256;
+#pragma unroll
+      for (int c0 = 0; c0 < kMaxBN; c0 += 16) {
+        if (c0 >= BN) continue;
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[j]);
+        for (int j = 0; j < 16; ++j) v[j] = acc[c0 + j];
         const int cbase = n0 + c0;
         const bool cfull = (cbase + 16 <= p.Cout);
         if (valid && cbase < p.Cout) {
@@ -386,12 +422,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
         if (p.stats) {
-          // column sums over the warp's 32 pixels by a butterfly transpose-reduce (15 + 15 shuffles):
-          // after the 4 halving steps lane l holds columns (l & 15) partial over lanes {l, l^16}... see below.
+          // column sums over the warp's 32 pixels by a butterfly transpose-reduce
           float s[16], q[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) { s[j] = v[j]; q[j] = v[j] * v[j]; }
-          // first fold the two half-warps together so that 16 columns map onto 16 lane pairs
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
@@ -417,10 +451,6 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
           }
         }
       }
-      // release the accumulator stage back to the MMA warp
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
 
       if (p.stats) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -434,19 +464,19 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
               a += cs[et * cpg + j]; b += cq[et * cpg + j];
               cs[et * cpg + j] = 0.f; cq[et * cpg + j] = 0.f;
             }
-            const int g = (n0 / cpg) + et;
-            if (g < p.G) {
-              atomicAdd(&p.stats[((long long)n * p.G + g) * 2], (double)a);
-              atomicAdd(&p.stats[((long long)n * p.G + g) * 2 + 1], (double)b);
+            const int gi = (n0 / cpg) + et;
+            if (gi < p.G) {
+              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)a);
+              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)b);
             }
           }
         } else {
           for (int j = et; j < BN; j += 128) {
             const int c = n0 + j;
             if (c < p.Cout) {
-              const int g = c / cpg;
-              atomicAdd(&p.stats[((long long)n * p.G + g) * 2], (double)cs[j]);
-              atomicAdd(&p.stats[((long long)n * p.G + g) * 2 + 1], (double)cq[j]);
+              const int gi = c / cpg;
+              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)cs[j]);
+              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)cq[j]);
             }
             cs[j] = 0.f; cq[j] = 0.f;
           }
@@ -506,13 +536,10 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   const int NP = d->a_lo2 ? 3 : 2;
   EMO_REQUIRE((d->a_lo2 == nullptr) == (d->w_lo2 == nullptr), "emo_conv_igemm: a_lo2 and w_lo2 must be given together");
   const int KC = (NP == 3) ? 32 : ((d->Cin % 64 == 0) ? 64 : 32);
-  // N tile: largest divisor-friendly width <= 256 (multiple of 16)
-  int BN = d->Cout_pad;
-  if (BN > 256) {
-    BN = 0;
-    for (int cand = 256; cand >= 16; cand -= 16)
-      if (d->Cout_pad % cand == 0) { BN = cand; break; }
-  }
+  // N tile: largest multiple of 16 that divides Cout_pad and fits the register-resident accumulator row
+  int BN = 0;
+  for (int cand = kMaxBN; cand >= 16; cand -= 16)
+    if (d->Cout_pad % cand == 0) { BN = cand; break; }
   // prefer 128-wide tiles when that fills the machine better (more tiles than SMs matters more than tile width)
   int sm_count = 148;
   {
@@ -538,7 +565,6 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   EMO_REQUIRE(p.tw * d->sw <= 256 && p.th * d->sh <= 256 && p.td * d->sd <= 256, "emo_conv_igemm: TMA box too large");
   p.tiles_w = cdiv(d->Wout, p.tw); p.tiles_h = cdiv(d->Hout, p.th); p.tiles_d = cdiv(d->Dout, p.td);
   p.m_tiles = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
-  if (BN > 128 && (BN / 2) % 16 == 0 && (long long)p.m_tiles * (d->Cout_pad / BN) < sm_count) BN /= 2;
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
   p.bias = d->bias; p.residual = d->residual; p.res_shift = d->res_shift; p.act = d->act;
@@ -556,6 +582,12 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   EMO_REQUIRE(stages >= 2, "emo_conv_igemm: tile does not fit shared memory (BN=%d KC=%d)", BN, KC);
   p.stages = stages;
+  {
+    // ~24 MMAs per accumulation chunk keeps the truncation bias of the tensor-core accumulator near 1e-6 relative
+    const int mmas_per_kstep = (KC / 16) * (NP == 3 ? 6 : 3);
+    const int target = d->acc_chunk_mmas > 0 ? d->acc_chunk_mmas : 24;
+    p.flush = target / mmas_per_kstep < 1 ? 1 : target / mmas_per_kstep;
+  }
   const size_t smem_bytes = stages * stage_bytes + tail_bytes + 1024;
 
   // ---- tensor maps ----

@@ -265,7 +265,7 @@ def set_conv_profiler(p: Optional[ConvProfiler]):
 
 def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=None, residual=None, res_shift: int = 0,
                act: int = ACT_NONE, post_add=None, out_nchw: bool = False, stats: Optional[torch.Tensor] = None,
-               G: int = 32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               G: int = 32, out: Optional[torch.Tensor] = None, acc_chunk_mmas: int = 0) -> torch.Tensor:
     N, Di, Hi, Wi, Ci = a.shape
     assert Ci == w.cin, (Ci, w.cin)
     three = a.lo2 is not None
@@ -280,7 +280,8 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
     d = L.ConvDesc(_p(a.hi), _p(a.lo), N, Di, Hi, Wi, Ci, _p(w.hi), _p(w.lo), w.cout, w.cout_pad, kd, kh, kw,
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
-                   G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None)
+                   G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None,
+                   acc_chunk_mmas)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -168,6 +168,9 @@ typedef struct {
    * (fp32-faithful) for the numerically sensitive embedding / warp networks.  Both or neither. */
   const void* a_lo2;
   const void* w_lo2;
+  /* MMAs accumulated in TMEM before the partial sum is promoted to fp32 registers (0 = default 24).  tcgen05
+   * accumulates with truncation; short chunks keep that bias ~1e-6 relative (DESIGN.md "precision"). */
+  int acc_chunk_mmas;
 } emo_conv_desc;
 int emo_conv_igemm(const emo_conv_desc* d, void* stream);
 
