@@ -27,6 +27,7 @@ static constexpr int kThreads = 192;
 static constexpr int kMaxStages = 8;
 static constexpr int kTileM = 128;
 static constexpr int kMaxBN = 128;  // N tile cap: the epilogue threads keep the whole row of accumulators in registers
+static constexpr int kAccBufs = 4;  // TMEM accumulation-chunk ring: 4 x 128 fp32 columns = the whole 512-column TMEM
 
 struct ConvKParams {
   int N, Dout, Hout, Wout, Cout;
@@ -154,8 +155,8 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   uint64_t* full_bar = (uint64_t*)tail;
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  uint64_t* tempty_bar = tfull_bar + kAccBufs;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + kAccBufs);
   float* col_sum = (float*)(tmem_slot + 4);  // [2][256]
   float* col_sq = col_sum + 2 * 256;         // [2][256]
 
@@ -172,7 +173,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kAccBufs; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
@@ -247,10 +248,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         if (chunk_first) {
           // the tensor core accumulates with truncation (measured: tools/accum_probe.py), so an accumulator only ever
           // takes a short chunk of MMAs; the epilogue warps add the chunks in fp32 registers (round-to-nearest).
-          as = (int)(g & 1);
-          mbar_wait(&tempty_bar[as], ((g >> 1) & 1) ^ 1);
+          as = (int)(g % kAccBufs);
+          mbar_wait(&tempty_bar[as], ((g / kAccBufs) & 1) ^ 1);
           tcgen05_fence_after();
-          tmem_d = tmem_base + (uint32_t)(as * BN);
+          tmem_d = tmem_base + (uint32_t)(as * kMaxBN);
         }
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -323,10 +324,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
 #pragma unroll
       for (int j = 0; j < kMaxBN; ++j) acc[j] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch, ++g) {
-        const int as = (int)(g & 1);
-        mbar_wait(&tfull_bar[as], (g >> 1) & 1);
+        const int as = (int)(g % kAccBufs);
+        mbar_wait(&tfull_bar[as], (g / kAccBufs) & 1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kMaxBN);
 #pragma unroll
         for (int c0 = 0; c0 < kMaxBN; c0 += 32) {
           if (c0 < BN) {
@@ -565,6 +566,15 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   EMO_REQUIRE(p.tw * d->sw <= 256 && p.th * d->sh <= 256 && p.td * d->sd <= 256, "emo_conv_igemm: TMA box too large");
   p.tiles_w = cdiv(d->Wout, p.tw); p.tiles_h = cdiv(d->Hout, p.th); p.tiles_d = cdiv(d->Dout, p.td);
   p.m_tiles = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
+  // small-M layers (ResNet tails, the first warp-generator blocks): a serial K loop on a handful of CTAs is latency
+  // bound, so narrow the N tile until the tile count fills the machine (the MMA time per k-step shrinks with N)
+  if ((long long)p.m_tiles * (d->Cout_pad / BN) < sm_count / 2) {
+    for (int cand = BN; cand >= 16; cand -= 16) {
+      if (d->Cout_pad % cand) continue;
+      BN = cand;
+      if ((long long)p.m_tiles * (d->Cout_pad / cand) >= sm_count) break;
+    }
+  }
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
   p.bias = d->bias; p.residual = d->residual; p.res_shift = d->res_shift; p.act = d->act;
@@ -576,7 +586,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)BN * KC * 2;
   const size_t stage_bytes = NP * (a_bytes + b_bytes);
-  const size_t tail_bytes = (2 * kMaxStages + 4) * 8 + 16 + 4 * 256 * sizeof(float);
+  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
   int stages = (int)((smem_limit - tail_bytes - 1024) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

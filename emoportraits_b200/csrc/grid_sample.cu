@@ -92,32 +92,31 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
     float gx, gy, gz;
     sample_coord(p, n, od, oh, ow, gx, gy, gz);
     const Corner8 k = corners(p, gx, gy, gz);
+    // branch-free corner set: out-of-range corners get weight 0 and a clamped (valid) address, so that all eight
+    // 16-byte gathers are issued back to back (memory-level parallelism) before the first FMA
+    float wgt[8];
+    const float4* src[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+      const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+      const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
+      const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
+      wgt[j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+      src[j] = in4 + (((long long)zc * p.Hin + yc) * p.Win + xc) * c4n + c4;
+    }
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldg(src[j]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int dz = 0; dz < 2; ++dz) {
-      const int z = k.z0 + dz;
-      const float wz = dz ? k.fz : 1.f - k.fz;
-      if (z < 0 || z >= p.Din) continue;
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const int y = k.y0 + dy;
-        const float wy = dy ? k.fy : 1.f - k.fy;
-        if (y < 0 || y >= p.Hin) continue;
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int x = k.x0 + dx;
-          const float wx = dx ? k.fx : 1.f - k.fx;
-          if (x < 0 || x >= p.Win) continue;
-          const float wgt = wx * wy * wz;
-          const float4 v = __ldg(in4 + (((long long)z * p.Hin + y) * p.Win + x) * c4n + c4);
-          acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y);
-          acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      acc.x = fmaf(v[j].x, wgt[j], acc.x); acc.y = fmaf(v[j].y, wgt[j], acc.y);
+      acc.z = fmaf(v[j].z, wgt[j], acc.z); acc.w = fmaf(v[j].w, wgt[j], acc.w);
     }
     const long long o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w + (long long)(c4 * 4) * p.os_c;
     if (p.os_c == 1) {
-      if (p.out) *(float4*)(p.out + o) = acc;
+      if (p.out) __stcs((float4*)(p.out + o), acc);  // streaming store: the output is not re-read by this kernel
       if (SPLIT) {
         uint2 hi, lo, lo2;
         if (p.out_lo2) {

@@ -348,7 +348,10 @@ __global__ void pose_theta_kernel(const emo_pose_desc d) {
   float S[16] = {q[0], 0, 0, 0, 0, q[1], 0, 0, 0, 0, q[2], 0, 0, 0, 0, 1};
   const float pi = 3.14159265358979323846f;
   const float yaw = fminf(fmaxf(q[3], -pi / 2), pi), pitch = fminf(fmaxf(q[4], -pi / 2), pi), roll = fminf(fmaxf(q[5], -pi / 2), pi);
-  const float cy = cosf(yaw), sy = sinf(yaw), cp = cosf(pitch), sp = sinf(pitch), cr = cosf(roll), sr = sinf(roll);
+  // sin/cos evaluated in double and rounded: agrees with the host libm float results the reference gets (cosf/sinf of
+  // the CUDA math library may differ from them by 1 ulp, which the 4x4 inverse downstream amplifies)
+  const float cy = (float)cos((double)yaw), sy = (float)sin((double)yaw), cp = (float)cos((double)pitch),
+              sp = (float)sin((double)pitch), cr = (float)cos((double)roll), sr = (float)sin((double)roll);
   float R[16] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr, 0,
                  sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr, 0,
                  -sp,     cp * sr,                cp * cr,                0,

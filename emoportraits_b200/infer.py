@@ -56,8 +56,10 @@ class Model:
 
     # ---- notebooks/infer.py:374-507 ----
     @torch.no_grad()
-    def source_pass(self, src: torch.Tensor, taps: Optional[dict] = None):
-        """src (1,3,H,W) fp32 in [0,1] on device, already masked.  Returns the cached source state."""
+    def source_pass(self, src: torch.Tensor, taps: Optional[dict] = None, pose_override=None):
+        """src (1,3,H,W) fp32 in [0,1] on device, already masked.  Returns the cached source state.
+        pose_override = (theta (1,4,4), warp (1,3,4), align2d (1,2,3)) replaces the on-device pose algebra (tests only:
+        lets a parity test inject the reference's own fp32 matrices, see tests/test_model_gpu.py)."""
         cfg = self.cfg
         src = src.contiguous().float()
         st = SimpleNamespace()
@@ -65,6 +67,8 @@ class Model:
         vol = self.local_encoder_nw(src)                               # (1,D,S,S,C)
         srt = self.head_pose_regressor(src)
         st.pred_source_theta, inv_warp, align = ops.pose_theta(srt, invert_warp=True)
+        if pose_override is not None:
+            st.pred_source_theta, inv_warp, align = [t.to(self.device).float().contiguous() for t in pose_override]
         st.source_theta_dev = st.pred_source_theta[0].contiguous()
         pose_embed, _ = self.expression_embedder_nw(src, align)
         st.pred_source_pose_embed = pose_embed
@@ -86,12 +90,14 @@ class Model:
     # ---- notebooks/infer.py:511-644 ----
     @torch.no_grad()
     def driver_pass(self, st, drv: torch.Tensor, mix: bool = True, target_theta: bool = True, taps: Optional[dict] = None,
-                    want_logits: bool = False):
+                    want_logits: bool = False, pose_override=None):
         """drv (1,3,H,W) fp32 on device -> (img (1,3,H,W), feat_2d, img_feat)."""
         cfg = self.cfg
         drv = drv.contiguous().float()
         srt = self.head_pose_regressor(drv)
         theta, warp, align = ops.pose_theta(srt, source_theta=st.source_theta_dev if mix else None, mix=mix)
+        if pose_override is not None:
+            theta, warp, align = [t.to(self.device).float().contiguous() for t in pose_override]
         if not target_theta:
             warp = st.pred_source_theta[:, :3].contiguous()
         pose_embed, aligned = self.expression_embedder_nw(drv, align, want_aligned=taps is not None)

@@ -10,8 +10,8 @@ pytestmark = pytest.mark.gpu
 
 
 def frame(size, seed):
-    a = (np.random.RandomState(seed).rand(size, size, 3) * 255).astype(np.uint8)
-    return torch.from_numpy(a).permute(2, 0, 1)[None].float().div(255).contiguous()
+    from oracle import frames as FR
+    return FR.frame(size, seed, "noise")
 
 
 def cl(x):
