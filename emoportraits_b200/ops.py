@@ -74,6 +74,7 @@ class PackedConvWeight:
     cin: int
     k: tuple  # (kd, kh, kw)
     lo2: Optional[torch.Tensor] = None
+    acc_chunk: int = 0  # MMAs per TMEM accumulation chunk (0 = kernel default: 48 with two planes, 24 with three)
 
 
 def split_host(w: torch.Tensor, planes: int = 2):
@@ -281,7 +282,7 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
                    G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None,
-                   acc_chunk_mmas)
+                   acc_chunk_mmas or w.acc_chunk)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
