@@ -23,6 +23,7 @@
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 namespace emo {
 
@@ -43,6 +44,8 @@ struct ConvKParams {
   int BN;
   int stages;
   int flush;  // k-steps per TMEM accumulation chunk
+  int cs;     // cluster size (1, 2, 4): CTAs of a cluster take consecutive pixel tiles of the same channel tile and
+              // share the weight tile through TMA multicast (each CTA loads 1/cs of it for everybody)
   const float* bias;
   const float* residual;
   int res_shift;
@@ -97,6 +100,33 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nid_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -112,6 +142,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
@@ -175,7 +211,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     }
     for (int i = 0; i < S; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], (uint32_t)p.cs);  // every CTA of the cluster reads what this CTA multicasts
     }
     for (int i = 0; i < kAccBufs; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -193,19 +229,28 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cs = p.cs;
+  if (cs > 1) cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
+  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1);
+  // tile walk: a cluster takes `cs` consecutive tiles (same channel tile: m_tiles % cs == 0) per round
+  const int tile_first = (cs > 1 ? (int)cluster_id_x() * cs + (int)crank : (int)blockIdx.x);
+  const int tile_step = (cs > 1 ? (int)cluster_nid_x() * cs : (int)gridDim.x);
 
   const int taps = p.kd * p.kh * p.kw;
   const int ksteps = taps * p.kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int rows_a = p.tw * p.th * p.td;
   const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes);
+  const int b_rows = BN / cs;                       // weight rows this CTA fetches (and multicasts)
+  const uint32_t b_slice = (uint32_t)b_rows * KC * 2;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int nt = tile / p.m_tiles;
         int mt = tile - nt * p.m_tiles;
         const int twi = mt % p.tiles_w; mt /= p.tiles_w;
@@ -227,7 +272,9 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
 #pragma unroll
                 for (int pl = 0; pl < NP; ++pl) {
                   tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
-                  tma_load_3d(&tm.b[pl], &full_bar[stage], st + NP * a_bytes + pl * b_bytes, kc * KC, n0, tap);
+                  uint8_t* bdst = st + NP * a_bytes + pl * b_bytes + crank * b_slice;
+                  if (cs > 1) tma_load_3d_mc(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0 + (int)crank * b_rows, tap, cmask);
+                  else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
                 }
                 if (++stage == S) { stage = 0; phase ^= 1; }
               }
@@ -243,7 +290,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     uint32_t phase = 0;
     uint32_t g = 0;  // running accumulation-chunk counter (continues across tiles)
     const int F = p.flush;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       uint32_t tmem_d = 0;
       int as = 0;
       for (int ks = 0; ks < ksteps; ++ks) {
@@ -285,7 +332,8 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
               umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);  // frees the stage in every CTA that multicasts into it
+          else umma_commit(&empty_bar[stage]);
           if (chunk_last) umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
@@ -307,7 +355,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     const int nchunks = (ksteps + F - 1) / F;
     uint32_t g = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
       const int nt = tile / p.m_tiles;
       int mt = tile - nt * p.m_tiles;
       const int twi = mt % p.tiles_w; mt /= p.tiles_w;
@@ -499,6 +547,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   // teardown
   tcgen05_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -587,6 +636,16 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   }
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
+  {
+    // cluster size: weight-tile multicast across consecutive pixel tiles (the conv main loop is L2->SM bandwidth
+    // bound: 64 KB per k-step per SM at 128x128; sharing the weight half of it across the cluster cuts it to 40-48 KB)
+    static int forced = -1;
+    if (forced < 0) { const char* e = getenv("EMO_CONV_CLUSTER"); forced = e ? atoi(e) : 0; }
+    int cs = forced > 0 ? forced : 2;
+    while (cs > 1 && (p.m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0 ||
+                      (long long)p.m_tiles * p.n_tiles < 2ll * cs)) cs >>= 1;
+    p.cs = cs;
+  }
   p.bias = d->bias; p.residual = d->residual; p.res_shift = d->res_shift; p.act = d->act;
   p.rD = d->Dout; p.rH = d->Hout >> d->res_shift; p.rW = d->Wout >> d->res_shift;
   p.post_add = d->post_add; p.out = d->out; p.out_nchw = d->out_nchw;
@@ -623,7 +682,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     const int taps = d->kd * d->kh * d->kw;
     cuuint64_t wdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout_pad, (cuuint64_t)taps};
     cuuint64_t wstr[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout_pad * d->Cin * 2};
-    cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)BN, 1};
+    cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)(BN / p.cs), 1};
     cuuint32_t wes[3] = {1, 1, 1};
     const void* ap[3] = {d->a_hi, d->a_lo, d->a_lo2};
     const void* wp[3] = {d->w_hi, d->w_lo, d->w_lo2};
@@ -642,7 +701,8 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   }
 
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int grid = total_tiles < sm_count ? total_tiles : sm_count;
+  int grid = total_tiles < sm_count ? total_tiles : sm_count;
+  grid = (grid / p.cs) * p.cs;  // whole clusters only (total_tiles % cs == 0 by construction)
   cudaError_t e;
 #define EMO_LAUNCH_CONV(KC_, NP_)                                                                                         \
   do {                                                                                                                    \
@@ -652,7 +712,21 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
       if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; } \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
-    conv_igemm_kernel<KC_, NP_><<<grid, kThreads, smem_bytes, stream>>>(tm, p);                                            \
+    cudaLaunchConfig_t cfg;                                                                                               \
+    memset(&cfg, 0, sizeof(cfg));                                                                                         \
+    cfg.gridDim = dim3((unsigned)grid);                                                                                   \
+    cfg.blockDim = dim3(kThreads);                                                                                        \
+    cfg.dynamicSmemBytes = smem_bytes;                                                                                    \
+    cfg.stream = stream;                                                                                                  \
+    cudaLaunchAttribute attr[1];                                                                                          \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
+    attr[0].val.clusterDim.x = (unsigned)p.cs;                                                                            \
+    attr[0].val.clusterDim.y = 1;                                                                                         \
+    attr[0].val.clusterDim.z = 1;                                                                                         \
+    cfg.attrs = attr;                                                                                                     \
+    cfg.numAttrs = 1;                                                                                                     \
+    e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_>, tm, p);                                                      \
+    if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
   if (NP == 3) EMO_LAUNCH_CONV(32, 3);
   else if (KC == 64) EMO_LAUNCH_CONV(64, 2);

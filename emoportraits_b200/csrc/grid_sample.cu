@@ -69,52 +69,70 @@ __device__ __forceinline__ Corner8 corners(const GS3Params& p, float gx, float g
 }
 
 // ------------------------------------------------------------------------------------------------
-// channels-last kernel: one thread = one float4 of channels of one output voxel.  A CTA walks a compact
-// (bd x bh x bw) brick of the output lattice so the 8-corner footprints of neighbouring voxels overlap in L1.
+// channels-last kernel.  A CTA owns a compact (bd x bh x bw) brick of the output lattice (L1 reuse of the overlapping
+// 8-corner footprints).  Phase 1: one thread per voxel computes the sample position, the eight clamped corner offsets
+// and trilinear weights ONCE and parks them in shared memory (the per-voxel arithmetic is ~200 instructions; doing it
+// in each of the C/4 channel threads made the kernel issue-bound).  Phase 2: one thread = one float4 of channels of
+// one voxel: two 16-byte broadcast LDS pairs, eight 16-byte gathers issued back to back, 32 FMAs, one store.
 // Every corner fetch is a 16-byte load inside a contiguous C*4-byte run.
 // ------------------------------------------------------------------------------------------------
+static constexpr int kBrickVox = 256;
+
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
+  __shared__ __align__(16) int s_off[kBrickVox][8];
+  __shared__ __align__(16) float s_wgt[kBrickVox][8];
+  __shared__ long long s_out[kBrickVox];  // output element offset of the voxel (or -1)
   const int c4n = p.C >> 2;
   int b = blockIdx.x;
   const int bwi = b % p.bricks_w; b /= p.bricks_w;
   const int bhi = b % p.bricks_h; b /= p.bricks_h;
   const int bdi = b % p.bricks_d; b /= p.bricks_d;
   const int n = b;
-  const int brick_vox = p.bw * p.bh * p.bd;
+  const int brick_vox = p.bw * p.bh * p.bd;  // <= kBrickVox
+  {
+    const int vox = threadIdx.x;
+    if (vox < brick_vox) {
+      const int lw = vox % p.bw, lh = (vox / p.bw) % p.bh, ld = vox / (p.bw * p.bh);
+      const int ow = bwi * p.bw + lw, oh = bhi * p.bh + lh, od = bdi * p.bd + ld;
+      long long o = -1;
+      if (ow < p.Wout && oh < p.Hout && od < p.Dout) {
+        float gx, gy, gz;
+        sample_coord(p, n, od, oh, ow, gx, gy, gz);
+        const Corner8 k = corners(p, gx, gy, gz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+          const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+          const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
+          const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
+          s_wgt[vox][j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+          s_off[vox][j] = ((zc * p.Hin + yc) * p.Win + xc) * c4n;
+        }
+        o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
+      }
+      s_out[vox] = o;
+    }
+  }
+  __syncthreads();
   const int work = brick_vox * c4n;
   const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
   for (int t = threadIdx.x; t < work; t += blockDim.x) {
     const int vox = t / c4n, c4 = t - vox * c4n;
-    const int lw = vox % p.bw, lh = (vox / p.bw) % p.bh, ld = vox / (p.bw * p.bh);
-    const int ow = bwi * p.bw + lw, oh = bhi * p.bh + lh, od = bdi * p.bd + ld;
-    if (ow >= p.Wout || oh >= p.Hout || od >= p.Dout) continue;
-    float gx, gy, gz;
-    sample_coord(p, n, od, oh, ow, gx, gy, gz);
-    const Corner8 k = corners(p, gx, gy, gz);
-    // branch-free corner set: out-of-range corners get weight 0 and a clamped (valid) address, so that all eight
-    // 16-byte gathers are issued back to back (memory-level parallelism) before the first FMA
-    float wgt[8];
-    const float4* src[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
-      const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
-      const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
-      const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
-      wgt[j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
-      src[j] = in4 + (((long long)zc * p.Hin + yc) * p.Win + xc) * c4n + c4;
-    }
-    float4 v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = __ldg(src[j]);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc.x = fmaf(v[j].x, wgt[j], acc.x); acc.y = fmaf(v[j].y, wgt[j], acc.y);
-      acc.z = fmaf(v[j].z, wgt[j], acc.z); acc.w = fmaf(v[j].w, wgt[j], acc.w);
-    }
-    const long long o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w + (long long)(c4 * 4) * p.os_c;
+    const long long ob = s_out[vox];
+    if (ob < 0) continue;
+    const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
+    const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
+    const float4* base = in4 + c4;
+    const float4 v0 = __ldg(base + o0.x), v1 = __ldg(base + o0.y), v2 = __ldg(base + o0.z), v3 = __ldg(base + o0.w);
+    const float4 v4 = __ldg(base + o1.x), v5 = __ldg(base + o1.y), v6 = __ldg(base + o1.z), v7 = __ldg(base + o1.w);
+    float4 acc;
+#define EMO_GS_ACC(f) \
+  acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
+          fmaf(v3.f, w0.w, fmaf(v2.f, w0.z, fmaf(v1.f, w0.y, v0.f * w0.x)))))));
+    EMO_GS_ACC(x) EMO_GS_ACC(y) EMO_GS_ACC(z) EMO_GS_ACC(w)
+#undef EMO_GS_ACC
+    const long long o = ob + (long long)(c4 * 4) * p.os_c;
     if (p.os_c == 1) {
       if (p.out) __stcs((float4*)(p.out + o), acc);  // streaming store: the output is not re-read by this kernel
       if (SPLIT) {
@@ -306,10 +324,13 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     if (d->os_c == 1)
       EMO_REQUIRE(d->os_n % 4 == 0 && d->os_d % 4 == 0 && d->os_h % 4 == 0 && d->os_w % 4 == 0,
                   "emo_grid_sample3d: vectorised output needs strides that are multiples of 4");
-    // brick: 8 x 4 x 2 voxels (w,h,d) -> 64 voxels * C/4 float4s per CTA pass
+    // brick: 8 x 8 x 4 voxels (w,h,d) = 256 voxels per CTA (one setup thread per voxel)
     p.bw = d->Wout >= 8 ? 8 : d->Wout;
-    p.bh = d->Hout >= 4 ? 4 : d->Hout;
-    p.bd = d->Dout >= 2 ? 2 : d->Dout;
+    p.bh = d->Hout >= 8 ? 8 : d->Hout;
+    p.bd = d->Dout >= 4 ? 4 : d->Dout;
+    // small lattices: shrink the brick until there are >= 4 CTAs per SM (load balance + latency hiding)
+    while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4 * 148 && p.bh > 2) p.bh >>= 1;
+    EMO_REQUIRE((long long)d->Din * d->Hin * d->Win * (d->C / 4) < (1ll << 31), "emo_grid_sample3d: volume too large for 32-bit offsets");
     p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
     const long long blocks = (long long)d->N * p.bricks_d * p.bricks_h * p.bricks_w;
     EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");

@@ -159,7 +159,7 @@ def test_inference_wrapper_api(setup, tmp_path):
     assert isinstance(pil, list) and pil[0].size == (size, size) and img.shape == (1, 3, size, size) and img.is_cuda
     assert _sub_err(img, case["frames"][0]["img"]) < IMG_TOL
     pil2, img2 = w.forward(None, drv, crop=False, mix=True, mix_old=False)
-    assert (img - img2).abs().max().item() < 1e-5
+    assert (img - img2).abs().max().item() < 2e-4  # GN statistics are accumulated with atomics (order varies run to run)
     assert w.forward(src, None, crop=False) is None
     with pytest.raises(NotImplementedError):
         w.forward(src, drv)  # crop=True needs the external face detector
