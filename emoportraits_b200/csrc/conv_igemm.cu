@@ -595,7 +595,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const int NP = d->a_lo2 ? 3 : 2;
   EMO_REQUIRE((d->a_lo2 == nullptr) == (d->w_lo2 == nullptr), "emo_conv_igemm: a_lo2 and w_lo2 must be given together");
-  const int KC = (NP == 3) ? 32 : ((d->Cin % 64 == 0) ? 64 : 32);
+  int KC = (d->Cin % 64 == 0) ? 64 : 32;  // three-plane tiles fall back to 32 below when 64 leaves < 3 pipeline stages
   // N tile: largest multiple of 16 that divides Cout_pad and fits the register-resident accumulator row
   int BN = 0;
   for (int cand = kMaxBN; cand >= 16; cand -= 16)
@@ -612,7 +612,6 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   p.N = d->N; p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
   p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
-  p.kchunks = d->Cin / KC;
   // pixel box: 128 pixels, widest along W first
   p.tw = pick_box(d->Wout, 16);
   p.th = pick_box(d->Hout, kTileM / p.tw > 0 ? kTileM / p.tw : 1);
@@ -641,7 +640,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     // bound: 64 KB per k-step per SM at 128x128; sharing the weight half of it across the cluster cuts it to 40-48 KB)
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("EMO_CONV_CLUSTER"); forced = e ? atoi(e) : 0; }
-    int cs = forced > 0 ? forced : 2;
+    int cs = forced > 0 ? forced : 1;  // measured: no gain at 2, loss at 4 (the main loop is smem-capacity x latency bound) -> opt-in
     while (cs > 1 && (p.m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0 ||
                       (long long)p.m_tiles * p.n_tiles < 2ll * cs)) cs >>= 1;
     p.cs = cs;
@@ -653,10 +652,12 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   EMO_REQUIRE(!d->residual || ((d->Hout % (1 << d->res_shift)) == 0 && (d->Wout % (1 << d->res_shift)) == 0),
               "emo_conv_igemm: residual shift does not divide the output size");
 
-  const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)BN * KC * 2;
-  const size_t stage_bytes = NP * (a_bytes + b_bytes);
   const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
+  if (KC == 64 && (smem_limit - tail_bytes - 1024) / ((size_t)NP * (kTileM + BN) * 64 * 2) < 3) KC = 32;
+  p.kchunks = d->Cin / KC;
+  const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)BN * KC * 2;
+  const size_t stage_bytes = NP * (a_bytes + b_bytes);
   int stages = (int)((smem_limit - tail_bytes - 1024) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   EMO_REQUIRE(stages >= 2, "emo_conv_igemm: tile does not fit shared memory (BN=%d KC=%d)", BN, KC);
@@ -728,7 +729,8 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
-  if (NP == 3) EMO_LAUNCH_CONV(32, 3);
+  if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3);
+  else if (NP == 3) EMO_LAUNCH_CONV(32, 3);
   else if (KC == 64) EMO_LAUNCH_CONV(64, 2);
   else EMO_LAUNCH_CONV(32, 2);
 #undef EMO_LAUNCH_CONV
