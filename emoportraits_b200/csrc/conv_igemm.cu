@@ -44,6 +44,8 @@ struct ConvKParams {
   int BN;
   int stages;
   int flush;  // k-steps per TMEM accumulation chunk
+  int ksplit;   // split-K factor: work item = (tile, K part); partial sums are red.add'ed into `ws`
+  float* ws;    // split-K fp32 workspace [N][Dout][Hout][Wout][Cout], zero on entry (the finalize kernel re-zeroes it)
   int cs;     // cluster size (1, 2, 4): CTAs of a cluster take consecutive pixel tiles of the same channel tile and
               // share the weight tile through TMA multicast (each CTA loads 1/cs of it for everybody)
   const float* bias;
@@ -236,10 +238,11 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   // tile walk: a cluster takes `cs` consecutive tiles (same channel tile: m_tiles % cs == 0) per round
   const int tile_first = (cs > 1 ? (int)cluster_id_x() * cs + (int)crank : (int)blockIdx.x);
   const int tile_step = (cs > 1 ? (int)cluster_nid_x() * cs : (int)gridDim.x);
+  const int ksplit = p.ksplit;  // work item = tile * ksplit + part (ksplit == 1: item == tile)
 
   const int taps = p.kd * p.kh * p.kw;
   const int ksteps = taps * p.kchunks;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items
   const int rows_a = p.tw * p.th * p.td;
   const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes);
   const int b_rows = BN / cs;                       // weight rows this CTA fetches (and multicasts)
@@ -250,7 +253,9 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      for (int item = tile_first; item < total_tiles; item += tile_step) {
+        const int tile = item / ksplit, part = item - tile * ksplit;
+        const int ks0 = (int)((long long)ksteps * part / ksplit), ks1 = (int)((long long)ksteps * (part + 1) / ksplit);
         const int nt = tile / p.m_tiles;
         int mt = tile - nt * p.m_tiles;
         const int twi = mt % p.tiles_w; mt /= p.tiles_w;
@@ -261,24 +266,21 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         const int y0 = thi * p.th * p.sh - p.ph;
         const int z0 = tdi * p.td * p.sd - p.pd;
         const int n0 = nt * BN;
-        for (int a = 0; a < p.kd; ++a)
-          for (int b = 0; b < p.kh; ++b)
-            for (int c = 0; c < p.kw; ++c) {
-              const int tap = (a * p.kh + b) * p.kw + c;
-              for (int kc = 0; kc < p.kchunks; ++kc) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* st = smem + (size_t)stage * stage_bytes;
-                mbar_expect_tx(&full_bar[stage], tx_bytes);
+        for (int ks = ks0; ks < ks1; ++ks) {
+          const int tap = ks / p.kchunks, kc = ks - tap * p.kchunks;
+          const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-                for (int pl = 0; pl < NP; ++pl) {
-                  tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
-                  uint8_t* bdst = st + NP * a_bytes + pl * b_bytes + crank * b_slice;
-                  if (cs > 1) tma_load_3d_mc(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0 + (int)crank * b_rows, tap, cmask);
-                  else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
-                }
-                if (++stage == S) { stage = 0; phase ^= 1; }
-              }
-            }
+          for (int pl = 0; pl < NP; ++pl) {
+            tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
+            uint8_t* bdst = st + NP * a_bytes + pl * b_bytes + crank * b_slice;
+            if (cs > 1) tma_load_3d_mc(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0 + (int)crank * b_rows, tap, cmask);
+            else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
+          }
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -290,12 +292,14 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     uint32_t phase = 0;
     uint32_t g = 0;  // running accumulation-chunk counter (continues across tiles)
     const int F = p.flush;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+    for (int item = tile_first; item < total_tiles; item += tile_step) {
       uint32_t tmem_d = 0;
       int as = 0;
-      for (int ks = 0; ks < ksteps; ++ks) {
+      const int part = item % ksplit;
+      const int nks = (int)((long long)ksteps * (part + 1) / ksplit) - (int)((long long)ksteps * part / ksplit);
+      for (int ks = 0; ks < nks; ++ks) {
         const bool chunk_first = (ks % F) == 0;
-        const bool chunk_last = ((ks + 1) % F) == 0 || ks == ksteps - 1;
+        const bool chunk_last = ((ks + 1) % F) == 0 || ks == nks - 1;
         if (chunk_first) {
           // the tensor core accumulates with truncation (measured: tools/accum_probe.py), so an accumulator only ever
           // takes a short chunk of MMAs; the epilogue warps add the chunks in fp32 registers (round-to-nearest).
@@ -352,10 +356,12 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     const int cbeg = half ? csplit : 0;           // this warp's column range inside the tile
     const int ncols = half ? BN - csplit : csplit;
     const int F = p.flush;
-    const int nchunks = (ksteps + F - 1) / F;
     uint32_t g = 0;
     int it = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++it) {
+    for (int item = tile_first; item < total_tiles; item += tile_step, ++it) {
+      const int tile = item / ksplit, part = item - tile * ksplit;
+      const int nks = (int)((long long)ksteps * (part + 1) / ksplit) - (int)((long long)ksteps * part / ksplit);
+      const int nchunks = (nks + F - 1) / F;
       const int nt = tile / p.m_tiles;
       int mt = tile - nt * p.m_tiles;
       const int twi = mt % p.tiles_w; mt /= p.tiles_w;
@@ -405,6 +411,17 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         if (lane == 0) mbar_arrive(&tempty_bar[as]);
       }
 
+      if (ksplit > 1) {
+        // split-K: add this part's partial tile into the fp32 workspace; bias/residual/activation/statistics are applied by
+        // splitk_finalize_kernel once every part has landed
+        if (valid) {
+          float* wrow = p.ws + pix * p.Cout + n0 + cbeg;
+#pragma unroll
+          for (int j = 0; j < kMaxBN / 2; ++j)
+            if (j < ncols && n0 + cbeg + j < p.Cout) atomicAdd(wrow + j, acc[j]);
+        }
+        continue;
+      }
       float* cs = col_sum + (it & 1) * 256;
       float* cq = col_sq + (it & 1) * 256;
 #pragma unroll
@@ -553,6 +570,55 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   }
 }
 
+// split-K finalize: out = act(ws + bias + residual) + post_add, statistics, and the workspace is zeroed for the next user
+struct FinParams {
+  float* ws;
+  float* out;
+  int N, C;
+  long long S;  // spatial positions per sample
+  const float* bias;
+  const float* residual;
+  const float* post_add;
+  int act, out_nchw;
+  double* stats;
+  int G;
+};
+
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f) {
+  extern __shared__ float sstat[];
+  const int n = blockIdx.y;
+  if (f.stats) {
+    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) sstat[i] = 0.f;
+    __syncthreads();
+  }
+  const long long per_n = f.S * f.C;
+  const int cpg = f.stats ? f.C / f.G : 1;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per_n; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = (long long)n * per_n + t;
+    const int c = (int)(t % f.C);
+    const long long sp = t / f.C;
+    float v = f.ws[i];
+    f.ws[i] = 0.f;
+    if (f.bias) v += __ldg(f.bias + c);
+    if (f.residual) v += __ldg(f.residual + i);
+    v = act_apply(v, f.act);
+    if (f.post_add) v += __ldg(f.post_add + t);
+    if (f.out_nchw) f.out[((long long)n * f.C + c) * f.S + sp] = v;
+    else f.out[i] = v;
+    if (f.stats) {
+      atomicAdd(&sstat[c / cpg], v);
+      atomicAdd(&sstat[f.G + c / cpg], v * v);
+    }
+  }
+  if (f.stats) {
+    __syncthreads();
+    for (int g = threadIdx.x; g < f.G; g += blockDim.x) {
+      atomicAdd(&f.stats[((long long)n * f.G + g) * 2], (double)sstat[g]);
+      atomicAdd(&f.stats[((long long)n * f.G + g) * 2 + 1], (double)sstat[f.G + g]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -624,9 +690,21 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   EMO_REQUIRE(p.tw * d->sw <= 256 && p.th * d->sh <= 256 && p.td * d->sd <= 256, "emo_conv_igemm: TMA box too large");
   p.tiles_w = cdiv(d->Wout, p.tw); p.tiles_h = cdiv(d->Hout, p.th); p.tiles_d = cdiv(d->Dout, p.td);
   p.m_tiles = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
-  // small-M layers (ResNet tails, the first warp-generator blocks): a serial K loop on a handful of CTAs is latency
-  // bound, so narrow the N tile until the tile count fills the machine (the MMA time per k-step shrinks with N)
-  if ((long long)p.m_tiles * (d->Cout_pad / BN) < sm_count / 2) {
+  // small-M layers (ResNet tails, the first warp-generator blocks): the serial K loop of a handful of CTAs is bound by the
+  // TMA->MMA->commit round trip (~2.4 us per pipeline turn), not by work.  With a workspace: split K over CTAs
+  // (partials red.add'ed in fp32, finalize pass).  Without: narrow the N tile until the tile count fills the machine.
+  const int ksteps_total = d->kd * d->kh * d->kw * (d->Cin / ((d->Cin % 64 == 0) ? 64 : 32));
+  int ksplit = 1;
+  {
+    const long long tiles = (long long)p.m_tiles * (d->Cout_pad / BN);
+    const long long out_elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;
+    if (d->splitk_ws && out_elems <= d->splitk_ws_elems && d->res_shift == 0 && tiles * 2 <= sm_count) {
+      long long parts = (2ll * sm_count) / tiles;
+      if (parts > ksteps_total / 4) parts = ksteps_total / 4;
+      if (parts >= 2) ksplit = (int)parts;
+    }
+  }
+  if (ksplit == 1 && (long long)p.m_tiles * (d->Cout_pad / BN) < sm_count / 2) {
     for (int cand = BN; cand >= 16; cand -= 16) {
       if (d->Cout_pad % cand) continue;
       BN = cand;
@@ -635,12 +713,14 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   }
   p.BN = BN;
   p.n_tiles = d->Cout_pad / BN;
+  p.ksplit = ksplit;
+  p.ws = d->splitk_ws;
   {
     // cluster size: weight-tile multicast across consecutive pixel tiles (the conv main loop is L2->SM bandwidth
     // bound: 64 KB per k-step per SM at 128x128; sharing the weight half of it across the cluster cuts it to 40-48 KB)
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("EMO_CONV_CLUSTER"); forced = e ? atoi(e) : 0; }
-    int cs = forced > 0 ? forced : 1;  // measured: no gain at 2, loss at 4 (the main loop is smem-capacity x latency bound) -> opt-in
+    int cs = (forced > 0 && ksplit == 1) ? forced : 1;  // measured: no gain at 2, loss at 4 (the main loop is smem-capacity x latency bound) -> opt-in
     while (cs > 1 && (p.m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0 ||
                       (long long)p.m_tiles * p.n_tiles < 2ll * cs)) cs >>= 1;
     p.cs = cs;
@@ -701,7 +781,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     }
   }
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   int grid = total_tiles < sm_count ? total_tiles : sm_count;
   grid = (grid / p.cs) * p.cs;  // whole clusters only (total_tiles % cs == 0 by construction)
   cudaError_t e;
@@ -734,5 +814,17 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   else if (KC == 64) EMO_LAUNCH_CONV(64, 2);
   else EMO_LAUNCH_CONV(32, 2);
 #undef EMO_LAUNCH_CONV
+  if (ksplit > 1) {
+    FinParams f;
+    f.ws = d->splitk_ws; f.out = d->out; f.N = d->N; f.C = d->Cout;
+    f.S = (long long)d->Dout * d->Hout * d->Wout;
+    f.bias = d->bias; f.residual = d->residual; f.post_add = d->post_add; f.act = d->act; f.out_nchw = d->out_nchw;
+    f.stats = d->stats; f.G = d->G;
+    long long bx = cdivll(f.S * f.C, 256 * 2);
+    if (bx > 148 * 4) bx = 148 * 4;
+    if (bx < 1) bx = 1;
+    dim3 fg((unsigned)bx, (unsigned)d->N);
+    splitk_finalize_kernel<<<fg, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(f);
+  }
   return check_launch("emo_conv_igemm");
 }

@@ -54,7 +54,8 @@ class ConvDesc(C.Structure):
                 ("pd", c_int), ("ph", c_int), ("pw", c_int), ("Dout", c_int), ("Hout", c_int), ("Wout", c_int),
                 ("bias", c_void_p), ("residual", c_void_p), ("res_shift", c_int), ("act", c_int),
                 ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int),
-                ("a_lo2", c_void_p), ("w_lo2", c_void_p), ("acc_chunk_mmas", c_int)]
+                ("a_lo2", c_void_p), ("w_lo2", c_void_p), ("acc_chunk_mmas", c_int),
+                ("splitk_ws", c_void_p), ("splitk_ws_elems", c_ll)]
 
 
 class ConvDirectDesc(C.Structure):

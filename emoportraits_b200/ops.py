@@ -233,6 +233,18 @@ def _out_dim(i, k, s, p):
     return (i + 2 * p - k) // s + 1
 
 
+_SPLITK_WS = {}
+
+
+def _splitk_workspace(device) -> torch.Tensor:
+    """Per-device zero-initialised fp32 workspace for split-K convolutions (the finalize kernel leaves it zeroed).
+    Launches on one stream use it back to back, which is how the model issues its convs."""
+    key = str(device)
+    if key not in _SPLITK_WS:
+        _SPLITK_WS[key] = torch.zeros(2 * 1024 * 1024, dtype=torch.float32, device=device)
+    return _SPLITK_WS[key]
+
+
 class ConvProfiler:
     """CUDA-event bracket around every tensor-core conv launch (bench.py roofline evidence; off by default)."""
 
@@ -266,9 +278,10 @@ def set_conv_profiler(p: Optional[ConvProfiler]):
 
 def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=None, residual=None, res_shift: int = 0,
                act: int = ACT_NONE, post_add=None, out_nchw: bool = False, stats: Optional[torch.Tensor] = None,
-               G: int = 32, out: Optional[torch.Tensor] = None, acc_chunk_mmas: int = 0) -> torch.Tensor:
+               G: int = 32, out: Optional[torch.Tensor] = None, acc_chunk_mmas: int = 0, split_k: bool = True) -> torch.Tensor:
     N, Di, Hi, Wi, Ci = a.shape
     assert Ci == w.cin, (Ci, w.cin)
+    ws = None if (L.DRY_RUN or not split_k) else _splitk_workspace(a.hi.device)
     three = a.lo2 is not None
     assert not three or w.lo2 is not None, "3-plane activations need 3-plane weights (pack_conv_weight(planes=3))"
     kd, kh, kw = w.k
@@ -282,7 +295,7 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
                    G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None,
-                   acc_chunk_mmas or w.acc_chunk)
+                   acc_chunk_mmas or w.acc_chunk, _p(ws), ws.numel() if ws is not None else 0)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -171,6 +171,11 @@ typedef struct {
   /* MMAs accumulated in TMEM before the partial sum is promoted to fp32 registers (0 = default 24).  tcgen05
    * accumulates with truncation; short chunks keep that bias ~1e-6 relative (DESIGN.md "precision"). */
   int acc_chunk_mmas;
+  /* optional split-K workspace: fp32, >= N*Dout*Hout*Wout*Cout elements, ALL ZERO on entry and left all zero on exit.
+   * When given, layers with too few tiles to fill the machine split their K loop over CTAs (partials red.add'ed here,
+   * then one finalize launch applies bias/residual/activation/statistics).  NULL: never split. */
+  float* splitk_ws;
+  long long splitk_ws_elems;
 } emo_conv_desc;
 int emo_conv_igemm(const emo_conv_desc* d, void* stream);
 
