@@ -77,23 +77,50 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 // ---- apply: y = act(x*A + B [+ res*A2 + B2]) -> fp32 / bf16 hi,lo, optional nearest x2 on H,W ----
 template <int UP>
 __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
+  extern __shared__ float sAB[];  // fused finalisation: A[C] then B[C] of this CTA's sample
   const int c4n = d.C >> 2;
   const long long S = (long long)d.D * d.H * d.W;
-  const long long total = (long long)d.N * S * c4n;
-  const float4* x4 = (const float4*)d.x;
-  const float4* r4 = (const float4*)d.res;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % c4n);
-    const long long sp = t / c4n;  // n*S + s
-    const int n = (int)(sp / S);
-    float4 v = __ldg(x4 + t);
-    if (d.A) {
+  const int n = blockIdx.y;
+  if (d.stats) {
+    const int cpg = d.C / d.G;
+    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double s = d.stats[((long long)n * d.G + g) * 2], q = d.stats[((long long)n * d.G + g) * 2 + 1];
+      const double mean = s / d.count;
+      double var = q / d.count - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+      float gam = d.gamma ? d.gamma[c] : 1.f, bet = d.beta ? d.beta[c] : 0.f;
+      if (d.ada_w) {
+        const float aw = d.ada_w[(long long)n * d.C + c], ab = d.ada_b[(long long)n * d.C + c];
+        bet = bet * aw + ab;
+        gam = gam * aw;
+      }
+      const float A = rstd * gam;
+      sAB[c] = A;
+      sAB[d.C + c] = bet - (float)mean * A;
+    }
+    __syncthreads();
+  }
+  const long long per_n = S * c4n;
+  const float4* x4 = (const float4*)d.x + (long long)n * per_n;
+  const float4* r4 = d.res ? (const float4*)d.res + (long long)n * per_n : nullptr;
+  for (long long tt = (long long)blockIdx.x * blockDim.x + threadIdx.x; tt < per_n; tt += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(tt % c4n);
+    const long long t = (long long)n * per_n + tt;  // flat float4 index
+    const long long sp = t / c4n;                   // n*S + s
+    float4 v = __ldg(x4 + tt);
+    if (d.stats) {
+      const float4 a = *(const float4*)&sAB[c4 * 4];
+      const float4 b = *(const float4*)&sAB[d.C + c4 * 4];
+      v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
+    } else if (d.A) {
       const float4 a = __ldg((const float4*)(d.A + (d.ab_per_sample ? (long long)n * d.C : 0)) + c4);
       const float4 b = __ldg((const float4*)(d.B + (d.ab_per_sample ? (long long)n * d.C : 0)) + c4);
       v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
     }
     if (r4) {
-      float4 r = __ldg(r4 + t);
+      float4 r = __ldg(r4 + tt);
       if (d.A2) {
         const float4 a = __ldg((const float4*)d.A2 + c4);
         const float4 b = __ldg((const float4*)d.B2 + c4);
@@ -190,12 +217,17 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   EMO_REQUIRE(d->C % 4 == 0, "emo_apply: C=%d must be a multiple of 4", d->C);
   EMO_REQUIRE(d->up == 1 || d->up == 2, "emo_apply: up must be 1 or 2");
   EMO_REQUIRE((d->A == nullptr) == (d->B == nullptr) && (d->A2 == nullptr) == (d->B2 == nullptr), "emo_apply: A/B must come in pairs");
-  const long long total = (long long)d->N * d->D * d->H * d->W * (d->C / 4);
-  long long blocks = cdivll(total, 256);
-  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  if (d->stats) EMO_REQUIRE(d->G > 0 && d->C % d->G == 0 && d->count > 0, "emo_apply: bad GroupNorm arguments");
+  const long long per_n = (long long)d->D * d->H * d->W * (d->C / 4);
+  long long blocks = cdivll(per_n, 256);
+  const long long cap = (148ll * 32) / (d->N > 0 ? d->N : 1);
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (d->up == 1) apply_kernel<1><<<(unsigned)blocks, 256, 0, stream>>>(*d);
-  else apply_kernel<2><<<(unsigned)blocks, 256, 0, stream>>>(*d);
+  const dim3 grid((unsigned)blocks, (unsigned)d->N);
+  const size_t smem = d->stats ? 2 * (size_t)d->C * sizeof(float) : 0;
+  EMO_REQUIRE(smem <= 48 * 1024, "emo_apply: C=%d too large for the fused finalisation", d->C);
+  if (d->up == 1) apply_kernel<1><<<grid, 256, smem, stream>>>(*d);
+  else apply_kernel<2><<<grid, 256, smem, stream>>>(*d);
   return check_launch("emo_apply");
 }
 

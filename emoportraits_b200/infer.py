@@ -62,6 +62,7 @@ class Model:
         lets a parity test inject the reference's own fp32 matrices, see tests/test_model_gpu.py)."""
         cfg = self.cfg
         src = src.contiguous().float()
+        ops.begin_pass(self.device)
         st = SimpleNamespace()
         st.idt_embed = self.idt_embedder_nw(src)                       # (1,512,4,4) NCHW
         vol = self.local_encoder_nw(src)                               # (1,D,S,S,C)
@@ -94,6 +95,7 @@ class Model:
         """drv (1,3,H,W) fp32 on device -> (img (1,3,H,W), feat_2d, img_feat)."""
         cfg = self.cfg
         drv = drv.contiguous().float()
+        ops.begin_pass(self.device)
         srt = self.head_pose_regressor(drv)
         theta, warp, align = ops.pose_theta(srt, source_theta=st.source_theta_dev if mix else None, mix=mix)
         if pose_override is not None:

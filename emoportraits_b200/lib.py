@@ -44,7 +44,8 @@ class ApplyDesc(C.Structure):
     _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("D", c_int), ("H", c_int), ("W", c_int),
                 ("A", c_void_p), ("B", c_void_p), ("ab_per_sample", c_int), ("res", c_void_p), ("A2", c_void_p),
                 ("B2", c_void_p), ("act", c_int), ("up", c_int), ("out", c_void_p), ("out_hi", c_void_p),
-                ("out_lo", c_void_p), ("out_lo2", c_void_p)]
+                ("out_lo", c_void_p), ("out_lo2", c_void_p), ("stats", c_void_p), ("G", c_int), ("count", c_double),
+                ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p), ("ada_w", c_void_p), ("ada_b", c_void_p)]
 
 
 class ConvDesc(C.Structure):

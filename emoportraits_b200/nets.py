@@ -54,6 +54,13 @@ class Norm:
             return ops.gn_finalize(stats, count, self.gamma, self.beta)
         return ops.gn_finalize(stats, count, self.gamma, self.beta, ada_w=ada[0], ada_b=ada[1])
 
+    def gn(self, stats, count, ada=None):
+        """arguments of the finalisation fused into ops.apply"""
+        d = dict(stats=stats, count=count, gamma=self.gamma, beta=self.beta)
+        if ada is not None:
+            d.update(ada_w=ada[0], ada_b=ada[1])
+        return d
+
 
 def _count(x):
     """elements per (sample, group) of a channels-last tensor"""
@@ -74,12 +81,10 @@ class ResBlock:
     def __call__(self, x, sx, up=1, down=None, ada=None, want_stats=True):
         dev = x.device
         N = x.shape[0]
-        A, B = self.n1.affine(sx, _count(x), ada[0] if ada else None)
-        a = ops.apply(x, A, B, act=ops.ACT_RELU, up=up, planes=self.planes)
+        a = ops.apply(x, gn=self.n1.gn(sx, _count(x), ada[0] if ada else None), act=ops.ACT_RELU, up=up, planes=self.planes)
         st1 = ops.new_stats(N, G, dev)
         y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1)
-        A, B = self.n2.affine(st1, _count(y), ada[1] if ada else None)
-        b = ops.apply(y, A, B, act=ops.ACT_RELU, planes=self.planes)
+        b = ops.apply(y, gn=self.n2.gn(st1, _count(y), ada[1] if ada else None), act=ops.ACT_RELU, planes=self.planes)
         # skip path: the 1x1 conv commutes with nearest-upsampling and with average pooling, so it runs at the smaller size
         s = ops.avgpool(x, down) if down else x
         if self.skip is not None:
@@ -122,8 +127,7 @@ class LocalEncoder:
         x = ops.conv_direct(x4, self.stem_w, 1, 3, self.stem_b, stats=st)
         for blk in self.blocks:
             x, st = blk(x, st, down=(1, 2, 2))
-        A, B = self.fin_norm.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
+        a = ops.apply(x, gn=self.fin_norm.gn(st, _count(x)), act=ops.ACT_RELU, planes=self.planes)
         y = ops.conv_igemm(a, self.fin.w, bias=self.fin.b)  # (1,1,S,S,D*C) == (h,w,d,c)
         vol = y.view(1, cfg.S, cfg.S, cfg.D, cfg.C).permute(0, 3, 1, 2, 4).contiguous()  # -> (1,D,S,S,C)
         return vol
@@ -186,13 +190,19 @@ class ResNet:
         y = ops.conv_igemm(a, cw.w, stride=(1, stride, stride), bias=cw.b, stats=st)
         return y, st
 
+    @staticmethod
+    def _napply(norm, y, st, **kw):
+        """norm + activation pass: eval-BatchNorm is a per-channel affine; GroupNorm is finalised inside the apply kernel"""
+        if norm.is_bn:
+            return ops.apply(y, norm.A, norm.B, per_sample=False, **kw)
+        return ops.apply(y, gn=norm.n.gn(st, _count(y)), **kw)
+
     def __call__(self, x4):
         """x4 (N,1,H,W,4) normalised image, channels-last padded -> (N,1,H/32,W/32,C) fp32."""
         N, dev = x4.shape[0], x4.device
         st = ops.new_stats(N, G, dev) if self.gn else None
         y = ops.conv_direct(x4, self.stem_w, 2, 3, self.stem_b, stats=st)
-        A, B = self.bn1.affine(st, _count(y))
-        y = ops.apply(y, A, B, act=ops.ACT_RELU, want_f32=True, want_split=False, per_sample=not self.bn1.is_bn)
+        y = self._napply(self.bn1, y, st, act=ops.ACT_RELU, want_f32=True, want_split=False)
         x = ops.maxpool2d_3x3s2(y)
         xs = ops.split_bf16(x, self.planes)
         P = self.planes
@@ -200,31 +210,24 @@ class ResNet:
             s = blk["stride"]
             if blk["bottleneck"]:
                 y, st = self._conv(xs, blk["c1"])
-                A, B = blk["n1"].affine(st, _count(y))
-                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn, planes=P)
+                a = self._napply(blk["n1"], y, st, act=ops.ACT_RELU, planes=P)
                 y, st = self._conv(a, blk["c2"], s)
-                A, B = blk["n2"].affine(st, _count(y))
-                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n2"].is_bn, planes=P)
+                a = self._napply(blk["n2"], y, st, act=ops.ACT_RELU, planes=P)
                 y, st = self._conv(a, blk["c3"])
-                A, B = blk["n3"].affine(st, _count(y))
-                last_bn = blk["n3"].is_bn
+                last = blk["n3"]
             else:
                 y, st = self._conv(xs, blk["c1"], s)
-                A, B = blk["n1"].affine(st, _count(y))
-                a = ops.apply(y, A, B, act=ops.ACT_RELU, per_sample=not blk["n1"].is_bn, planes=P)
+                a = self._napply(blk["n1"], y, st, act=ops.ACT_RELU, planes=P)
                 y, st = self._conv(a, blk["c2"])
-                A, B = blk["n2"].affine(st, _count(y))
-                last_bn = blk["n2"].is_bn
+                last = blk["n2"]
             if "cd" in blk:
                 r, std = self._conv(xs, blk["cd"], s)
                 A2, B2 = blk["nd"].affine(std, _count(r))
                 # residual affine is per-channel in the kernel; with GN and N == 1 the per-sample row is that vector
-                assert last_bn or N == 1, "GN ResNet path runs one image at a time"
-                x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=r, A2=A2, B2=B2, want_f32=True, want_split=True,
-                                  per_sample=not last_bn, planes=P)
+                assert last.is_bn or N == 1, "GN ResNet path runs one image at a time"
+                x, xs = self._napply(last, y, st, act=ops.ACT_RELU, res=r, A2=A2, B2=B2, want_f32=True, want_split=True, planes=P)
             else:
-                x, xs = ops.apply(y, A, B, act=ops.ACT_RELU, res=x, want_f32=True, want_split=True, per_sample=not last_bn,
-                                  planes=P)
+                x, xs = self._napply(last, y, st, act=ops.ACT_RELU, res=x, want_f32=True, want_split=True, planes=P)
         return x, xs
 
 
@@ -369,8 +372,7 @@ class WarpGenerator:
             if down_depth:
                 st = ops.new_stats(1, G, dev)
                 x = ops.avgpool(x, (2, 1, 1), stats=st)
-        A, B = self.pre_head.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
+        a = ops.apply(x, gn=self.pre_head.gn(st, _count(x)), act=ops.ACT_RELU, planes=self.planes)
         return ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_TANH, post_add=self.idg)
 
 
@@ -443,8 +445,7 @@ class Unet3D:
             if kind == "down":
                 st = ops.new_stats(1, G, dev)
                 x = ops.avgpool(x, (2, 1, 1), stats=st)
-        A, B = self.head_norm.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
+        a = ops.apply(x, gn=self.head_norm.gn(st, _count(x)), act=ops.ACT_RELU, planes=self.planes)
         return ops.conv_igemm(a, self.head.w, bias=self.head.b)
 
 
@@ -476,8 +477,7 @@ class Decoder:
         feat2d = x
         for j, blk in enumerate(self.img):
             x, st = blk(x, st, up=2 if (j % self.lrs == 0) else 1)
-        A, B = self.head_norm.affine(st, _count(x))
-        a = ops.apply(x, A, B, act=ops.ACT_RELU, planes=self.planes)
+        a = ops.apply(x, gn=self.head_norm.gn(st, _count(x)), act=ops.ACT_RELU, planes=self.planes)
         img = ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_NONE if want_logits else ops.ACT_SIGMOID,
                              out_nchw=True)
         return img[:, :, 0], feat2d, x

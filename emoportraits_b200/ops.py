@@ -178,7 +178,28 @@ def resize_bilinear(img: torch.Tensor, out_hw, mean=None, std=None, c_pad: int =
 # ------------------------------------------------------------------------------------------------
 # GroupNorm pieces
 # ------------------------------------------------------------------------------------------------
+_ARENA = {}
+_ARENA_SLOT = 2 * 32 * 2  # doubles per slot: up to N=2 samples x 32 groups x (sum, sumsq)
+
+
+def begin_pass(device, slots: int = 384):
+    """Start a source/driver pass: ONE memset zeroes the whole GroupNorm-statistics arena; new_stats() then hands out
+    slices of it instead of launching a fill kernel per normalisation (57 per driver frame otherwise)."""
+    key = str(device)
+    ar = _ARENA.get(key)
+    if ar is None or ar["buf"].shape[0] < slots:
+        ar = {"buf": torch.zeros((slots, _ARENA_SLOT), dtype=torch.float64, device=device), "idx": 0}
+        _ARENA[key] = ar
+    ar["buf"].zero_()
+    ar["idx"] = 0
+
+
 def new_stats(N: int, G: int, device) -> torch.Tensor:
+    ar = _ARENA.get(str(device))
+    if ar is not None and N * G * 2 <= _ARENA_SLOT and ar["idx"] < ar["buf"].shape[0]:
+        t = ar["buf"][ar["idx"]][: N * G * 2].view(N, G, 2)
+        ar["idx"] += 1
+        return t
     return torch.zeros((N, G, 2), dtype=torch.float64, device=device)
 
 
@@ -204,15 +225,19 @@ def gn_finalize(stats: torch.Tensor, count: float, gamma, beta, eps: float = 1e-
 
 
 def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
-          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes: int = 2):
-    """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W)."""
+          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes: int = 2, gn=None):
+    """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W).
+    gn = dict(stats, count, gamma, beta[, ada_w, ada_b, eps]) fuses the GroupNorm finalisation (replaces A/B)."""
     _chk(x)
     N, D, H, W, Cc = x.shape
     shape = (N, D, H * up, W * up, Cc)
     out = torch.empty(shape, dtype=torch.float32, device=x.device) if want_f32 else None
     sp = Split.empty(shape, x.device, planes) if want_split else None
     d = L.ApplyDesc(_p(x), N, Cc, D, H, W, _p(A), _p(B), 1 if per_sample else 0, _p(res), _p(A2), _p(B2), act, up,
-                    _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, _p(sp.lo2) if sp else None)
+                    _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, _p(sp.lo2) if sp else None,
+                    _p(gn["stats"]) if gn else None, gn["stats"].shape[1] if gn else 0, float(gn["count"]) if gn else 0.0,
+                    float(gn.get("eps", 1e-5)) if gn else 0.0, _p(gn["gamma"]) if gn else None, _p(gn["beta"]) if gn else None,
+                    _p(gn.get("ada_w")) if gn else None, _p(gn.get("ada_b")) if gn else None)
     L.call("emo_apply", C.byref(d), _stream())
     if want_f32 and want_split:
         return out, sp

@@ -135,6 +135,16 @@ typedef struct {
   void* out_hi; /* optional bf16 planes, same shape as out */
   void* out_lo;
   void* out_lo2; /* optional third plane (needs out_hi/out_lo) */
+  /* fused GroupNorm finalisation (replaces A/B): when `stats` is given the kernel derives the per-(n,c) scale/shift
+   * from the statistics itself (same arithmetic as emo_gn_finalize), saving a launch per normalisation. */
+  const double* stats; /* [N][G][2] or NULL */
+  int G;
+  double count;
+  float eps;
+  const float* gamma; /* [C] */
+  const float* beta;  /* [C] */
+  const float* ada_w; /* [N][C] or NULL */
+  const float* ada_b;
 } emo_apply_desc;
 int emo_apply(const emo_apply_desc* d, void* stream);
 
