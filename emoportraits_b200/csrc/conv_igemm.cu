@@ -31,8 +31,8 @@ static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epil
 static constexpr int kEpiThreads = 256;
 static constexpr int kMaxStages = 8;
 static constexpr int kTileM = 128;
-static constexpr int kMaxBN = 128;  // N tile cap: the epilogue threads keep the whole row of accumulators in registers
-static constexpr int kAccBufs = 4;  // TMEM accumulation-chunk ring: 4 x 128 fp32 columns = the whole 512-column TMEM
+static constexpr int kMaxBN = 192;  // N tile cap: each epilogue thread keeps half a row of accumulators in registers
+static constexpr int kAccBufs = 4;  // max depth of the TMEM accumulation-chunk ring (512 columns / BN, at most 4)
 
 struct ConvKParams {
   int N, Dout, Hout, Wout, Cout;
@@ -44,6 +44,7 @@ struct ConvKParams {
   int BN;
   int stages;
   int flush;  // k-steps per TMEM accumulation chunk
+  int nbuf;   // depth of the TMEM chunk ring = min(4, 512 / BN)
   int ksplit;   // split-K factor: work item = (tile, K part); partial sums are red.add'ed into `ws`
   float* ws;    // split-K fp32 workspace [N][Dout][Hout][Wout][Cout], zero on entry (the finalize kernel re-zeroes it)
   int cs;     // cluster size (1, 2, 4): CTAs of a cluster take consecutive pixel tiles of the same channel tile and
@@ -303,10 +304,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         if (chunk_first) {
           // the tensor core accumulates with truncation (measured: tools/accum_probe.py), so an accumulator only ever
           // takes a short chunk of MMAs; the epilogue warps add the chunks in fp32 registers (round-to-nearest).
-          as = (int)(g % kAccBufs);
-          mbar_wait(&tempty_bar[as], ((g / kAccBufs) & 1) ^ 1);
+          as = (int)(g % (uint32_t)p.nbuf);
+          mbar_wait(&tempty_bar[as], ((g / (uint32_t)p.nbuf) & 1) ^ 1);
           tcgen05_fence_after();
-          tmem_d = tmem_base + (uint32_t)(as * kMaxBN);
+          tmem_d = tmem_base + (uint32_t)(as * BN);
         }
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
@@ -387,10 +388,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
 #pragma unroll
       for (int j = 0; j < kMaxBN / 2; ++j) acc[j] = 0.f;
       for (int ch = 0; ch < nchunks; ++ch, ++g) {
-        const int as = (int)(g % kAccBufs);
-        mbar_wait(&tfull_bar[as], (g / kAccBufs) & 1);
+        const int as = (int)(g % (uint32_t)p.nbuf);
+        mbar_wait(&tfull_bar[as], (g / (uint32_t)p.nbuf) & 1);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * kMaxBN + cbeg);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + cbeg);
 #pragma unroll
         for (int c0 = 0; c0 < kMaxBN / 2; c0 += 32) {
           if (c0 < ncols) {
@@ -742,6 +743,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   if (stages > kMaxStages) stages = kMaxStages;
   EMO_REQUIRE(stages >= 2, "emo_conv_igemm: tile does not fit shared memory (BN=%d KC=%d)", BN, KC);
   p.stages = stages;
+  p.nbuf = 512 / BN > kAccBufs ? kAccBufs : 512 / BN;
   {
     // ~24 MMAs per accumulation chunk keeps the truncation bias of the tensor-core accumulator near 1e-6 relative
     const int mmas_per_kstep = (KC / 16) * (NP == 3 ? 6 : 3);
