@@ -302,6 +302,8 @@ def run_ours(args):
     ops.set_conv_profiler(None)
     conv_ms, conv_flops, n_conv = prof.summary()
     try:
+        if os.environ.get("EMO_NO_LAYER_CSV"):
+            raise OSError("disabled")
         (ROOT / "gpurun_out").mkdir(exist_ok=True)
         with open(ROOT / "gpurun_out" / "conv_layers.csv", "w") as f:
             f.write("shape,launches(3 frames),ms_total,algorithmic_TFLOPs,mma_TFLOPs\n")

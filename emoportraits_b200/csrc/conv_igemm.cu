@@ -31,7 +31,7 @@ static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epil
 static constexpr int kEpiThreads = 256;
 static constexpr int kMaxStages = 8;
 static constexpr int kTileM = 128;
-static constexpr int kMaxBN = 192;  // N tile cap: each epilogue thread keeps half a row of accumulators in registers
+static constexpr int kMaxBN = 160;  // N tile cap: each epilogue thread keeps half a row of accumulators in registers
 static constexpr int kAccBufs = 4;  // max depth of the TMEM accumulation-chunk ring (512 columns / BN, at most 4)
 
 struct ConvKParams {
