@@ -367,6 +367,47 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_stage2(args):
+    """BASELINE config 5 (secondary workload, `--workload stage2`): stage-2 refinement encoder+decoder @1024^2, batch 4."""
+    from emoportraits_b200 import lib as L
+    from emoportraits_b200 import ops
+    from emoportraits_b200.stage2 import Stage2Config, Stage2Model, synthetic_state_dict_s2
+
+    torch.cuda.set_device(0)
+    cfg = Stage2Config(output_size=1024)
+    model = Stage2Model(cfg, synthetic_state_dict_s2(cfg, 0), "cuda")
+    B = 4
+    img = torch.rand(B, 3, 512, 512, device="cuda")
+    K, W = args.steps, max(args.warmup, 3)
+    for _ in range(W):
+        model.forward(img)
+    torch.cuda.synchronize()
+    prof = ops.ConvProfiler()
+    l0 = L.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        model.forward(img)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = (L.launch_count - l0) // K
+    ops.set_conv_profiler(prof)
+    model.forward(img)
+    ops.set_conv_profiler(None)
+    conv_ms, conv_flops, n_conv = prof.summary()
+    peaks = measured_peaks()
+    line = {"metric": "stage-2 refinement images/s @1024^2, batch 4 (BASELINE configs[4])", "value": B * 1000.0 / ms, "unit": "images/s",
+            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x2-split operands, fp32 accumulate", "data": "synthetic",
+            "config": {"workload": "stage-2 LocalEncoderOld + Decoder_stage2, output_size_s2 1024, batch 4, default stage-2 args"},
+            "gpu_launches": launches * K,
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv layers of one step)", "achieved": conv_flops / conv_ms / 1e9,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": conv_flops / conv_ms / 1e9 / peaks["bf16_tflops_sustained"],
+                         "traffic": None, "tensor_pipe_frac_est": prof.mma_flops / conv_ms / 1e9 / peaks["bf16_tflops_sustained"]}}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -375,9 +416,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="do not capture the driver frame in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="driver", choices=["driver", "stage2"],
+                    help="driver = the headline metric (default); stage2 = BASELINE config 5, secondary")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "stage2":
+        run_stage2(args)
     else:
         run_ours(args)
 

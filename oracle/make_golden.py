@@ -120,8 +120,44 @@ def run(image_size: int):
     return out
 
 
+def run_stage2(output_size: int = 512, batch: int = 1):
+    """Golden fixtures of the stage-2 refinement path: reference notebooks/infer_s2.py InferenceWrapper.forward with the
+    seeded synthetic stage-2 checkpoint (load_state_dict strict), smooth synthetic frames at 256^2 resized up."""
+    import oracle.ref_harness as H
+    from emoportraits_b200.stage2 import Stage2Config, state_dict_spec_s2, synthetic_state_dict_s2
+    from oracle import frames as FR
+
+    w, msd, lines = H.build_reference_stage2(output_size, 0)
+    cfg = Stage2Config(output_size=output_size)
+    (GOLD / f"state_dict_manifest_s2_{output_size}.txt").write_text("".join(f"{k} {tuple(v.shape)}\n" for k, v in msd.items()))
+    (GOLD / f"args_s2_{output_size}.txt").write_text("".join(lines))
+    assert {k: tuple(v.shape) for k, v in msd.items()} == {k: tuple(v) for k, v in state_dict_spec_s2(cfg).items()}
+    sd = synthetic_state_dict_s2(cfg, 0)
+    w.model_two.load_state_dict(sd, strict=True)
+    w.model_two.eval()
+    taps = {}
+    h = w.model_two.decoder.register_forward_hook(lambda m, i, o: taps.__setitem__("add", o[0].detach().clone()))
+    h2 = w.model_two.local_encoder.register_forward_hook(lambda m, i, o: taps.__setitem__("vol", o.detach().clone()))
+    seeds = list(range(50, 50 + batch))
+    img = torch.cat([FR.frame(256, s, "smooth") for s in seeds])
+    with torch.no_grad():
+        pil, pil_resized, pil_ffhq, mask = w.forward(img)
+    h.remove(); h2.remove()
+    import numpy as np
+    ffhq8 = np.stack([np.asarray(p) for p in pil_ffhq])
+    out = {"output_size": output_size, "seeds": seeds, "input_size": 256, "vol": sub(taps["vol"], 40000), "add": sub(taps["add"], 60000),
+           "ffhq_uint8": sub(torch.from_numpy(ffhq8.astype(np.float32)), 60000)}
+    print(f"[golden s2 {output_size} b{batch}] add range [{taps['add'].min().item():.3f}, {taps['add'].max().item():.3f}] vol max {taps['vol'].abs().max().item():.2f}")
+    torch.save(out, GOLD / f"s2_{output_size}_b{batch}.pt")
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    sizes = [int(a) for a in sys.argv[1:]] or [256, 512]
-    for s in sizes:
-        run(s)
+    if sys.argv[1:2] == ["s2"]:
+        run_stage2(int(sys.argv[2]) if len(sys.argv) > 2 else 512, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+    else:
+        sizes = [int(a) for a in sys.argv[1:]] or [256, 512]
+        for s in sizes:
+            run(s)
+
+

@@ -333,3 +333,56 @@ def synthetic_frame(image_size: int, seed: int):
 
     a = (np.random.RandomState(seed).rand(image_size, image_size, 3) * 255).astype(np.uint8)
     return Image.fromarray(a)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stage 2 (notebooks/infer_s2.py:53-387, models/stage_2/base/volumetric_avatar_two.py)
+# ------------------------------------------------------------------------------------------------------------------
+def reference_args_lines_s2(output_size: int = 512) -> list[str]:
+    """Stage-2 `args.txt` lines from the argparse defaults (the shipped stage-2 args.txt is a download, README.md:127-129):
+    train.py flags + DataModule flags + models/stage_2/base/volumetric_avatar_two.py Model.add_argparse_args."""
+    install_stubs()
+    import argparse
+
+    from utils import args as args_utils
+
+    parser = argparse.ArgumentParser(conflict_handler="resolve")
+    parser.add = parser.add_argument
+    src = (REF / "train.py").read_text()
+    env = {"parser": parser, "args_utils": args_utils, "str": str, "int": int, "float": float}
+    for l in [l.strip() for l in src.splitlines() if l.strip().startswith(("parser.add(", "parser.add_argument("))]:
+        try:
+            exec(l, env)
+        except Exception:
+            pass
+    if "datasets.voxceleb2hq_pairs" not in sys.modules:
+        vp = importlib.util.spec_from_file_location("_ref_vox", REF / "datasets" / "voxceleb2hq_pairs.py")
+        vox = importlib.util.module_from_spec(vp)
+        sys.modules["datasets.voxceleb2hq_pairs"] = vox
+        vp.loader.exec_module(vox)
+    parser = sys.modules["datasets.voxceleb2hq_pairs"].DataModule.add_argparse_args(parser)
+    _stub("datasets.Retinaface")
+    two = importlib.import_module("models.stage_2.base.volumetric_avatar_two")
+    parser = two.Model.add_argparse_args(parser)
+    args, _ = parser.parse_known_args([])
+    d = vars(args)
+    d.update(output_size_s2=output_size, num_gpus=0, model_name="volumetric_avatar")
+    return [f"{k}: {v}\n" for k, v in sorted(d.items())]
+
+
+def build_reference_stage2(output_size: int = 512, seed: int = 0, workdir: str | None = None):
+    """Reference stage-2 InferenceWrapper on CPU, seeded random init.  Returns (wrapper, state_dict, args lines)."""
+    install_stubs()
+    work = pathlib.Path(workdir or tempfile.mkdtemp(prefix="emo_oracle_s2_"))
+    exp = "oracle_exp_s2"
+    (work / "logs_s2" / exp / "checkpoints").mkdir(parents=True, exist_ok=True)
+    lines = reference_args_lines_s2(output_size)
+    (work / "logs_s2" / exp / "args.txt").write_text("".join(lines))
+    sys.argv = [sys.argv[0]]
+    torch.manual_seed(seed)
+    infer_s2 = importlib.import_module("notebooks.infer_s2")
+    w = infer_s2.InferenceWrapper(experiment_name=exp, model_file_name="none.pth", use_gpu=False, num_gpus=0,
+                                  project_dir=str(work))
+    w.model_two.eval()
+    sd = {k: v.detach().clone() for k, v in w.model_two.state_dict().items()}
+    return w, sd, lines

@@ -489,3 +489,80 @@ def driver_pass(sd, hsd, st, drv_img, cfg: OracleConfig, taps=None, mix=True):
         taps.update(srt=srt, theta=th34, pose_embed=pose_embed, embed=embed, uv_warp=uv_warp, aligned_volume=vol,
                     logits=logits, dec_feat=feat, aligned_face=aligned)
     return img
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stage 2 (notebooks/infer_s2.py:351-387; local_encoder_old.py:25-117; decoder_s2_old.py:18-217, 346-475)
+# ------------------------------------------------------------------------------------------------------------------
+def _bn2d(x, sd, p):
+    return F.batch_norm(x, sd[p + ".running_mean"].float(), sd[p + ".running_var"].float(), sd[p + ".weight"].float(),
+                        sd[p + ".bias"].float(), False, 0.0, 1e-5)
+
+
+def res_block_bn(x, sd, p, up=None, down=None):
+    """utils.py:661-788 with eval-mode BatchNorm2d norms (stage-2 default norm_layer_type 'bn'), all convs SN."""
+    inp = x
+    if up:
+        x = F.interpolate(x, scale_factor=up, mode="nearest")
+    w1, b1 = conv_params(sd, p + ".block_feats.2")
+    w2, b2 = conv_params(sd, p + ".block.0")
+    h = F.relu(_bn2d(x, sd, p + ".block_feats.0"))
+    h = F.conv2d(h, w1, b1, padding=1)
+    h = F.relu(_bn2d(h, sd, p + ".block_feats.3"))
+    h = F.conv2d(h, w2, b2, padding=1)
+    if down:
+        h = F.avg_pool2d(h, down)
+    s = inp
+    if up:
+        s = F.interpolate(s, scale_factor=up, mode="nearest")
+    if (p + ".skip.0.weight_orig") in sd:
+        ws_, bs_ = conv_params(sd, p + ".skip.0")
+        s = F.conv2d(s, ws_, bs_)
+    if down:
+        s = F.avg_pool2d(s, down)
+    return h + s
+
+
+def stage2_local_encoder(sd, img):
+    """local_encoder_old.py:105-117."""
+    p = "local_encoder"
+    s = img.shape[2]
+    w, b = conv_params(sd, f"{p}.from_rgb_{s}px")
+    x = F.conv2d(img, w, b, padding=3)
+    i = 0
+    while f"{p}.enc_{i}_block={s}px.block.0.weight_orig" in sd:
+        x = res_block_bn(x, sd, f"{p}.enc_{i}_block={s}px", down=2)
+        s //= 2
+        i += 1
+    x = F.relu(_bn2d(x, sd, p + ".finale_layers.0"))
+    w, b = conv_params(sd, p + ".finale_layers.2")
+    return F.conv2d(x, w, b)
+
+
+def stage2_decoder(sd, vol):
+    """decoder_s2_old.py:130-217 + ImageDecoder_stage2.forward :461-475 (gen_use_adanorm False)."""
+    p = "decoder"
+    w, _ = conv_params(sd, p + ".res_decoder.0")
+    x = F.conv2d(vol, w)
+    i = 1
+    while f"{p}.res_decoder.{i}.block.0.weight_orig" in sd:
+        x = res_block_bn(x, sd, f"{p}.res_decoder.{i}")
+        i += 1
+    i = 0
+    while f"{p}.img_decoder.dec_img_blocks.{i}.block.0.weight_orig" in sd:
+        x = res_block_bn(x, sd, f"{p}.img_decoder.dec_img_blocks.{i}", up=2)
+        i += 1
+    for i in range(4):
+        x = res_block_bn(x, sd, f"{p}.img_decoder.dec_img_feat_blocks.{i}", up=2 if i == 0 else None)
+    h = F.relu(_bn2d(x.float(), sd, p + ".img_decoder.dec_img_head.0"))
+    w, b = conv_params(sd, p + ".img_decoder.dec_img_head.2")
+    return torch.tanh(F.conv2d(h, w, b))
+
+
+def stage2_forward(sd, img, output_size):
+    """infer_s2.py:351-376 with all masks == 1 (MODNet / BiSeNet out of scope).  Returns (resized, add, ffhq)."""
+    resized = F.interpolate(img, mode="bilinear", size=(output_size, output_size), align_corners=False)
+    vol = stage2_local_encoder(sd, resized)
+    add = stage2_decoder(sd, vol)
+    ffhq = (resized + add).clamp(min=0, max=1)
+    return resized, add, ffhq
