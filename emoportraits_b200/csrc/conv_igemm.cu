@@ -47,6 +47,8 @@ struct ConvKParams {
   int nbuf;   // depth of the TMEM chunk ring = min(4, 512 / BN)
   int ksplit;   // split-K factor: work item = (tile, K part); partial sums are red.add'ed into `ws`
   float* ws;    // split-K fp32 workspace [N][Dout][Hout][Wout][Cout], zero on entry (the finalize kernel re-zeroes it)
+  int cg;     // 1, or 2: CTA pairs issue cta_group::2 MMAs (M = 256: two pixel tiles; the weight tile is split across the
+              // pair's shared memories, so each SM ingests A 128 x KC + B (BN/2) x KC per k-step instead of A + B BN x KC)
   int cs;     // cluster size (1, 2, 4): CTAs of a cluster take consecutive pixel tiles of the same channel tile and
               // share the weight tile through TMA multicast (each CTA loads 1/cs of it for everybody)
   const float* bias;
@@ -110,6 +112,26 @@ __device__ __forceinline__ void tma_load_3d_mc(const CUtensorMap* map, uint64_t*
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
       : "memory");
 }
+// cta_group::2 variants (pair = even/odd CTA of a 2-CTA cluster; the even CTA is the leader).  The barrier operand has
+// the peer bit cleared, i.e. it names the LEADER's barrier at the same shared-memory offset (cute Sm100MmaPeerBitMask).
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_5d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -145,6 +167,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint64_t* bar) {  // arrives on the barrier of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
 }
 
 __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
@@ -190,7 +228,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
 
   const int BN = p.BN;
   const uint32_t a_bytes = kTileM * KC * 2;
-  const uint32_t b_bytes = (uint32_t)BN * KC * 2;
+  const uint32_t b_bytes = (uint32_t)(BN / p.cg) * KC * 2;  // pair mode: this CTA stages half of the weight tile
   const uint32_t stage_bytes = NP * a_bytes + NP * b_bytes;
   const int S = p.stages;
 
@@ -218,34 +256,42 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     }
     for (int i = 0; i < kAccBufs; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads / 32);
+      mbar_init(&tempty_bar[i], (uint32_t)(kEpiThreads / 32) * (uint32_t)p.cg);  // pair mode: both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 4 * 256; i += kThreads) col_sum[i] = 0.f;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (p.cg == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int cs = p.cs;
-  if (cs > 1) cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
-  const uint32_t crank = cs > 1 ? cluster_ctarank() : 0;
+  const bool cg2 = p.cg == 2;
+  if (cs > 1 || cg2) cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
+  const uint32_t crank = (cs > 1 || cg2) ? cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1);
   // tile walk: a cluster takes `cs` consecutive tiles (same channel tile: m_tiles % cs == 0) per round
-  const int tile_first = (cs > 1 ? (int)cluster_id_x() * cs + (int)crank : (int)blockIdx.x);
-  const int tile_step = (cs > 1 ? (int)cluster_nid_x() * cs : (int)gridDim.x);
+  const int csz = cg2 ? 2 : cs;  // CTAs per cluster
+  const int tile_first = (csz > 1 ? (int)cluster_id_x() * csz + (int)crank : (int)blockIdx.x);
+  const int tile_step = (csz > 1 ? (int)cluster_nid_x() * csz : (int)gridDim.x);
   const int ksplit = p.ksplit;  // work item = tile * ksplit + part (ksplit == 1: item == tile)
 
   const int taps = p.kd * p.kh * p.kw;
   const int ksteps = taps * p.kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items
   const int rows_a = p.tw * p.th * p.td;
-  const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes);
+  const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes) * (uint32_t)p.cg;  // pair: both CTAs' bytes
   const int b_rows = BN / cs;                       // weight rows this CTA fetches (and multicasts)
   const uint32_t b_slice = (uint32_t)b_rows * KC * 2;
 
@@ -272,23 +318,34 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
           const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * stage_bytes;
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          if (cg2) {
+            // pair mode: both CTAs load (own pixel tile, own half of the weight tile) and complete_tx on the LEADER's barrier
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
-            tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
-            uint8_t* bdst = st + NP * a_bytes + pl * b_bytes + crank * b_slice;
-            if (cs > 1) tma_load_3d_mc(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0 + (int)crank * b_rows, tap, cmask);
-            else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
+            for (int pl = 0; pl < NP; ++pl) {
+              tma_load_5d_2sm(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
+              tma_load_3d_2sm(&tm.b[pl], &full_bar[stage], st + NP * a_bytes + pl * b_bytes, kc * KC, n0 + (int)crank * (BN / 2), tap);
+            }
+          } else {
+            mbar_expect_tx(&full_bar[stage], tx_bytes);
+#pragma unroll
+            for (int pl = 0; pl < NP; ++pl) {
+              tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
+              uint8_t* bdst = st + NP * a_bytes + pl * b_bytes + crank * b_slice;
+              if (cs > 1) tma_load_3d_mc(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0 + (int)crank * b_rows, tap, cmask);
+              else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
+            }
           }
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && !(cg2 && crank != 0)) {
+    // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)((kTileM * p.cg) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t g = 0;  // running accumulation-chunk counter (continues across tiles)
@@ -323,7 +380,20 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);  // 16 bf16 = 32 B = 2 x 16B units
             const uint32_t acc0 = (chunk_first && kk == 0) ? 0u : 1u;
-            if (NP == 2) {
+            if (cg2) {
+              if (NP == 2) {
+                umma_bf16_cg2(tmem_d, dA[1] + adv, dB[0] + adv, idesc, acc0);
+                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
+                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
+              } else {
+                umma_bf16_cg2(tmem_d, dA[NP - 1] + adv, dB[0] + adv, idesc, acc0);
+                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[NP - 1] + adv, idesc, 1);
+                umma_bf16_cg2(tmem_d, dA[1] + adv, dB[1] + adv, idesc, 1);
+                umma_bf16_cg2(tmem_d, dA[1] + adv, dB[0] + adv, idesc, 1);
+                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
+                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
+              }
+            } else if (NP == 2) {
               umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, acc0);
               umma_bf16(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
               umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
@@ -337,16 +407,21 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
               umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
             }
           }
-          if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);  // frees the stage in every CTA that multicasts into it
-          else umma_commit(&empty_bar[stage]);
-          if (chunk_last) umma_commit(&tfull_bar[as]);
+          if (cg2) {
+            umma_commit_cg2(&empty_bar[stage]);  // frees the stage in both CTAs of the pair
+            if (chunk_last) umma_commit_cg2(&tfull_bar[as]);
+          } else {
+            if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);  // frees the stage in every CTA that multicasts into it
+            else umma_commit(&empty_bar[stage]);
+            if (chunk_last) umma_commit(&tfull_bar[as]);
+          }
         }
         __syncwarp();
         if (chunk_last) ++g;
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue (warps 2..9) =====================
     // two warps per TMEM lane quadrant; each owns one half of the tile's columns (multiple of 16)
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
@@ -409,7 +484,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        if (lane == 0) {
+          if (cg2) mbar_arrive_leader(&tempty_bar[as]);  // the leader's MMA warp waits for both CTAs' epilogues
+          else mbar_arrive(&tempty_bar[as]);
+        }
       }
 
       if (ksplit > 1) {
@@ -565,9 +643,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   // teardown
   tcgen05_fence_before();
   __syncthreads();
-  if (cs > 1) cluster_sync_all();  // nobody leaves while a peer may still multicast into / arrive on this CTA
+  if (cs > 1 || cg2) cluster_sync_all();  // nobody leaves while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (cg2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -717,11 +796,18 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   p.ksplit = ksplit;
   p.ws = d->splitk_ws;
   {
+    // pair mode (cta_group::2) for the layers with enough tiles to keep every SM pair busy
+    static int cg_env = -1;
+    if (cg_env < 0) { const char* e = getenv("EMO_CONV_CG2"); cg_env = e ? atoi(e) : 0; }
+    p.cg = (cg_env == 1 && ksplit == 1 && (p.m_tiles % 2) == 0 && BN % 32 == 0 &&
+            (long long)p.m_tiles * (d->Cout_pad / BN) >= sm_count) ? 2 : 1;
+  }
+  {
     // cluster size: weight-tile multicast across consecutive pixel tiles (the conv main loop is L2->SM bandwidth
     // bound: 64 KB per k-step per SM at 128x128; sharing the weight half of it across the cluster cuts it to 40-48 KB)
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("EMO_CONV_CLUSTER"); forced = e ? atoi(e) : 0; }
-    int cs = (forced > 0 && ksplit == 1) ? forced : 1;  // measured: no gain at 2, loss at 4 (the main loop is smem-capacity x latency bound) -> opt-in
+    int cs = (forced > 0 && ksplit == 1 && p.cg == 1) ? forced : 1;  // measured: no gain at 2, loss at 4 (the main loop is smem-capacity x latency bound) -> opt-in
     while (cs > 1 && (p.m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0 ||
                       (long long)p.m_tiles * p.n_tiles < 2ll * cs)) cs >>= 1;
     p.cs = cs;
@@ -735,9 +821,9 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
-  if (KC == 64 && (smem_limit - tail_bytes - 1024) / ((size_t)NP * (kTileM + BN) * 64 * 2) < 3) KC = 32;
+  if (KC == 64 && (smem_limit - tail_bytes - 1024) / ((size_t)NP * (kTileM + BN / p.cg) * 64 * 2) < 3) KC = 32;
   p.kchunks = d->Cin / KC;
-  const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)BN * KC * 2;
+  const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)(BN / p.cg) * KC * 2;
   const size_t stage_bytes = NP * (a_bytes + b_bytes);
   int stages = (int)((smem_limit - tail_bytes - 1024) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -765,7 +851,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     const int taps = d->kd * d->kh * d->kw;
     cuuint64_t wdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout_pad, (cuuint64_t)taps};
     cuuint64_t wstr[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout_pad * d->Cin * 2};
-    cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)(BN / p.cs), 1};
+    cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)(BN / p.cs / p.cg), 1};
     cuuint32_t wes[3] = {1, 1, 1};
     const void* ap[3] = {d->a_hi, d->a_lo, d->a_lo2};
     const void* wp[3] = {d->w_hi, d->w_lo, d->w_lo2};
@@ -785,7 +871,8 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   int grid = total_tiles < sm_count ? total_tiles : sm_count;
-  grid = (grid / p.cs) * p.cs;  // whole clusters only (total_tiles % cs == 0 by construction)
+  const int csz = p.cg == 2 ? 2 : p.cs;
+  grid = (grid / csz) * csz;  // whole clusters only (total_tiles % csz == 0 by construction)
   cudaError_t e;
 #define EMO_LAUNCH_CONV(KC_, NP_)                                                                                         \
   do {                                                                                                                    \
@@ -803,7 +890,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cfg.stream = stream;                                                                                                  \
     cudaLaunchAttribute attr[1];                                                                                          \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
-    attr[0].val.clusterDim.x = (unsigned)p.cs;                                                                            \
+    attr[0].val.clusterDim.x = (unsigned)csz;                                                                             \
     attr[0].val.clusterDim.y = 1;                                                                                         \
     attr[0].val.clusterDim.z = 1;                                                                                         \
     cfg.attrs = attr;                                                                                                     \
