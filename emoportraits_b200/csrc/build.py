@@ -31,6 +31,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for f in SOURCES + HEADERS + ["build.py"]:
         h.update((HERE / f).read_bytes())
+    h.update(os.environ.get("EMO_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -42,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false"]
     cmd = [c for c in cmd if c != "--use_fast_math=false"]
     cmd += ["-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
+    cmd += os.environ.get("EMO_NVCC_EXTRA", "").split()  # e.g. -DEMO_CONV_DEBUG for tools/conv_bound_probe.py
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", str(LIB)] + [str(HERE / s) for s in SOURCES]

@@ -47,6 +47,8 @@ struct ConvKParams {
   int nbuf;   // depth of the TMEM chunk ring = min(4, 512 / BN)
   int ksplit;   // split-K factor: work item = (tile, K part); partial sums are red.add'ed into `ws`
   float* ws;    // split-K fp32 workspace [N][Dout][Hout][Wout][Cout], zero on entry (the finalize kernel re-zeroes it)
+  int dbg;    // EMO_CONV_DEBUG builds only (tools/conv_bound_probe.py): 1 skip TMA loads, 2 skip MMAs, 4 skip the tile epilogue's
+              // global traffic, 8 skip the TMEM chunk reads, 16 / 32 / 64 skip the residual reads / output stores / statistics.  Results are garbage; only the timing is of interest.
   int cg;     // 1, or 2: CTA pairs issue cta_group::2 MMAs (M = 256: two pixel tiles; the weight tile is split across the
               // pair's shared memories, so each SM ingests A 128 x KC + B (BN/2) x KC per k-step instead of A + B BN x KC)
   int cs;     // cluster size (1, 2, 4): CTAs of a cluster take consecutive pixel tiles of the same channel tile and
@@ -132,6 +134,15 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// One elected lane of a converged warp.  Code guarded by `lane == 0` makes ptxas wrap every TMA / MMA issue in an
+// ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall (the descriptors live in uniform registers): measured 91 clk per MMA issue
+// against a 64 clk tensor floor (tools/mma_probe.cu).  Behind elect.sync the operands are provably uniform.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -210,6 +221,51 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// Tile statistics for the fused GroupNorm: `acc` holds this thread's row (pixel) of finished outputs, kMaxBN/2 columns.
+// R adjacent columns (R | channels per group, R | 16) are summed inside the thread; the resulting 32/R values per
+// 16-column block (sums, then sums of squares) are packed 32 to a pass and transpose-reduced over the warp's 32 rows
+// (16+8+4+2+1 shuffles); lane l ends up with the warp total of value l and adds it to the CTA's column accumulators
+// (only the first column of every R-group receives data; the per-group pass that follows sums whole groups).
+template <int R>
+__device__ __forceinline__ void tile_stats(const float (&acc)[kMaxBN / 2], int ncols, int lane, float* cs, float* cq) {
+  constexpr int kBlocks = kMaxBN / 32;           // 16-column blocks a thread can own
+  constexpr int VPB = 32 / R;                    // values per block
+  constexpr int GPB = 16 / R;                    // column groups per block
+  constexpr int BPP = R < kBlocks ? R : kBlocks; // blocks per pass
+#pragma unroll
+  for (int b0 = 0; b0 < kBlocks; b0 += BPP) {
+    if (b0 * 16 < ncols) {
+      float val[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int bl = i / VPB, kind = (i % VPB) / GPB, gi = i % GPB;
+        float a = 0.f;
+        if (bl < BPP && b0 + bl < kBlocks) {
+#pragma unroll
+          for (int t = 0; t < R; ++t) {
+            const float x = acc[(b0 + bl) * 16 + gi * R + t];
+            a += kind ? x * x : x;
+          }
+        }
+        val[i] = a;
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+          const float send = upper ? val[j] : val[j + off];
+          const float keep = upper ? val[j + off] : val[j];
+          val[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      const int bl = lane / VPB, kind = (lane % VPB) / GPB, gi = lane % GPB;
+      const int col = (b0 + bl) * 16 + gi * R;
+      if (bl < BPP && col < ncols) atomicAdd(kind ? &cq[col] : &cs[col], val[0]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -219,7 +275,7 @@ struct TMaps {
 };
 
 // NP = number of bf16 planes per operand: 2 -> 3 products (~2^-16 relative), 3 -> 6 products (~2^-24, fp32-faithful)
-template <int KC, int NP>
+template <int KC, int NP, int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -228,7 +284,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
 
   const int BN = p.BN;
   const uint32_t a_bytes = kTileM * KC * 2;
-  const uint32_t b_bytes = (uint32_t)(BN / p.cg) * KC * 2;  // pair mode: this CTA stages half of the weight tile
+  const uint32_t b_bytes = (uint32_t)(BN / CG) * KC * 2;  // pair mode: this CTA stages half of the weight tile
   const uint32_t stage_bytes = NP * a_bytes + NP * b_bytes;
   const int S = p.stages;
 
@@ -256,13 +312,13 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     }
     for (int i = 0; i < kAccBufs; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], (uint32_t)(kEpiThreads / 32) * (uint32_t)p.cg);  // pair mode: both CTAs' epilogue warps
+      mbar_init(&tempty_bar[i], (uint32_t)(kEpiThreads / 32) * (uint32_t)CG);  // pair mode: both CTAs' epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < 4 * 256; i += kThreads) col_sum[i] = 0.f;
   if (warp == 1) {
-    if (p.cg == 2) {
+    if (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -277,27 +333,27 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int cs = p.cs;
-  const bool cg2 = p.cg == 2;
+  constexpr bool cg2 = CG == 2;  // compile-time: a kernel holding cta_group::2 instructions cannot be launched without clusters
   if (cs > 1 || cg2) cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
-  const uint32_t crank = (cs > 1 || cg2) ? cluster_ctarank() : 0;
+  const int csz = cg2 ? 2 : cs;  // CTAs per cluster (1-D grid, cluster dims (csz,1,1): rank and id follow from blockIdx)
+  const uint32_t crank = (uint32_t)blockIdx.x % (uint32_t)csz;
   const uint16_t cmask = (uint16_t)((1u << cs) - 1);
   // tile walk: a cluster takes `cs` consecutive tiles (same channel tile: m_tiles % cs == 0) per round
-  const int csz = cg2 ? 2 : cs;  // CTAs per cluster
-  const int tile_first = (csz > 1 ? (int)cluster_id_x() * csz + (int)crank : (int)blockIdx.x);
-  const int tile_step = (csz > 1 ? (int)cluster_nid_x() * csz : (int)gridDim.x);
+  const int tile_first = (int)blockIdx.x;
+  const int tile_step = (int)gridDim.x;  // whole clusters only (host), so this is nclusters * csz
   const int ksplit = p.ksplit;  // work item = tile * ksplit + part (ksplit == 1: item == tile)
 
   const int taps = p.kd * p.kh * p.kw;
   const int ksteps = taps * p.kchunks;
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items
   const int rows_a = p.tw * p.th * p.td;
-  const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes) * (uint32_t)p.cg;  // pair: both CTAs' bytes
+  const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes) * (uint32_t)CG;  // pair: both CTAs' bytes
   const int b_rows = BN / cs;                       // weight rows this CTA fetches (and multicasts)
   const uint32_t b_slice = (uint32_t)b_rows * KC * 2;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = tile_first; item < total_tiles; item += tile_step) {
@@ -318,7 +374,14 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
           const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * stage_bytes;
-          if (cg2) {
+          if (!elect_one()) {
+          }
+#ifdef EMO_CONV_DEBUG
+          else if (p.dbg & 1) {
+            if (!cg2 || crank == 0) mbar_expect_tx(&full_bar[stage], 0);
+          }
+#endif
+          else if (cg2) {
             // pair mode: both CTAs load (own pixel tile, own half of the weight tile) and complete_tx on the LEADER's barrier
             if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
@@ -336,6 +399,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
               else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
             }
           }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -345,7 +409,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)((kTileM * p.cg) >> 4) << 24);
+                           ((uint32_t)((kTileM * CG) >> 4) << 24);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t g = 0;  // running accumulation-chunk counter (continues across tiles)
@@ -368,7 +432,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         }
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           uint64_t dA[NP], dB[NP];
 #pragma unroll
@@ -376,6 +440,9 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
             dA[pl] = make_kmajor_desc<KC>(sa + pl * a_bytes);
             dB[pl] = make_kmajor_desc<KC>(sa + NP * a_bytes + pl * b_bytes);
           }
+#ifdef EMO_CONV_DEBUG
+          if (!(p.dbg & 2))
+#endif
 #pragma unroll
           for (int kk = 0; kk < KC / 16; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 2);  // 16 bf16 = 32 B = 2 x 16B units
@@ -457,6 +524,20 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         rpix = (((long long)n * p.rD + od) * p.rH + rh) * p.rW + rw;
       }
       const long long ppix = (((long long)od) * p.Hout + oh) * p.Wout + ow;
+      // the tile's residual rows are first touched ~one tile of MMAs from now: pull them into L2 so that the final phase
+      // of the epilogue (the serial resource once the MMAs run at the tensor floor) does not sit on HBM latency
+      if (valid && ksplit == 1) {
+        const int c_lo = n0 + cbeg;
+        const int nb = (ncols < p.Cout - c_lo ? ncols : p.Cout - c_lo) * 4;
+        if (p.residual) {
+          const char* rp = (const char*)(p.residual + rpix * p.Cout + c_lo);
+          for (int b = 0; b < nb + 127; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (b < nb ? b : nb - 1)));
+        }
+        if (p.post_add) {
+          const char* rp = (const char*)(p.post_add + ppix * p.Cout + c_lo);
+          for (int b = 0; b < nb + 127; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (b < nb ? b : nb - 1)));
+        }
+      }
 
       // ---- fp32 register accumulation of the short TMEM chunks ----
       float acc[kMaxBN / 2];
@@ -467,6 +548,9 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         mbar_wait(&tfull_bar[as], (g / (uint32_t)p.nbuf) & 1);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + cbeg);
+#ifdef EMO_CONV_DEBUG
+        if (!(p.dbg & 8))
+#endif
 #pragma unroll
         for (int c0 = 0; c0 < kMaxBN / 2; c0 += 32) {
           if (c0 < ncols) {
@@ -490,6 +574,12 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         }
       }
 
+#ifdef EMO_CONV_DEBUG
+      if (p.dbg & 4) {
+        if (acc[0] == 123.456f) p.out[0] = acc[1];  // keeps the accumulation alive
+        continue;
+      }
+#endif
       if (ksplit > 1) {
         // split-K: add this part's partial tile into the fp32 workspace; bias/residual/activation/statistics are applied by
         // splitk_finalize_kernel once every part has landed
@@ -521,7 +611,11 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
                 v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
               }
             }
-            if (p.residual) {
+            if (p.residual
+#ifdef EMO_CONV_DEBUG
+                && !(p.dbg & 16)
+#endif
+            ) {
               const float4* r4 = (const float4*)(p.residual + rpix * p.Cout + cbase);
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -541,6 +635,10 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
                 v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
               }
             }
+#ifdef EMO_CONV_DEBUG
+            if ((p.dbg & 32) && v[3] != 123.456f) {
+            } else
+#endif
             if (!p.out_nchw) {
               float4* o4 = (float4*)(p.out + pix * p.Cout + cbase);
 #pragma unroll
@@ -577,37 +675,24 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
         }
         if (p.stats) {
-          // column sums over the warp's 32 pixels by a butterfly transpose-reduce
-          float s[16], q[16];
+          // keep the finished values (zero for pixels / channels outside the tensor) for the tile statistics below
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { s[j] = v[j]; q[j] = v[j] * v[j]; }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            s[j] += __shfl_xor_sync(0xffffffffu, s[j], 16);
-            q[j] += __shfl_xor_sync(0xffffffffu, q[j], 16);
-          }
-#pragma unroll
-          for (int off = 8; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int j = 0; j < off; ++j) {
-              const float send_s = upper ? s[j] : s[j + off];
-              const float send_q = upper ? q[j] : q[j + off];
-              const float keep_s = upper ? s[j + off] : s[j];
-              const float keep_q = upper ? q[j + off] : q[j];
-              s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-              q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-            }
-          }
-          // lane l (and l^16, identical) now holds the sum of column (l & 15)
-          if (lane < 16) {
-            atomicAdd(&cs[c0 + lane], s[0]);
-            atomicAdd(&cq[c0 + lane], q[0]);
-          }
+          for (int j = 0; j < 16; ++j) acc[cl0 + j] = v[j];
         }
       }
 
-      if (p.stats) {
+      if (p.stats
+#ifdef EMO_CONV_DEBUG
+          && !(p.dbg & 64)
+#endif
+      ) {
+        // R = largest power of two (<= 16) dividing the channels per group: that many adjacent columns fold inside the thread
+        const int r = p.cpg & -p.cpg;
+        if (r >= 16) tile_stats<16>(acc, ncols, lane, cs + cbeg, cq + cbeg);
+        else if (r == 8) tile_stats<8>(acc, ncols, lane, cs + cbeg, cq + cbeg);
+        else if (r == 4) tile_stats<4>(acc, ncols, lane, cs + cbeg, cq + cbeg);
+        else if (r == 2) tile_stats<2>(acc, ncols, lane, cs + cbeg, cq + cbeg);
+        else tile_stats<1>(acc, ncols, lane, cs + cbeg, cq + cbeg);
         asm volatile("bar.sync 1, 256;" ::: "memory");
         // one double RED per (group, quantity): thread g sums the cpg columns of its group
         const int cpg = p.cpg;
@@ -795,12 +880,17 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   p.n_tiles = d->Cout_pad / BN;
   p.ksplit = ksplit;
   p.ws = d->splitk_ws;
+  p.dbg = 0;
+#ifdef EMO_CONV_DEBUG
+  { const char* e = getenv("EMO_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
+#endif
   {
-    // pair mode (cta_group::2) for the layers with enough tiles to keep every SM pair busy
+    // pair mode (cta_group::2, M = 256): an SS-mode 128 x 128 x 16 MMA of a single CTA reads 8 KB of operands from shared
+    // memory and takes 82 clk against the 64 clk tensor floor (tools/mma_probe.cu: ~100 B/clk of operand bandwidth); in a pair
+    // each CTA supplies half of the weight tile (6 KB per MMA) and the floor is reached.  EMO_CONV_CG2=0 turns it off.
     static int cg_env = -1;
-    if (cg_env < 0) { const char* e = getenv("EMO_CONV_CG2"); cg_env = e ? atoi(e) : 0; }
-    p.cg = (cg_env == 1 && ksplit == 1 && (p.m_tiles % 2) == 0 && BN % 32 == 0 &&
-            (long long)p.m_tiles * (d->Cout_pad / BN) >= sm_count) ? 2 : 1;
+    if (cg_env < 0) { const char* e = getenv("EMO_CONV_CG2"); cg_env = e ? atoi(e) : 1; }
+    p.cg = (cg_env == 1 && ksplit == 1 && (p.m_tiles % 2) == 0 && BN % 32 == 0) ? 2 : 1;
   }
   {
     // cluster size: weight-tile multicast across consecutive pixel tiles (the conv main loop is L2->SM bandwidth
@@ -874,11 +964,11 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   const int csz = p.cg == 2 ? 2 : p.cs;
   grid = (grid / csz) * csz;  // whole clusters only (total_tiles % csz == 0 by construction)
   cudaError_t e;
-#define EMO_LAUNCH_CONV(KC_, NP_)                                                                                         \
+#define EMO_LAUNCH_CONV(KC_, NP_, CG_)                                                                                        \
   do {                                                                                                                    \
     static bool attr_set = false; /* the opt-in is per function, set once (227 KB covers every configuration) */           \
     if (!attr_set) {                                                                                                      \
-      e = cudaFuncSetAttribute(conv_igemm_kernel<KC_, NP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
+      e = cudaFuncSetAttribute(conv_igemm_kernel<KC_, NP_, CG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
       if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; } \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
@@ -895,13 +985,20 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     attr[0].val.clusterDim.z = 1;                                                                                         \
     cfg.attrs = attr;                                                                                                     \
     cfg.numAttrs = 1;                                                                                                     \
-    e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_>, tm, p);                                                      \
+    e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_, CG_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
-  if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3);
-  else if (NP == 3) EMO_LAUNCH_CONV(32, 3);
-  else if (KC == 64) EMO_LAUNCH_CONV(64, 2);
-  else EMO_LAUNCH_CONV(32, 2);
+  if (p.cg == 2) {
+    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2);
+    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2);
+    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2);
+    else EMO_LAUNCH_CONV(32, 2, 2);
+  } else {
+    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 1);
+    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 1);
+    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 1);
+    else EMO_LAUNCH_CONV(32, 2, 1);
+  }
 #undef EMO_LAUNCH_CONV
   if (ksplit > 1) {
     FinParams f;

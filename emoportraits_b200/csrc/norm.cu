@@ -75,10 +75,11 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 }
 
 // ---- apply: y = act(x*A + B [+ res*A2 + B2]) -> fp32 / bf16 hi,lo, optional nearest x2 on H,W ----
-template <int UP>
+// V = float4s per thread (2 when C % 8 == 0: 32 B loads, 16-byte bf16 plane stores)
+template <int UP, int V>
 __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
   extern __shared__ float sAB[];  // fused finalisation: A[C] then B[C] of this CTA's sample
-  const int c4n = d.C >> 2;
+  const int cvn = d.C / (4 * V);  // channel-vector slots per position
   const long long S = (long long)d.D * d.H * d.W;
   const int n = blockIdx.y;
   if (d.stats) {
@@ -102,47 +103,69 @@ __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
     }
     __syncthreads();
   }
-  const long long per_n = S * c4n;
-  const float4* x4 = (const float4*)d.x + (long long)n * per_n;
-  const float4* r4 = d.res ? (const float4*)d.res + (long long)n * per_n : nullptr;
+  const long long per_n = S * cvn;
+  const float4* x4 = (const float4*)d.x + (long long)n * per_n * V;
+  const float4* r4 = d.res ? (const float4*)d.res + (long long)n * per_n * V : nullptr;
+  const float* gA = d.A ? d.A + (d.ab_per_sample ? (long long)n * d.C : 0) : nullptr;
+  const float* gB = d.B ? d.B + (d.ab_per_sample ? (long long)n * d.C : 0) : nullptr;
   for (long long tt = (long long)blockIdx.x * blockDim.x + threadIdx.x; tt < per_n; tt += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(tt % c4n);
-    const long long t = (long long)n * per_n + tt;  // flat float4 index
-    const long long sp = t / c4n;                   // n*S + s
-    float4 v = __ldg(x4 + tt);
-    if (d.stats) {
-      const float4 a = *(const float4*)&sAB[c4 * 4];
-      const float4 b = *(const float4*)&sAB[d.C + c4 * 4];
-      v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
-    } else if (d.A) {
-      const float4 a = __ldg((const float4*)(d.A + (d.ab_per_sample ? (long long)n * d.C : 0)) + c4);
-      const float4 b = __ldg((const float4*)(d.B + (d.ab_per_sample ? (long long)n * d.C : 0)) + c4);
-      v.x = fmaf(v.x, a.x, b.x); v.y = fmaf(v.y, a.y, b.y); v.z = fmaf(v.z, a.z, b.z); v.w = fmaf(v.w, a.w, b.w);
-    }
-    if (r4) {
-      float4 r = __ldg(r4 + tt);
-      if (d.A2) {
-        const float4 a = __ldg((const float4*)d.A2 + c4);
-        const float4 b = __ldg((const float4*)d.B2 + c4);
-        r.x = fmaf(r.x, a.x, b.x); r.y = fmaf(r.y, a.y, b.y); r.z = fmaf(r.z, a.z, b.z); r.w = fmaf(r.w, a.w, b.w);
+    const int cv = (int)(tt % cvn);
+    const long long s = tt / cvn;  // spatial position inside the sample
+    float4 v[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) v[u] = __ldg(x4 + tt * V + u);
+#pragma unroll
+    for (int u = 0; u < V; ++u) {
+      const int c = (cv * V + u) * 4;
+      if (d.stats) {
+        const float4 a = *(const float4*)&sAB[c];
+        const float4 b = *(const float4*)&sAB[d.C + c];
+        v[u].x = fmaf(v[u].x, a.x, b.x); v[u].y = fmaf(v[u].y, a.y, b.y); v[u].z = fmaf(v[u].z, a.z, b.z); v[u].w = fmaf(v[u].w, a.w, b.w);
+      } else if (gA) {
+        const float4 a = __ldg((const float4*)(gA + c));
+        const float4 b = __ldg((const float4*)(gB + c));
+        v[u].x = fmaf(v[u].x, a.x, b.x); v[u].y = fmaf(v[u].y, a.y, b.y); v[u].z = fmaf(v[u].z, a.z, b.z); v[u].w = fmaf(v[u].w, a.w, b.w);
       }
-      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+      if (r4) {
+        float4 r = __ldg(r4 + tt * V + u);
+        if (d.A2) {
+          const float4 a = __ldg((const float4*)(d.A2 + c));
+          const float4 b = __ldg((const float4*)(d.B2 + c));
+          r.x = fmaf(r.x, a.x, b.x); r.y = fmaf(r.y, a.y, b.y); r.z = fmaf(r.z, a.z, b.z); r.w = fmaf(r.w, a.w, b.w);
+        }
+        v[u].x += r.x; v[u].y += r.y; v[u].z += r.z; v[u].w += r.w;
+      }
+      v[u].x = act_apply(v[u].x, d.act); v[u].y = act_apply(v[u].y, d.act);
+      v[u].z = act_apply(v[u].z, d.act); v[u].w = act_apply(v[u].w, d.act);
     }
-    v.x = act_apply(v.x, d.act); v.y = act_apply(v.y, d.act); v.z = act_apply(v.z, d.act); v.w = act_apply(v.w, d.act);
-    uint2 hi, lo, lo2;
+    uint2 hi[V], lo[V], lo2[V];
     if (d.out_hi) {
-      if (d.out_lo2) split4x3(v, hi, lo, lo2);
-      else split4(v, hi, lo);
-    }
-    if (UP == 1) {
-      if (d.out) ((float4*)d.out)[t] = v;
-      if (d.out_hi) {
-        ((uint2*)d.out_hi)[t] = hi;
-        ((uint2*)d.out_lo)[t] = lo;
-        if (d.out_lo2) ((uint2*)d.out_lo2)[t] = lo2;
+#pragma unroll
+      for (int u = 0; u < V; ++u) {
+        if (d.out_lo2) split4x3(v[u], hi[u], lo[u], lo2[u]);
+        else split4(v[u], hi[u], lo[u]);
       }
+    }
+    auto store = [&](long long o) {  // o = float4-slot index of the first vector of this thread in the output tensor
+      if (d.out) {
+#pragma unroll
+        for (int u = 0; u < V; ++u) ((float4*)d.out)[o + u] = v[u];
+      }
+      if (d.out_hi) {
+        if (V == 2) {
+          ((uint4*)d.out_hi)[o >> 1] = make_uint4(hi[0].x, hi[0].y, hi[V - 1].x, hi[V - 1].y);
+          ((uint4*)d.out_lo)[o >> 1] = make_uint4(lo[0].x, lo[0].y, lo[V - 1].x, lo[V - 1].y);
+          if (d.out_lo2) ((uint4*)d.out_lo2)[o >> 1] = make_uint4(lo2[0].x, lo2[0].y, lo2[V - 1].x, lo2[V - 1].y);
+        } else {
+          ((uint2*)d.out_hi)[o] = hi[0];
+          ((uint2*)d.out_lo)[o] = lo[0];
+          if (d.out_lo2) ((uint2*)d.out_lo2)[o] = lo2[0];
+        }
+      }
+    };
+    if (UP == 1) {
+      store(((long long)n * per_n + tt) * V);
     } else {
-      const long long s = sp - (long long)n * S;
       const int w = (int)(s % d.W);
       const int h = (int)((s / d.W) % d.H);
       const int dd = (int)(s / ((long long)d.W * d.H));
@@ -150,15 +173,8 @@ __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
 #pragma unroll
       for (int uy = 0; uy < UP; ++uy)
 #pragma unroll
-        for (int ux = 0; ux < UP; ++ux) {
-          const long long o = ((((long long)n * d.D + dd) * H2 + (h * UP + uy)) * W2 + (w * UP + ux)) * c4n + c4;
-          if (d.out) ((float4*)d.out)[o] = v;
-          if (d.out_hi) {
-            ((uint2*)d.out_hi)[o] = hi;
-            ((uint2*)d.out_lo)[o] = lo;
-            if (d.out_lo2) ((uint2*)d.out_lo2)[o] = lo2;
-          }
-        }
+        for (int ux = 0; ux < UP; ++ux)
+          store((((((long long)n * d.D + dd) * H2 + (h * UP + uy)) * W2 + (w * UP + ux)) * cvn + cv) * V);
     }
   }
 }
@@ -218,7 +234,8 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   EMO_REQUIRE(d->up == 1 || d->up == 2, "emo_apply: up must be 1 or 2");
   EMO_REQUIRE((d->A == nullptr) == (d->B == nullptr) && (d->A2 == nullptr) == (d->B2 == nullptr), "emo_apply: A/B must come in pairs");
   if (d->stats) EMO_REQUIRE(d->G > 0 && d->C % d->G == 0 && d->count > 0, "emo_apply: bad GroupNorm arguments");
-  const long long per_n = (long long)d->D * d->H * d->W * (d->C / 4);
+  const int V = (d->C % 8 == 0) ? 2 : 1;
+  const long long per_n = (long long)d->D * d->H * d->W * (d->C / (4 * V));
   long long blocks = cdivll(per_n, 256);
   const long long cap = (148ll * 32) / (d->N > 0 ? d->N : 1);
   if (blocks > cap) blocks = cap;
@@ -226,8 +243,10 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   const dim3 grid((unsigned)blocks, (unsigned)d->N);
   const size_t smem = d->stats ? 2 * (size_t)d->C * sizeof(float) : 0;
   EMO_REQUIRE(smem <= 48 * 1024, "emo_apply: C=%d too large for the fused finalisation", d->C);
-  if (d->up == 1) apply_kernel<1><<<grid, 256, smem, stream>>>(*d);
-  else apply_kernel<2><<<grid, 256, smem, stream>>>(*d);
+  if (d->up == 1 && V == 2) apply_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
+  else if (d->up == 1) apply_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
+  else if (V == 2) apply_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
+  else apply_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
   return check_launch("emo_apply");
 }
 
