@@ -118,9 +118,18 @@ class Model:
         return img, deep_f, img_f, st_out
 
 
-    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True):
-        """Capture one driver frame (all ~350 kernel launches) into a CUDA graph: removes the Python/ctypes launch
-        overhead from the per-frame loop.  Returns replay(drv (1,3,H,W) on device) -> img (1,3,H,W) (static buffer)."""
+    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True, slot: int = 0):
+        """Capture one driver frame (all ~240 kernel launches) into a CUDA graph: removes the Python/ctypes launch
+        overhead from the per-frame loop.  Returns replay(drv (1,3,H,W) on device) -> img (1,3,H,W) (static buffer).
+        `slot` selects the scratch set (ops.set_slot) the captured frame uses; graphs that may replay concurrently on
+        different streams need different slots."""
+        prev = ops.set_slot(slot)
+        try:
+            return self._make_driver_graph(st, mix, target_theta)
+        finally:
+            ops.set_slot(prev)
+
+    def _make_driver_graph(self, st, mix, target_theta):
         s = self.cfg.image_size
         static_in = torch.zeros((1, 3, s, s), dtype=torch.float32, device=self.device)
         side = torch.cuda.Stream(device=self.device)
@@ -140,7 +149,49 @@ class Model:
             return static_out
 
         replay.graph = graph
+        replay.static_in, replay.static_out = static_in, static_out
         return replay
+
+
+class DriverPipeline:
+    """Keeps `depth` driver frames in flight on one GPU.  Driver frames are independent given the cached source state
+    (notebooks/infer.py:511-644 reads only self.* source tensors), and roughly a quarter of a frame is a chain of ~120
+    tiny launches (head-pose and expression encoders at 4^2..56^2) that leaves most SMs idle; replaying the captured
+    frames of consecutive inputs on alternating streams lets one frame's big decoder kernels fill those holes.
+    Frame i's result is produced in order on stream i % depth; nothing is batched and every frame runs the same
+    kernels as the single-stream path."""
+
+    def __init__(self, model: "Model", st, depth: int = 2, mix: bool = True, target_theta: bool = True):
+        self.model, self.depth, self.n = model, depth, 0
+        self.slots = []
+        for k in range(depth):
+            run = model.make_driver_graph(st, mix=mix, target_theta=target_theta, slot=k)
+            self.slots.append(SimpleNamespace(run=run, stream=torch.cuda.Stream(device=model.device),
+                                              done=torch.cuda.Event(), busy=False))
+
+    def submit(self, drv: torch.Tensor, host_out: Optional[torch.Tensor] = None):
+        """Queue one frame (device tensor, or pinned host tensor -> asynchronous H2D on the frame's stream).  If `host_out`
+        (pinned) is given the image is copied into it on the same stream.  Returns the slot; slot.done is recorded when
+        the frame (and its copy-out) has finished; slot.run.static_out is valid until the slot's next submit."""
+        sl = self.slots[self.n % self.depth]
+        self.n += 1
+        if not drv.is_contiguous():
+            drv = drv.contiguous()  # a strided host tensor would otherwise take torch's staged, synchronous copy path
+        sl.stream.wait_stream(torch.cuda.current_stream(self.model.device))
+        with torch.cuda.stream(sl.stream):
+            sl.run.static_in.copy_(drv, non_blocking=True)
+            sl.run.graph.replay()
+            if host_out is not None:
+                host_out.copy_(sl.run.static_out, non_blocking=True)
+            sl.done.record()
+        sl.busy = True
+        return sl
+
+    def drain(self):
+        cur = torch.cuda.current_stream(self.model.device)
+        for sl in self.slots:
+            cur.wait_stream(sl.stream)
+            sl.busy = False
 
 
 class InferenceWrapper(torch.nn.Module):

@@ -139,6 +139,27 @@ def test_driver_pass_matches_cpu_oracle_on_fresh_inputs(setup):
     assert err < IMG_TOL
 
 
+def test_frames_in_flight_match_sequential(setup):
+    """DriverPipeline (CUDA graphs of consecutive frames replayed on alternating streams, separate scratch slots) returns,
+    frame by frame, what the plain one-after-the-other driver pass returns (up to the order of the fp32/fp64 atomics)."""
+    size, cfg, model, gold = setup
+    from emoportraits_b200.infer import DriverPipeline
+
+    st = model.source_pass(FR.frame(size, 41, "smooth").cuda())
+    drv = [FR.frame(size, 50 + i, "smooth").cuda() for i in range(5)]
+    want = [model.driver_pass(st, d, mix=True)[0].clone() for d in drv]
+    pipe = DriverPipeline(model, st, depth=2, mix=True)
+    hosts = [torch.empty((1, 3, size, size)).pin_memory() for _ in drv]
+    for d, h in zip(drv, hosts):
+        pipe.submit(d, host_out=h)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for i, (h, w) in enumerate(zip(hosts, want)):
+        err = (h - w.cpu()).abs().max().item()
+        assert err < 2e-4, (i, err)
+    assert (want[0] - want[1]).abs().max().item() > 1e-2  # the frames do differ
+
+
 def test_inference_wrapper_api(setup, tmp_path):
     """drop-in API: same ctor/forward signature and return types as notebooks/infer.py InferenceWrapper"""
     size, cfg, model, gold = setup
