@@ -29,6 +29,8 @@ namespace emo {
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 static constexpr int kEpiThreads = 256;
+static constexpr int kThreadsEpi1 = 512;  // EPI = 1 layout: warps 0..3 TMA / MMA / idle, 4..11 accumulators, 12..15 store warps
+static constexpr int kStoreThreads = 128;
 static constexpr int kMaxStages = 8;
 static constexpr int kTileM = 128;
 static constexpr int kMaxBN = 160;  // N tile cap: each epilogue thread keeps half a row of accumulators in registers
@@ -266,6 +268,92 @@ __device__ __forceinline__ void tile_stats(const float (&acc)[kMaxBN / 2], int n
   }
 }
 
+// Second half of the tile statistics: the CTA's column accumulators (filled by tile_stats / the store warps, then a named
+// barrier) are folded per GroupNorm group and added to the fp64 global sums; the accumulators are left zeroed.
+__device__ __forceinline__ void tile_group_stats(const ConvKParams& p, float* cs, float* cq, int n, int n0, int BN, int et, int nthreads) {
+  const int cpg = p.cpg;
+  if (BN % cpg == 0 && (n0 % cpg) == 0) {
+    const int ng = BN / cpg;
+    for (int g = et; g < ng; g += nthreads) {
+      float a = 0.f, b = 0.f;
+      for (int j = 0; j < cpg; ++j) {
+        a += cs[g * cpg + j]; b += cq[g * cpg + j];
+        cs[g * cpg + j] = 0.f; cq[g * cpg + j] = 0.f;
+      }
+      const int gi = (n0 / cpg) + g;
+      if (gi < p.G) {
+        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)a);
+        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)b);
+      }
+    }
+  } else {
+    for (int j = et; j < BN; j += nthreads) {
+      const int c = n0 + j;
+      if (c < p.Cout) {
+        const int gi = c / cpg;
+        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)cs[j]);
+        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)cq[j]);
+      }
+      cs[j] = 0.f; cq[j] = 0.f;
+    }
+  }
+}
+
+// Store-warp row loop (EPI = 1).  `chunk0` = 0 or 32: which 16-byte chunk of every staged row this lane owns in this pass;
+// `cg` = first global channel of that chunk.  PLAIN = no activation, no post-add, residual at the output resolution.
+struct StoreRowCtx {
+  int off, roff, poff;  // this lane's row: element offsets of the pixel in out / residual / post_add (-1: no pixel)
+  const float* stg;     // first staged row of this warp
+  int BN, lane, row0;
+  float* out;
+  const float* residual;
+  const float* post_add;
+  int act;
+};
+template <bool PLAIN>
+__device__ __forceinline__ void store_rows(const StoreRowCtx& c, int chunk0, int cg, bool ok, const float4 bias, float4& s, float4& q) {
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    float4 v[8], e[8];
+    int off[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int r = r0 + u;
+      off[u] = __shfl_sync(0xffffffffu, c.off, r);
+      const bool live = ok && off[u] >= 0;
+      // staged rows are [BN] floats; chunk q of row r sits at q ^ (r & 7) (row0 is a multiple of 8)
+      v[u] = *((const float4*)(c.stg + (size_t)r * c.BN) + ((chunk0 + c.lane) ^ (r & 7)));
+      e[u] = zero;
+      if (c.residual) {
+        const int ro = PLAIN ? off[u] : __shfl_sync(0xffffffffu, c.roff, r);
+        if (live) e[u] = __ldg((const float4*)(c.residual + ro + cg));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const bool live = ok && off[u] >= 0;
+      float4 a = v[u];
+      a.x += bias.x + e[u].x; a.y += bias.y + e[u].y; a.z += bias.z + e[u].z; a.w += bias.w + e[u].w;
+      if (!PLAIN) {
+        a.x = act_apply(a.x, c.act); a.y = act_apply(a.y, c.act); a.z = act_apply(a.z, c.act); a.w = act_apply(a.w, c.act);
+        if (c.post_add) {
+          const int po = __shfl_sync(0xffffffffu, c.poff, r0 + u);
+          if (live) {
+            const float4 t = __ldg((const float4*)(c.post_add + po + cg));
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+          }
+        }
+      }
+      if (live) {
+        *(float4*)(c.out + off[u] + cg) = a;
+        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
+        q.x = fmaf(a.x, a.x, q.x); q.y = fmaf(a.y, a.y, q.y); q.z = fmaf(a.z, a.z, q.z); q.w = fmaf(a.w, a.w, q.w);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -275,8 +363,14 @@ struct TMaps {
 };
 
 // NP = number of bf16 planes per operand: 2 -> 3 products (~2^-16 relative), 3 -> 6 products (~2^-24, fp32-faithful)
-template <int KC, int NP, int CG>
-__global__ void __launch_bounds__(kThreads, 1)
+// EPI = 0: the eight epilogue warps (2..9) accumulate the TMEM chunks AND run the tile's final phase (bias, residual,
+//          activation, statistics, stores), one output row per thread.  Used for split-K, ragged channel tails, NCHW output.
+// EPI = 1: 16 warps.  Warps 4..11 only accumulate and drop the finished fp32 tile into a shared-memory staging buffer;
+//          warps 12..15 ("store warps") run the final phase from there with whole rows per instruction (512-byte coalesced
+//          residual reads / output writes, statistics in registers without shuffles) while the accumulators already serve
+//          the next tile.  Register budget moved with setmaxnreg (TMA/MMA group 64, store group 112, accumulators 168).
+template <int KC, int NP, int CG, int EPI>
+__global__ void __launch_bounds__(EPI ? kThreadsEpi1 : kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ ConvKParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16B-aligned by the API; realign to 1024 for the swizzle atoms.
@@ -293,9 +387,12 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + kAccBufs;
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + kAccBufs);
+  uint64_t* sfull_bar = tempty_bar + kAccBufs;   // EPI = 1: staging buffer holds a finished tile / has been drained
+  uint64_t* sempty_bar = sfull_bar + 1;
+  uint32_t* tmem_slot = (uint32_t*)(sempty_bar + 1);
   float* col_sum = (float*)(tmem_slot + 4);  // [2][256]
   float* col_sq = col_sum + 2 * 256;         // [2][256]
+  float* stg = col_sq + 2 * 256;             // EPI = 1: [128][BN] fp32, 16-byte chunks XOR-swizzled with (row & 7)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -314,9 +411,11 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], (uint32_t)(kEpiThreads / 32) * (uint32_t)CG);  // pair mode: both CTAs' epilogue warps
     }
+    mbar_init(sfull_bar, kEpiThreads / 32);
+    mbar_init(sempty_bar, kStoreThreads / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 4 * 256; i += kThreads) col_sum[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * 256; i += (EPI ? kThreadsEpi1 : kThreads)) col_sum[i] = 0.f;
   if (warp == 1) {
     if (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
@@ -332,6 +431,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  constexpr int ew0 = EPI ? 4 : 2;  // first accumulator warp
   const int cs = p.cs;
   constexpr bool cg2 = CG == 2;  // compile-time: a kernel holding cta_group::2 instructions cannot be launched without clusters
   if (cs > 1 || cg2) cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
@@ -351,7 +451,7 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
   const int b_rows = BN / cs;                       // weight rows this CTA fetches (and multicasts)
   const uint32_t b_slice = (uint32_t)b_rows * KC * 2;
 
-  if (warp == 0) {
+  auto role_producer = [&]() {
     // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====================
     {
       int stage = 0;
@@ -404,7 +504,8 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         }
       }
     }
-  } else if (warp == 1 && !(cg2 && crank != 0)) {
+  };
+  auto role_mma = [&]() {
     // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
     // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1,
     // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
@@ -488,13 +589,14 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 2) {
-    // ===================== epilogue (warps 2..9) =====================
+  };
+  auto role_accumulate = [&]() {
+    // ===================== epilogue / accumulator warps (2..9, EPI = 1: 4..11) =====================
     // two warps per TMEM lane quadrant; each owns one half of the tile's columns (multiple of 16)
     const int quad = warp & 3;          // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;   // accumulator row == pixel index inside the tile box
-    const int et = threadIdx.x - 64;    // 0..255 among the epilogue threads
-    const int half = (warp - 2) >> 2;
+    const int et = threadIdx.x - ew0 * 32;  // 0..255 among the epilogue threads
+    const int half = (warp - ew0) >> 2;
     const int csplit = ((BN / 16 + 1) / 2) * 16;
     const int cbeg = half ? csplit : 0;           // this warp's column range inside the tile
     const int ncols = half ? BN - csplit : csplit;
@@ -574,6 +676,19 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         }
       }
 
+      if (EPI) {
+        // hand the finished sums to the store warps: row-major [128][BN] fp32, chunk q of row r at q ^ (r & 7)
+        mbar_wait(sempty_bar, ((uint32_t)it & 1) ^ 1);
+        float4* srow = (float4*)(stg + (size_t)row * BN);
+        const int q0 = cbeg >> 2;
+#pragma unroll
+        for (int j4 = 0; j4 < kMaxBN / 8; ++j4)
+          if (j4 * 4 < ncols)
+            srow[(q0 + j4) ^ (row & 7)] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfull_bar);
+        continue;
+      }
 #ifdef EMO_CONV_DEBUG
       if (p.dbg & 4) {
         if (acc[0] == 123.456f) p.out[0] = acc[1];  // keeps the accumulation alive
@@ -694,35 +809,106 @@ conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ Conv
         else if (r == 2) tile_stats<2>(acc, ncols, lane, cs + cbeg, cq + cbeg);
         else tile_stats<1>(acc, ncols, lane, cs + cbeg, cq + cbeg);
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        // one double RED per (group, quantity): thread g sums the cpg columns of its group
-        const int cpg = p.cpg;
-        if (BN % cpg == 0 && (n0 % cpg) == 0) {
-          const int ng = BN / cpg;
-          if (et < ng) {
-            float a = 0.f, b = 0.f;
-            for (int j = 0; j < cpg; ++j) {
-              a += cs[et * cpg + j]; b += cq[et * cpg + j];
-              cs[et * cpg + j] = 0.f; cq[et * cpg + j] = 0.f;
-            }
-            const int gi = (n0 / cpg) + et;
-            if (gi < p.G) {
-              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)a);
-              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)b);
-            }
-          }
-        } else {
-          for (int j = et; j < BN; j += kEpiThreads) {
-            const int c = n0 + j;
-            if (c < p.Cout) {
-              const int gi = c / cpg;
-              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)cs[j]);
-              atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)cq[j]);
-            }
-            cs[j] = 0.f; cq[j] = 0.f;
-          }
-        }
+        tile_group_stats(p, cs, cq, n, n0, BN, et, kEpiThreads);
       }
     }
+  };
+  auto role_store = [&]() {
+    // ===================== store warps (EPI = 1): final phase of every tile from the staging buffer =====================
+    // Warp sw owns rows sw*32 .. sw*32+31 of the tile.  One pass = one row: lane l holds the 16-byte chunk l (and 32 + l
+    // for tiles wider than 128 channels), so a warp instruction reads / writes 512 contiguous bytes of a pixel's channels.
+    // A single warp per scheduler issues this loop, so it is kept to ~30 instructions per row (store_rows below).
+    const int sw = warp - 12;
+    const int st = threadIdx.x - 12 * 32;  // 0..127 among the store threads
+    int it = 0;
+    for (int item = tile_first; item < total_tiles; item += tile_step, ++it) {
+      const int tile = item;
+      const int nt = tile / p.m_tiles;
+      int mt = tile - nt * p.m_tiles;
+      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
+      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
+      const int tdi = mt % p.tiles_d; mt /= p.tiles_d;
+      const int n = mt;
+      const int n0 = nt * BN;
+      // lane r prepares the element offsets of row sw*32 + r (-1: outside the tensor); the row loop broadcasts them
+      StoreRowCtx c;
+      c.off = -1; c.roff = 0; c.poff = 0;
+      {
+        const int row = sw * 32 + lane;
+        const int wl = row % p.tw;
+        const int hl = (row / p.tw) % p.th;
+        const int dl = row / (p.tw * p.th);
+        const int ow = twi * p.tw + wl, oh = thi * p.th + hl, od = tdi * p.td + dl;
+        if ((row < rows_a) && ow < p.Wout && oh < p.Hout && od < p.Dout) {
+          c.off = (((n * p.Dout + od) * p.Hout + oh) * p.Wout + ow) * p.Cout;
+          c.roff = (((n * p.rD + od) * p.rH + (oh >> p.res_shift)) * p.rW + (ow >> p.res_shift)) * p.Cout;
+          c.poff = ((od * p.Hout + oh) * p.Wout + ow) * p.Cout;
+        }
+      }
+      c.stg = stg + (size_t)(sw * 32) * BN;
+      c.BN = BN; c.lane = lane; c.row0 = sw * 32;
+      c.out = p.out; c.residual = p.residual; c.post_add = p.post_add; c.act = p.act;
+      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
+      const int c0 = n0 + 4 * lane, c1 = c0 + 128;
+      const bool ok0 = 4 * lane < BN && c0 < p.Cout, ok1 = 128 + 4 * lane < BN && c1 < p.Cout;
+      float4 bias0 = make_float4(0.f, 0.f, 0.f, 0.f), bias1 = bias0;
+      if (p.bias) {
+        if (ok0) bias0 = __ldg((const float4*)(p.bias + c0));
+        if (ok1) bias1 = __ldg((const float4*)(p.bias + c1));
+      }
+      mbar_wait(sfull_bar, (uint32_t)it & 1);
+#ifdef EMO_CONV_DEBUG
+      if (p.dbg & 128) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sempty_bar);
+        continue;
+      }
+#endif
+      const bool plain = p.act == EMO_ACT_NONE && !p.post_add && p.res_shift == 0;
+      if (plain) store_rows<true>(c, 0, c0, ok0, bias0, s0, q0);
+      else store_rows<false>(c, 0, c0, ok0, bias0, s0, q0);
+      if (BN > 128) {
+        if (plain) store_rows<true>(c, 32, c1, ok1, bias1, s1, q1);
+        else store_rows<false>(c, 32, c1, ok1, bias1, s1, q1);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sempty_bar);  // the accumulators may overwrite the staging buffer
+      if (p.stats) {
+        float* cs = col_sum + (it & 1) * 256;
+        float* cq = col_sq + (it & 1) * 256;
+        if (ok0) {
+          atomicAdd(&cs[4 * lane], s0.x); atomicAdd(&cs[4 * lane + 1], s0.y); atomicAdd(&cs[4 * lane + 2], s0.z); atomicAdd(&cs[4 * lane + 3], s0.w);
+          atomicAdd(&cq[4 * lane], q0.x); atomicAdd(&cq[4 * lane + 1], q0.y); atomicAdd(&cq[4 * lane + 2], q0.z); atomicAdd(&cq[4 * lane + 3], q0.w);
+        }
+        if (BN > 128 && ok1) {
+          atomicAdd(&cs[128 + 4 * lane], s1.x); atomicAdd(&cs[129 + 4 * lane], s1.y); atomicAdd(&cs[130 + 4 * lane], s1.z); atomicAdd(&cs[131 + 4 * lane], s1.w);
+          atomicAdd(&cq[128 + 4 * lane], q1.x); atomicAdd(&cq[129 + 4 * lane], q1.y); atomicAdd(&cq[130 + 4 * lane], q1.z); atomicAdd(&cq[131 + 4 * lane], q1.w);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        tile_group_stats(p, cs, cq, n, n0, BN, st, kStoreThreads);
+      }
+    }
+  };
+  // Role dispatch.  With EPI = 1 every warpgroup first moves its register budget (setmaxnreg must sit at the top of a
+  // branch that never rejoins the others before the teardown, or ptxas keeps the 128-register cap of the 512-thread launch
+  // for everybody): TMA / MMA group 64, store warps 112, accumulators 168.
+  if (EPI) {
+    const int wg = warp >> 2;
+    if (wg == 0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      if (warp == 0) role_producer();
+      else if (warp == 1 && !(cg2 && crank != 0)) role_mma();
+    } else if (wg == 3) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+      role_store();
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+      role_accumulate();
+    }
+  } else {
+    if (warp == 0) role_producer();
+    else if (warp == 1 && !(cg2 && crank != 0)) role_mma();
+    else if (warp >= 2) role_accumulate();
   }
 
   // teardown
@@ -909,14 +1095,40 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   EMO_REQUIRE(!d->residual || ((d->Hout % (1 << d->res_shift)) == 0 && (d->Wout % (1 << d->res_shift)) == 0),
               "emo_conv_igemm: residual shift does not divide the output size");
 
-  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs) * 8 + 16 + 4 * 256 * sizeof(float);
+  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
-  if (KC == 64 && (smem_limit - tail_bytes - 1024) / ((size_t)NP * (kTileM + BN / p.cg) * 64 * 2) < 3) KC = 32;
+  // store-warp epilogue (EPI = 1): pair-mode, full-K tiles with vectorisable channels-last output; needs a [128][BN] fp32
+  // staging buffer next to >= 3 pipeline stages (measured: 3 stages cost nothing against 4, 2 stages cost 10-25%)
+  int epi = 0;
+  {
+    static int epi_env = -1;
+    if (epi_env < 0) { const char* e = getenv("EMO_CONV_EPI"); epi_env = e ? atoi(e) : 1; }
+    const long long elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;  // 32-bit element offsets in the store warps
+    // pays when a CTA walks several tiles (the final phase of tile t then overlaps the MMAs of tile t+1: 512^2 x 128 -> 128
+    // 221 -> 197 us); a single tile per CTA has nothing to overlap and loses ~5% to the extra hand-over
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    if (epi_env == 1 && p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0 && elems < (1ll << 31) &&
+        tiles >= 2ll * sm_count) epi = 1;
+    if (epi_env == 2 && p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0 && elems < (1ll << 31)) epi = 1;  // tests: force
+  }
+  size_t staging = 0, stage_bytes = 0;
+  int stages = 0;
+  const int KC0 = KC;
+  for (;;) {
+    staging = epi ? (size_t)kTileM * BN * sizeof(float) : 0;
+    const size_t avail = smem_limit - tail_bytes - 1024 - staging;
+    KC = KC0;
+    if (KC == 64 && avail / ((size_t)NP * (kTileM + BN / p.cg) * 64 * 2) < 3) KC = 32;
+    stage_bytes = (size_t)NP * (kTileM + BN / p.cg) * KC * 2;
+    stages = (int)(avail / stage_bytes);
+    if (epi && stages < 3) { epi = 0; continue; }
+    break;
+  }
   p.kchunks = d->Cin / KC;
-  const size_t a_bytes = (size_t)kTileM * KC * 2, b_bytes = (size_t)(BN / p.cg) * KC * 2;
-  const size_t stage_bytes = NP * (a_bytes + b_bytes);
-  int stages = (int)((smem_limit - tail_bytes - 1024) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+#ifdef EMO_CONV_DEBUG
+  { const char* e = getenv("EMO_CONV_MAXSTAGES"); if (e && atoi(e) >= 2 && stages > atoi(e)) stages = atoi(e); }
+#endif
   EMO_REQUIRE(stages >= 2, "emo_conv_igemm: tile does not fit shared memory (BN=%d KC=%d)", BN, KC);
   p.stages = stages;
   p.nbuf = 512 / BN > kAccBufs ? kAccBufs : 512 / BN;
@@ -926,7 +1138,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     const int target = d->acc_chunk_mmas > 0 ? d->acc_chunk_mmas : (NP == 3 ? 24 : 48);
     p.flush = target / mmas_per_kstep < 1 ? 1 : target / mmas_per_kstep;
   }
-  const size_t smem_bytes = stages * stage_bytes + tail_bytes + 1024;
+  const size_t smem_bytes = stages * stage_bytes + tail_bytes + staging + 1024;
 
   // ---- tensor maps ----
   TMaps tm;
@@ -964,18 +1176,18 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   const int csz = p.cg == 2 ? 2 : p.cs;
   grid = (grid / csz) * csz;  // whole clusters only (total_tiles % csz == 0 by construction)
   cudaError_t e;
-#define EMO_LAUNCH_CONV(KC_, NP_, CG_)                                                                                        \
+#define EMO_LAUNCH_CONV(KC_, NP_, CG_, EPI_)                                                                                        \
   do {                                                                                                                    \
     static bool attr_set = false; /* the opt-in is per function, set once (227 KB covers every configuration) */           \
     if (!attr_set) {                                                                                                      \
-      e = cudaFuncSetAttribute(conv_igemm_kernel<KC_, NP_, CG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
+      e = cudaFuncSetAttribute(conv_igemm_kernel<KC_, NP_, CG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
       if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; } \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
     cudaLaunchConfig_t cfg;                                                                                               \
     memset(&cfg, 0, sizeof(cfg));                                                                                         \
     cfg.gridDim = dim3((unsigned)grid);                                                                                   \
-    cfg.blockDim = dim3(kThreads);                                                                                        \
+    cfg.blockDim = dim3(EPI_ ? kThreadsEpi1 : kThreads);                                                                                        \
     cfg.dynamicSmemBytes = smem_bytes;                                                                                    \
     cfg.stream = stream;                                                                                                  \
     cudaLaunchAttribute attr[1];                                                                                          \
@@ -985,19 +1197,24 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     attr[0].val.clusterDim.z = 1;                                                                                         \
     cfg.attrs = attr;                                                                                                     \
     cfg.numAttrs = 1;                                                                                                     \
-    e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_, CG_>, tm, p);                                                      \
+    e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_, CG_, EPI_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
-  if (p.cg == 2) {
-    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2);
-    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2);
-    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2);
-    else EMO_LAUNCH_CONV(32, 2, 2);
+  if (epi) {
+    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 1);
+    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 1);
+    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 1);
+    else EMO_LAUNCH_CONV(32, 2, 2, 1);
+  } else if (p.cg == 2) {
+    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 0);
+    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 0);
+    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 0);
+    else EMO_LAUNCH_CONV(32, 2, 2, 0);
   } else {
-    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 1);
-    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 1);
-    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 1);
-    else EMO_LAUNCH_CONV(32, 2, 1);
+    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 1, 0);
+    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 1, 0);
+    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 1, 0);
+    else EMO_LAUNCH_CONV(32, 2, 1, 0);
   }
 #undef EMO_LAUNCH_CONV
   if (ksplit > 1) {

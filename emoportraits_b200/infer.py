@@ -141,7 +141,8 @@ class Model:
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            static_out = self.driver_pass(st, static_in, mix=mix, target_theta=target_theta)[0]
+            out = self.driver_pass(st, static_in, mix=mix, target_theta=target_theta)
+            static_out = out[0]
 
         def replay(drv: torch.Tensor) -> torch.Tensor:
             static_in.copy_(drv, non_blocking=True)
@@ -149,7 +150,7 @@ class Model:
             return static_out
 
         replay.graph = graph
-        replay.static_in, replay.static_out = static_in, static_out
+        replay.static_in, replay.static_out, replay.static_state = static_in, static_out, out[3]
         return replay
 
 
@@ -169,10 +170,10 @@ class DriverPipeline:
             self.slots.append(SimpleNamespace(run=run, stream=torch.cuda.Stream(device=model.device),
                                               done=torch.cuda.Event(), busy=False))
 
-    def submit(self, drv: torch.Tensor, host_out: Optional[torch.Tensor] = None):
+    def submit(self, drv: torch.Tensor, host_out: Optional[torch.Tensor] = None, dev_out: Optional[torch.Tensor] = None):
         """Queue one frame (device tensor, or pinned host tensor -> asynchronous H2D on the frame's stream).  If `host_out`
-        (pinned) is given the image is copied into it on the same stream.  Returns the slot; slot.done is recorded when
-        the frame (and its copy-out) has finished; slot.run.static_out is valid until the slot's next submit."""
+        (pinned) / `dev_out` is given the image is copied into it on the same stream.  Returns the slot; slot.done is
+        recorded when the frame (and its copy-out) has finished; slot.run.static_out is valid until the slot's next submit."""
         sl = self.slots[self.n % self.depth]
         self.n += 1
         if not drv.is_contiguous():
@@ -183,6 +184,8 @@ class DriverPipeline:
             sl.run.graph.replay()
             if host_out is not None:
                 host_out.copy_(sl.run.static_out, non_blocking=True)
+            if dev_out is not None:
+                dev_out.copy_(sl.run.static_out, non_blocking=True)
             sl.done.record()
         sl.busy = True
         return sl
@@ -240,6 +243,7 @@ class InferenceWrapper(torch.nn.Module):
         self.resize_warp = False
         self.use_seg = getattr(self.args, 'use_seg', True)
         self._state = None
+        self._pipeline = self._pipeline_key = None
 
     # -- notebooks/infer.py:229-243
     def convert_to_tensor(self, image):
@@ -313,14 +317,22 @@ class InferenceWrapper(torch.nn.Module):
         if self._state is None:
             raise RuntimeError("forward(driver_image=...) called before a source image was given")
         drv = self._prep(driver_image)
-        imgs = []
-        for i in range(drv.shape[0]):
-            img, deep_f, img_f, so = self.model.driver_pass(self._state, drv[i:i + 1].contiguous(), mix=mix,
-                                                            target_theta=target_theta)
-            imgs.append(img)
+        if drv.shape[0] >= 2:
+            # a list of driver frames: captured frames, two in flight (DriverPipeline); same kernels as the eager pass below
+            key = (id(self._state), bool(mix), bool(target_theta))
+            if self._pipeline is None or self._pipeline_key != key:
+                self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=2, mix=mix,
+                                                                    target_theta=target_theta), key
+            img = torch.empty_like(drv)
+            for i in range(drv.shape[0]):
+                sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1])
+            self._pipeline.drain()
+            self.pred_target_theta = sl.run.static_state.pred_target_theta.clone()
+            self.target_pose_embed = sl.run.static_state.target_pose_embed.clone()
+        else:
+            img, deep_f, img_f, so = self.model.driver_pass(self._state, drv[0:1].contiguous(), mix=mix, target_theta=target_theta)
             self.pred_target_theta = so.pred_target_theta
             self.target_pose_embed = so.target_pose_embed
-        img = torch.cat(imgs)
         from PIL import Image
 
         host = (img.detach().clamp(0, 1) * 255).byte().permute(0, 2, 3, 1).cpu().numpy()  # ToPILImage: mul(255).byte()

@@ -141,7 +141,10 @@ def test_driver_pass_matches_cpu_oracle_on_fresh_inputs(setup):
 
 def test_frames_in_flight_match_sequential(setup):
     """DriverPipeline (CUDA graphs of consecutive frames replayed on alternating streams, separate scratch slots) returns,
-    frame by frame, what the plain one-after-the-other driver pass returns (up to the order of the fp32/fp64 atomics)."""
+    frame by frame, what the plain one-after-the-other driver pass returns.  Two runs of the SAME path already differ by up
+    to ~1e-4 at 512^2 (GroupNorm statistics are accumulated with fp32 shared-memory / fp64 global atomics whose order
+    varies, and the warp network amplifies it; tools/flight_debug.py prints eager-vs-eager next to pipeline-vs-eager), so
+    the bound is 5e-4, half the parity tolerance; a scratch-sharing bug between the in-flight frames shows up as 1e-2+."""
     size, cfg, model, gold = setup
     from emoportraits_b200.infer import DriverPipeline
 
@@ -156,7 +159,7 @@ def test_frames_in_flight_match_sequential(setup):
     torch.cuda.synchronize()
     for i, (h, w) in enumerate(zip(hosts, want)):
         err = (h - w.cpu()).abs().max().item()
-        assert err < 2e-4, (i, err)
+        assert err < 5e-4, (i, err)
     assert (want[0] - want[1]).abs().max().item() > 1e-2  # the frames do differ
 
 
@@ -180,7 +183,13 @@ def test_inference_wrapper_api(setup, tmp_path):
     assert isinstance(pil, list) and pil[0].size == (size, size) and img.shape == (1, 3, size, size) and img.is_cuda
     assert _sub_err(img, case["frames"][0]["img"]) < IMG_TOL
     pil2, img2 = w.forward(None, drv, crop=False, mix=True, mix_old=False)
-    assert (img - img2).abs().max().item() < 2e-4  # GN statistics are accumulated with atomics (order varies run to run)
+    assert (img - img2).abs().max().item() < 5e-4  # GN statistics are accumulated with atomics (order varies run to run)
+    # a list of driver frames goes through the captured two-in-flight pipeline; same images, in order
+    drv_b = FR.pil(size, case["frames"][0]["seed"] + 7, "smooth")
+    pil3, img3 = w.forward(None, [drv, drv_b, drv], crop=False, mix=True, mix_old=False)
+    assert len(pil3) == 3 and img3.shape == (3, 3, size, size)
+    assert (img3[0:1] - img).abs().max().item() < 5e-4 and (img3[2:3] - img).abs().max().item() < 5e-4
+    assert (img3[1:2] - img).abs().max().item() > 1e-2
     assert w.forward(src, None, crop=False) is None
     with pytest.raises(NotImplementedError):
         w.forward(src, drv)  # crop=True needs the external face detector
