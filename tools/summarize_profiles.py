@@ -33,6 +33,32 @@ def launches():
            "| kernel | launches | total us | share |", "|---|---:|---:|---:|"]
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {v[0]} | {v[1]:.1f} | {100*v[1]/tot:.1f}% |")
+    # one driver frame = the launches between two consecutive pose_theta_kernel launches (taken near the end of the run)
+    idx = [i for i, (n, _) in enumerate(order) if "pose_theta" in n]
+    if len(idx) >= 3:
+        a, b = idx[-3], idx[-2]
+        fr = collections.OrderedDict()
+        for n, t in order[a:b]:
+            v = fr.setdefault(n, [0, 0.0]); v[0] += 1; v[1] += t
+        ftot = sum(v[1] for v in fr.values())
+        out += ["", f"## One driver frame ({b - a} launches, {ftot/1000:.2f} ms summed cold-cache durations)", "",
+                "| kernel | launches | total us | share |", "|---|---:|---:|---:|"]
+        for k, v in sorted(fr.items(), key=lambda kv: -kv[1][1]):
+            out.append(f"| `{k}` | {v[0]} | {v[1]:.1f} | {100*v[1]/ftot:.1f}% |")
+        # phases by position in the launch order of the frame (see the sequence in Model.driver_pass)
+        seq = order[a:b]
+        gs = [i for i, (n, _) in enumerate(seq) if "gs3_cl" in n]
+        rs = [i for i, (n, _) in enumerate(seq) if "resize_bilinear" in n]
+        if gs and rs:
+            lin = [i for i, (n, _) in enumerate(seq) if "linear_kernel" in n and i < gs[0]]
+            marks = [("pose_theta + expression encoder (aligned 224^2 crop, ResNet)", 0, lin[0] if lin else gs[0]),
+                     ("embedding MLPs + warp generator (3-D convs, three planes)", lin[0] if lin else gs[0], gs[0]),
+                     ("grid_sample_3d x2", gs[0], gs[-1] + 1),
+                     ("decoder (two planes)", gs[-1] + 1, rs[0]),
+                     ("head-pose regressor of the next frame (ResNet18)", rs[0], len(seq))]
+            out += ["", "| phase | launches | us |", "|---|---:|---:|"]
+            for name, lo, hi in marks:
+                out.append(f"| {name} | {hi - lo} | {sum(t for _, t in seq[lo:hi]):.1f} |")
     (PR / f"launches_{tag}_summary.md").write_text("\n".join(out) + "\n")
     print("\n".join(out[:14]))
 
