@@ -323,7 +323,7 @@ __device__ __forceinline__ void store_rows(const StoreRowCtx& c, int chunk0, int
       off[u] = __shfl_sync(0xffffffffu, c.off, r);
       const bool live = ok && off[u] >= 0;
       // staged rows are [BN] floats; chunk q of row r sits at q ^ (r & 7) (row0 is a multiple of 8)
-      v[u] = *((const float4*)(c.stg + (size_t)r * c.BN) + ((chunk0 + c.lane) ^ (r & 7)));
+      v[u] = ok ? *((const float4*)(c.stg + (size_t)r * c.BN) + ((chunk0 + c.lane) ^ (r & 7))) : zero;
       e[u] = zero;
       if (c.residual) {
         const int ro = PLAIN ? off[u] : __shfl_sync(0xffffffffu, c.roff, r);

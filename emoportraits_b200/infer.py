@@ -172,8 +172,11 @@ class DriverPipeline:
 
     def submit(self, drv: torch.Tensor, host_out: Optional[torch.Tensor] = None, dev_out: Optional[torch.Tensor] = None):
         """Queue one frame (device tensor, or pinned host tensor -> asynchronous H2D on the frame's stream).  If `host_out`
-        (pinned) / `dev_out` is given the image is copied into it on the same stream.  Returns the slot; slot.done is
-        recorded when the frame (and its copy-out) has finished; slot.run.static_out is valid until the slot's next submit."""
+        (pinned) / `dev_out` is given the image is copied into it on the same stream.  Returns a ticket: ticket.done is an
+        event recorded when this frame (and its copy-out) has finished (ticket.slot.done is the same event, i.e. always the
+        slot's latest frame); slot.run.static_out is valid until the slot's next submit.  A slot's frames are ordered by
+        its stream, so a caller may queue further frames on a busy slot — it only has to keep the host_out / dev_out
+        buffers of unfinished frames apart."""
         sl = self.slots[self.n % self.depth]
         self.n += 1
         if not drv.is_contiguous():
@@ -186,9 +189,10 @@ class DriverPipeline:
                 host_out.copy_(sl.run.static_out, non_blocking=True)
             if dev_out is not None:
                 dev_out.copy_(sl.run.static_out, non_blocking=True)
+            sl.done = torch.cuda.Event()
             sl.done.record()
         sl.busy = True
-        return sl
+        return SimpleNamespace(done=sl.done, slot=sl, index=self.n - 1)
 
     def drain(self):
         cur = torch.cuda.current_stream(self.model.device)
@@ -325,7 +329,7 @@ class InferenceWrapper(torch.nn.Module):
                                                                     target_theta=target_theta), key
             img = torch.empty_like(drv)
             for i in range(drv.shape[0]):
-                sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1])
+                sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1]).slot
             self._pipeline.drain()
             self.pred_target_theta = sl.run.static_state.pred_target_theta.clone()
             self.target_pose_embed = sl.run.static_state.target_pose_embed.clone()

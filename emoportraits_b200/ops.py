@@ -182,6 +182,15 @@ _ARENA = {}
 _SLOT = 0  # which set of per-pass scratch (statistics arena, split-K workspace) the calls below use
 
 
+def _dev_key(device):
+    """Canonical (index-resolved) key of a CUDA device: torch.device('cuda') and tensor.device ('cuda:0') must name the
+    same scratch — begin_pass() is called with the model's device, new_stats() with a tensor's."""
+    d = torch.device(device)
+    if d.type != "cuda":
+        return (d.type, -1)
+    return ("cuda", d.index if d.index is not None else torch.cuda.current_device())
+
+
 def set_slot(k: int) -> int:
     """Select the scratch set for subsequent passes.  Passes that may be in flight at the same time on different streams
     (infer.DriverPipeline keeps several driver frames in flight) must not share the statistics arena or the
@@ -196,7 +205,7 @@ _ARENA_SLOT = 2 * 32 * 2  # doubles per slot: up to N=2 samples x 32 groups x (s
 def begin_pass(device, slots: int = 384):
     """Start a source/driver pass: ONE memset zeroes the whole GroupNorm-statistics arena; new_stats() then hands out
     slices of it instead of launching a fill kernel per normalisation (57 per driver frame otherwise)."""
-    key = (str(device), _SLOT)
+    key = (_dev_key(device), _SLOT)
     ar = _ARENA.get(key)
     if ar is None or ar["buf"].shape[0] < slots:
         ar = {"buf": torch.zeros((slots, _ARENA_SLOT), dtype=torch.float64, device=device), "idx": 0}
@@ -206,7 +215,7 @@ def begin_pass(device, slots: int = 384):
 
 
 def new_stats(N: int, G: int, device) -> torch.Tensor:
-    ar = _ARENA.get((str(device), _SLOT))
+    ar = _ARENA.get((_dev_key(device), _SLOT))
     if ar is not None and N * G * 2 <= _ARENA_SLOT and ar["idx"] < ar["buf"].shape[0]:
         t = ar["buf"][ar["idx"]][: N * G * 2].view(N, G, 2)
         ar["idx"] += 1
@@ -275,7 +284,7 @@ _SPLITK_WS = {}
 def _splitk_workspace(device) -> torch.Tensor:
     """Per-device (and per scratch slot, see set_slot) zero-initialised fp32 workspace for split-K convolutions (the
     finalize kernel leaves it zeroed).  Launches on one stream use it back to back, which is how the model issues its convs."""
-    key = (str(device), _SLOT)
+    key = (_dev_key(device), _SLOT)
     if key not in _SPLITK_WS:
         _SPLITK_WS[key] = torch.zeros(2 * 1024 * 1024, dtype=torch.float32, device=device)
     return _SPLITK_WS[key]

@@ -157,9 +157,18 @@ def test_frames_in_flight_match_sequential(setup):
         pipe.submit(d, host_out=h)
     pipe.drain()
     torch.cuda.synchronize()
-    for i, (h, w) in enumerate(zip(hosts, want)):
-        err = (h - w.cpu()).abs().max().item()
-        assert err < 5e-4, (i, err)
+    errs = [(h - w.cpu()).abs().max().item() for h, w in zip(hosts, want)]
+    if max(errs) >= 5e-4:  # diagnostics: is it the pipeline or the eager pass, and does it persist?
+        again = [torch.empty((1, 3, size, size)).pin_memory() for _ in drv]
+        for d, h in zip(drv, again):
+            pipe.submit(d, host_out=h)
+        pipe.drain()
+        torch.cuda.synchronize()
+        errs2 = [(h - w.cpu()).abs().max().item() for h, w in zip(again, want)]
+        want2 = [model.driver_pass(st, d, mix=True)[0] for d in drv]
+        errs3 = [(a - b).abs().max().item() for a, b in zip(want, want2)]
+        errs4 = [(h - w.cpu()).abs().max().item() for h, w in zip(hosts, want2)]
+        raise AssertionError(f"pipeline vs eager {errs}; second pipeline run {errs2}; eager vs eager {errs3}; first pipeline vs second eager {errs4}")
     assert (want[0] - want[1]).abs().max().item() > 1e-2  # the frames do differ
 
 

@@ -273,3 +273,21 @@ def test_pose_theta(ops):
     th2, warp2, align2 = ops.pose_theta(srt[1:2].cuda(), source_theta=src.cuda().contiguous(), mix=True)
     assert (th2.cpu()[:, :3] - mixed_ref).abs().max().item() < 1e-5
     assert (align2.cpu() - R.align_theta_2d(mixed_ref)).abs().max().item() < 1e-5
+
+
+def test_stats_arena_is_keyed_by_resolved_device(ops):
+    """begin_pass() gets the model's device ('cuda'), new_stats() a tensor's ('cuda:0'): both must name the same arena,
+    otherwise a captured frame accumulates into slices that its own begin_pass never zeroes (regression: the second
+    replay of a graph captured after another model had used the 'cuda:0' spelling returned garbage)."""
+    import torch
+    ops.begin_pass(torch.device("cuda"))
+    t = ops.new_stats(1, 32, torch.zeros(1, device="cuda").device)
+    buf = ops._ARENA[(ops._dev_key("cuda"), ops._SLOT)]["buf"]
+    assert buf.data_ptr() <= t.data_ptr() < buf.data_ptr() + buf.numel() * 8
+    prev = ops.set_slot(1)
+    try:
+        ops.begin_pass("cuda:0")
+        t1 = ops.new_stats(1, 32, "cuda")
+        assert t1.data_ptr() != t.data_ptr()
+    finally:
+        ops.set_slot(prev)
