@@ -481,6 +481,12 @@ def main():
     ap.add_argument("--workload", default="driver", choices=["driver", "stage2"],
                     help="driver = the headline metric (default); stage2 = BASELINE config 5, secondary")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner at the first collective)
+    # are sent to stderr for the duration of the run, and print() is bound to the saved descriptor.
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "stage2":
