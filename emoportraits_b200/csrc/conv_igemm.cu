@@ -16,9 +16,14 @@
 //   The tensor core ACCUMULATES WITH TRUNCATION (tools/accum_probe.py), so an accumulator only takes a short chunk
 //   of MMAs (24 / 48); the epilogue warps promote every chunk to fp32 registers (round-to-nearest adds) through a
 //   4-deep TMEM chunk ring.  Plain bf16/tf32 operands, or one long accumulation chain, do not hold the 1e-3 budget.
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-//   warps 2..9 = epilogue, two per TMEM lane quadrant, each owning half of the tile's columns
-//   (chunk promotion during the main loop; then bias/residual/activation -> global and the GN statistics).
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both issue behind elect.sync),
+//   8 accumulator warps, two per TMEM lane quadrant, each owning half of the tile's columns (chunk promotion during
+//   the main loop).  EPI = 0 (320 threads): the accumulator warps also run the tile's final phase (bias / residual /
+//   activation -> global, GN statistics).  EPI = 1 (512 threads, setmaxnreg budgets): they hand the finished tile to
+//   four store warps through a swizzled shared-memory staging tile.  See the template comment at the kernel.
+// CG = 2: CTA pairs (2-CTA clusters) issue cta_group::2 M = 256 MMAs; each CTA stages its own 128 pixels and half of
+//   the weight tile, which halves the weight ingest and brings the shared-memory operand reads per MMA under the
+//   tensor floor (measured in tools/mma_probe.cu).
 // Persistent CTAs walk tiles round-robin; the chunk ring lets the MMA of the next tile run ahead of the epilogue.
 #include "common.cuh"
 
@@ -1079,11 +1084,11 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     p.cg = (cg_env == 1 && ksplit == 1 && (p.m_tiles % 2) == 0 && BN % 32 == 0) ? 2 : 1;
   }
   {
-    // cluster size: weight-tile multicast across consecutive pixel tiles (the conv main loop is L2->SM bandwidth
-    // bound: 64 KB per k-step per SM at 128x128; sharing the weight half of it across the cluster cuts it to 40-48 KB)
+    // cluster size (single-CTA MMAs only): weight-tile multicast across consecutive pixel tiles.  Experiment switch:
+    // measured no gain at 2 and a loss at 4 (multicast does not lower the per-SM fill; pair mode above does)
     static int forced = -1;
     if (forced < 0) { const char* e = getenv("EMO_CONV_CLUSTER"); forced = e ? atoi(e) : 0; }
-    int cs = (forced > 0 && ksplit == 1 && p.cg == 1) ? forced : 1;  // measured: no gain at 2, loss at 4 (the main loop is smem-capacity x latency bound) -> opt-in
+    int cs = (forced > 0 && ksplit == 1 && p.cg == 1) ? forced : 1;
     while (cs > 1 && (p.m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0 ||
                       (long long)p.m_tiles * p.n_tiles < 2ll * cs)) cs >>= 1;
     p.cs = cs;

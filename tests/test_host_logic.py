@@ -38,3 +38,31 @@ def test_dry_run_shapes_256_and_512():
         r = subprocess.run([sys.executable, "-c", SCRIPT % str(ROOT), str(size)], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "launches per driver frame" in r.stdout
+
+
+SLOT_SCRIPT = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from emoportraits_b200 import ops
+# one arena / workspace set per (device, slot); the device key does not depend on how the device is spelled
+assert ops._dev_key("cpu") == ops._dev_key(torch.device("cpu")) == ops._dev_key(torch.zeros(1).device)
+ops.begin_pass("cpu")
+a0 = ops.new_stats(1, 32, torch.zeros(1).device)
+prev = ops.set_slot(1)
+assert prev == 0
+ops.begin_pass(torch.device("cpu"))
+a1 = ops.new_stats(1, 32, "cpu")
+assert a0.data_ptr() != a1.data_ptr()
+assert ops.set_slot(prev) == 1
+ops.begin_pass("cpu")
+b0 = ops.new_stats(1, 32, "cpu")
+assert b0.data_ptr() == a0.data_ptr()          # begin_pass rewinds the slot's arena
+assert ops.new_stats(1, 32, "cpu").data_ptr() != b0.data_ptr()
+print("ok")
+"""
+
+
+def test_scratch_slots_and_device_key():
+    env = dict(os.environ, EMO_DRY_RUN="1")
+    r = subprocess.run([sys.executable, "-c", SLOT_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
