@@ -179,6 +179,75 @@ __global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
   }
 }
 
+// Image head (emo_gn_head): one warp handles 8 pixels per step.  Lane l owns channels 4l..4l+3 (+128k): a warp load reads a
+// pixel's whole channel vector (512 B at C = 128); the 8 x 4 per-lane partial dot products are transpose-reduced over the
+// warp with 31 shuffles, after which lane l = 4u + o holds output o of pixel u.
+__global__ void __launch_bounds__(256) gn_head_kernel(const emo_gn_head_desc d) {
+  extern __shared__ float sAB[];  // A[C], B[C] of this CTA's sample, then w[4][C] (rows >= Cout are zero)
+  const int n = blockIdx.y;
+  const int C = d.C;
+  float* sW = sAB + 2 * C;
+  {
+    const int cpg = C / d.G;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const int g = c / cpg;
+      const double s = d.stats[((long long)n * d.G + g) * 2], q = d.stats[((long long)n * d.G + g) * 2 + 1];
+      const double mean = s / d.count;
+      double var = q / d.count - mean * mean;
+      if (var < 0) var = 0;
+      const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+      const float A = rstd * d.gamma[c];
+      sAB[c] = A;
+      sAB[C + c] = d.beta[c] - (float)mean * A;
+      for (int o = 0; o < 4; ++o) sW[o * C + c] = o < d.Cout ? d.w[(long long)o * C + c] : 0.f;
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = gridDim.x * (blockDim.x >> 5);
+  const int warp_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long S = d.S;
+  const float* xn = d.x + (long long)n * S * C;
+  float bo = 0.f;
+  if (d.bias && (lane & 3) < d.Cout) bo = d.bias[lane & 3];
+  for (long long p0 = (long long)warp_id * 8; p0 < S; p0 += (long long)warps_per_grid * 8) {
+    float val[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) val[i] = 0.f;
+    for (int c = 4 * lane; c < C; c += 128) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (p0 + u < S) ? __ldg((const float4*)(xn + (p0 + u) * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 a = *(const float4*)&sAB[c];
+      const float4 b = *(const float4*)&sAB[C + c];
+      float4 w[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) w[o] = *(const float4*)&sW[o * C + c];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float y0 = fmaxf(fmaf(v[u].x, a.x, b.x), 0.f), y1 = fmaxf(fmaf(v[u].y, a.y, b.y), 0.f);
+        const float y2 = fmaxf(fmaf(v[u].z, a.z, b.z), 0.f), y3 = fmaxf(fmaf(v[u].w, a.w, b.w), 0.f);
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+          val[u * 4 + o] += y0 * w[o].x + y1 * w[o].y + y2 * w[o].z + y3 * w[o].w;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < off; ++j) {
+        const float send = upper ? val[j] : val[j + off];
+        const float keep = upper ? val[j + off] : val[j];
+        val[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    const int u = lane >> 2, o = lane & 3;
+    if (o < d.Cout && p0 + u < S) d.out[((long long)n * d.Cout + o) * S + p0 + u] = act_apply(val[0] + bo, d.act_out);
+  }
+}
+
 __global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
                              uint2* __restrict__ lo2) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
@@ -248,6 +317,22 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   else if (V == 2) apply_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
   else apply_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
   return check_launch("emo_apply");
+}
+
+extern "C" int emo_gn_head(const emo_gn_head_desc* d, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(d && d->x && d->stats && d->gamma && d->beta && d->w && d->out, "emo_gn_head: null pointer");
+  EMO_REQUIRE(d->Cout >= 1 && d->Cout <= 4, "emo_gn_head: Cout=%d must be 1..4", d->Cout);
+  EMO_REQUIRE(d->C % 4 == 0 && d->G > 0 && d->C % d->G == 0, "emo_gn_head: C=%d must be a multiple of 4 and of G=%d", d->C, d->G);
+  EMO_REQUIRE(((uintptr_t)d->x % 16) == 0, "emo_gn_head: x must be 16-byte aligned");
+  if (d->N == 0 || d->S == 0) return EMO_OK;
+  const size_t smem = 6 * (size_t)d->C * sizeof(float);
+  EMO_REQUIRE(smem <= 48 * 1024, "emo_gn_head: C=%d too large", d->C);
+  long long blocks = cdivll(d->S, 8 * 8);  // 8 warps x 8 pixels per step
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  gn_head_kernel<<<dim3((unsigned)blocks, (unsigned)d->N), 256, smem, stream>>>(*d);
+  return check_launch("emo_gn_head");
 }
 
 extern "C" int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* lo2, void* stream_) {

@@ -48,6 +48,12 @@ class ApplyDesc(C.Structure):
                 ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p), ("ada_w", c_void_p), ("ada_b", c_void_p)]
 
 
+class GnHeadDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("N", c_int), ("C", c_int), ("S", c_ll), ("stats", c_void_p), ("G", c_int),
+                ("count", c_double), ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p), ("w", c_void_p),
+                ("bias", c_void_p), ("Cout", c_int), ("act_out", c_int), ("out", c_void_p)]
+
+
 class ConvDesc(C.Structure):
     _fields_ = [("a_hi", c_void_p), ("a_lo", c_void_p), ("N", c_int), ("Din", c_int), ("Hin", c_int), ("Win", c_int),
                 ("Cin", c_int), ("w_hi", c_void_p), ("w_lo", c_void_p), ("Cout", c_int), ("Cout_pad", c_int),
@@ -92,6 +98,7 @@ SYMBOLS = {
     "emo_gn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "emo_gn_finalize": (c_int, [C.POINTER(GnFinalizeDesc), c_void_p]),
     "emo_apply": (c_int, [C.POINTER(ApplyDesc), c_void_p]),
+    "emo_gn_head": (c_int, [C.POINTER(GnHeadDesc), c_void_p]),
     "emo_conv_igemm": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "emo_conv_direct": (c_int, [C.POINTER(ConvDirectDesc), c_void_p]),
     "emo_linear": (c_int, [C.POINTER(LinearDesc), c_void_p]),

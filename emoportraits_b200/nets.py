@@ -465,7 +465,11 @@ class Decoder:
             j += 1
         self.lrs = cfg.im_dec_lrs
         self.head_norm = Norm(sd, p + ".img_decoder.dec_img_head.0", dev)
-        self.head = ConvW(sd, p + ".img_decoder.dec_img_head.2", dev, ws=True, planes=planes)
+        # dec_img_head (decoder.py:398-410): norm -> ReLU -> 1x1 Conv2d_ws -> sigmoid runs as ONE exact-fp32 pass (ops.gn_head)
+        hw, hb = fold_conv(sd, p + ".img_decoder.dec_img_head.2", ws=True)
+        assert tuple(hw.shape[2:]) == (1, 1) and hw.shape[0] <= 4, hw.shape
+        self.head_w = hw.reshape(hw.shape[0], hw.shape[1]).float().to(dev).contiguous()
+        self.head_b = hb.float().to(dev).contiguous() if hb is not None else None
 
     def __call__(self, feat: "ops.Split", want_logits: bool = False):
         """feat: Split (N,1,S,S,C*D) in (h,w,d,c) order -> img (N,3,H,W) fp32 NCHW, feat_2d, img_feat."""
@@ -477,7 +481,6 @@ class Decoder:
         feat2d = x
         for j, blk in enumerate(self.img):
             x, st = blk(x, st, up=2 if (j % self.lrs == 0) else 1)
-        a = ops.apply(x, gn=self.head_norm.gn(st, _count(x)), act=ops.ACT_RELU, planes=self.planes)
-        img = ops.conv_igemm(a, self.head.w, bias=self.head.b, act=ops.ACT_NONE if want_logits else ops.ACT_SIGMOID,
-                             out_nchw=True)
+        img = ops.gn_head(x, self.head_norm.gn(st, _count(x)), self.head_w, self.head_b,
+                          act_out=ops.ACT_NONE if want_logits else ops.ACT_SIGMOID)
         return img[:, :, 0], feat2d, x

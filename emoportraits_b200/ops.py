@@ -264,6 +264,20 @@ def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=Non
     return out if want_f32 else sp
 
 
+def gn_head(x: torch.Tensor, gn: dict, w: torch.Tensor, bias: Optional[torch.Tensor], act_out: int = ACT_NONE) -> torch.Tensor:
+    """(N,D,H,W,C) fp32 channels-last -> (N,Cout,D,H,W): act_out(bias + w . relu(GroupNorm(x))) in one exact-fp32 pass
+    (the image head, decoder.py:398-410).  w (Cout<=4, C) fp32, gn as in apply()."""
+    _chk(x); _chk(w)
+    N, D, H, W, Cc = x.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, Cc) and 1 <= Cout <= 4
+    out = torch.empty((N, Cout, D, H, W), dtype=torch.float32, device=x.device)
+    d = L.GnHeadDesc(_p(x), N, Cc, D * H * W, _p(gn["stats"]), gn["stats"].shape[1], float(gn["count"]), float(gn.get("eps", 1e-5)),
+                     _p(gn["gamma"]), _p(gn["beta"]), _p(w), _p(bias), Cout, act_out, _p(out))
+    L.call("emo_gn_head", C.byref(d), _stream())
+    return out
+
+
 def split_bf16(x: torch.Tensor, planes: int = 2) -> Split:
     _chk(x)
     sp = Split.empty(x.shape, x.device, planes)

@@ -148,6 +148,28 @@ typedef struct {
 } emo_apply_desc;
 int emo_apply(const emo_apply_desc* d, void* stream);
 
+/* Fused image head: out[n][o][s] = act_out( bias[o] + sum_c w[o][c] * relu(GN(x)[n][s][c]) ), Cout <= 4, NCHW output.
+ * Replaces the tail of ImageDecoder (decoder.py:398-410: dec_img_head = norm -> ReLU -> 1x1 Conv2d_ws -> sigmoid, applied at
+ * decoder.py:238): one pass over the 512^2 x 128 fp32 tensor in exact fp32 instead of a GN-apply pass writing bf16 planes
+ * plus a 3-channel tensor-core conv.  GroupNorm scale/shift are derived from `stats` in the kernel (as in emo_apply). */
+typedef struct {
+  const float* x; /* [N][S][C] fp32 channels-last */
+  int N, C;
+  long long S;         /* spatial positions per sample */
+  const double* stats; /* [N][G][2] */
+  int G;
+  double count;
+  float eps;
+  const float* gamma; /* [C] */
+  const float* beta;  /* [C] */
+  const float* w;     /* [Cout][C] fp32 (already folded: weight standardisation / spectral norm) */
+  const float* bias;  /* [Cout] or NULL */
+  int Cout;           /* 1..4 */
+  int act_out;        /* EMO_ACT_* applied to the head output */
+  float* out;         /* [N][Cout][S] fp32 */
+} emo_gn_head_desc;
+int emo_gn_head(const emo_gn_head_desc* d, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution on tcgen05 (2-D and 3-D, kernel 1 or 3 per dim, stride 1 or 2,
  * zero padding), bf16x2-split operands, fp32 accumulation in TMEM.

@@ -291,3 +291,26 @@ def test_stats_arena_is_keyed_by_resolved_device(ops):
         assert t1.data_ptr() != t.data_ptr()
     finally:
         ops.set_slot(prev)
+
+
+@pytest.mark.parametrize("C,Cout,S,act", [(128, 3, (64, 64), "sigmoid"), (128, 3, (37, 21), "none"), (256, 4, (16, 16), "sigmoid"), (32, 1, (8, 8), "none")])
+def test_gn_head(ops, C, Cout, S, act):
+    """image head: act(bias + w . relu(GroupNorm(x))) in one pass == torch group_norm -> relu -> 1x1 conv -> act"""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    N = 2
+    x = (torch.randn(N, 1, *S, C, generator=g) * 1.7 + 0.3).cuda()
+    gamma, beta = (torch.rand(C, generator=g) + 0.5).cuda(), torch.randn(C, generator=g).cuda()
+    w, b = (torch.randn(Cout, C, generator=g) / C ** 0.5).cuda(), torch.randn(Cout, generator=g).cuda()
+    st = ops.gn_stats(x, 32)
+    cnt = x.numel() / N / 32
+    out = ops.gn_head(x, dict(stats=st, count=cnt, gamma=gamma, beta=beta), w, b,
+                      act_out=ops.ACT_SIGMOID if act == "sigmoid" else ops.ACT_NONE)
+    xr = x[:, 0].permute(0, 3, 1, 2).double()
+    ref = F.conv2d(F.relu(F.group_norm(xr, 32, gamma.double(), beta.double(), 1e-5)), w.double()[:, :, None, None], b.double())
+    if act == "sigmoid":
+        ref = torch.sigmoid(ref)
+    assert out.shape == (N, Cout, 1, *S)
+    err = (out[:, :, 0].double() - ref).abs().max().item()
+    assert err < 2e-5, err
