@@ -18,7 +18,6 @@ tensor (double (N,32,2)), produced by the epilogue of whichever kernel wrote it.
 from __future__ import annotations
 
 import math
-from typing import Optional
 
 import torch
 

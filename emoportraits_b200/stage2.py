@@ -17,7 +17,6 @@ from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Optional
 
-import numpy as np
 import torch
 
 from . import nets, ops
