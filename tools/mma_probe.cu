@@ -3,7 +3,8 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_probe tools/mma_probe.cu && tools/mma_probe
 // mode bits: 1 commit per k-step, 2 producer<->issuer mbarrier handshake per k-step (3 stages), 4 one MMA per 16-wide k
 // slice instead of three, 8 the three MMAs of a slice go to different accumulators, 16 a second warp streams global memory
-// into the stage buffers with st.shared while the MMAs run, 32 cta_group::2 pairs (M = 256).
+// into the stage buffers with st.shared while the MMAs run, 64 A operand from TMEM: each 16-wide k slice of both A planes is
+// copied smem -> TMEM once (tcgen05.cp 128x256b) and the three MMAs read A from there (cta_group::1 only; next-round experiment).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +48,14 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
   return pred != 0;
+}
+__device__ __forceinline__ void utccp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+               "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+               : "memory");
 }
 __device__ __forceinline__ uint64_t kdesc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -98,7 +107,7 @@ __global__ void __launch_bounds__(128) probe(int mode, int BN, int ksteps, int S
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   const uint32_t tmem_base = *slot;
-  const int nbuf = 512 / BN > 4 ? 4 : 512 / BN;
+  const int nbuf = (mode & 64) ? (448 / BN > 4 ? 4 : 448 / BN) : (512 / BN > 4 ? 4 : 512 / BN);
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
   const bool hs = mode & 2;
 
@@ -126,6 +135,20 @@ __global__ void __launch_bounds__(128) probe(int mode, int BN, int ksteps, int S
         const uint32_t d0 = tmem_base + (uint32_t)(buf * BN);
         const uint32_t d1 = (mode & 8) ? tmem_base + (uint32_t)(((buf + 1) % nbuf) * BN) : d0;
         const uint32_t d2 = (mode & 8) ? tmem_base + (uint32_t)(((buf + 2) % nbuf) * BN) : d0;
+        if (CG == 1 && (mode & 64)) {
+          // A from TMEM: columns 448.. hold two double-buffered {A_hi, A_lo} k slices of 8 columns each
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            const uint32_t acc0 = ((ks % 4) == 0 && kk == 0) ? 0u : 1u;
+            const uint32_t ta = tmem_base + 448u + (uint32_t)((kk & 1) * 16);
+            utccp_128x256b(ta, dA0 + adv);
+            utccp_128x256b(ta + 8, dA1 + adv);
+            umma_ts(d0, ta + 8, dB0 + adv, idesc, acc0);
+            umma_ts(d0, ta, dB1 + adv, idesc, 1);
+            umma_ts(d0, ta, dB0 + adv, idesc, 1);
+          }
+        } else
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t adv = (uint64_t)(kk * 2);
@@ -218,6 +241,8 @@ int main() {
   const int ks = 20000;
   for (int BN : {128, 256, 64, 160})
     for (int mode : {0, 1, 3, 4, 8}) { run<1, false>(mode, BN, ks, sms, src, dout); run<1, true>(mode, BN, ks, sms, src, dout); }
+  for (int BN : {32, 64, 128, 160})
+    for (int mode : {0, 64, 65, 67}) run<1, true>(mode, BN, ks, sms, src, dout);  // A from shared memory vs A from TMEM
   for (int BN : {128, 256})
     for (int mode : {0, 1}) { run<2, false>(mode, BN, ks, sms, src, dout); run<2, true>(mode, BN, ks, sms, src, dout); }
   return 0;
