@@ -9,6 +9,8 @@
 //  emo_resize_bilinear      F.interpolate(mode='bilinear') of head_pose_regressor.py:24-25.
 //
 // Un-normalisation (align_corners=False): ix = ((x + 1) * W - 1) / 2  (utils.py:24-27 restates it).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace emo {
@@ -77,6 +79,87 @@ __device__ __forceinline__ Corner8 corners(const GS3Params& p, float gx, float g
 // Every corner fetch is a 16-byte load inside a contiguous C*4-byte run.
 // ------------------------------------------------------------------------------------------------
 static constexpr int kBrickVox = 256;
+
+// The two device functions below restate the brick kernel's two phases for the balanced variant further down (the
+// brick kernel keeps its own inline copy: routing it through these functions changed its register allocation, 40 -> 44,
+// i.e. 6 -> 5 resident CTAs per SM).
+// phase 1 for one output voxel: sample position -> eight clamped corner offsets (in float4 units) and trilinear
+// weights (0 for corners outside the volume: zeros padding) -> shared memory slot `vox`
+__device__ __forceinline__ void gs3_setup_voxel(const GS3Params& p, int n, int od, int oh, int ow, int vox,
+                                                int (*s_off)[8], float (*s_wgt)[8], long long* s_out) {
+  const int c4n = p.C >> 2;
+  long long o = -1;
+  if (ow < p.Wout && oh < p.Hout && od < p.Dout) {
+    float gx, gy, gz;
+    sample_coord(p, n, od, oh, ow, gx, gy, gz);
+    const Corner8 k = corners(p, gx, gy, gz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+      const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+      const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
+      const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
+      s_wgt[vox][j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+      s_off[vox][j] = ((zc * p.Hin + yc) * p.Win + xc) * c4n;
+    }
+    o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
+  }
+  s_out[vox] = o;
+}
+
+// phase 2: the CTA's threads sweep (voxel, float4-of-channels) items of `nvox` voxels set up in shared memory
+template <bool SPLIT>
+__device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int nvox, const int (*s_off)[8],
+                                                 const float (*s_wgt)[8], const long long* s_out) {
+  const int c4n = p.C >> 2;
+  const int work = nvox * c4n;
+  const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
+  for (int t = threadIdx.x; t < work; t += blockDim.x) {
+    const int vox = t / c4n, c4 = t - vox * c4n;
+    const long long ob = s_out[vox];
+    if (ob < 0) continue;
+    const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
+    const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
+    const float4* base = in4 + c4;
+    const float4 v0 = __ldg(base + o0.x), v1 = __ldg(base + o0.y), v2 = __ldg(base + o0.z), v3 = __ldg(base + o0.w);
+    const float4 v4 = __ldg(base + o1.x), v5 = __ldg(base + o1.y), v6 = __ldg(base + o1.z), v7 = __ldg(base + o1.w);
+    float4 acc;
+#define EMO_GS_ACC(f) \
+  acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
+          fmaf(v3.f, w0.w, fmaf(v2.f, w0.z, fmaf(v1.f, w0.y, v0.f * w0.x)))))));
+    EMO_GS_ACC(x) EMO_GS_ACC(y) EMO_GS_ACC(z) EMO_GS_ACC(w)
+#undef EMO_GS_ACC
+    const long long o = ob + (long long)(c4 * 4) * p.os_c;
+    if (p.os_c == 1) {
+      if (p.out) __stcs((float4*)(p.out + o), acc);  // streaming store: the output is not re-read by this kernel
+      if (SPLIT) {
+        uint2 hi, lo, lo2;
+        if (p.out_lo2) {
+          split4x3(acc, hi, lo, lo2);
+          *(uint2*)(p.out_lo2 + o) = lo2;
+        } else {
+          split4(acc, hi, lo);
+        }
+        *(uint2*)(p.out_hi + o) = hi;
+        *(uint2*)(p.out_lo + o) = lo;
+      }
+    } else {
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.out) p.out[o + j * p.os_c] = a[j];
+        if (SPLIT) {
+          __nv_bfloat16 h, l, l2;
+          split_bf16x3(a[j], h, l, l2);
+          if (!p.out_lo2) split_bf16(a[j], h, l);
+          p.out_hi[o + j * p.os_c] = h;
+          p.out_lo[o + j * p.os_c] = l;
+          if (p.out_lo2) p.out_lo2[o + j * p.os_c] = l2;
+        }
+      }
+    }
+  }
+}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
@@ -161,6 +244,42 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
         }
       }
     }
+  }
+}
+
+// Balanced variant (EMO_GS3_BALANCED=1; opt-in until measured on the GPU).  The brick kernel above launches one CTA
+// per 256-voxel brick: 1024 CTAs for a 64^3 lattice against 148 SMs x 6 resident CTAs = 888 slots, so 136 bricks run
+// in a second, nearly empty wave whose lone CTA per SM is latency-bound (24 dependent gather rounds).  Here the grid
+// is exactly (SMs x resident CTAs) and every CTA takes an equal contiguous share of the brick-ordered voxel
+// enumeration, processed in chunks of <= 256 voxels; a chunk never straddles two samples.  Same per-voxel and per-item
+// arithmetic as the brick kernel (shared device functions), so the outputs are bit-identical.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const GS3Params p) {
+  __shared__ __align__(16) int s_off[kBrickVox][8];
+  __shared__ __align__(16) float s_wgt[kBrickVox][8];
+  __shared__ long long s_out[kBrickVox];
+  const int brick_vox = p.bw * p.bh * p.bd;
+  const int per_sample = p.bricks_w * p.bricks_h * p.bricks_d * brick_vox;  // padded lattice; N * per_sample < 2^31 (host)
+  const long long total = (long long)per_sample * p.N;
+  const int v_begin = (int)(total * blockIdx.x / gridDim.x), v_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  for (int base = v_begin; base < v_end;) {
+    const int n = base / per_sample;
+    const int stop = min(min(base + kBrickVox, v_end), (n + 1) * per_sample);
+    const int nvox = stop - base;
+    if ((int)threadIdx.x < nvox) {
+      const int v = base + (int)threadIdx.x - n * per_sample;
+      int b = v / brick_vox;
+      const int l = v - b * brick_vox;
+      const int bwi = b % p.bricks_w; b /= p.bricks_w;
+      const int bhi = b % p.bricks_h; b /= p.bricks_h;
+      const int bdi = b;
+      const int lw = l % p.bw, lh = (l / p.bw) % p.bh, ld = l / (p.bw * p.bh);
+      gs3_setup_voxel(p, n, bdi * p.bd + ld, bhi * p.bh + lh, bwi * p.bw + lw, threadIdx.x, s_off, s_wgt, s_out);
+    }
+    __syncthreads();
+    gs3_gather_items<SPLIT>(p, n, nvox, s_off, s_wgt, s_out);
+    __syncthreads();  // the next chunk overwrites the shared-memory slots
+    base = stop;
   }
 }
 
@@ -328,9 +447,33 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     p.bw = d->Wout >= 8 ? 8 : d->Wout;
     p.bh = d->Hout >= 8 ? 8 : d->Hout;
     p.bd = d->Dout >= 4 ? 4 : d->Dout;
+    EMO_REQUIRE((long long)d->Din * d->Hin * d->Win * (d->C / 4) < (1ll << 31), "emo_grid_sample3d: volume too large for 32-bit offsets");
+    const char* bal = getenv("EMO_GS3_BALANCED");  // read per call so that one process can compare both kernels
+    if (bal && atoi(bal) > 0) {
+      p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
+      const long long total = (long long)d->N * p.bricks_w * p.bricks_h * p.bricks_d * (p.bw * p.bh * p.bd);
+      EMO_REQUIRE(total < (1ll << 31) - kBrickVox, "emo_grid_sample3d: lattice too large for the balanced kernel");
+      static int slots[2] = {0, 0};  // SMs x resident CTAs of the two instantiations (same for every device of a box)
+      const int k = d->out_hi ? 1 : 0;
+      if (!slots[k]) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess)
+          e = k ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<true>, 256, 0)
+                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<false>, 256, 0);
+        EMO_REQUIRE(e == cudaSuccess && sms > 0 && occ > 0, "emo_grid_sample3d: occupancy query failed (%s)", cudaGetErrorString(e));
+        slots[k] = sms * occ;
+      }
+      // at least 64 voxels per CTA (atoi(bal) > 1 overrides the CTA count: tuning sweeps)
+      long long ctas = atoi(bal) > 1 ? atoi(bal) : slots[k];
+      if (ctas > cdivll(total, 64)) ctas = cdivll(total, 64);
+      if (d->out_hi) gs3_cl_balanced_kernel<true><<<(unsigned)ctas, 256, 0, stream>>>(p);
+      else gs3_cl_balanced_kernel<false><<<(unsigned)ctas, 256, 0, stream>>>(p);
+      return check_launch("emo_grid_sample3d");
+    }
     // small lattices: shrink the brick until there are >= 4 CTAs per SM (load balance + latency hiding)
     while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4 * 148 && p.bh > 2) p.bh >>= 1;
-    EMO_REQUIRE((long long)d->Din * d->Hin * d->Win * (d->C / 4) < (1ll << 31), "emo_grid_sample3d: volume too large for 32-bit offsets");
     p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
     const long long blocks = (long long)d->N * p.bricks_d * p.bricks_h * p.bricks_w;
     EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");
