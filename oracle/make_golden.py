@@ -3,6 +3,7 @@
 so the fixtures are committed together with this script:
 
     python -m oracle.make_golden            # writes tests/golden/*.pt and the checkpoint-layout manifests
+    python -m oracle.make_golden options    # tests/golden/va256_options.pt: the non-default forward() arguments
 
 What is recorded, for image_size 256 and 512 (shipped config, experiments/args.txt):
   * the checkpoint layout (key -> shape) of va.Model.state_dict() and of the head-pose resnet18;
@@ -151,9 +152,85 @@ def run_stage2(output_size: int = 512, batch: int = 1):
     torch.save(out, GOLD / f"s2_{output_size}_b{batch}.pt")
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# the non-default arguments of InferenceWrapper.forward (notebooks/infer.py:355-357) that change the hot path
+# ------------------------------------------------------------------------------------------------------------------
+OPT_SRC, OPT_DRV = 10, (11, 12, 13)
+
+
+def option_inputs(image_size: int, cfg):
+    """Seeded inputs of the option cases, shared by this generator and the tests (tests/test_forward_options*.py)."""
+    g = torch.Generator().manual_seed(1234)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, image_size), torch.linspace(-1, 1, image_size), indexing="ij")
+    r = (xx * xx + (yy * 1.1) ** 2).sqrt()
+    mask = ((0.85 - r) / 0.2).clamp(0, 1)[None, None].contiguous()          # soft disc, exactly 0 near the corners
+    return {
+        "source_mask": mask,
+        "driver_mask": (1 - mask).contiguous(),                               # must not change the result (use_seg=False)
+        "pose_embed": (torch.randn(1, 128, generator=g) * 0.1),
+        "theta_embed": (torch.tensor([[1.05, 0.95, 1.0]]), torch.tensor([[0.25, -0.12, 0.08]]),
+                        torch.tensor([[0.04, 0.02, -0.03]])),
+        "c_source_latent_volume": torch.randn(1, cfg.C, cfg.D, cfg.S, cfg.S, generator=g) * 0.5,
+        "c_target_latent_volume": torch.randn(1, cfg.C, cfg.D, cfg.S, cfg.S, generator=g) * 0.5,
+    }
+
+
+def run_options(image_size: int = 256):
+    """Runs the UNMODIFIED reference wrapper with each non-default forward() argument that reaches the hot path and
+    records the image (strided) and the pose it used: mix_old=True, smooth_pose=True over three frames,
+    custome_target_pose_embed, custome_target_theta_embed, source_mask (+ a driver_mask that must be ignored),
+    target_theta=False, c_source_latent_volume, c_target_latent_volume, mix=False."""
+    import oracle.ref_harness as H
+    from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
+    from emoportraits_b200.config import shipped_config
+    from oracle import frames as FR
+
+    w, msd, hsd, lines = H.build_reference_wrapper(image_size, 0)
+    cfg = shipped_config(image_size)
+    sd = synthetic_state_dict(cfg, seed=0)
+    sd["expression_embedder_nw.aligned_keypoints"] = msd["expression_embedder_nw.aligned_keypoints"]
+    w.model.load_state_dict(sd, strict=True)
+    w.model.head_pose_regressor.net.load_state_dict(synthetic_head_pose_state_dict(seed=0), strict=True)
+    w.model.eval()
+    w.model.head_pose_regressor.net.eval()
+    kind = "smooth"
+    src = FR.pil(image_size, OPT_SRC, kind)
+    drv = [FR.pil(image_size, s, kind) for s in OPT_DRV]
+    X = option_inputs(image_size, cfg)
+    base = dict(crop=False, mix=True, mix_old=False)
+    out = {"image_size": image_size, "kind": kind, "src_seed": OPT_SRC, "drv_seeds": list(OPT_DRV), "cases": {}}
+
+    def rec(name, res, **extra):
+        d = {"img": sub(res[1], 50000), "pred_target_theta": w.pred_target_theta.clone(),
+             "target_pose_embed": w.target_pose_embed.clone()}
+        d.update(extra)
+        out["cases"][name] = d
+        print(f"[golden options {image_size}] {name}: img mean {res[1].mean().item():.4f}")
+
+    with torch.no_grad():
+        rec("default", w.forward(src, drv[0], **base))
+        rec("mix_old", w.forward(src, drv[0], crop=False, mix=True, mix_old=True))
+        rec("no_mix", w.forward(src, drv[0], crop=False, mix=False))
+        rec("target_theta_false", w.forward(src, drv[0], target_theta=False, **base))
+        # smooth_pose: self.theta starts at the first frame's pose and is smoothed over the next calls (pose_momentum 0.5)
+        w.forward(src, None, **base)
+        for i, d in enumerate(drv):
+            rec(f"smooth_pose_{i}", w.forward(None, d, smooth_pose=True, reset_tracking=(i == 0), **base))
+        rec("custome_target_pose_embed", w.forward(src, drv[0], custome_target_pose_embed=X["pose_embed"].clone(), **base))
+        rec("custome_target_theta_embed", w.forward(src, drv[0], custome_target_theta_embed=tuple(t.clone() for t in X["theta_embed"]), **base))
+        rec("source_mask", w.forward(src, drv[0], source_mask=X["source_mask"].clone(), driver_mask=X["driver_mask"].clone(), **base),
+            idt_embed=w.idt_embed.clone(), pred_source_theta=w.pred_source_theta.clone())
+        rec("c_source_latent_volume", w.forward(src, drv[0], c_source_latent_volume=X["c_source_latent_volume"].clone(), **base))
+        rec("c_target_latent_volume", w.forward(src, drv[0], c_target_latent_volume=X["c_target_latent_volume"].clone(), **base))
+    torch.save(out, GOLD / f"va{image_size}_options.pt")
+    return out
+
+
 if __name__ == "__main__":
     GOLD.mkdir(parents=True, exist_ok=True)
-    if sys.argv[1:2] == ["s2"]:
+    if sys.argv[1:2] == ["options"]:
+        run_options(int(sys.argv[2]) if len(sys.argv) > 2 else 256)
+    elif sys.argv[1:2] == ["s2"]:
         run_stage2(int(sys.argv[2]) if len(sys.argv) > 2 else 512, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
     else:
         sizes = [int(a) for a in sys.argv[1:]] or [256, 512]

@@ -107,8 +107,9 @@ def get_transform_matrix(scale, rotation, translation):
     return S_ @ R @ T
 
 
-def get_mixing_theta(source_theta, target_theta):
-    """notebooks/infer.py:686-736 with mix_old=False, B = T = 1 per call.  Returns (T,3,4) float32."""
+def get_mixing_theta(source_theta, target_theta, mix_old=False):
+    """notebooks/infer.py:686-736, B = T = 1 per call.  mix_old=False: stretch_s * mean(stretch_t)/mean(stretch_s) @
+    rotation_t @ translation_t (:729); mix_old=True: translation_t @ rotation_t @ stretch_s (:727).  Returns (T,3,4) fp32."""
     from scipy import linalg
 
     source_theta = source_theta[:, :3, :]
@@ -129,8 +130,23 @@ def get_mixing_theta(source_theta, target_theta):
         s_rot, s_str = linalg.polar(sl[b])
         for t in range(Tn):
             t_rot, t_str = linalg.polar(tl[b * Tn + t])
-            out.append(s_str * t_str.mean() / s_str.mean() @ t_rot @ tt[b * Tn + t])
+            if mix_old:
+                out.append(tt[b * Tn + t] @ t_rot @ s_str)
+            else:
+                out.append(s_str * t_str.mean() / s_str.mean() @ t_rot @ tt[b * Tn + t])
     return torch.from_numpy(np.stack(out))[:, :3].float()
+
+
+def smooth_theta(state, theta34, momentum):
+    """notebooks/infer.py:571-581 (smooth_pose=True): exponential smoothing of the driver pose over successive frames.
+    state: dict holding 'theta' ((3,4) or None, the wrapper's self.theta); theta34 (b,3,4).  fp32, torch op order."""
+    if state.get("theta") is None:
+        state["theta"] = theta34[0].clone()
+    out = []
+    for i in range(theta34.shape[0]):
+        state["theta"] = theta34[i] * momentum + state["theta"] * (1 - momentum)
+        out.append(state["theta"].clone())
+    return torch.stack(out)
 
 
 def align_theta_2d(theta34):
@@ -445,13 +461,18 @@ def decoder(sd, feat2d, taps=None):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# the two passes of InferenceWrapper.forward (crop=False, masks of ones, mix=True, mix_old=False, target_theta=True)
+# the two passes of InferenceWrapper.forward (crop=False; the external mask networks are ones, as in oracle/ref_harness.py)
 # ------------------------------------------------------------------------------------------------------------------
-def source_pass(sd, hsd, src_img, cfg: OracleConfig, taps=None):
-    """notebooks/infer.py:374-507.  src_img (1,3,H,W) in [0,1] already at image_size."""
+def source_pass(sd, hsd, src_img, cfg: OracleConfig, taps=None, src_mask=None, c_source_latent_volume=None,
+                c_target_latent_volume=None):
+    """notebooks/infer.py:374-507.  src_img (1,3,H,W) in [0,1] already at image_size.  src_mask (1,1,H,W) or None (ones):
+    the identity embedder and the local encoder see src_img * mask (:425-426); the head-pose regressor (:430) and the
+    expression embedder (use_seg=False, expression_embedder.py:134-137) see the image itself.  c_*_latent_volume replace
+    the volumes exactly where the reference substitutes them (:491, :500)."""
     st = {}
-    st["idt_embed"] = idt_embed(sd, src_img, cfg)
-    latents = local_encoder(sd, src_img)
+    masked = src_img if src_mask is None else src_img * src_mask
+    st["idt_embed"] = idt_embed(sd, masked, cfg)
+    latents = local_encoder(sd, masked)
     srt = head_pose(hsd, src_img)
     theta_s = get_transform_matrix(srt[:, :3], srt[:, 3:6], srt[:, 6:9])
     st["source_theta"] = theta_s
@@ -462,7 +483,11 @@ def source_pass(sd, hsd, src_img, cfg: OracleConfig, taps=None):
     xy_warp, _ = warp_generator(sd, "xy_generator_nw", embed, cfg)
     vol = latents.view(1, cfg.C, cfg.D, cfg.S, cfg.S)
     vol = volume_source(sd, vol)
+    if c_source_latent_volume is not None:
+        vol = c_source_latent_volume
     warped = grid_sample(grid_sample(vol, rot_warp), xy_warp)
+    if c_target_latent_volume is not None:
+        warped = c_target_latent_volume
     st["target_latent_volume"] = unet3d(sd, warped, cfg)
     if taps is not None:
         taps.update(latents=latents, source_pose_embed=pose_embed, source_embed=embed, xy_warp=xy_warp, vol_source=vol,
@@ -470,16 +495,27 @@ def source_pass(sd, hsd, src_img, cfg: OracleConfig, taps=None):
     return st
 
 
-def driver_pass(sd, hsd, st, drv_img, cfg: OracleConfig, taps=None, mix=True):
-    """notebooks/infer.py:511-644.  drv_img (b,3,H,W).  Returns img (b,3,H,W) fp32 (before the clamp/PIL step)."""
+def driver_pass(sd, hsd, st, drv_img, cfg: OracleConfig, taps=None, mix=True, mix_old=False, target_theta=True,
+                smooth=None, pose_momentum=0.5, custome_target_pose_embed=None, custome_target_theta_embed=None):
+    """notebooks/infer.py:511-644.  drv_img (b,3,H,W).  Returns img (b,3,H,W) fp32 (before the clamp/PIL step).
+    smooth: None, or the dict that carries the wrapper's self.theta between calls (smooth_pose=True, :571-581);
+    custome_target_theta_embed = (scale, rotation, translation) replaces the regressed pose (:566-567);
+    custome_target_pose_embed replaces the expression embedding (:602-603); target_theta=False rotates the volume by the
+    SOURCE pose (:587-588)."""
     srt = head_pose(hsd, drv_img)
     theta_d = get_transform_matrix(srt[:, :3], srt[:, 3:6], srt[:, 6:9])
+    if custome_target_theta_embed is not None:
+        theta_d = get_transform_matrix(*custome_target_theta_embed)
     if mix:
-        th34 = get_mixing_theta(st["source_theta"], theta_d)
+        th34 = get_mixing_theta(st["source_theta"], theta_d, mix_old)
     else:
         th34 = theta_d[:, :3]
-    rot_warp = rotation_warp(th34, cfg.D, cfg.S)
+    if smooth is not None:
+        th34 = smooth_theta(smooth, th34, pose_momentum)
+    rot_warp = rotation_warp(th34 if target_theta else st["source_theta"][:, :3], cfg.D, cfg.S)
     pose_embed, aligned = expression_embed(sd, drv_img, th34, cfg)
+    if custome_target_pose_embed is not None:
+        pose_embed = custome_target_pose_embed
     embed = predict_embed(sd, pose_embed, st["idt_embed"], cfg)
     uv_warp, deltas = warp_generator(sd, "uv_generator_nw", embed, cfg, taps)
     vol = grid_sample(grid_sample(st["target_latent_volume"], uv_warp), rot_warp)
