@@ -16,7 +16,7 @@ import sys
 HERE = pathlib.Path(__file__).resolve().parent
 LIB = HERE / "libemoport.so"
 SOURCES = ["conv_igemm.cu", "grid_sample.cu", "norm.cu", "misc.cu"]
-HEADERS = ["common.cuh", "../../include/emoportraits_b200.h"]
+HEADERS = ["common.cuh", "pose_math.cuh", "../../include/emoportraits_b200.h"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -46,11 +46,14 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     cmd += os.environ.get("EMO_NVCC_EXTRA", "").split()  # e.g. -DEMO_CONV_DEBUG for tools/conv_bound_probe.py
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB)] + [str(HERE / s) for s in SOURCES]
+    tmp = LIB.with_name(LIB.name + ".tmp")  # link into a temporary name, then rename: a reader (or a gpurun snapshot)
+    cmd += ["-o", str(tmp)] + [str(HERE / s) for s in SOURCES]  # never sees a half-written library
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
+        tmp.unlink(missing_ok=True)
         raise RuntimeError("nvcc failed building libemoport.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
     stamp.write_text(dig)

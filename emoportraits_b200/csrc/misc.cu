@@ -1,5 +1,6 @@
 // Small dense ops (fp32 SIMT, exact): linear layers, the RGB stem convolutions, resampling, pose algebra.
 #include "common.cuh"
+#include "pose_math.cuh"
 
 #include <stdarg.h>
 
@@ -271,152 +272,17 @@ __global__ void global_avgpool_kernel(const float* __restrict__ x, int N, long l
 }
 
 // ------------------------------------------------------------------------------------------------
-// pose algebra (single thread per sample; a few hundred flops)
+// pose algebra: pose_math.cuh (host+device source, also compiled for the CPU by tests/test_pose_math_host.py)
 // ------------------------------------------------------------------------------------------------
-__device__ void mat4_mul(const float* a, const float* b, float* c) {
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      float s = 0.f;
-      for (int k = 0; k < 4; ++k) s += a[i * 4 + k] * b[k * 4 + j];
-      c[i * 4 + j] = s;
-    }
-}
-
-// general 4x4 inverse by Gauss-Jordan with partial pivoting, fp32 in/out, fp64 inside
-// (torch.inverse is LU in fp32; the fp64 inside only makes us closer to the exact inverse)
-__device__ void mat4_inv(const float* a, float* out) {
-  double m[4][8];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) { m[i][j] = a[i * 4 + j]; m[i][4 + j] = (i == j) ? 1.0 : 0.0; }
-  for (int c = 0; c < 4; ++c) {
-    int piv = c;
-    double best = fabs(m[c][c]);
-    for (int r = c + 1; r < 4; ++r)
-      if (fabs(m[r][c]) > best) { best = fabs(m[r][c]); piv = r; }
-    if (piv != c)
-      for (int j = 0; j < 8; ++j) { double t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
-    const double inv = 1.0 / m[c][c];
-    for (int j = 0; j < 8; ++j) m[c][j] *= inv;
-    for (int r = 0; r < 4; ++r)
-      if (r != c) {
-        const double f = m[r][c];
-        for (int j = 0; j < 8; ++j) m[r][j] -= f * m[c][j];
-      }
-  }
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) out[i * 4 + j] = (float)m[i][4 + j];
-}
-
-// polar decomposition A = U P of a 3x3 matrix in fp64 (Newton iteration on the orthogonal factor,
-// quadratically convergent; scipy.linalg.polar gets the same U, P via SVD)
-__device__ void polar3(const double* A, double* U, double* P) {
-  double X[9];
-  for (int i = 0; i < 9; ++i) X[i] = A[i];
-  for (int it = 0; it < 60; ++it) {
-    // inverse transpose of X via cofactors
-    double c[9];
-    c[0] = X[4] * X[8] - X[5] * X[7]; c[1] = X[5] * X[6] - X[3] * X[8]; c[2] = X[3] * X[7] - X[4] * X[6];
-    c[3] = X[2] * X[7] - X[1] * X[8]; c[4] = X[0] * X[8] - X[2] * X[6]; c[5] = X[1] * X[6] - X[0] * X[7];
-    c[6] = X[1] * X[5] - X[2] * X[4]; c[7] = X[2] * X[3] - X[0] * X[5]; c[8] = X[0] * X[4] - X[1] * X[3];
-    const double det = X[0] * c[0] + X[1] * c[1] + X[2] * c[2];
-    double diff = 0.0;
-    for (int i = 0; i < 9; ++i) {
-      const double nx = 0.5 * (X[i] + c[i] / det);  // c/det = X^{-T}
-      diff += fabs(nx - X[i]);
-      X[i] = nx;
-    }
-    if (diff < 1e-15) break;
-  }
-  for (int i = 0; i < 9; ++i) U[i] = X[i];
-  // P = U^T A
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      double s = 0.0;
-      for (int k = 0; k < 3; ++k) s += U[k * 3 + i] * A[k * 3 + j];
-      P[i * 3 + j] = s;
-    }
-  // symmetrise (exact P is symmetric)
-  for (int i = 0; i < 3; ++i)
-    for (int j = i + 1; j < 3; ++j) { const double s = 0.5 * (P[i * 3 + j] + P[j * 3 + i]); P[i * 3 + j] = s; P[j * 3 + i] = s; }
-}
-
 __global__ void pose_theta_kernel(const emo_pose_desc d) {
+  if (d.smooth_state) {
+    // exponential smoothing carries state from sample to sample: one thread walks the samples in order
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (int n = 0; n < d.N; ++n) pose::pose_sample(d, n);
+    return;
+  }
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= d.N) return;
-  const float* q = d.srt + n * 9;
-  // utils/point_transforms.py:187-240
-  float S[16] = {q[0], 0, 0, 0, 0, q[1], 0, 0, 0, 0, q[2], 0, 0, 0, 0, 1};
-  const float pi = 3.14159265358979323846f;
-  const float yaw = fminf(fmaxf(q[3], -pi / 2), pi), pitch = fminf(fmaxf(q[4], -pi / 2), pi), roll = fminf(fmaxf(q[5], -pi / 2), pi);
-  // sin/cos evaluated in double and rounded: agrees with the host libm float results the reference gets (cosf/sinf of
-  // the CUDA math library may differ from them by 1 ulp, which the 4x4 inverse downstream amplifies)
-  const float cy = (float)cos((double)yaw), sy = (float)sin((double)yaw), cp = (float)cos((double)pitch),
-              sp = (float)sin((double)pitch), cr = (float)cos((double)roll), sr = (float)sin((double)roll);
-  float R[16] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr, 0,
-                 sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr, 0,
-                 -sp,     cp * sr,                cp * cr,                0,
-                 0, 0, 0, 1};
-  float T[16] = {1, 0, 0, q[6], 0, 1, 0, q[7], 0, 0, 1, q[8], 0, 0, 0, 1};
-  float SR[16], th[16];
-  mat4_mul(S, R, SR);
-  mat4_mul(SR, T, th);
-
-  if (d.mix) {
-    // notebooks/infer.py:686-736 with mix_old=False, B=T=1:
-    //   source_rotation, source_stretch = polar(source_linear); target_rotation, target_stretch = polar(target_linear)
-    //   theta = (source_stretch * target_stretch.mean() / source_stretch.mean()) @ target_rotation @ target_translation
-    // all on 4x4 float64 matrices whose last row/col is that of the identity.
-    double As[9], At[9];
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) { As[i * 3 + j] = d.source_theta[i * 4 + j]; At[i * 3 + j] = th[i * 4 + j]; }
-    double Us[9], Ps[9], Ut[9], Pt[9];
-    polar3(As, Us, Ps);
-    polar3(At, Ut, Pt);
-    // .mean() over the 4x4 matrices (15 zeros + the trailing 1 included)
-    double ms = 1.0, mt = 1.0;
-    for (int i = 0; i < 9; ++i) { ms += Ps[i]; mt += Pt[i]; }
-    ms /= 16.0; mt /= 16.0;
-    const double k = mt / ms;
-    double M1[16] = {0}, M2[16] = {0}, M3[16] = {0}, Tm[16] = {0}, Rt[16] = {0};
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) { M1[i * 4 + j] = Ps[i * 3 + j] * k; Rt[i * 4 + j] = Ut[i * 3 + j]; }
-    M1[15] = 1.0 * k; Rt[15] = 1.0;
-    for (int i = 0; i < 4; ++i) Tm[i * 4 + i] = 1.0;
-    Tm[3] = th[3]; Tm[7] = th[7]; Tm[11] = th[11];
-    for (int i = 0; i < 4; ++i)
-      for (int j = 0; j < 4; ++j) {
-        double s = 0.0;
-        for (int kk = 0; kk < 4; ++kk) s += M1[i * 4 + kk] * Rt[kk * 4 + j];
-        M2[i * 4 + j] = s;
-      }
-    for (int i = 0; i < 4; ++i)
-      for (int j = 0; j < 4; ++j) {
-        double s = 0.0;
-        for (int kk = 0; kk < 4; ++kk) s += M2[i * 4 + kk] * Tm[kk * 4 + j];
-        M3[i * 4 + j] = s;
-      }
-    // the reference keeps rows [:3] only; the 4th row used downstream is [0,0,0,1] (expression_embedder.py:163-168)
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 4; ++j) th[i * 4 + j] = (float)M3[i * 4 + j];
-    th[12] = 0.f; th[13] = 0.f; th[14] = 0.f; th[15] = 1.f;
-  }
-  if (d.theta_out)
-    for (int i = 0; i < 16; ++i) d.theta_out[n * 16 + i] = th[i];
-  float inv[16];
-  if (d.invert_warp || d.align2d) mat4_inv(th, inv);
-  if (d.theta_warp) {
-    const float* src = d.invert_warp ? inv : th;
-    for (int i = 0; i < 12; ++i) d.theta_warp[n * 12 + i] = src[i];
-  }
-  if (d.align2d) {
-    // inverse()[:, :, [0,1,3]][:, [0,1,3]] then @ diag(0.5, 0.5, 1), rows [:2]
-    const int idx[3] = {0, 1, 3};
-    for (int i = 0; i < 2; ++i)
-      for (int j = 0; j < 3; ++j) {
-        const float v = inv[idx[i] * 4 + idx[j]];
-        d.align2d[n * 6 + i * 3 + j] = (j < 2) ? v * 0.5f : v;
-      }
-  }
+  if (n < d.N) pose::pose_sample(d, n);
 }
 
 }  // namespace emo
@@ -512,8 +378,11 @@ extern "C" int emo_global_avgpool(const float* x, int N, long long S, int C, flo
 
 extern "C" int emo_pose_theta(const emo_pose_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  EMO_REQUIRE(d && d->srt, "emo_pose_theta: null pointer");
+  EMO_REQUIRE(d && (d->srt || d->theta_in), "emo_pose_theta: srt or theta_in is required");
+  EMO_REQUIRE(d->N > 0, "emo_pose_theta: N must be positive (N=%d)", d->N);
   EMO_REQUIRE(!d->mix || d->source_theta, "emo_pose_theta: mix needs source_theta");
+  EMO_REQUIRE(!d->smooth_state || (d->smooth_momentum >= 0.f && d->smooth_momentum <= 1.f),
+              "emo_pose_theta: smooth_momentum must be in [0,1]");
   pose_theta_kernel<<<cdiv(d->N, 32), 32, 0, stream>>>(*d);
   return check_launch("emo_pose_theta");
 }

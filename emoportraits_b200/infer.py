@@ -56,16 +56,23 @@ class Model:
 
     # ---- notebooks/infer.py:374-507 ----
     @torch.no_grad()
-    def source_pass(self, src: torch.Tensor, taps: Optional[dict] = None, pose_override=None):
-        """src (1,3,H,W) fp32 in [0,1] on device, already masked.  Returns the cached source state.
+    def source_pass(self, src: torch.Tensor, taps: Optional[dict] = None, pose_override=None,
+                    mask: Optional[torch.Tensor] = None, c_source_latent_volume: Optional[torch.Tensor] = None,
+                    c_target_latent_volume: Optional[torch.Tensor] = None):
+        """src (1,3,H,W) fp32 in [0,1] on device.  Returns the cached source state.
+        mask (1,1,H,W) or None (= ones): the identity embedder and the local encoder see src * mask (infer.py:425-426);
+        the head-pose regressor (:430) and the expression embedder (called with use_seg=False, :455) see src itself.
+        c_source_latent_volume / c_target_latent_volume (1,C,D,S,S) replace the volumes where the reference substitutes
+        them (:491, :500).
         pose_override = (theta (1,4,4), warp (1,3,4), align2d (1,2,3)) replaces the on-device pose algebra (tests only:
         lets a parity test inject the reference's own fp32 matrices, see tests/test_model_gpu.py)."""
         cfg = self.cfg
         src = src.contiguous().float()
+        masked = src if mask is None else (src * mask.to(self.device).float()).contiguous()
         ops.begin_pass(self.device)
         st = SimpleNamespace()
-        st.idt_embed = self.idt_embedder_nw(src)                       # (1,512,4,4) NCHW
-        vol = self.local_encoder_nw(src)                               # (1,D,S,S,C)
+        st.idt_embed = self.idt_embedder_nw(masked)                    # (1,512,4,4) NCHW
+        vol = self.local_encoder_nw(masked)                            # (1,D,S,S,C)
         srt = self.head_pose_regressor(src)
         st.pred_source_theta, inv_warp, align = ops.pose_theta(srt, invert_warp=True)
         if pose_override is not None:
@@ -77,32 +84,57 @@ class Model:
         xy_warp = self.xy_generator_nw(E)                              # (1,D,S,S,3)
         if self.volume_source_nw is not None:
             vol = self.volume_source_nw(vol)
+        if c_source_latent_volume is not None:
+            vol = self._volume_cl(c_source_latent_volume)
         st.source_latent_volume = vol
         st.source_rotation_warp_theta = inv_warp
         st.source_xy_warp_resize = xy_warp
         v = ops.grid_sample3d(vol, theta=inv_warp, out_size=(cfg.D, cfg.S, cfg.S), in_layout="cl")
         v = ops.grid_sample3d(v, grid=xy_warp, in_layout="cl")
+        if c_target_latent_volume is not None:
+            v = self._volume_cl(c_target_latent_volume)
         st.target_latent_volume_1 = v
         st.target_latent_volume = self.volume_process_nw(v)           # (1,D,S,S,C) channels-last
         if taps is not None:
             taps.update(srt_source=srt, source_pose_embed=pose_embed, source_embed=E, xy_warp=xy_warp)
         return st
 
+    def _volume_cl(self, vol: torch.Tensor) -> torch.Tensor:
+        """caller-supplied latent volume in the reference's (1,C,D,S,S) layout -> channels-last (1,D,S,S,C) on device"""
+        cfg = self.cfg
+        if tuple(vol.shape) != (1, cfg.C, cfg.D, cfg.S, cfg.S):
+            raise ValueError(f"latent volume must be (1,{cfg.C},{cfg.D},{cfg.S},{cfg.S}), got {tuple(vol.shape)}")
+        return vol.to(self.device).float().permute(0, 2, 3, 4, 1).contiguous()
+
     # ---- notebooks/infer.py:511-644 ----
     @torch.no_grad()
     def driver_pass(self, st, drv: torch.Tensor, mix: bool = True, target_theta: bool = True, taps: Optional[dict] = None,
-                    want_logits: bool = False, pose_override=None):
-        """drv (1,3,H,W) fp32 on device -> (img (1,3,H,W), feat_2d, img_feat)."""
+                    want_logits: bool = False, pose_override=None, mix_old: bool = False,
+                    custom_srt: Optional[torch.Tensor] = None, custom_pose_embed: Optional[torch.Tensor] = None,
+                    smooth_state: Optional[torch.Tensor] = None, smooth_momentum: float = 0.5, smooth_init: bool = False):
+        """drv (1,3,H,W) fp32 on device -> (img (1,3,H,W), feat_2d, img_feat, state).
+        mix / mix_old: get_mixing_theta (infer.py:569-570, 686-736).  custom_srt (1,9) = the caller's
+        custome_target_theta_embed (scale, rotation, translation) replacing the regressed pose (:566-567).
+        custom_pose_embed (1,128) replaces the expression embedding (:602-603).  smooth_state (3,4) on device: the
+        wrapper's self.theta, smoothed in place with smooth_momentum (smooth_pose=True, :571-581)."""
         cfg = self.cfg
         drv = drv.contiguous().float()
         ops.begin_pass(self.device)
         srt = self.head_pose_regressor(drv)
-        theta, warp, align = ops.pose_theta(srt, source_theta=st.source_theta_dev if mix else None, mix=mix)
+        srt_used = srt if custom_srt is None else custom_srt.to(self.device).float().reshape(1, 9).contiguous()
+        theta, warp, align = ops.pose_theta(srt_used, source_theta=st.source_theta_dev if mix else None, mix=mix,
+                                            mix_old=mix_old, smooth_state=smooth_state, smooth_momentum=smooth_momentum,
+                                            smooth_init=smooth_init)
         if pose_override is not None:
             theta, warp, align = [t.to(self.device).float().contiguous() for t in pose_override]
         if not target_theta:
             warp = st.pred_source_theta[:, :3].contiguous()
-        pose_embed, aligned = self.expression_embedder_nw(drv, align, want_aligned=taps is not None)
+        if custom_pose_embed is not None and taps is None:
+            pose_embed, aligned = None, None      # the expression encoder's output would be discarded (infer.py:602-603)
+        else:
+            pose_embed, aligned = self.expression_embedder_nw(drv, align, want_aligned=taps is not None)
+        if custom_pose_embed is not None:
+            pose_embed = custom_pose_embed.to(self.device).float().reshape(1, -1).contiguous()
         E = self.predict_embed(pose_embed, st.idt_embed)
         uv_warp = self.uv_generator_nw(E)
         v = ops.grid_sample3d(st.target_latent_volume, grid=uv_warp, in_layout="cl")
@@ -118,30 +150,30 @@ class Model:
         return img, deep_f, img_f, st_out
 
 
-    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True, slot: int = 0):
+    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True, slot: int = 0, mix_old: bool = False):
         """Capture one driver frame (all ~240 kernel launches) into a CUDA graph: removes the Python/ctypes launch
         overhead from the per-frame loop.  Returns replay(drv (1,3,H,W) on device) -> img (1,3,H,W) (static buffer).
         `slot` selects the scratch set (ops.set_slot) the captured frame uses; graphs that may replay concurrently on
         different streams need different slots."""
         prev = ops.set_slot(slot)
         try:
-            return self._make_driver_graph(st, mix, target_theta)
+            return self._make_driver_graph(st, mix, target_theta, mix_old)
         finally:
             ops.set_slot(prev)
 
-    def _make_driver_graph(self, st, mix, target_theta):
+    def _make_driver_graph(self, st, mix, target_theta, mix_old=False):
         s = self.cfg.image_size
         static_in = torch.zeros((1, 3, s, s), dtype=torch.float32, device=self.device)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.driver_pass(st, static_in, mix=mix, target_theta=target_theta)
+                self.driver_pass(st, static_in, mix=mix, target_theta=target_theta, mix_old=mix_old)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.driver_pass(st, static_in, mix=mix, target_theta=target_theta)
+            out = self.driver_pass(st, static_in, mix=mix, target_theta=target_theta, mix_old=mix_old)
             static_out = out[0]
 
         def replay(drv: torch.Tensor) -> torch.Tensor:
@@ -162,11 +194,11 @@ class DriverPipeline:
     Frame i's result is produced in order on stream i % depth; nothing is batched and every frame runs the same
     kernels as the single-stream path."""
 
-    def __init__(self, model: "Model", st, depth: int = 2, mix: bool = True, target_theta: bool = True):
+    def __init__(self, model: "Model", st, depth: int = 2, mix: bool = True, target_theta: bool = True, mix_old: bool = False):
         self.model, self.depth, self.n = model, depth, 0
         self.slots = []
         for k in range(depth):
-            run = model.make_driver_graph(st, mix=mix, target_theta=target_theta, slot=k)
+            run = model.make_driver_graph(st, mix=mix, target_theta=target_theta, slot=k, mix_old=mix_old)
             self.slots.append(SimpleNamespace(run=run, stream=torch.cuda.Stream(device=model.device),
                                               done=torch.cuda.Event(), busy=False))
 
@@ -285,27 +317,32 @@ class InferenceWrapper(torch.nn.Module):
                                       "with pre-cropped images, as notebooks/E_emo_infer_video.ipynb does")
         if modnet_mask:
             raise NotImplementedError("modnet_mask=True needs the external MODNet (out of scope)")
-        if mix and mix_old:
-            raise NotImplementedError("mix_old=True pose mixing is not implemented (the notebook uses mix_old=False)")
-        if smooth_pose or custome_target_pose_embed is not None or custome_target_theta_embed is not None or \
-                c_source_latent_volume is not None or c_target_latent_volume is not None:
-            raise NotImplementedError("smooth_pose / custom embeddings / custom volumes are not implemented")
+        # hard_normalize, soft_normalize, cloth, thetas_pass, theta_n are accepted and unused, exactly as in the reference
+        # (infer.py:355-357 declares them; nothing in :358-647 reads them).  driver_mask only travels in the reference's
+        # data_dict: the expression embedder is called with use_seg=False (:597) and never multiplies by it.
+        self.no_grad_infer = no_grad_infer
         self.target_theta, self.mix, self.mix_old = target_theta, mix, mix_old
         if reset_tracking:
             self.center = self.size = self.theta = self.delta_yaw = self.delta_pitch = None
+        if delta_yaw is not None:
+            self.delta_yaw = delta_yaw
+        if delta_pitch is not None:
+            self.delta_pitch = delta_pitch
 
         if source_image is not None:
             src = self._prep(source_image)
-            self.source_image = src
-            if source_mask is None:
-                source_mask = torch.ones_like(src[:, :1])
-            source_mask = source_mask.to(self.device).float()
-            if source_mask_add:
-                source_mask = source_mask.clamp_(max=1, min=0)
-            self.source_img_mask = source_mask
-            masked = (src * source_mask).contiguous()
-            self.source_img = src
-            st = self.model.source_pass(masked)
+            if src.shape[0] != 1:
+                raise ValueError("one source image per call (the reference reshapes the latents with view(1, c, d, s, s), infer.py:483)")
+            self.source_image = self.source_image_crop = src
+            mask = None
+            if source_mask is not None:
+                mask = source_mask.to(self.device).float()
+                if source_mask_add:
+                    mask = mask.clamp_(max=1, min=0)
+            self.source_img_mask = mask if mask is not None else torch.ones_like(src[:, :1])
+            self.source_img = self.source_img_crop_m = src
+            st = self.model.source_pass(src, mask=mask, c_source_latent_volume=c_source_latent_volume,
+                                        c_target_latent_volume=c_target_latent_volume)
             self._state = st
             # cached attributes of the reference wrapper (infer.py:405-507)
             self.idt_embed = st.idt_embed
@@ -321,12 +358,16 @@ class InferenceWrapper(torch.nn.Module):
         if self._state is None:
             raise RuntimeError("forward(driver_image=...) called before a source image was given")
         drv = self._prep(driver_image)
-        if drv.shape[0] >= 2:
+        custom_srt = None
+        if custome_target_theta_embed is not None:   # (scale, rotation, translation), each (1,3): infer.py:566-567
+            custom_srt = torch.cat([torch.as_tensor(t).float().reshape(1, 3) for t in custome_target_theta_embed], 1)
+        per_frame = smooth_pose or custom_srt is not None or custome_target_pose_embed is not None
+        if drv.shape[0] >= 2 and not per_frame:
             # a list of driver frames: captured frames, two in flight (DriverPipeline); same kernels as the eager pass below
-            key = (id(self._state), bool(mix), bool(target_theta))
+            key = (id(self._state), bool(mix), bool(target_theta), bool(mix_old))
             if self._pipeline is None or self._pipeline_key != key:
                 self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=2, mix=mix,
-                                                                    target_theta=target_theta), key
+                                                                    target_theta=target_theta, mix_old=mix_old), key
             img = torch.empty_like(drv)
             for i in range(drv.shape[0]):
                 sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1]).slot
@@ -334,8 +375,23 @@ class InferenceWrapper(torch.nn.Module):
             self.pred_target_theta = sl.run.static_state.pred_target_theta.clone()
             self.target_pose_embed = sl.run.static_state.target_pose_embed.clone()
         else:
-            img, deep_f, img_f, so = self.model.driver_pass(self._state, drv[0:1].contiguous(), mix=mix, target_theta=target_theta)
+            imgs = []
+            for i in range(drv.shape[0]):
+                kw = {}
+                if smooth_pose:
+                    # self.theta is the smoothed (3,4) pose carried from frame to frame (infer.py:571-581); the device
+                    # kernel seeds it with the first frame's pose and updates it in place
+                    init = self.theta is None
+                    if init:
+                        self.theta = torch.zeros((3, 4), dtype=torch.float32, device=self.device)
+                    kw = dict(smooth_state=self.theta, smooth_momentum=self.pose_momentum, smooth_init=init)
+                im, deep_f, img_f, so = self.model.driver_pass(self._state, drv[i:i + 1].contiguous(), mix=mix,
+                                                               target_theta=target_theta, mix_old=mix_old, custom_srt=custom_srt,
+                                                               custom_pose_embed=custome_target_pose_embed, **kw)
+                imgs.append(im)
+            img = imgs[0] if len(imgs) == 1 else torch.cat(imgs)
             self.pred_target_theta = so.pred_target_theta
+            self.pred_target_srt = (so.srt[:, :3], so.srt[:, 3:6], so.srt[:, 6:9])
             self.target_pose_embed = so.target_pose_embed
         from PIL import Image
 

@@ -439,16 +439,28 @@ def global_avgpool(x: torch.Tensor):
     return out
 
 
-def pose_theta(srt: torch.Tensor, source_theta: Optional[torch.Tensor] = None, mix: bool = False,
-               invert_warp: bool = False):
-    """srt (N,9) -> theta (N,4,4), theta_warp (N,3,4), align2d (N,2,3). See emo_pose_theta."""
-    _chk(srt)
-    N = srt.shape[0]
-    dev = srt.device
+def pose_theta(srt: Optional[torch.Tensor], source_theta: Optional[torch.Tensor] = None, mix: bool = False,
+               invert_warp: bool = False, mix_old: bool = False, theta_in: Optional[torch.Tensor] = None,
+               smooth_state: Optional[torch.Tensor] = None, smooth_momentum: float = 0.5, smooth_init: bool = False):
+    """srt (N,9) [or theta_in (N,4,4)] -> theta (N,4,4), theta_warp (N,3,4), align2d (N,2,3). See emo_pose_theta.
+    smooth_state (3,4) fp32 on device is updated in place (smooth_pose=True, notebooks/infer.py:571-581)."""
+    ref = srt if srt is not None else theta_in
+    if ref is None:
+        raise ValueError("pose_theta: srt or theta_in is required")
+    for t in (srt, theta_in, source_theta, smooth_state):
+        if t is not None:
+            _chk(t)
+    N = ref.shape[0]
+    dev = ref.device
+    if theta_in is not None and tuple(theta_in.shape) != (N, 4, 4):
+        raise ValueError(f"pose_theta: theta_in must be (N,4,4), got {tuple(theta_in.shape)}")
+    if smooth_state is not None and tuple(smooth_state.shape) != (3, 4):
+        raise ValueError(f"pose_theta: smooth_state must be (3,4), got {tuple(smooth_state.shape)}")
     theta = torch.empty((N, 4, 4), dtype=torch.float32, device=dev)
     warp = torch.empty((N, 3, 4), dtype=torch.float32, device=dev)
     align = torch.empty((N, 2, 3), dtype=torch.float32, device=dev)
-    d = L.PoseDesc(_p(srt), _p(source_theta), N, 1 if mix else 0, 1 if invert_warp else 0, _p(theta), _p(warp), _p(align))
+    d = L.PoseDesc(_p(srt), _p(source_theta), N, 1 if mix else 0, 1 if invert_warp else 0, _p(theta), _p(warp), _p(align),
+                   _p(theta_in), 1 if mix_old else 0, 1 if smooth_init else 0, _p(smooth_state), float(smooth_momentum))
     L.call("emo_pose_theta", C.byref(d), _stream())
     return theta, warp, align
 

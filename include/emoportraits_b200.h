@@ -271,16 +271,20 @@ int emo_global_avgpool(const float* x, int N, long long S, int C, float* out, vo
 
 /* ------------------------------------------------------------------------------------------------
  * Pose algebra on device (removes the per-frame host sync of infer.py:568-569, 699-736).
- *   srt [N][9] = (scale xyz, yaw pitch roll, translation xyz) from the head-pose regressor
- *   theta = S.R.T (utils/point_transforms.py:187-240)
- *   mix != 0: get_mixing_theta(source_theta, theta) with mix_old=False (infer.py:686-736):
- *             polar decompositions in fp64 (scipy.linalg.polar), result rows [:3]
+ *   srt [N][9] = (scale xyz, yaw pitch roll, translation xyz) from the head-pose regressor, or from the caller's
+ *             custome_target_theta_embed (infer.py:566-567)
+ *   theta = S.R.T (utils/point_transforms.py:187-240), or theta_in when given
+ *   mix != 0: get_mixing_theta(source_theta, theta) (infer.py:686-736): polar decompositions in fp64
+ *             (scipy.linalg.polar), result rows [:3]; mix_old selects the product of :727 (1) or :729 (0)
+ *   smooth_state != NULL: smooth_pose=True (infer.py:571-581): state = theta_n * momentum + state * (1 - momentum)
+ *             on rows [:3], sample after sample in order, the state (self.theta) carried across calls in
+ *             smooth_state [3][4]; smooth_init != 0 seeds the state with the first sample's theta (self.theta is None)
  *   outputs: theta_out [N][4][4]; theta_warp [N][3][4] = (invert ? inverse(theta) : theta)[:3]
  *            (infer.py:443 / :586); align2d [N][2][3] = (inverse(theta4)[[0,1,3]][:, [0,1,3]] . diag(.5,.5,1))[:2]
  *            (expression_embedder.py:176-203).
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {
-  const float* srt;          /* [N][9] */
+  const float* srt;          /* [N][9], or NULL when theta_in is given */
   const float* source_theta; /* [4][4] or NULL (required when mix) */
   int N;
   int mix;
@@ -288,6 +292,11 @@ typedef struct {
   float* theta_out;  /* [N][4][4] */
   float* theta_warp; /* [N][3][4] */
   float* align2d;    /* [N][2][3] */
+  const float* theta_in; /* [N][4][4] or NULL: start from this theta instead of S.R.T(srt) */
+  int mix_old;           /* with mix: 1 = translation_t . rotation_t . stretch_s (infer.py:727) */
+  int smooth_init;       /* with smooth_state: 1 = seed the state with sample 0's theta first */
+  float* smooth_state;   /* [3][4] or NULL */
+  float smooth_momentum; /* pose_momentum (infer.py:64, default 0.5) */
 } emo_pose_desc;
 int emo_pose_theta(const emo_pose_desc* d, void* stream);
 

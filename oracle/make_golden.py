@@ -170,9 +170,19 @@ def option_inputs(image_size: int, cfg):
         "pose_embed": (torch.randn(1, 128, generator=g) * 0.1),
         "theta_embed": (torch.tensor([[1.05, 0.95, 1.0]]), torch.tensor([[0.25, -0.12, 0.08]]),
                         torch.tensor([[0.04, 0.02, -0.03]])),
-        "c_source_latent_volume": torch.randn(1, cfg.C, cfg.D, cfg.S, cfg.S, generator=g) * 0.5,
-        "c_target_latent_volume": torch.randn(1, cfg.C, cfg.D, cfg.S, cfg.S, generator=g) * 0.5,
+        "c_source_latent_volume": _smooth_volume(cfg, g),
+        "c_target_latent_volume": _smooth_volume(cfg, g),
     }
+
+
+def _smooth_volume(cfg, g):
+    """band-limited (1,C,D,S,S) volume: one seeded plane wave per channel, amplitude 0.5 (a white-noise volume would make
+    the trilinear warps differentiate rounding noise, like the white-noise frames of tests/test_oracle_golden.py)"""
+    z, y, x = torch.meshgrid(torch.linspace(-1, 1, cfg.D), torch.linspace(-1, 1, cfg.S), torch.linspace(-1, 1, cfg.S), indexing="ij")
+    k = (torch.rand(cfg.C, 3, generator=g) * 2 - 1) * 4.0
+    ph = torch.rand(cfg.C, generator=g) * 6.2831853
+    v = torch.sin(k[:, 0, None, None, None] * x + k[:, 1, None, None, None] * y + k[:, 2, None, None, None] * z + ph[:, None, None, None])
+    return (0.5 * v)[None].contiguous()
 
 
 def run_options(image_size: int = 256):

@@ -66,3 +66,44 @@ def test_scratch_slots_and_device_key():
     env = dict(os.environ, EMO_DRY_RUN="1")
     r = subprocess.run([sys.executable, "-c", SLOT_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+OPTIONS_SCRIPT = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from emoportraits_b200 import lib as L
+assert L.DRY_RUN
+from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
+from emoportraits_b200.config import shipped_config
+from emoportraits_b200.infer import Model
+size = 256
+cfg = shipped_config(size)
+model = Model(cfg, synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0), "cpu")
+x = torch.rand(1, 3, size, size)
+vol = torch.rand(1, cfg.C, cfg.D, cfg.S, cfg.S)
+st = model.source_pass(x, mask=torch.rand(1, 1, size, size), c_source_latent_volume=vol, c_target_latent_volume=vol)
+assert st.source_latent_volume.shape == (1, cfg.D, cfg.S, cfg.S, cfg.C)
+assert torch.equal(st.target_latent_volume_1, vol.permute(0, 2, 3, 4, 1))      # the caller's volume, channels-last
+try:
+    model.source_pass(x, c_source_latent_volume=vol[:, :, :1])
+    raise SystemExit("bad volume shape accepted")
+except ValueError:
+    pass
+state = torch.zeros(3, 4)
+n0 = L.launch_count
+img, _, _, so = model.driver_pass(st, x, mix=True, mix_old=True, custom_srt=torch.rand(1, 9), smooth_state=state,
+                                  smooth_momentum=0.5, smooth_init=True)
+full = L.launch_count - n0
+n0 = L.launch_count
+img2, _, _, so2 = model.driver_pass(st, x, mix=True, custom_pose_embed=torch.rand(1, 128))
+assert img.shape == img2.shape == (1, 3, size, size)
+assert L.launch_count - n0 < full        # the expression encoder is skipped when its output is replaced
+assert so2.target_pose_embed.shape == (1, 128)
+print("ok")
+"""
+
+
+def test_dry_run_forward_options():
+    env = dict(os.environ, EMO_DRY_RUN="1")
+    r = subprocess.run([sys.executable, "-c", OPTIONS_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
