@@ -144,6 +144,11 @@ def grid_sample3d(inp: torch.Tensor, grid: Optional[torch.Tensor] = None, theta:
         raise ValueError(out_layout)
     out = torch.empty(shape, dtype=torch.float32, device=inp.device) if want_f32 else None
     sp = Split.empty(shape, inp.device, planes) if want_split else None
+    if N == 0 or Do * Ho * Wo == 0:
+        # empty batch / empty lattice: F.grid_sample returns an empty tensor; nothing to launch
+        if want_f32 and want_split:
+            return out, sp
+        return out if want_f32 else sp
     d = L.GridSample3dDesc(_p(inp), 1 if in_layout == "cl" else 0, N, Cc, Di, Hi, Wi, _p(grid), _p(theta), Do, Ho, Wo,
                            _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, os_["n"], os_["c"],
                            os_["d"], os_["h"], os_["w"], _p(sp.lo2) if sp else None)
