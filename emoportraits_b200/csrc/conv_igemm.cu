@@ -70,6 +70,12 @@ struct ConvKParams {
   int out_nchw;
   double* stats;
   int G, cpg;
+  // sub-pixel mode (conv_igemm_ps_kernel): 3x3 conv over the nearest-x2 upsampling of the input, evaluated on the LOW-resolution
+  // planes.  Dout/Hout/Wout above then describe the low-resolution pixel grid the tiles walk; the output tensor is
+  // [N][Dout][oH = 2 Hout][oW = 2 Wout][Cout].  The N-tile index carries the output phase: nt = phase * ntc + channel tile,
+  // phase = 2 * (row parity) + (column parity); each phase has its own four 2x2 taps (weights [phase * 4 + tap]).
+  int oH, oW;
+  int ntc;  // channel tiles per phase (= Cout_pad / BN)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -367,564 +373,16 @@ struct TMaps {
   CUtensorMap b[3];  // weight planes
 };
 
-// NP = number of bf16 planes per operand: 2 -> 3 products (~2^-16 relative), 3 -> 6 products (~2^-24, fp32-faithful)
-// EPI = 0: the eight epilogue warps (2..9) accumulate the TMEM chunks AND run the tile's final phase (bias, residual,
-//          activation, statistics, stores), one output row per thread.  Used for split-K, ragged channel tails, NCHW output.
-// EPI = 1: 16 warps.  Warps 4..11 only accumulate and drop the finished fp32 tile into a shared-memory staging buffer;
-//          warps 12..15 ("store warps") run the final phase from there with whole rows per instruction (512-byte coalesced
-//          residual reads / output writes, statistics in registers without shuffles) while the accumulators already serve
-//          the next tile.  Register budget moved with setmaxnreg (TMA/MMA group 64, store group 112, accumulators 168).
-template <int KC, int NP, int CG, int EPI>
-__global__ void __launch_bounds__(EPI ? kThreadsEpi1 : kThreads, 1)
-conv_igemm_kernel(const __grid_constant__ TMaps tm, const __grid_constant__ ConvKParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem is only guaranteed 16B-aligned by the API; realign to 1024 for the swizzle atoms.
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-
-  const int BN = p.BN;
-  const uint32_t a_bytes = kTileM * KC * 2;
-  const uint32_t b_bytes = (uint32_t)(BN / CG) * KC * 2;  // pair mode: this CTA stages half of the weight tile
-  const uint32_t stage_bytes = NP * a_bytes + NP * b_bytes;
-  const int S = p.stages;
-
-  uint8_t* tail = smem + (size_t)S * stage_bytes;
-  uint64_t* full_bar = (uint64_t*)tail;
-  uint64_t* empty_bar = full_bar + kMaxStages;
-  uint64_t* tfull_bar = empty_bar + kMaxStages;
-  uint64_t* tempty_bar = tfull_bar + kAccBufs;
-  uint64_t* sfull_bar = tempty_bar + kAccBufs;   // EPI = 1: staging buffer holds a finished tile / has been drained
-  uint64_t* sempty_bar = sfull_bar + 1;
-  uint32_t* tmem_slot = (uint32_t*)(sempty_bar + 1);
-  float* col_sum = (float*)(tmem_slot + 4);  // [2][256]
-  float* col_sq = col_sum + 2 * 256;         // [2][256]
-  float* stg = col_sq + 2 * 256;             // EPI = 1: [128][BN] fp32, 16-byte chunks XOR-swizzled with (row & 7)
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < NP; ++i) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.a[i]) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.b[i]) : "memory");
-    }
-    for (int i = 0; i < S; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], (uint32_t)p.cs);  // every CTA of the cluster reads what this CTA multicasts
-    }
-    for (int i = 0; i < kAccBufs; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], (uint32_t)(kEpiThreads / 32) * (uint32_t)CG);  // pair mode: both CTAs' epilogue warps
-    }
-    mbar_init(sfull_bar, kEpiThreads / 32);
-    mbar_init(sempty_bar, kStoreThreads / 32);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = threadIdx.x; i < 4 * 256; i += (EPI ? kThreadsEpi1 : kThreads)) col_sum[i] = 0.f;
-  if (warp == 1) {
-    if (CG == 2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  constexpr int ew0 = EPI ? 4 : 2;  // first accumulator warp
-  const int cs = p.cs;
-  constexpr bool cg2 = CG == 2;  // compile-time: a kernel holding cta_group::2 instructions cannot be launched without clusters
-  if (cs > 1 || cg2) cluster_sync_all();  // barriers of every CTA initialised before any remote arrive / multicast
-  const int csz = cg2 ? 2 : cs;  // CTAs per cluster (1-D grid, cluster dims (csz,1,1): rank and id follow from blockIdx)
-  const uint32_t crank = (uint32_t)blockIdx.x % (uint32_t)csz;
-  const uint16_t cmask = (uint16_t)((1u << cs) - 1);
-  // tile walk: a cluster takes `cs` consecutive tiles (same channel tile: m_tiles % cs == 0) per round
-  const int tile_first = (int)blockIdx.x;
-  const int tile_step = (int)gridDim.x;  // whole clusters only (host), so this is nclusters * csz
-  const int ksplit = p.ksplit;  // work item = tile * ksplit + part (ksplit == 1: item == tile)
-
-  const int taps = p.kd * p.kh * p.kw;
-  const int ksteps = taps * p.kchunks;
-  const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;  // work items
-  const int rows_a = p.tw * p.th * p.td;
-  const uint32_t tx_bytes = (uint32_t)NP * ((uint32_t)rows_a * KC * 2 + b_bytes) * (uint32_t)CG;  // pair: both CTAs' bytes
-  const int b_rows = BN / cs;                       // weight rows this CTA fetches (and multicasts)
-  const uint32_t b_slice = (uint32_t)b_rows * KC * 2;
-
-  auto role_producer = [&]() {
-    // ===================== TMA producer (whole warp walks the loop; one elected lane issues) =====================
-    {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int item = tile_first; item < total_tiles; item += tile_step) {
-        const int tile = item / ksplit, part = item - tile * ksplit;
-        const int ks0 = (int)((long long)ksteps * part / ksplit), ks1 = (int)((long long)ksteps * (part + 1) / ksplit);
-        const int nt = tile / p.m_tiles;
-        int mt = tile - nt * p.m_tiles;
-        const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-        const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-        const int tdi = mt % p.tiles_d; mt /= p.tiles_d;
-        const int n = mt;
-        const int x0 = twi * p.tw * p.sw - p.pw;
-        const int y0 = thi * p.th * p.sh - p.ph;
-        const int z0 = tdi * p.td * p.sd - p.pd;
-        const int n0 = nt * BN;
-        for (int ks = ks0; ks < ks1; ++ks) {
-          const int tap = ks / p.kchunks, kc = ks - tap * p.kchunks;
-          const int c = tap % p.kw, b = (tap / p.kw) % p.kh, a = tap / (p.kw * p.kh);
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + (size_t)stage * stage_bytes;
-          if (!elect_one()) {
-          }
-#ifdef EMO_CONV_DEBUG
-          else if (p.dbg & 1) {
-            if (!cg2 || crank == 0) mbar_expect_tx(&full_bar[stage], 0);
-          }
-#endif
-          else if (cg2) {
-            // pair mode: both CTAs load (own pixel tile, own half of the weight tile) and complete_tx on the LEADER's barrier
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {
-              tma_load_5d_2sm(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
-              tma_load_3d_2sm(&tm.b[pl], &full_bar[stage], st + NP * a_bytes + pl * b_bytes, kc * KC, n0 + (int)crank * (BN / 2), tap);
-            }
-          } else {
-            mbar_expect_tx(&full_bar[stage], tx_bytes);
-#pragma unroll
-            for (int pl = 0; pl < NP; ++pl) {
-              tma_load_5d(&tm.a[pl], &full_bar[stage], st + pl * a_bytes, kc * KC, x0 + c, y0 + b, z0 + a, n);
-              uint8_t* bdst = st + NP * a_bytes + pl * b_bytes + crank * b_slice;
-              if (cs > 1) tma_load_3d_mc(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0 + (int)crank * b_rows, tap, cmask);
-              else tma_load_3d(&tm.b[pl], &full_bar[stage], bdst, kc * KC, n0, tap);
-            }
-          }
-          __syncwarp();
-          if (++stage == S) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  };
-  auto role_mma = [&]() {
-    // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
-    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format BF16 [7,10)=[10,13)=1,
-    // K-major A and B, N>>3 at [17,23), M>>4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                           ((uint32_t)((kTileM * CG) >> 4) << 24);
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t g = 0;  // running accumulation-chunk counter (continues across tiles)
-    const int F = p.flush;
-    for (int item = tile_first; item < total_tiles; item += tile_step) {
-      uint32_t tmem_d = 0;
-      int as = 0;
-      const int part = item % ksplit;
-      const int nks = (int)((long long)ksteps * (part + 1) / ksplit) - (int)((long long)ksteps * part / ksplit);
-      for (int ks = 0; ks < nks; ++ks) {
-        const bool chunk_first = (ks % F) == 0;
-        const bool chunk_last = ((ks + 1) % F) == 0 || ks == nks - 1;
-        if (chunk_first) {
-          // the tensor core accumulates with truncation (measured: tools/accum_probe.py), so an accumulator only ever
-          // takes a short chunk of MMAs; the epilogue warps add the chunks in fp32 registers (round-to-nearest).
-          as = (int)(g % (uint32_t)p.nbuf);
-          mbar_wait(&tempty_bar[as], ((g / (uint32_t)p.nbuf) & 1) ^ 1);
-          tcgen05_fence_after();
-          tmem_d = tmem_base + (uint32_t)(as * BN);
-        }
-        mbar_wait(&full_bar[stage], phase);
-        tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          uint64_t dA[NP], dB[NP];
-#pragma unroll
-          for (int pl = 0; pl < NP; ++pl) {
-            dA[pl] = make_kmajor_desc<KC>(sa + pl * a_bytes);
-            dB[pl] = make_kmajor_desc<KC>(sa + NP * a_bytes + pl * b_bytes);
-          }
-#ifdef EMO_CONV_DEBUG
-          if (!(p.dbg & 2))
-#endif
-#pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk) {
-            const uint64_t adv = (uint64_t)(kk * 2);  // 16 bf16 = 32 B = 2 x 16B units
-            const uint32_t acc0 = (chunk_first && kk == 0) ? 0u : 1u;
-            if (cg2) {
-              if (NP == 2) {
-                umma_bf16_cg2(tmem_d, dA[1] + adv, dB[0] + adv, idesc, acc0);
-                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
-                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
-              } else {
-                umma_bf16_cg2(tmem_d, dA[NP - 1] + adv, dB[0] + adv, idesc, acc0);
-                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[NP - 1] + adv, idesc, 1);
-                umma_bf16_cg2(tmem_d, dA[1] + adv, dB[1] + adv, idesc, 1);
-                umma_bf16_cg2(tmem_d, dA[1] + adv, dB[0] + adv, idesc, 1);
-                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
-                umma_bf16_cg2(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
-              }
-            } else if (NP == 2) {
-              umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, acc0);
-              umma_bf16(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
-              umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
-            } else {
-              // smallest terms first: lo2*hi, hi*lo2, lo*lo, lo*hi, hi*lo, hi*hi
-              umma_bf16(tmem_d, dA[NP - 1] + adv, dB[0] + adv, idesc, acc0);
-              umma_bf16(tmem_d, dA[0] + adv, dB[NP - 1] + adv, idesc, 1);
-              umma_bf16(tmem_d, dA[1] + adv, dB[1] + adv, idesc, 1);
-              umma_bf16(tmem_d, dA[1] + adv, dB[0] + adv, idesc, 1);
-              umma_bf16(tmem_d, dA[0] + adv, dB[1] + adv, idesc, 1);
-              umma_bf16(tmem_d, dA[0] + adv, dB[0] + adv, idesc, 1);
-            }
-          }
-          if (cg2) {
-            umma_commit_cg2(&empty_bar[stage]);  // frees the stage in both CTAs of the pair
-            if (chunk_last) umma_commit_cg2(&tfull_bar[as]);
-          } else {
-            if (cs > 1) umma_commit_mc(&empty_bar[stage], cmask);  // frees the stage in every CTA that multicasts into it
-            else umma_commit(&empty_bar[stage]);
-            if (chunk_last) umma_commit(&tfull_bar[as]);
-          }
-        }
-        __syncwarp();
-        if (chunk_last) ++g;
-        if (++stage == S) { stage = 0; phase ^= 1; }
-      }
-    }
-  };
-  auto role_accumulate = [&]() {
-    // ===================== epilogue / accumulator warps (2..9, EPI = 1: 4..11) =====================
-    // two warps per TMEM lane quadrant; each owns one half of the tile's columns (multiple of 16)
-    const int quad = warp & 3;          // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;   // accumulator row == pixel index inside the tile box
-    const int et = threadIdx.x - ew0 * 32;  // 0..255 among the epilogue threads
-    const int half = (warp - ew0) >> 2;
-    const int csplit = ((BN / 16 + 1) / 2) * 16;
-    const int cbeg = half ? csplit : 0;           // this warp's column range inside the tile
-    const int ncols = half ? BN - csplit : csplit;
-    const int F = p.flush;
-    uint32_t g = 0;
-    int it = 0;
-    for (int item = tile_first; item < total_tiles; item += tile_step, ++it) {
-      const int tile = item / ksplit, part = item - tile * ksplit;
-      const int nks = (int)((long long)ksteps * (part + 1) / ksplit) - (int)((long long)ksteps * part / ksplit);
-      const int nchunks = (nks + F - 1) / F;
-      const int nt = tile / p.m_tiles;
-      int mt = tile - nt * p.m_tiles;
-      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-      const int tdi = mt % p.tiles_d; mt /= p.tiles_d;
-      const int n = mt;
-      const int n0 = nt * BN;
-      const int wl = row % p.tw;
-      const int hl = (row / p.tw) % p.th;
-      const int dl = row / (p.tw * p.th);
-      const int ow = twi * p.tw + wl, oh = thi * p.th + hl, od = tdi * p.td + dl;
-      const bool valid = (row < rows_a) && ow < p.Wout && oh < p.Hout && od < p.Dout;
-      const long long pix = (((long long)n * p.Dout + od) * p.Hout + oh) * p.Wout + ow;
-      long long rpix = 0;
-      if (p.residual) {
-        const int rw = ow >> p.res_shift, rh = oh >> p.res_shift;
-        rpix = (((long long)n * p.rD + od) * p.rH + rh) * p.rW + rw;
-      }
-      const long long ppix = (((long long)od) * p.Hout + oh) * p.Wout + ow;
-      // the tile's residual rows are first touched ~one tile of MMAs from now: pull them into L2 so that the final phase
-      // of the epilogue (the serial resource once the MMAs run at the tensor floor) does not sit on HBM latency
-      if (valid && ksplit == 1) {
-        const int c_lo = n0 + cbeg;
-        const int nb = (ncols < p.Cout - c_lo ? ncols : p.Cout - c_lo) * 4;
-        if (p.residual) {
-          const char* rp = (const char*)(p.residual + rpix * p.Cout + c_lo);
-          for (int b = 0; b < nb + 127; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (b < nb ? b : nb - 1)));
-        }
-        if (p.post_add) {
-          const char* rp = (const char*)(p.post_add + ppix * p.Cout + c_lo);
-          for (int b = 0; b < nb + 127; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + (b < nb ? b : nb - 1)));
-        }
-      }
-
-      // ---- fp32 register accumulation of the short TMEM chunks ----
-      float acc[kMaxBN / 2];
-#pragma unroll
-      for (int j = 0; j < kMaxBN / 2; ++j) acc[j] = 0.f;
-      for (int ch = 0; ch < nchunks; ++ch, ++g) {
-        const int as = (int)(g % (uint32_t)p.nbuf);
-        mbar_wait(&tfull_bar[as], (g / (uint32_t)p.nbuf) & 1);
-        tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + cbeg);
-#ifdef EMO_CONV_DEBUG
-        if (!(p.dbg & 8))
-#endif
-#pragma unroll
-        for (int c0 = 0; c0 < kMaxBN / 2; c0 += 32) {
-          if (c0 < ncols) {
-            uint32_t r0[16], r1[16];
-            tmem_ld16(taddr + (uint32_t)c0, r0);
-            if (c0 + 16 < ncols) tmem_ld16(taddr + (uint32_t)(c0 + 16), r1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r0[j]);
-            if (c0 + 16 < ncols) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) acc[c0 + 16 + j] += __uint_as_float(r1[j]);
-            }
-          }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (cg2) mbar_arrive_leader(&tempty_bar[as]);  // the leader's MMA warp waits for both CTAs' epilogues
-          else mbar_arrive(&tempty_bar[as]);
-        }
-      }
-
-      if (EPI) {
-        // hand the finished sums to the store warps: row-major [128][BN] fp32, chunk q of row r at q ^ (r & 7)
-        mbar_wait(sempty_bar, ((uint32_t)it & 1) ^ 1);
-        float4* srow = (float4*)(stg + (size_t)row * BN);
-        const int q0 = cbeg >> 2;
-#pragma unroll
-        for (int j4 = 0; j4 < kMaxBN / 8; ++j4)
-          if (j4 * 4 < ncols)
-            srow[(q0 + j4) ^ (row & 7)] = make_float4(acc[4 * j4], acc[4 * j4 + 1], acc[4 * j4 + 2], acc[4 * j4 + 3]);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sfull_bar);
-        continue;
-      }
-#ifdef EMO_CONV_DEBUG
-      if (p.dbg & 4) {
-        if (acc[0] == 123.456f) p.out[0] = acc[1];  // keeps the accumulation alive
-        continue;
-      }
-#endif
-      if (ksplit > 1) {
-        // split-K: add this part's partial tile into the fp32 workspace; bias/residual/activation/statistics are applied by
-        // splitk_finalize_kernel once every part has landed
-        if (valid) {
-          float* wrow = p.ws + pix * p.Cout + n0 + cbeg;
-#pragma unroll
-          for (int j = 0; j < kMaxBN / 2; ++j)
-            if (j < ncols && n0 + cbeg + j < p.Cout) atomicAdd(wrow + j, acc[j]);
-        }
-        continue;
-      }
-      float* cs = col_sum + (it & 1) * 256;
-      float* cq = col_sq + (it & 1) * 256;
-#pragma unroll
-      for (int cl0 = 0; cl0 < kMaxBN / 2; cl0 += 16) {
-        if (cl0 >= ncols) continue;
-        const int c0 = cbeg + cl0;  // column inside the tile
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = acc[cl0 + j];
-        const int cbase = n0 + c0;
-        const bool cfull = (cbase + 16 <= p.Cout);
-        if (valid && cbase < p.Cout) {
-          if (cfull) {
-            if (p.bias) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 b4 = __ldg((const float4*)(p.bias + cbase) + q);
-                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-              }
-            }
-            if (p.residual
-#ifdef EMO_CONV_DEBUG
-                && !(p.dbg & 16)
-#endif
-            ) {
-              const float4* r4 = (const float4*)(p.residual + rpix * p.Cout + cbase);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 b4 = __ldg(r4 + q);
-                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-              }
-            }
-            if (p.act != EMO_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = act_apply(v[j], p.act);
-            }
-            if (p.post_add) {
-              const float4* r4 = (const float4*)(p.post_add + ppix * p.Cout + cbase);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 b4 = __ldg(r4 + q);
-                v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
-              }
-            }
-#ifdef EMO_CONV_DEBUG
-            if ((p.dbg & 32) && v[3] != 123.456f) {
-            } else
-#endif
-            if (!p.out_nchw) {
-              float4* o4 = (float4*)(p.out + pix * p.Cout + cbase);
-#pragma unroll
-              for (int q = 0; q < 4; ++q) o4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            } else {
-              const long long sp = (long long)p.Dout * p.Hout * p.Wout;
-              const long long spi = ((long long)od * p.Hout + oh) * p.Wout + ow;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) p.out[((long long)n * p.Cout + cbase + j) * sp + spi] = v[j];
-            }
-          } else {
-            // ragged channel tail (e.g. Cout = 3): scalar path
-            const long long sp = (long long)p.Dout * p.Hout * p.Wout;
-            const long long spi = ((long long)od * p.Hout + oh) * p.Wout + ow;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = cbase + j;
-              if (c < p.Cout) {
-                float x = v[j];
-                if (p.bias) x += __ldg(p.bias + c);
-                if (p.residual) x += __ldg(p.residual + rpix * p.Cout + c);
-                x = act_apply(x, p.act);
-                if (p.post_add) x += __ldg(p.post_add + ppix * p.Cout + c);
-                v[j] = x;
-                if (!p.out_nchw) p.out[pix * p.Cout + c] = x;
-                else p.out[((long long)n * p.Cout + c) * sp + spi] = x;
-              } else {
-                v[j] = 0.f;
-              }
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-        }
-        if (p.stats) {
-          // keep the finished values (zero for pixels / channels outside the tensor) for the tile statistics below
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[cl0 + j] = v[j];
-        }
-      }
-
-      if (p.stats
-#ifdef EMO_CONV_DEBUG
-          && !(p.dbg & 64)
-#endif
-      ) {
-        // R = largest power of two (<= 16) dividing the channels per group: that many adjacent columns fold inside the thread
-        const int r = p.cpg & -p.cpg;
-        if (r >= 16) tile_stats<16>(acc, ncols, lane, cs + cbeg, cq + cbeg);
-        else if (r == 8) tile_stats<8>(acc, ncols, lane, cs + cbeg, cq + cbeg);
-        else if (r == 4) tile_stats<4>(acc, ncols, lane, cs + cbeg, cq + cbeg);
-        else if (r == 2) tile_stats<2>(acc, ncols, lane, cs + cbeg, cq + cbeg);
-        else tile_stats<1>(acc, ncols, lane, cs + cbeg, cq + cbeg);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        tile_group_stats(p, cs, cq, n, n0, BN, et, kEpiThreads);
-      }
-    }
-  };
-  auto role_store = [&]() {
-    // ===================== store warps (EPI = 1): final phase of every tile from the staging buffer =====================
-    // Warp sw owns rows sw*32 .. sw*32+31 of the tile.  One pass = one row: lane l holds the 16-byte chunk l (and 32 + l
-    // for tiles wider than 128 channels), so a warp instruction reads / writes 512 contiguous bytes of a pixel's channels.
-    // A single warp per scheduler issues this loop, so it is kept to ~30 instructions per row (store_rows below).
-    const int sw = warp - 12;
-    const int st = threadIdx.x - 12 * 32;  // 0..127 among the store threads
-    int it = 0;
-    for (int item = tile_first; item < total_tiles; item += tile_step, ++it) {
-      const int tile = item;
-      const int nt = tile / p.m_tiles;
-      int mt = tile - nt * p.m_tiles;
-      const int twi = mt % p.tiles_w; mt /= p.tiles_w;
-      const int thi = mt % p.tiles_h; mt /= p.tiles_h;
-      const int tdi = mt % p.tiles_d; mt /= p.tiles_d;
-      const int n = mt;
-      const int n0 = nt * BN;
-      // lane r prepares the element offsets of row sw*32 + r (-1: outside the tensor); the row loop broadcasts them
-      StoreRowCtx c;
-      c.off = -1; c.roff = 0; c.poff = 0;
-      {
-        const int row = sw * 32 + lane;
-        const int wl = row % p.tw;
-        const int hl = (row / p.tw) % p.th;
-        const int dl = row / (p.tw * p.th);
-        const int ow = twi * p.tw + wl, oh = thi * p.th + hl, od = tdi * p.td + dl;
-        if ((row < rows_a) && ow < p.Wout && oh < p.Hout && od < p.Dout) {
-          c.off = (((n * p.Dout + od) * p.Hout + oh) * p.Wout + ow) * p.Cout;
-          c.roff = (((n * p.rD + od) * p.rH + (oh >> p.res_shift)) * p.rW + (ow >> p.res_shift)) * p.Cout;
-          c.poff = ((od * p.Hout + oh) * p.Wout + ow) * p.Cout;
-        }
-      }
-      c.stg = stg + (size_t)(sw * 32) * BN;
-      c.BN = BN; c.lane = lane; c.row0 = sw * 32;
-      c.out = p.out; c.residual = p.residual; c.post_add = p.post_add; c.act = p.act;
-      float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), q0 = s0, s1 = s0, q1 = s0;
-      const int c0 = n0 + 4 * lane, c1 = c0 + 128;
-      const bool ok0 = 4 * lane < BN && c0 < p.Cout, ok1 = 128 + 4 * lane < BN && c1 < p.Cout;
-      float4 bias0 = make_float4(0.f, 0.f, 0.f, 0.f), bias1 = bias0;
-      if (p.bias) {
-        if (ok0) bias0 = __ldg((const float4*)(p.bias + c0));
-        if (ok1) bias1 = __ldg((const float4*)(p.bias + c1));
-      }
-      mbar_wait(sfull_bar, (uint32_t)it & 1);
-#ifdef EMO_CONV_DEBUG
-      if (p.dbg & 128) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sempty_bar);
-        continue;
-      }
-#endif
-      const bool plain = p.act == EMO_ACT_NONE && !p.post_add && p.res_shift == 0;
-      if (plain) store_rows<true>(c, 0, c0, ok0, bias0, s0, q0);
-      else store_rows<false>(c, 0, c0, ok0, bias0, s0, q0);
-      if (BN > 128) {
-        if (plain) store_rows<true>(c, 32, c1, ok1, bias1, s1, q1);
-        else store_rows<false>(c, 32, c1, ok1, bias1, s1, q1);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sempty_bar);  // the accumulators may overwrite the staging buffer
-      if (p.stats) {
-        float* cs = col_sum + (it & 1) * 256;
-        float* cq = col_sq + (it & 1) * 256;
-        if (ok0) {
-          atomicAdd(&cs[4 * lane], s0.x); atomicAdd(&cs[4 * lane + 1], s0.y); atomicAdd(&cs[4 * lane + 2], s0.z); atomicAdd(&cs[4 * lane + 3], s0.w);
-          atomicAdd(&cq[4 * lane], q0.x); atomicAdd(&cq[4 * lane + 1], q0.y); atomicAdd(&cq[4 * lane + 2], q0.z); atomicAdd(&cq[4 * lane + 3], q0.w);
-        }
-        if (BN > 128 && ok1) {
-          atomicAdd(&cs[128 + 4 * lane], s1.x); atomicAdd(&cs[129 + 4 * lane], s1.y); atomicAdd(&cs[130 + 4 * lane], s1.z); atomicAdd(&cs[131 + 4 * lane], s1.w);
-          atomicAdd(&cq[128 + 4 * lane], q1.x); atomicAdd(&cq[129 + 4 * lane], q1.y); atomicAdd(&cq[130 + 4 * lane], q1.z); atomicAdd(&cq[131 + 4 * lane], q1.w);
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        tile_group_stats(p, cs, cq, n, n0, BN, st, kStoreThreads);
-      }
-    }
-  };
-  // Role dispatch.  With EPI = 1 every warpgroup first moves its register budget (setmaxnreg must sit at the top of a
-  // branch that never rejoins the others before the teardown, or ptxas keeps the 128-register cap of the 512-thread launch
-  // for everybody): TMA / MMA group 64, store warps 112, accumulators 168.
-  if (EPI) {
-    const int wg = warp >> 2;
-    if (wg == 0) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-      if (warp == 0) role_producer();
-      else if (warp == 1 && !(cg2 && crank != 0)) role_mma();
-    } else if (wg == 3) {
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-      role_store();
-    } else {
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-      role_accumulate();
-    }
-  } else {
-    if (warp == 0) role_producer();
-    else if (warp == 1 && !(cg2 && crank != 0)) role_mma();
-    else if (warp >= 2) role_accumulate();
-  }
-
-  // teardown
-  tcgen05_fence_before();
-  __syncthreads();
-  if (cs > 1 || cg2) cluster_sync_all();  // nobody leaves while a peer may still multicast into / arrive on this CTA
-  if (warp == 1) {
-    if (cg2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
+#define EMO_CONV_PS 0
+#define EMO_CONV_KERNEL_NAME conv_igemm_kernel
+#include "conv_igemm_kernel.inc"
+#undef EMO_CONV_PS
+#undef EMO_CONV_KERNEL_NAME
+#define EMO_CONV_PS 1
+#define EMO_CONV_KERNEL_NAME conv_igemm_ps_kernel
+#include "conv_igemm_kernel.inc"
+#undef EMO_CONV_PS
+#undef EMO_CONV_KERNEL_NAME
 
 // split-K finalize: out = act(ws + bias + residual) + post_add, statistics, and the workspace is zeroed for the next user
 struct FinParams {
@@ -1017,6 +475,20 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const int NP = d->a_lo2 ? 3 : 2;
   EMO_REQUIRE((d->a_lo2 == nullptr) == (d->w_lo2 == nullptr), "emo_conv_igemm: a_lo2 and w_lo2 must be given together");
+  // sub-pixel mode: the descriptor describes conv3x3(pad 1)(nearest_x2(input)) with the input given at LOW resolution and
+  // the weights pre-folded to [4 phases][2x2 taps][Cout_pad][Cin] (emoportraits_b200/ops.py: pack_upconv_weight)
+  const int ps = d->upconv ? 1 : 0;
+  if (ps) {
+    EMO_REQUIRE(d->kd == 1 && d->kh == 3 && d->kw == 3 && d->sd == 1 && d->sh == 1 && d->sw == 1 && d->pd == 0 && d->ph == 1 && d->pw == 1,
+                "emo_conv_igemm: upconv needs a 1x3x3 stride-1 pad-1 convolution");
+    EMO_REQUIRE(d->Din == 1 && d->Dout == 1 && d->Hout == 2 * d->Hin && d->Wout == 2 * d->Win,
+                "emo_conv_igemm: upconv output must be (2 Hin, 2 Win) (got %d x %d from %d x %d)", d->Hout, d->Wout, d->Hin, d->Win);
+    EMO_REQUIRE(NP == 2 && d->Cin % 64 == 0 && d->Cout == d->Cout_pad && !d->out_nchw,
+                "emo_conv_igemm: upconv needs two-plane operands, Cin %% 64 == 0, Cout %% 16 == 0, channels-last output");
+  }
+  const int gH = ps ? d->Hin : d->Hout, gW = ps ? d->Win : d->Wout;  // the pixel grid the tiles walk
+  const int taps_k = ps ? 4 : d->kd * d->kh * d->kw;                  // taps in one tile's K loop
+  const int nt_mult = ps ? 4 : 1;                                     // N tiles per channel tile (one per output phase)
   int KC = (d->Cin % 64 == 0) ? 64 : 32;  // three-plane tiles fall back to 32 below when 64 leaves < 3 pipeline stages
   // N tile: largest multiple of 16 that divides Cout_pad and fits the register-resident accumulator row
   int BN = 0;
@@ -1031,44 +503,46 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   ConvKParams p;
   memset(&p, 0, sizeof(p));
-  p.N = d->N; p.Dout = d->Dout; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
-  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+  p.N = d->N; p.Dout = d->Dout; p.Hout = gH; p.Wout = gW; p.Cout = d->Cout;
+  p.oH = d->Hout; p.oW = d->Wout;
+  p.kd = d->kd; p.kh = ps ? 2 : d->kh; p.kw = ps ? 2 : d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
   p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
   // pixel box: 128 pixels, widest along W first
-  p.tw = pick_box(d->Wout, 16);
-  p.th = pick_box(d->Hout, kTileM / p.tw > 0 ? kTileM / p.tw : 1);
+  p.tw = pick_box(gW, 16);
+  p.th = pick_box(gH, kTileM / p.tw > 0 ? kTileM / p.tw : 1);
   p.td = pick_box(d->Dout, kTileM / (p.tw * p.th) > 0 ? kTileM / (p.tw * p.th) : 1);
-  if (p.tw * p.th * p.td < kTileM && p.tw < d->Wout) {  // shallow/short tensor: widen along W
+  if (p.tw * p.th * p.td < kTileM && p.tw < gW) {  // shallow/short tensor: widen along W
     int tw = p.tw;
-    while (tw * 2 <= d->Wout && tw * 2 * p.th * p.td <= kTileM && tw * 2 * d->sw <= 256) tw *= 2;
+    while (tw * 2 <= gW && tw * 2 * p.th * p.td <= kTileM && tw * 2 * d->sw <= 256) tw *= 2;
     p.tw = tw;
   }
   EMO_REQUIRE(p.tw * d->sw <= 256 && p.th * d->sh <= 256 && p.td * d->sd <= 256, "emo_conv_igemm: TMA box too large");
-  p.tiles_w = cdiv(d->Wout, p.tw); p.tiles_h = cdiv(d->Hout, p.th); p.tiles_d = cdiv(d->Dout, p.td);
+  p.tiles_w = cdiv(gW, p.tw); p.tiles_h = cdiv(gH, p.th); p.tiles_d = cdiv(d->Dout, p.td);
   p.m_tiles = d->N * p.tiles_d * p.tiles_h * p.tiles_w;
   // small-M layers (ResNet tails, the first warp-generator blocks): the serial K loop of a handful of CTAs is bound by the
   // TMA->MMA->commit round trip (~2.4 us per pipeline turn), not by work.  With a workspace: split K over CTAs
   // (partials red.add'ed in fp32, finalize pass).  Without: narrow the N tile until the tile count fills the machine.
-  const int ksteps_total = d->kd * d->kh * d->kw * (d->Cin / ((d->Cin % 64 == 0) ? 64 : 32));
+  const int ksteps_total = taps_k * (d->Cin / ((d->Cin % 64 == 0) ? 64 : 32));
   int ksplit = 1;
   {
-    const long long tiles = (long long)p.m_tiles * (d->Cout_pad / BN);
+    const long long tiles = (long long)p.m_tiles * (d->Cout_pad / BN) * nt_mult;
     const long long out_elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;
-    if (d->splitk_ws && out_elems <= d->splitk_ws_elems && d->res_shift == 0 && tiles * 2 <= sm_count) {
+    if (!ps && d->splitk_ws && out_elems <= d->splitk_ws_elems && d->res_shift == 0 && tiles * 2 <= sm_count) {
       long long parts = (2ll * sm_count) / tiles;
       if (parts > ksteps_total / 4) parts = ksteps_total / 4;
       if (parts >= 2) ksplit = (int)parts;
     }
   }
-  if (ksplit == 1 && (long long)p.m_tiles * (d->Cout_pad / BN) < sm_count / 2) {
+  if (ksplit == 1 && (long long)p.m_tiles * (d->Cout_pad / BN) * nt_mult < sm_count / 2) {
     for (int cand = BN; cand >= 16; cand -= 16) {
       if (d->Cout_pad % cand) continue;
       BN = cand;
-      if ((long long)p.m_tiles * (d->Cout_pad / cand) >= sm_count) break;
+      if ((long long)p.m_tiles * (d->Cout_pad / cand) * nt_mult >= sm_count) break;
     }
   }
   p.BN = BN;
-  p.n_tiles = d->Cout_pad / BN;
+  p.ntc = d->Cout_pad / BN;
+  p.n_tiles = p.ntc * nt_mult;
   p.ksplit = ksplit;
   p.ws = d->splitk_ws;
   p.dbg = 0;
@@ -1099,6 +573,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   p.stats = d->stats; p.G = d->G; p.cpg = d->G > 0 ? d->Cout / d->G : 1;
   EMO_REQUIRE(!d->residual || ((d->Hout % (1 << d->res_shift)) == 0 && (d->Wout % (1 << d->res_shift)) == 0),
               "emo_conv_igemm: residual shift does not divide the output size");
+  EMO_REQUIRE(!ps || p.cg == 2, "emo_conv_igemm: upconv needs an even number of pixel tiles and BN %% 32 == 0 (pair mode)");
 
   const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
@@ -1155,7 +630,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(p.tw * d->sw), (cuuint32_t)(p.th * d->sh), (cuuint32_t)(p.td * d->sd), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->sd, 1};
     const CUtensorMapSwizzle sw = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    const int taps = d->kd * d->kh * d->kw;
+    const int taps = ps ? 16 : d->kd * d->kh * d->kw;  // sub-pixel mode: [4 phases][2x2 taps]
     cuuint64_t wdim[3] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Cout_pad, (cuuint64_t)taps};
     cuuint64_t wstr[2] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Cout_pad * d->Cin * 2};
     cuuint32_t wbox[3] = {(cuuint32_t)KC, (cuuint32_t)(BN / p.cs / p.cg), 1};
@@ -1181,11 +656,12 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   const int csz = p.cg == 2 ? 2 : p.cs;
   grid = (grid / csz) * csz;  // whole clusters only (total_tiles % csz == 0 by construction)
   cudaError_t e;
-#define EMO_LAUNCH_CONV(KC_, NP_, CG_, EPI_)                                                                                        \
+#define EMO_LAUNCH_CONV(KC_, NP_, CG_, EPI_) EMO_LAUNCH_CONV5(conv_igemm_kernel, KC_, NP_, CG_, EPI_)
+#define EMO_LAUNCH_CONV5(KERNEL_, KC_, NP_, CG_, EPI_)                                                                                        \
   do {                                                                                                                    \
     static bool attr_set = false; /* the opt-in is per function, set once (227 KB covers every configuration) */           \
     if (!attr_set) {                                                                                                      \
-      e = cudaFuncSetAttribute(conv_igemm_kernel<KC_, NP_, CG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
+      e = cudaFuncSetAttribute(KERNEL_<KC_, NP_, CG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
       if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; } \
       attr_set = true;                                                                                                    \
     }                                                                                                                     \
@@ -1202,10 +678,14 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     attr[0].val.clusterDim.z = 1;                                                                                         \
     cfg.attrs = attr;                                                                                                     \
     cfg.numAttrs = 1;                                                                                                     \
-    e = cudaLaunchKernelEx(&cfg, conv_igemm_kernel<KC_, NP_, CG_, EPI_>, tm, p);                                                      \
+    e = cudaLaunchKernelEx(&cfg, KERNEL_<KC_, NP_, CG_, EPI_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
-  if (epi) {
+  if (ps) {
+    EMO_REQUIRE(KC == 64, "emo_conv_igemm: upconv tile does not fit with KC = 64");
+    if (epi) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 1);
+    else EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 0);
+  } else if (epi) {
     if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 1);
     else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 1);
     else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 1);
@@ -1222,6 +702,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     else EMO_LAUNCH_CONV(32, 2, 1, 0);
   }
 #undef EMO_LAUNCH_CONV
+#undef EMO_LAUNCH_CONV5
   if (ksplit > 1) {
     FinParams f;
     f.ws = d->splitk_ws; f.out = d->out; f.N = d->N; f.C = d->Cout;

@@ -62,7 +62,7 @@ class ConvDesc(C.Structure):
                 ("bias", c_void_p), ("residual", c_void_p), ("res_shift", c_int), ("act", c_int),
                 ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int),
                 ("a_lo2", c_void_p), ("w_lo2", c_void_p), ("acc_chunk_mmas", c_int),
-                ("splitk_ws", c_void_p), ("splitk_ws_elems", c_ll)]
+                ("splitk_ws", c_void_p), ("splitk_ws_elems", c_ll), ("upconv", c_int)]
 
 
 class ConvDirectDesc(C.Structure):

@@ -17,6 +17,8 @@ tensor (double (N,32,2)), produced by the epilogue of whichever kernel wrote it.
 """
 from __future__ import annotations
 
+import os
+
 import math
 
 import torch
@@ -26,6 +28,7 @@ from .checkpoint import fold_conv
 from .config import HotPathConfig
 
 G = 32
+SUBPIXEL_UP = os.environ.get("EMO_UPCONV_PS") == "1"  # sub-pixel up-sampling convolutions in the image decoder (opt-in)
 
 
 class ConvW:
@@ -69,10 +72,18 @@ def _count(x):
 class ResBlock:
     """utils.py:661-788: [nearest up] -> norm -> relu -> conv -> norm -> relu -> conv [-> avgpool]; skip = [up] -> [1x1] -> [pool]."""
 
-    def __init__(self, sd, p, dev, ws_first=True, planes=2):
+    def __init__(self, sd, p, dev, ws_first=True, planes=2, subpixel_up=False):
         self.planes = planes
         self.n1 = Norm(sd, p + ".block_feats.0", dev)
         self.c1 = ConvW(sd, p + ".block_feats.2", dev, ws=ws_first, planes=planes)
+        # sub-pixel form of `nearest x2 -> norm -> relu -> 3x3 conv` for blocks called with up=2 (ops.pack_upconv_weight):
+        # the conv then reads the LOW-resolution planes (4/9 of the MMAs, no upsampled operand).  Opt-in (EMO_UPCONV_PS=1)
+        # until it has been measured on the GPU.
+        self.c1_ps = None
+        if subpixel_up and planes == 2:
+            w, _ = fold_conv(sd, p + ".block_feats.2", ws=ws_first)
+            if tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 16 == 0 and w.shape[1] % 64 == 0:
+                self.c1_ps = ops.pack_upconv_weight(w, device=dev)
         self.n2 = Norm(sd, p + ".block_feats.3", dev)
         self.c2 = ConvW(sd, p + ".block.0", dev, planes=planes)
         self.skip = ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
@@ -80,9 +91,13 @@ class ResBlock:
     def __call__(self, x, sx, up=1, down=None, ada=None, want_stats=True):
         dev = x.device
         N = x.shape[0]
-        a = ops.apply(x, gn=self.n1.gn(sx, _count(x), ada[0] if ada else None), act=ops.ACT_RELU, up=up, planes=self.planes)
         st1 = ops.new_stats(N, G, dev)
-        y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1)
+        if up == 2 and self.c1_ps is not None and x.shape[1] == 1 and (x.shape[2] * x.shape[3]) % 256 == 0:
+            a = ops.apply(x, gn=self.n1.gn(sx, _count(x), ada[0] if ada else None), act=ops.ACT_RELU, up=1, planes=self.planes)
+            y = ops.conv_igemm(a, self.c1_ps, bias=self.c1.b, stats=st1, upconv=True)
+        else:
+            a = ops.apply(x, gn=self.n1.gn(sx, _count(x), ada[0] if ada else None), act=ops.ACT_RELU, up=up, planes=self.planes)
+            y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1)
         b = ops.apply(y, gn=self.n2.gn(st1, _count(y), ada[1] if ada else None), act=ops.ACT_RELU, planes=self.planes)
         # skip path: the 1x1 conv commutes with nearest-upsampling and with average pooling, so it runs at the smaller size
         s = ops.avgpool(x, down) if down else x
@@ -460,7 +475,8 @@ class Decoder:
         self.img = []
         j = 0
         while f"{p}.img_decoder.dec_img_blocks.{j}.block.0.weight_orig" in sd:
-            self.img.append(ResBlock(sd, f"{p}.img_decoder.dec_img_blocks.{j}", dev, planes=planes))
+            self.img.append(ResBlock(sd, f"{p}.img_decoder.dec_img_blocks.{j}", dev, planes=planes,
+                                     subpixel_up=SUBPIXEL_UP and (j % cfg.im_dec_lrs == 0)))
             j += 1
         self.lrs = cfg.im_dec_lrs
         self.head_norm = Norm(sd, p + ".img_decoder.dec_img_head.0", dev)

@@ -105,6 +105,36 @@ def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tenso
                             pl[2].contiguous().to(dev) if planes == 3 else None)
 
 
+def fold_upconv_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) weights of `nearest x2 -> 3x3 conv (pad 1)` -> (4 phases, 2, 2, Cout, Cin) weights of the four
+    2x2 convolutions over the LOW-resolution map that compute the same thing (sub-pixel form).  Output pixel
+    (2i + a, 2j + b) reads upsampled rows 2i+a-1 .. 2i+a+1, i.e. low-res rows {i-1, i, i} for a = 0 and {i, i, i+1} for
+    a = 1: row taps {w0, w1 + w2} at offsets {-1, 0} (a = 0) and {w0 + w1, w2} at offsets {0, +1} (a = 1); columns alike.
+    Zero padding of the upsampled map coincides with zero padding of the low-res map.  phase = 2a + b, taps (ty, tx)."""
+    assert w.dim() == 4 and tuple(w.shape[2:]) == (3, 3), w.shape
+    w = w.detach().float()
+    rows = [torch.stack([w[:, :, 0], w[:, :, 1] + w[:, :, 2]], 2), torch.stack([w[:, :, 0] + w[:, :, 1], w[:, :, 2]], 2)]  # (Co,Ci,2,3) per a
+    out = []
+    for a in (0, 1):
+        r = rows[a]
+        for b in (0, 1):
+            c = torch.stack([r[..., 0], r[..., 1] + r[..., 2]], 3) if b == 0 else torch.stack([r[..., 0] + r[..., 1], r[..., 2]], 3)
+            out.append(c.permute(2, 3, 0, 1))                                  # (ty, tx, Co, Ci)
+    return torch.stack(out)                                                    # (4, 2, 2, Co, Ci)
+
+
+def pack_upconv_weight(w: torch.Tensor, device=None, planes: int = 2) -> PackedConvWeight:
+    """OIHW 3x3 fp32 (already SN/WS-folded) -> phase-folded PackedConvWeight [16 = phase*4 + ty*2 + tx][Cout][Cin] for
+    conv_igemm(..., upconv=True).  Cout must be a multiple of 16 (no padding rows in this mode)."""
+    assert planes == 2, "the sub-pixel convolution runs with two-plane operands"
+    co, ci = w.shape[:2]
+    assert co % 16 == 0 and ci % 64 == 0, (co, ci)
+    wp = fold_upconv_weight(w).reshape(16, co, ci).contiguous()
+    hi, lo = split_host(wp, 2)
+    dev = device or "cuda"
+    return PackedConvWeight(hi.contiguous().to(dev), lo.contiguous().to(dev), co, co, ci, (1, 3, 3))
+
+
 # ------------------------------------------------------------------------------------------------
 # grid_sample
 # ------------------------------------------------------------------------------------------------
@@ -342,7 +372,10 @@ def set_conv_profiler(p: Optional[ConvProfiler]):
 
 def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=None, residual=None, res_shift: int = 0,
                act: int = ACT_NONE, post_add=None, out_nchw: bool = False, stats: Optional[torch.Tensor] = None,
-               G: int = 32, out: Optional[torch.Tensor] = None, acc_chunk_mmas: int = 0, split_k: bool = True) -> torch.Tensor:
+               G: int = 32, out: Optional[torch.Tensor] = None, acc_chunk_mmas: int = 0, split_k: bool = True,
+               upconv: bool = False) -> torch.Tensor:
+    """upconv=True: `a` holds the LOW-resolution planes and `w` a pack_upconv_weight(): the result is
+    conv3x3(pad 1)(nearest_x2(a)) at (2H, 2W), evaluated in sub-pixel form (see emo_conv_desc.upconv)."""
     N, Di, Hi, Wi, Ci = a.shape
     assert Ci == w.cin, (Ci, w.cin)
     ws = None if (L.DRY_RUN or not split_k) else _splitk_workspace(a.hi.device)
@@ -352,6 +385,9 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
     if pad is None:
         pad = (kd // 2, kh // 2, kw // 2)
     Do, Ho, Wo = _out_dim(Di, kd, stride[0], pad[0]), _out_dim(Hi, kh, stride[1], pad[1]), _out_dim(Wi, kw, stride[2], pad[2])
+    if upconv:
+        assert w.hi.shape[0] == 16 and (kd, kh, kw) == (1, 3, 3) and tuple(stride) == (1, 1, 1) and Di == 1, "upconv needs pack_upconv_weight()"
+        Ho, Wo = 2 * Hi, 2 * Wi
     if out is None:
         shape = (N, w.cout, Do, Ho, Wo) if out_nchw else (N, Do, Ho, Wo, w.cout)
         out = torch.empty(shape, dtype=torch.float32, device=a.hi.device)
@@ -359,7 +395,7 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
                    G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None,
-                   acc_chunk_mmas or w.acc_chunk, _p(ws), ws.numel() if ws is not None else 0)
+                   acc_chunk_mmas or w.acc_chunk, _p(ws), ws.numel() if ws is not None else 0, 1 if upconv else 0)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -35,7 +35,7 @@ extern "C" {
 enum { EMO_ACT_NONE = 0, EMO_ACT_RELU = 1, EMO_ACT_SIGMOID = 2, EMO_ACT_TANH = 3 };
 
 const char* emo_last_error(void);
-int emo_version(void);
+int emo_version(void); /* 101: emo_pose_desc and emo_conv_desc gained trailing fields (zero = previous behaviour) */
 /* sm count, and cc major*10+minor of the current device */
 int emo_device_info(int* sm_count, int* cc);
 
@@ -208,6 +208,13 @@ typedef struct {
    * then one finalize launch applies bias/residual/activation/statistics).  NULL: never split. */
   float* splitk_ws;
   long long splitk_ws_elems;
+  /* sub-pixel evaluation of `nearest x2 -> 3x3 conv` (ImageDecoder up blocks, decoder.py:241-358 / utils.py:761-788 with
+   * upsample): when non-zero, a_hi/a_lo are the LOW-resolution planes [N][1][Hin][Win][Cin], Hout = 2 Hin, Wout = 2 Win,
+   * kd,kh,kw = 1,3,3 / pad 0,1,1 describe the convolution being replaced, and w_hi/w_lo hold the phase-folded weights
+   * [16 = 4 output phases x 2x2 taps][Cout_pad][Cin]: a 3x3 conv over a nearest-upsampled map is, per output-pixel parity,
+   * a 2x2 conv over the low-resolution map (4/9 of the MMAs, no upsampled operand in HBM).  residual/res_shift/post_add
+   * are indexed at the output resolution as usual.  Two-plane operands only. */
+  int upconv;
 } emo_conv_desc;
 int emo_conv_igemm(const emo_conv_desc* d, void* stream);
 

@@ -99,6 +99,14 @@ img2, _, _, so2 = model.driver_pass(st, x, mix=True, custom_pose_embed=torch.ran
 assert img.shape == img2.shape == (1, 3, size, size)
 assert L.launch_count - n0 < full        # the expression encoder is skipped when its output is replaced
 assert so2.target_pose_embed.shape == (1, 128)
+# sub-pixel up-sampling convolutions (opt-in): same shapes, one conv reads the low-resolution planes
+from emoportraits_b200 import nets
+nets.SUBPIXEL_UP = True
+m2 = Model(cfg, synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0), "cpu")
+ps = [b.c1_ps for b in m2.decoder_nw.img if b.c1_ps is not None]
+assert ps and ps[0].hi.shape[0] == 16 and ps[0].hi.shape[1] == ps[0].cout
+img3, deep_f, img_f, _ = m2.driver_pass(st, x, mix=True)
+assert img3.shape == (1, 3, size, size) and img_f.shape == (1, 1, size, size, cfg.dec_channels[-1])
 print("ok")
 """
 

@@ -1,0 +1,59 @@
+"""CPU tests of the sub-pixel form of `nearest x2 -> 3x3 conv` (emo_conv_desc.upconv, ops.fold_upconv_weight):
+the weight folding is exact algebra, and the index arithmetic the CUDA kernel uses (conv_igemm_kernel.inc, EMO_CONV_PS
+blocks: tile origin - pad + phase shift + tap, weight row phase * 4 + tap, output pixel 2 g + parity) is restated here
+with torch gathers and compared with F.conv2d on the upsampled map."""
+import torch
+import torch.nn.functional as F
+
+
+def _ref(x, w):
+    return F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+
+
+def test_fold_matches_conv_on_upsampled_map():
+    from emoportraits_b200.ops import fold_upconv_weight
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 7, 9, generator=g)
+    w = torch.randn(4, 5, 3, 3, generator=g)
+    fw = fold_upconv_weight(w)                                        # (4 phases, 2, 2, Co, Ci)
+    ref = _ref(x, w)
+    out = torch.zeros_like(ref)
+    for ph in range(4):
+        pa, pb = ph >> 1, ph & 1
+        k = fw[ph].permute(2, 3, 0, 1)                                # (Co, Ci, 2, 2)
+        # parity 0 reads offsets {-1, 0}: pad one row/column before; parity 1 reads {0, +1}: pad one after
+        xp = F.pad(x, (1 - pb, pb, 1 - pa, pa))
+        out[:, :, pa::2, pb::2] = F.conv2d(xp, k)
+    assert (out - ref).abs().max().item() < 1e-4 * ref.abs().max().item()
+
+
+def test_kernel_index_arithmetic():
+    """the integer formulas of the kernel, one 'tile' covering the whole low-res grid"""
+    from emoportraits_b200.ops import fold_upconv_weight
+
+    g = torch.Generator().manual_seed(1)
+    N, Ci, Co, H, W = 1, 6, 4, 5, 8
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, generator=g)
+    wk = fold_upconv_weight(w).reshape(16, Co, Ci)                    # weight rows as the tensor map sees them
+    ref = _ref(x, w)
+    out = torch.full_like(ref, float("nan"))
+    ph_pad, pw_pad, kh, kw = 1, 1, 2, 2                               # p.ph, p.pw of the descriptor; p.kh = p.kw = 2
+    xcl = x.permute(0, 2, 3, 1)                                       # channels-last, as the TMA box reads it
+    for ph in range(4):                                               # nt / p.ntc
+        xs, ys = (1 if (ph & 1) else 0), (1 if (ph >> 1) else 0)
+        acc = torch.zeros(N, H, W, Co)
+        for tap in range(kh * kw):
+            c, b = tap % kw + xs, (tap // kw) % kh + ys
+            wtap = ph * 4 + tap
+            for gh in range(H):
+                for gw in range(W):
+                    yy, xx = gh - ph_pad + b, gw - pw_pad + c         # y0 + b, x0 + c with tile origin (gh, gw)
+                    if 0 <= yy < H and 0 <= xx < W:                   # TMA zero fill outside
+                        acc[:, gh, gw] += xcl[:, yy, xx] @ wk[wtap].T
+        for gh in range(H):
+            for gw in range(W):
+                out[:, :, 2 * gh + (ph >> 1), 2 * gw + (ph & 1)] = acc[:, gh, gw]
+    assert not torch.isnan(out).any()
+    assert (out - ref).abs().max().item() < 1e-4

@@ -128,3 +128,67 @@ def test_wrapper_forward_options(ctx, tmp_path):
     assert w.source_img_mask.shape == (1, 1, SIZE, SIZE)
     _, img = w.forward(src, drv[0], c_target_latent_volume=X["c_target_latent_volume"], **base)
     assert _img_err(img, gold["c_target_latent_volume"]["img"]) < IMG_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sub-pixel up-sampling convolution (emo_conv_desc.upconv; opt-in in the model via EMO_UPCONV_PS=1).  Same status as the
+# tests above: written after the round-1 GPU budget was spent, first GPU run pending.  The weight folding and the
+# kernel's index arithmetic are checked on the CPU by tests/test_upconv_fold.py.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Cin,Cout,S,residual", [(192, 128, 64, False), (320, 192, 32, True), (512, 320, 32, False),
+                                                 (192, 128, 256, True)])
+def test_upconv_subpixel_matches_conv_on_upsampled_planes(Cin, Cout, S, residual):
+    """conv_igemm(low-res planes, folded weights, upconv=True) == conv_igemm(nearest-x2 planes, 3x3 weights): same operands
+    up to the fp32 pre-summing of the folded taps, so agreement to ~2^-15 of the output scale; statistics likewise.
+    S = 256 (-> 512^2, 2048 tiles) takes the store-warp (EPI = 1) variant of the kernel, the others EPI = 0."""
+    import math
+
+    from emoportraits_b200 import ops
+
+    g = torch.Generator().manual_seed(Cin + S)
+    x = torch.randn((1, 1, S, S, Cin), generator=g).cuda()
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn((1, 1, S, S, Cout), generator=g).cuda() if residual else None   # low-res skip, read with res_shift = 1
+    a_lo = ops.apply(x, act=ops.ACT_RELU, up=1)
+    a_up = ops.apply(x, act=ops.ACT_RELU, up=2)
+    st_ref, st_ps = ops.new_stats(1, 32, "cuda"), ops.new_stats(1, 32, "cuda")
+    ref = ops.conv_igemm(a_up, ops.pack_conv_weight(w), bias=b, residual=res, res_shift=1 if residual else 0, stats=st_ref)
+    out = ops.conv_igemm(a_lo, ops.pack_upconv_weight(w), bias=b, residual=res, res_shift=1 if residual else 0, stats=st_ps,
+                         upconv=True)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape == (1, 1, 2 * S, 2 * S, Cout)
+    scale = ref.abs().max().item()
+    err = (out - ref).abs().max().item()
+    print(f"\n[upconv sub-pixel vs upsampled planes] {Cin}->{Cout} @{S}^2: max-abs {err:.2e} (scale {scale:.2f})")
+    assert err < scale * 2 ** -13
+    assert ((st_ps - st_ref).abs() / st_ref.abs().clamp_min(1.0)).max().item() < 1e-5
+    if S <= 64:   # and against torch fp32 on the CPU
+        xr = torch.relu(x[0, 0].permute(2, 0, 1)[None].cpu())
+        want = F_conv_up(xr, w, b.cpu(), res)
+        assert (out[0, 0].permute(2, 0, 1)[None].cpu() - want).abs().max().item() < 2e-4 * max(1.0, scale)
+
+
+def F_conv_up(xr, w, b, res):
+    import torch.nn.functional as F
+
+    y = F.conv2d(F.interpolate(xr.double(), scale_factor=2, mode="nearest"), w.double(), b.double(), padding=1)
+    if res is not None:
+        y = y + F.interpolate(res[0, 0].permute(2, 0, 1)[None].cpu().double(), scale_factor=2, mode="nearest")
+    return y.float()
+
+
+def test_model_with_subpixel_up_convolutions_matches_reference(ctx, monkeypatch):
+    """whole driver pass with the three up-sampling convolutions of the image decoder in sub-pixel form vs the reference
+    fixture (same 1e-3 bar as the default path)"""
+    from emoportraits_b200 import nets
+    from emoportraits_b200.infer import Model
+
+    monkeypatch.setattr(nets, "SUBPIXEL_UP", True)
+    model = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda")
+    assert any(b.c1_ps is not None for b in model.decoder_nw.img)
+    st = model.source_pass(ctx["src"])
+    img, _, _, so = model.driver_pass(st, ctx["drv"][0], mix=True)
+    _check(ctx["gold"]["default"], img, so, "default+subpixel_up")
+    base, _, _, _ = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True)
+    print(f"[subpixel vs plain decoder] image max-abs {(img - base).abs().max().item():.2e}")
