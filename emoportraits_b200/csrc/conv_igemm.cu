@@ -492,8 +492,10 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   int KC = (d->Cin % 64 == 0) ? 64 : 32;  // three-plane tiles fall back to 32 below when 64 leaves < 3 pipeline stages
   // N tile: largest multiple of 16 that divides Cout_pad and fits the register-resident accumulator row
   int BN = 0;
+  const int bn_step_ok = d->upconv ? 32 : 16;  // sub-pixel mode always runs in pair mode, which needs BN % 32 == 0
   for (int cand = kMaxBN; cand >= 16; cand -= 16)
-    if (d->Cout_pad % cand == 0) { BN = cand; break; }
+    if (d->Cout_pad % cand == 0 && cand % bn_step_ok == 0) { BN = cand; break; }
+  EMO_REQUIRE(BN > 0, "emo_conv_igemm: no N tile for Cout_pad=%d", d->Cout_pad);
   // prefer 128-wide tiles when that fills the machine better (more tiles than SMs matters more than tile width)
   int sm_count = 148;
   {
@@ -535,7 +537,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   }
   if (ksplit == 1 && (long long)p.m_tiles * (d->Cout_pad / BN) * nt_mult < sm_count / 2) {
     for (int cand = BN; cand >= 16; cand -= 16) {
-      if (d->Cout_pad % cand) continue;
+      if (d->Cout_pad % cand || cand % bn_step_ok) continue;
       BN = cand;
       if ((long long)p.m_tiles * (d->Cout_pad / cand) * nt_mult >= sm_count) break;
     }

@@ -82,7 +82,7 @@ class ResBlock:
         self.c1_ps = None
         if subpixel_up and planes == 2:
             w, _ = fold_conv(sd, p + ".block_feats.2", ws=ws_first)
-            if tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 16 == 0 and w.shape[1] % 64 == 0:
+            if tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 32 == 0 and w.shape[1] % 64 == 0:
                 self.c1_ps = ops.pack_upconv_weight(w, device=dev)
         self.n2 = Norm(sd, p + ".block_feats.3", dev)
         self.c2 = ConvW(sd, p + ".block.0", dev, planes=planes)

@@ -125,10 +125,10 @@ def fold_upconv_weight(w: torch.Tensor) -> torch.Tensor:
 
 def pack_upconv_weight(w: torch.Tensor, device=None, planes: int = 2) -> PackedConvWeight:
     """OIHW 3x3 fp32 (already SN/WS-folded) -> phase-folded PackedConvWeight [16 = phase*4 + ty*2 + tx][Cout][Cin] for
-    conv_igemm(..., upconv=True).  Cout must be a multiple of 16 (no padding rows in this mode)."""
+    conv_igemm(..., upconv=True).  Cout must be a multiple of 32 (no padding rows; pair-mode N tiles)."""
     assert planes == 2, "the sub-pixel convolution runs with two-plane operands"
     co, ci = w.shape[:2]
-    assert co % 16 == 0 and ci % 64 == 0, (co, ci)
+    assert co % 32 == 0 and ci % 64 == 0, (co, ci)
     wp = fold_upconv_weight(w).reshape(16, co, ci).contiguous()
     hi, lo = split_host(wp, 2)
     dev = device or "cuda"

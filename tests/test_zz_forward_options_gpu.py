@@ -15,7 +15,8 @@ import torch
 from oracle import frames as FR
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run pending (round-1 GPU budget was spent before these were written)")]
+              pytest.mark.xfail(strict=False, reason="first GPU run pending (round-1 GPU budget was spent before these were written)"),
+              pytest.mark.timeout(600, method="thread")]   # never-run kernels: bound a hang instead of blocking the suite
 GOLD = pathlib.Path(__file__).parent / "golden"
 SIZE = 256
 IMG_TOL = 1e-3      # BASELINE.json north_star: max-abs per pixel on the fp32 image
