@@ -156,18 +156,27 @@ class _BN:
 class ResBlockBN:
     """utils.py:661-788 with norm_layer_type 'bn' in eval mode: no statistics are needed, the norm is an affine."""
 
-    def __init__(self, sd, p, dev, planes=2):
+    def __init__(self, sd, p, dev, planes=2, subpixel_up=False):
         self.planes = planes
         self.n1 = _BN(sd, p + ".block_feats.0", dev)
         self.c1 = nets.ConvW(sd, p + ".block_feats.2", dev, planes=planes)
+        self.c1_ps = None  # sub-pixel form of `nearest x2 -> bn -> relu -> 3x3 conv` (see nets.ResBlock; opt-in EMO_UPCONV_PS=1)
+        if subpixel_up and planes == 2:
+            w, _ = fold_conv(sd, p + ".block_feats.2")
+            if tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 32 == 0 and w.shape[1] % 64 == 0:
+                self.c1_ps = ops.pack_upconv_weight(w, device=dev)
         self.n2 = _BN(sd, p + ".block_feats.3", dev)
         self.c2 = nets.ConvW(sd, p + ".block.0", dev, planes=planes)
         self.skip = nets.ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
 
     def __call__(self, x, up=1, down=None):
         P = self.planes
-        a = ops.apply(x, self.n1.A, self.n1.B, per_sample=False, act=ops.ACT_RELU, up=up, planes=P)
-        y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b)
+        if up == 2 and self.c1_ps is not None and x.shape[1] == 1 and (x.shape[0] * x.shape[2] * x.shape[3]) % 256 == 0:
+            a = ops.apply(x, self.n1.A, self.n1.B, per_sample=False, act=ops.ACT_RELU, up=1, planes=P)
+            y = ops.conv_igemm(a, self.c1_ps, bias=self.c1.b, upconv=True)
+        else:
+            a = ops.apply(x, self.n1.A, self.n1.B, per_sample=False, act=ops.ACT_RELU, up=up, planes=P)
+            y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b)
         b = ops.apply(y, self.n2.A, self.n2.B, per_sample=False, act=ops.ACT_RELU, planes=P)
         s = ops.avgpool(x, down) if down else x
         if self.skip is not None:
@@ -202,8 +211,9 @@ class Stage2Model:
         p = "decoder"
         self.inp = nets.ConvW(sd, p + ".res_decoder.0", dev, planes=planes)
         self.res = [ResBlockBN(sd, f"{p}.res_decoder.{i + 1}", dev, planes) for i in range(cfg.dec_num_blocks)]
-        self.up = [ResBlockBN(sd, f"{p}.img_decoder.dec_img_blocks.{i}", dev, planes) for i in range(len(cfg.up_channels) - 1)]
-        self.feat = [ResBlockBN(sd, f"{p}.img_decoder.dec_img_feat_blocks.{i}", dev, planes) for i in range(4)]
+        ps = nets.SUBPIXEL_UP
+        self.up = [ResBlockBN(sd, f"{p}.img_decoder.dec_img_blocks.{i}", dev, planes, subpixel_up=ps) for i in range(len(cfg.up_channels) - 1)]
+        self.feat = [ResBlockBN(sd, f"{p}.img_decoder.dec_img_feat_blocks.{i}", dev, planes, subpixel_up=ps and i == 0) for i in range(4)]
         self.head_norm = _BN(sd, p + ".img_decoder.dec_img_head.0", dev)
         self.head = nets.ConvW(sd, p + ".img_decoder.dec_img_head.2", dev, planes=planes)
 

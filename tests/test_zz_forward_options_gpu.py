@@ -193,3 +193,23 @@ def test_model_with_subpixel_up_convolutions_matches_reference(ctx, monkeypatch)
     _check(ctx["gold"]["default"], img, so, "default+subpixel_up")
     base, _, _, _ = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True)
     print(f"[subpixel vs plain decoder] image max-abs {(img - base).abs().max().item():.2e}")
+
+
+@pytest.mark.parametrize("fixture", ["s2_512_b1.pt", "s2_1024_b4.pt"])
+def test_stage2_with_subpixel_up_convolutions_matches_reference(fixture, monkeypatch):
+    """stage-2 refinement decoder (four nearest-x2 up blocks, batch 1 and 4) with the sub-pixel convolutions vs the
+    reference fixtures; same bars as tests/test_stage2.py"""
+    from emoportraits_b200 import nets
+    from emoportraits_b200.stage2 import Stage2Config, Stage2Model, synthetic_state_dict_s2
+    from test_stage2 import _inputs, _sub_err   # tests/ is on sys.path under pytest (rootdir conftest)
+
+    monkeypatch.setattr(nets, "SUBPIXEL_UP", True)
+    gold = torch.load(GOLD / fixture, weights_only=False)
+    cfg = Stage2Config(output_size=gold["output_size"])
+    model = Stage2Model(cfg, synthetic_state_dict_s2(cfg, 0), "cuda")
+    assert sum(b.c1_ps is not None for b in model.up + model.feat) >= 3
+    resized, add, ffhq = model.forward(_inputs(gold).cuda())
+    e_add = _sub_err(add, gold["add"])
+    e_img = _sub_err((ffhq * 255).floor().clamp(0, 255).permute(0, 2, 3, 1).contiguous(), gold["ffhq_uint8"])
+    print(f"\n[stage-2 + sub-pixel up convs vs reference golden {fixture}] add {e_add:.2e} ffhq(uint8 steps) {e_img:.0f}")
+    assert e_add < 1e-3 and e_img <= 1.0
