@@ -401,8 +401,12 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
         e0.record()
         L.call("emo_conv_igemm", C.byref(d), _stream())
         e1.record()
-        _conv_profiler.rec.append((e0, e1, 2.0 * N * Do * Ho * Wo * w.cout * Ci * kd * kh * kw, 6 if three else 3,
-                                   f"{N}x{Di}x{Hi}x{Wi}x{Ci}->{w.cout} k{kd}{kh}{kw} s{stride[1]} p{3 if three else 2}"))
+        # algorithmic flops of the convolution being computed; MMA passes actually issued per algorithmic product
+        # (sub-pixel mode issues 4 of the 9 taps)
+        _conv_profiler.rec.append((e0, e1, 2.0 * N * Do * Ho * Wo * w.cout * Ci * kd * kh * kw,
+                                   (6 if three else 3) * (4.0 / 9.0 if upconv else 1.0),
+                                   f"{N}x{Di}x{Hi}x{Wi}x{Ci}->{w.cout} k{kd}{kh}{kw} s{stride[1]} p{3 if three else 2}"
+                                   + (" up2-subpixel" if upconv else "")))
     else:
         L.call("emo_conv_igemm", C.byref(d), _stream())
     return out
