@@ -151,6 +151,7 @@ def test_upconv_subpixel_matches_conv_on_upsampled_planes(Cin, Cout, S, residual
     w = torch.randn((Cout, Cin, 3, 3), generator=g) / math.sqrt(9 * Cin)
     b = torch.randn(Cout, generator=g).cuda()
     res = torch.randn((1, 1, S, S, Cout), generator=g).cuda() if residual else None   # low-res skip, read with res_shift = 1
+    ops.begin_pass("cuda")                      # zeroed statistics arena for new_stats()
     a_lo = ops.apply(x, act=ops.ACT_RELU, up=1)
     a_up = ops.apply(x, act=ops.ACT_RELU, up=2)
     st_ref, st_ps = ops.new_stats(1, 32, "cuda"), ops.new_stats(1, 32, "cuda")
