@@ -40,8 +40,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     dig = _digest()
     if LIB.exists() and not force and stamp.exists() and stamp.read_text() == dig:
         return LIB
-    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false"]
-    cmd = [c for c in cmd if c != "--use_fast_math=false"]
+    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo"]  # no --use_fast_math: expf/tanhf/division stay IEEE-accurate
     cmd += ["-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
     cmd += os.environ.get("EMO_NVCC_EXTRA", "").split()  # e.g. -DEMO_CONV_DEBUG for tools/conv_bound_probe.py
     if verbose:
