@@ -29,6 +29,7 @@ from .config import HotPathConfig
 
 G = 32
 SUBPIXEL_UP = os.environ.get("EMO_UPCONV_PS") == "1"  # sub-pixel up-sampling convolutions in the image decoder (opt-in)
+POOLCONV_FOLD = os.environ.get("EMO_POOLCONV_FOLD") == "1"  # `3x3 conv -> 2x2 avgpool` as one 4x4 stride-2 conv (opt-in)
 
 
 class ConvW:
@@ -72,7 +73,7 @@ def _count(x):
 class ResBlock:
     """utils.py:661-788: [nearest up] -> norm -> relu -> conv -> norm -> relu -> conv [-> avgpool]; skip = [up] -> [1x1] -> [pool]."""
 
-    def __init__(self, sd, p, dev, ws_first=True, planes=2, subpixel_up=False):
+    def __init__(self, sd, p, dev, ws_first=True, planes=2, subpixel_up=False, pool_fold=False):
         self.planes = planes
         self.n1 = Norm(sd, p + ".block_feats.0", dev)
         self.c1 = ConvW(sd, p + ".block_feats.2", dev, ws=ws_first, planes=planes)
@@ -87,6 +88,14 @@ class ResBlock:
         self.n2 = Norm(sd, p + ".block_feats.3", dev)
         self.c2 = ConvW(sd, p + ".block.0", dev, planes=planes)
         self.skip = ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
+        # `conv -> avgpool (1,2,2)` of down-sampling blocks folded into one 4x4 stride-2 conv (ops.fold_poolconv_weight):
+        # 16 taps per pooled output instead of 36 and no full-resolution conv output.  Opt-in (EMO_POOLCONV_FOLD=1) until
+        # it has been measured on the GPU.
+        self.c2_pool = None
+        if pool_fold:
+            w, _ = fold_conv(sd, p + ".block.0")
+            if tuple(w.shape[2:]) == (3, 3):
+                self.c2_pool = ops.pack_conv_weight(ops.fold_poolconv_weight(w), device=dev, planes=planes)
 
     def __call__(self, x, sx, up=1, down=None, ada=None, want_stats=True):
         dev = x.device
@@ -104,7 +113,9 @@ class ResBlock:
         if self.skip is not None:
             s = ops.conv_igemm(ops.split_bf16(s, self.planes), self.skip.w, bias=self.skip.b)
         st2 = ops.new_stats(N, G, dev) if want_stats else None
-        if down:
+        if down and self.c2_pool is not None and tuple(down) == (1, 2, 2) and b.shape[2] % 2 == 0 and b.shape[3] % 2 == 0:
+            out = ops.conv_igemm(b, self.c2_pool, stride=(1, 2, 2), pad=(0, 1, 1), bias=self.c2.b, residual=s, stats=st2)
+        elif down:
             full = ops.conv_igemm(b, self.c2.w, bias=self.c2.b)
             out = ops.avgpool(full, down, add=s, stats=st2)
         else:
@@ -124,7 +135,7 @@ class LocalEncoder:
         self.stem_w, self.stem_b = wc.to(dev).contiguous(), b.to(dev).contiguous()
         self.blocks = []
         for i in range(len(cfg.enc_channels) - 1):
-            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev, planes=planes))
+            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev, planes=planes, pool_fold=POOLCONV_FOLD))
             s //= 2
         self.fin_norm = Norm(sd, p + ".finale_layers.0", dev)
         # output channel o = c*D + d in the reference (infer.py:485 view(1,c,d,s,s)); emit d*C + c so the map is (h,w,d,c)

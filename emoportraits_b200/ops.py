@@ -123,6 +123,22 @@ def fold_upconv_weight(w: torch.Tensor) -> torch.Tensor:
     return torch.stack(out)                                                    # (4, 2, 2, Co, Ci)
 
 
+def fold_poolconv_weight(w: torch.Tensor) -> torch.Tensor:
+    """(Cout, Cin, 3, 3) weights of `3x3 conv (pad 1) -> 2x2 average pool` -> (Cout, Cin, 4, 4) weights of the ONE
+    4x4 stride-2 pad-1 convolution that computes the same thing:
+        avgpool2(conv3(x))[i, j] = 1/4 sum_{a,b in {0,1}} sum_{p,q} w[p, q] x[2i+a+p-1, 2j+b+q-1]
+                                 = sum_{u,v in 0..3} w4[u, v] x[2i+u-1, 2j+v-1],   w4[u, v] = 1/4 sum_{a,b} w[u-a, v-b].
+    16 taps per pooled output instead of 4 x 9, and the full-resolution conv output never exists.  The conv bias passes
+    through the pool unchanged."""
+    assert w.dim() == 4 and tuple(w.shape[2:]) == (3, 3), w.shape
+    w = w.detach().float()
+    w4 = torch.zeros(w.shape[0], w.shape[1], 4, 4, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            w4[:, :, a:a + 3, b:b + 3] += w
+    return 0.25 * w4
+
+
 def pack_upconv_weight(w: torch.Tensor, device=None, planes: int = 2) -> PackedConvWeight:
     """OIHW 3x3 fp32 (already SN/WS-folded) -> phase-folded PackedConvWeight [16 = phase*4 + ty*2 + tx][Cout][Cin] for
     conv_igemm(..., upconv=True).  Cout must be a multiple of 32 (no padding rows; pair-mode N tiles)."""

@@ -156,7 +156,7 @@ class _BN:
 class ResBlockBN:
     """utils.py:661-788 with norm_layer_type 'bn' in eval mode: no statistics are needed, the norm is an affine."""
 
-    def __init__(self, sd, p, dev, planes=2, subpixel_up=False):
+    def __init__(self, sd, p, dev, planes=2, subpixel_up=False, pool_fold=False):
         self.planes = planes
         self.n1 = _BN(sd, p + ".block_feats.0", dev)
         self.c1 = nets.ConvW(sd, p + ".block_feats.2", dev, planes=planes)
@@ -168,6 +168,11 @@ class ResBlockBN:
         self.n2 = _BN(sd, p + ".block_feats.3", dev)
         self.c2 = nets.ConvW(sd, p + ".block.0", dev, planes=planes)
         self.skip = nets.ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
+        self.c2_pool = None  # `conv -> avgpool (1,2,2)` as one 4x4 stride-2 conv (see nets.ResBlock; opt-in EMO_POOLCONV_FOLD=1)
+        if pool_fold:
+            w, _ = fold_conv(sd, p + ".block.0")
+            if tuple(w.shape[2:]) == (3, 3):
+                self.c2_pool = ops.pack_conv_weight(ops.fold_poolconv_weight(w), device=dev, planes=planes)
 
     def __call__(self, x, up=1, down=None):
         P = self.planes
@@ -181,6 +186,8 @@ class ResBlockBN:
         s = ops.avgpool(x, down) if down else x
         if self.skip is not None:
             s = ops.conv_igemm(ops.split_bf16(s, P), self.skip.w, bias=self.skip.b)
+        if down and self.c2_pool is not None and tuple(down) == (1, 2, 2) and b.shape[2] % 2 == 0 and b.shape[3] % 2 == 0:
+            return ops.conv_igemm(b, self.c2_pool, stride=(1, 2, 2), pad=(0, 1, 1), bias=self.c2.b, residual=s)
         if down:
             full = ops.conv_igemm(b, self.c2.w, bias=self.c2.b)
             return ops.avgpool(full, down, add=s)
@@ -204,7 +211,7 @@ class Stage2Model:
         self.stem_w, self.stem_b = wc.to(dev).contiguous(), b.to(dev).contiguous()
         self.enc = []
         for i in range(len(cfg.enc_channels) - 1):
-            self.enc.append(ResBlockBN(sd, f"{p}.enc_{i}_block={s}px", dev, planes))
+            self.enc.append(ResBlockBN(sd, f"{p}.enc_{i}_block={s}px", dev, planes, pool_fold=nets.POOLCONV_FOLD))
             s //= 2
         self.fin_norm = _BN(sd, p + ".finale_layers.0", dev)
         self.fin = nets.ConvW(sd, p + ".finale_layers.2", dev, planes=planes)

@@ -57,3 +57,17 @@ def test_kernel_index_arithmetic():
                 out[:, :, 2 * gh + (ph >> 1), 2 * gw + (ph & 1)] = acc[:, gh, gw]
     assert not torch.isnan(out).any()
     assert (out - ref).abs().max().item() < 1e-4
+
+
+def test_poolconv_fold_matches_conv_then_avgpool():
+    """ops.fold_poolconv_weight: avgpool2(conv3x3(x, pad 1) + bias) == conv4x4(x, stride 2, pad 1) + bias"""
+    from emoportraits_b200.ops import fold_poolconv_weight
+
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 6, 10, 14, generator=g)
+    w = torch.randn(5, 6, 3, 3, generator=g)
+    b = torch.randn(5, generator=g)
+    ref = F.avg_pool2d(F.conv2d(x, w, b, padding=1), 2)
+    out = F.conv2d(x, fold_poolconv_weight(w), b, stride=2, padding=1)
+    assert out.shape == ref.shape
+    assert (out - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())

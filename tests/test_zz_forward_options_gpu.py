@@ -214,3 +214,61 @@ def test_stage2_with_subpixel_up_convolutions_matches_reference(fixture, monkeyp
     e_img = _sub_err((ffhq * 255).floor().clamp(0, 255).permute(0, 2, 3, 1).contiguous(), gold["ffhq_uint8"])
     print(f"\n[stage-2 + sub-pixel up convs vs reference golden {fixture}] add {e_add:.2e} ffhq(uint8 steps) {e_img:.0f}")
     assert e_add < 1e-3 and e_img <= 1.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# `3x3 conv -> 2x2 average pool` folded into one 4x4 stride-2 convolution (ops.fold_poolconv_weight; opt-in in the models
+# via EMO_POOLCONV_FOLD=1).  No kernel change: the implicit-GEMM kernel is generic in the tap count.  First GPU run pending.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Cin,Cout,S,planes", [(128, 128, 64, 2), (256, 256, 128, 2), (128, 256, 32, 3)])
+def test_poolconv_fold_matches_conv_then_avgpool(Cin, Cout, S, planes):
+    import math
+
+    import torch.nn.functional as F
+
+    from emoportraits_b200 import ops
+
+    g = torch.Generator().manual_seed(Cin + S + planes)
+    x = torch.randn((1, Cin, S, S), generator=g)
+    w = torch.randn((Cout, Cin, 3, 3), generator=g) / math.sqrt(9 * Cin)
+    b = torch.randn(Cout, generator=g)
+    skip = torch.randn((1, Cout, S // 2, S // 2), generator=g)
+    want = (F.avg_pool2d(F.conv2d(x.double(), w.double(), b.double(), padding=1), 2) + skip.double()).float()
+    ops.begin_pass("cuda")
+    a = ops.split_bf16(x.permute(0, 2, 3, 1)[:, None].contiguous().cuda(), planes)
+    st = ops.new_stats(1, 32, "cuda")
+    out = ops.conv_igemm(a, ops.pack_conv_weight(ops.fold_poolconv_weight(w), planes=planes), stride=(1, 2, 2), pad=(0, 1, 1),
+                         bias=b.cuda(), residual=skip.permute(0, 2, 3, 1)[:, None].contiguous().cuda(), stats=st)
+    torch.cuda.synchronize()
+    got = out[:, 0].permute(0, 3, 1, 2).cpu()
+    err = (got - want).abs().max().item()
+    print(f"\n[4x4 stride-2 fold vs conv3x3 -> avgpool] {Cin}->{Cout} @{S}^2 planes {planes}: max-abs {err:.2e}")
+    assert err < (2e-4 if planes == 2 else 2e-5) * max(1.0, want.abs().max().item())
+    # statistics of the result, as the next GroupNorm needs them
+    grp = want.view(1, 32, -1)
+    ref_st = torch.stack([grp.double().sum(-1), (grp.double() ** 2).sum(-1)], -1)
+    assert ((st.cpu() - ref_st).abs() / ref_st.abs().clamp_min(1.0)).max().item() < 1e-3
+
+
+def test_models_with_poolconv_fold_match_reference(ctx, monkeypatch):
+    """LocalEncoder (source pass) and the stage-2 encoder with the folded down-sampling convolutions vs the fixtures"""
+    from emoportraits_b200 import nets
+    from emoportraits_b200.infer import Model
+    from emoportraits_b200.stage2 import Stage2Config, Stage2Model, synthetic_state_dict_s2
+    from test_stage2 import _inputs, _sub_err
+
+    monkeypatch.setattr(nets, "POOLCONV_FOLD", True)
+    model = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda")
+    assert all(b.c2_pool is not None for b in model.local_encoder_nw.blocks)
+    st = model.source_pass(ctx["src"])
+    img, _, _, so = model.driver_pass(st, ctx["drv"][0], mix=True)
+    _check(ctx["gold"]["default"], img, so, "default+poolconv_fold")
+    gold = torch.load(GOLD / "s2_512_b1.pt", weights_only=False)
+    cfg = Stage2Config(output_size=gold["output_size"])
+    s2 = Stage2Model(cfg, synthetic_state_dict_s2(cfg, 0), "cuda")
+    assert all(b.c2_pool is not None for b in s2.enc)
+    resized, add, ffhq = s2.forward(_inputs(gold).cuda())
+    e_add = _sub_err(add, gold["add"])
+    e_img = _sub_err((ffhq * 255).floor().clamp(0, 255).permute(0, 2, 3, 1).contiguous(), gold["ffhq_uint8"])
+    print(f"[stage-2 + folded encoder convs vs reference golden] add {e_add:.2e} ffhq(uint8 steps) {e_img:.0f}")
+    assert e_add < 1e-3 and e_img <= 1.0
