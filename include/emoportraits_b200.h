@@ -171,8 +171,9 @@ typedef struct {
 int emo_gn_head(const emo_gn_head_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Implicit-GEMM convolution on tcgen05 (2-D and 3-D, kernel 1 or 3 per dim, stride 1 or 2,
- * zero padding), bf16x2-split operands, fp32 accumulation in TMEM.
+ * Implicit-GEMM convolution on tcgen05 (2-D and 3-D, any kernel extent per dim — the path uses 1, 3 and the folded
+ * 4x4 stride-2 form of `3x3 conv -> 2x2 avgpool` —, stride 1 or 2, zero padding), bf16x2-split operands, fp32
+ * accumulation in TMEM.
  * Replaces: F.conv2d / F.conv3d call sites of utils.py:661-788 (ResBlock), :894-915 (Conv*_ws),
  *           decoder.py:77-81,349-356, local_encoder.py:104-108, warp_generator_resnet.py:99-106.
  * ------------------------------------------------------------------------------------------------ */
