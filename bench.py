@@ -462,7 +462,8 @@ def run_stage2(args):
     line = {"metric": "stage-2 refinement images/s @1024^2, batch 4 (BASELINE configs[4])", "value": B * 1000.0 / ms, "unit": "images/s",
             "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x2-split operands, fp32 accumulate", "data": "synthetic",
-            "config": {"workload": "stage-2 LocalEncoderOld + Decoder_stage2, output_size_s2 1024, batch 4, default stage-2 args"},
+            "config": {"workload": "stage-2 LocalEncoderOld + Decoder_stage2, output_size_s2 1024, batch 4, default stage-2 args",
+                       "experimental": {k: os.environ[k] for k in ("EMO_UPCONV_PS", "EMO_POOLCONV_FOLD") if os.environ.get(k)}},
             "gpu_launches": launches * K,
             "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv layers of one step)", "achieved": conv_flops / conv_ms / 1e9,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": conv_flops / conv_ms / 1e9 / peaks["bf16_tflops_sustained"],
