@@ -71,3 +71,68 @@ def test_poolconv_fold_matches_conv_then_avgpool():
     out = F.conv2d(x, fold_poolconv_weight(w), b, stride=2, padding=1)
     assert out.shape == ref.shape
     assert (out - ref).abs().max().item() < 1e-5 * max(1.0, ref.abs().max().item())
+
+
+def _pick_box(dim, want):
+    b = want
+    while b > dim:
+        b >>= 1
+    return max(b, 1)
+
+
+def test_subpixel_tile_walk_restated():
+    """Host parameters (emo_conv_igemm, upconv branch) and device index logic (conv_igemm_kernel.inc, EMO_CONV_PS blocks)
+    restated for a multi-tile case: 128-pixel boxes over the low-res grid, N tile = (phase, channel tile), TMA box gather
+    with zero fill, pixel-shuffle store.  Every output element must be written exactly once with the reference value."""
+    from emoportraits_b200.ops import fold_upconv_weight
+
+    g = torch.Generator().manual_seed(3)
+    N, Ci, Co, H, W = 2, 8, 64, 16, 32          # low-res grid 16 x 32 -> output 32 x 64
+    x = torch.randn(N, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, generator=g)
+    ref = _ref(x, w).permute(0, 2, 3, 1).contiguous()               # channels-last (N, 2H, 2W, Co)
+    wk = fold_upconv_weight(w).reshape(16, Co, Ci)
+    xcl = x.permute(0, 2, 3, 1).contiguous()
+    # ---- host (emo_conv_igemm with d->upconv) ----
+    BN = 32                                                          # a pair-compatible N tile dividing Cout_pad
+    gH, gW, oH, oW = H, W, 2 * H, 2 * W
+    tw = _pick_box(gW, 16); th = _pick_box(gH, 128 // tw); td = 1
+    tiles_w, tiles_h, tiles_d = -(-gW // tw), -(-gH // th), 1
+    m_tiles = N * tiles_d * tiles_h * tiles_w
+    ntc = Co // BN
+    n_tiles = 4 * ntc
+    kh = kw = 2; ph_pad = pw_pad = 1
+    assert m_tiles % 2 == 0                                          # pair mode
+    out = torch.full((N, oH, oW, Co), float("nan"))
+    writes = torch.zeros((N, oH, oW, Co), dtype=torch.int32)
+    rows_a = tw * th * td
+    for tile in range(m_tiles * n_tiles):
+        nt = tile // m_tiles
+        mt = tile - nt * m_tiles
+        twi = mt % tiles_w; mt //= tiles_w
+        thi = mt % tiles_h; mt //= tiles_h
+        n = mt
+        # ---- producer ----
+        x0, y0 = twi * tw - pw_pad, thi * th - ph_pad
+        ph = nt // ntc
+        n0 = (nt - ph * ntc) * BN
+        xs, ys = (1 if ph & 1 else 0), (1 if ph >> 1 else 0)
+        acc = torch.zeros(rows_a, BN)
+        for tap in range(kh * kw):
+            c, b = tap % kw + xs, (tap // kw) % kh + ys
+            wtap = ph * 4 + tap
+            A = torch.zeros(rows_a, Ci)                               # TMA box {Ci, tw, th} at (x0 + c, y0 + b), zero fill
+            for r in range(rows_a):
+                xx, yy = x0 + c + r % tw, y0 + b + r // tw
+                if 0 <= xx < W and 0 <= yy < H:
+                    A[r] = xcl[n, yy, xx]
+            acc += A @ wk[wtap, n0:n0 + BN].T
+        # ---- accumulate / store role ----
+        for row in range(rows_a):
+            gw, gh = twi * tw + row % tw, thi * th + (row // tw) % th
+            if gw < gW and gh < gH:
+                ow, oh = 2 * gw + (ph & 1), 2 * gh + (ph >> 1)
+                out[n, oh, ow, n0:n0 + BN] = acc[row]
+                writes[n, oh, ow, n0:n0 + BN] += 1
+    assert int(writes.min()) == 1 and int(writes.max()) == 1
+    assert (out - ref).abs().max().item() < 1e-4
