@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -71,6 +72,31 @@ __device__ __forceinline__ void split4x3(const float4& v, uint2& hi, uint2& lo, 
   hi.x = pack_bf16x2(h[0], h[1]); hi.y = pack_bf16x2(h[2], h[3]);
   lo.x = pack_bf16x2(l[0], l[1]); lo.y = pack_bf16x2(l[2], l[3]);
   lo2.x = pack_bf16x2(m[0], m[1]); lo2.y = pack_bf16x2(m[2], m[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> (fp16 hi, fp16 lo) split of a value pre-multiplied by a power of two: x*s ~= hi + lo to ~2^-22 |x*s| while the
+// planes stay in fp16's normal range (|x*s| >= 2^-3 keeps lo normal; smaller values lose only absolute 2^-25).  Three
+// fp16 MMAs (hi*hi + hi*lo + lo*hi) then carry ~22 mantissa bits: the fp32-faithful operand mode at half the MMAs of the
+// three-plane bf16 mode (tools/split_precision_emulation.py: 7e-8 relative vs 6e-9 for bf16 x3 and 4e-6 for bf16 x2).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_f16x2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ void split4_h(const float4& v, float s, uint2& hi, uint2& lo) {
+  __half h0, h1, h2, h3, l0, l1, l2, l3;
+  split_f16(v.x * s, h0, l0);
+  split_f16(v.y * s, h1, l1);
+  split_f16(v.z * s, h2, l2);
+  split_f16(v.w * s, h3, l3);
+  hi.x = pack_f16x2(h0, h1);
+  hi.y = pack_f16x2(h2, h3);
+  lo.x = pack_f16x2(l0, l1);
+  lo.y = pack_f16x2(l2, l3);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

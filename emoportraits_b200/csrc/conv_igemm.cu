@@ -76,6 +76,7 @@ struct ConvKParams {
   // phase = 2 * (row parity) + (column parity); each phase has its own four 2x2 taps (weights [phase * 4 + tap]).
   int oH, oW;
   int ntc;  // channel tiles per phase (= Cout_pad / BN)
+  float out_scale;  // conv_igemm_f16_kernel: 1 / (activation plane scale * weight plane scale)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -374,6 +375,7 @@ struct TMaps {
 };
 
 #define EMO_CONV_PS 0
+#define EMO_CONV_F16 0
 #define EMO_CONV_KERNEL_NAME conv_igemm_kernel
 #include "conv_igemm_kernel.inc"
 #undef EMO_CONV_PS
@@ -382,6 +384,14 @@ struct TMaps {
 #define EMO_CONV_KERNEL_NAME conv_igemm_ps_kernel
 #include "conv_igemm_kernel.inc"
 #undef EMO_CONV_PS
+#undef EMO_CONV_F16
+#undef EMO_CONV_KERNEL_NAME
+#define EMO_CONV_PS 0
+#define EMO_CONV_F16 1
+#define EMO_CONV_KERNEL_NAME conv_igemm_f16_kernel
+#include "conv_igemm_kernel.inc"
+#undef EMO_CONV_PS
+#undef EMO_CONV_F16
 #undef EMO_CONV_KERNEL_NAME
 
 // split-K finalize: out = act(ws + bias + residual) + post_add, statistics, and the workspace is zeroed for the next user
@@ -486,6 +496,8 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     EMO_REQUIRE(NP == 2 && d->Cin % 64 == 0 && d->Cout == d->Cout_pad && !d->out_nchw,
                 "emo_conv_igemm: upconv needs two-plane operands, Cin %% 64 == 0, Cout %% 16 == 0, channels-last output");
   }
+  const int f16 = d->operand_fp16 ? 1 : 0;
+  if (f16) EMO_REQUIRE(NP == 2 && !ps && d->out_scale > 0.f, "emo_conv_igemm: fp16 operands need two planes, no upconv, out_scale > 0");
   const int gH = ps ? d->Hin : d->Hout, gW = ps ? d->Win : d->Wout;  // the pixel grid the tiles walk
   const int taps_k = ps ? 4 : d->kd * d->kh * d->kw;                  // taps in one tile's K loop
   const int nt_mult = ps ? 4 : 1;                                     // N tiles per channel tile (one per output phase)
@@ -573,6 +585,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   p.rD = d->Dout; p.rH = d->Hout >> d->res_shift; p.rW = d->Wout >> d->res_shift;
   p.post_add = d->post_add; p.out = d->out; p.out_nchw = d->out_nchw;
   p.stats = d->stats; p.G = d->G; p.cpg = d->G > 0 ? d->Cout / d->G : 1;
+  p.out_scale = f16 ? d->out_scale : 1.f;
   EMO_REQUIRE(!d->residual || ((d->Hout % (1 << d->res_shift)) == 0 && (d->Wout % (1 << d->res_shift)) == 0),
               "emo_conv_igemm: residual shift does not divide the output size");
   EMO_REQUIRE(!ps || p.cg == 2, "emo_conv_igemm: upconv needs an even number of pixel tiles and BN %% 32 == 0 (pair mode)");
@@ -683,7 +696,18 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     e = cudaLaunchKernelEx(&cfg, KERNEL_<KC_, NP_, CG_, EPI_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
-  if (ps) {
+  if (f16) {
+    if (epi) {
+      if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 2, 1);
+      else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 2, 1);
+    } else if (p.cg == 2) {
+      if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 2, 0);
+      else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 2, 0);
+    } else {
+      if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 1, 0);
+      else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 1, 0);
+    }
+  } else if (ps) {
     EMO_REQUIRE(KC == 64, "emo_conv_igemm: upconv tile does not fit with KC = 64");
     if (epi) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 1);
     else EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 0);

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
   }
 }
 
-// Balanced variant (EMO_GS3_BALANCED=1; opt-in until measured on the GPU).  The brick kernel above launches one CTA
+// Balanced variant (chosen by emo_grid_sample3d when the brick kernel would run a partial second wave, see there; measured
+// in profiles/gs3_check_r1.txt).  The brick kernel above launches one CTA
 // per 256-voxel brick: 1024 CTAs for a 64^3 lattice against 148 SMs x 6 resident CTAs = 888 slots, so 136 bricks run
 // in a second, nearly empty wave whose lone CTA per SM is latency-bound (24 dependent gather rounds).  Here the grid
 // is exactly (SMs x resident CTAs) and every CTA takes an equal contiguous share of the brick-ordered voxel
@@ -448,35 +449,47 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     p.bh = d->Hout >= 8 ? 8 : d->Hout;
     p.bd = d->Dout >= 4 ? 4 : d->Dout;
     EMO_REQUIRE((long long)d->Din * d->Hin * d->Win * (d->C / 4) < (1ll << 31), "emo_grid_sample3d: volume too large for 32-bit offsets");
-    const char* bal = getenv("EMO_GS3_BALANCED");  // read per call so that one process can compare both kernels
-    if (bal && atoi(bal) > 0) {
+    // SMs x resident CTAs of the two instantiations (brick and balanced kernels have the same footprint: 40 registers,
+    // 18 KB of shared memory -> 6 CTAs of 256 threads per SM)
+    static int slots[2] = {0, 0};
+    const int k = d->out_hi ? 1 : 0;
+    if (!slots[k]) {
+      int dev = 0, sms = 0, occ = 0;
+      cudaError_t e = cudaGetDevice(&dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e == cudaSuccess)
+        e = k ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<true>, 256, 0)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<false>, 256, 0);
+      EMO_REQUIRE(e == cudaSuccess && sms > 0 && occ > 0, "emo_grid_sample3d: occupancy query failed (%s)", cudaGetErrorString(e));
+      slots[k] = sms * occ;
+    }
+    // brick decomposition of the brick kernel: small lattices shrink the brick until there are >= 4 CTAs per SM
+    int bh_brick = p.bh;
+    while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, bh_brick) * cdiv(d->Dout, p.bd) < 4 * 148 && bh_brick > 2) bh_brick >>= 1;
+    const long long blocks = (long long)d->N * cdiv(d->Dout, p.bd) * cdiv(d->Hout, bh_brick) * cdiv(d->Wout, p.bw);
+    EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");
+    // Kernel choice (measured with tools/gs3_check on a B200, profiles/gs3_check_r1.txt; outputs are bit-identical):
+    // when the brick kernel needs more CTAs than fit at once but at most twice as many, its second wave is a nearly
+    // empty tail of lone latency-bound CTAs and the balanced kernel wins (64^3 x 96ch: 69.8 -> 61.4 us, 16x64x64: 24.5 ->
+    // 22.5 us); with many waves the tail is negligible and the brick kernel is faster (batch 8 of 64^3: 373 vs 433 us).
+    // EMO_GS3_BALANCED=0 / 1 forces the brick / balanced kernel, > 1 also sets the balanced kernel's CTA count (read per
+    // call so that one process can compare them).
+    const char* bal = getenv("EMO_GS3_BALANCED");
+    const int force = bal ? atoi(bal) : -1;
+    const bool balanced = force > 0 || (force < 0 && blocks > slots[k] && blocks <= 2ll * slots[k]);
+    if (balanced) {
       p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
       const long long total = (long long)d->N * p.bricks_w * p.bricks_h * p.bricks_d * (p.bw * p.bh * p.bd);
       EMO_REQUIRE(total < (1ll << 31) - kBrickVox, "emo_grid_sample3d: lattice too large for the balanced kernel");
-      static int slots[2] = {0, 0};  // SMs x resident CTAs of the two instantiations (same for every device of a box)
-      const int k = d->out_hi ? 1 : 0;
-      if (!slots[k]) {
-        int dev = 0, sms = 0, occ = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess)
-          e = k ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<true>, 256, 0)
-                : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<false>, 256, 0);
-        EMO_REQUIRE(e == cudaSuccess && sms > 0 && occ > 0, "emo_grid_sample3d: occupancy query failed (%s)", cudaGetErrorString(e));
-        slots[k] = sms * occ;
-      }
-      // at least 64 voxels per CTA (atoi(bal) > 1 overrides the CTA count: tuning sweeps)
-      long long ctas = atoi(bal) > 1 ? atoi(bal) : slots[k];
+      // at least 64 voxels per CTA
+      long long ctas = force > 1 ? force : slots[k];
       if (ctas > cdivll(total, 64)) ctas = cdivll(total, 64);
       if (d->out_hi) gs3_cl_balanced_kernel<true><<<(unsigned)ctas, 256, 0, stream>>>(p);
       else gs3_cl_balanced_kernel<false><<<(unsigned)ctas, 256, 0, stream>>>(p);
       return check_launch("emo_grid_sample3d");
     }
-    // small lattices: shrink the brick until there are >= 4 CTAs per SM (load balance + latency hiding)
-    while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4 * 148 && p.bh > 2) p.bh >>= 1;
+    p.bh = bh_brick;
     p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
-    const long long blocks = (long long)d->N * p.bricks_d * p.bricks_h * p.bricks_w;
-    EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");
     if (d->out_hi) gs3_cl_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
     else gs3_cl_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
   } else {

@@ -74,110 +74,16 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
   d.B[idx] = bet - (float)mean * A;
 }
 
-// ---- apply: y = act(x*A + B [+ res*A2 + B2]) -> fp32 / bf16 hi,lo, optional nearest x2 on H,W ----
-// V = float4s per thread (2 when C % 8 == 0: 32 B loads, 16-byte bf16 plane stores)
-template <int UP, int V>
-__global__ void __launch_bounds__(256) apply_kernel(const emo_apply_desc d) {
-  extern __shared__ float sAB[];  // fused finalisation: A[C] then B[C] of this CTA's sample
-  const int cvn = d.C / (4 * V);  // channel-vector slots per position
-  const long long S = (long long)d.D * d.H * d.W;
-  const int n = blockIdx.y;
-  if (d.stats) {
-    const int cpg = d.C / d.G;
-    for (int c = threadIdx.x; c < d.C; c += blockDim.x) {
-      const int g = c / cpg;
-      const double s = d.stats[((long long)n * d.G + g) * 2], q = d.stats[((long long)n * d.G + g) * 2 + 1];
-      const double mean = s / d.count;
-      double var = q / d.count - mean * mean;
-      if (var < 0) var = 0;
-      const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
-      float gam = d.gamma ? d.gamma[c] : 1.f, bet = d.beta ? d.beta[c] : 0.f;
-      if (d.ada_w) {
-        const float aw = d.ada_w[(long long)n * d.C + c], ab = d.ada_b[(long long)n * d.C + c];
-        bet = bet * aw + ab;
-        gam = gam * aw;
-      }
-      const float A = rstd * gam;
-      sAB[c] = A;
-      sAB[d.C + c] = bet - (float)mean * A;
-    }
-    __syncthreads();
-  }
-  const long long per_n = S * cvn;
-  const float4* x4 = (const float4*)d.x + (long long)n * per_n * V;
-  const float4* r4 = d.res ? (const float4*)d.res + (long long)n * per_n * V : nullptr;
-  const float* gA = d.A ? d.A + (d.ab_per_sample ? (long long)n * d.C : 0) : nullptr;
-  const float* gB = d.B ? d.B + (d.ab_per_sample ? (long long)n * d.C : 0) : nullptr;
-  for (long long tt = (long long)blockIdx.x * blockDim.x + threadIdx.x; tt < per_n; tt += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(tt % cvn);
-    const long long s = tt / cvn;  // spatial position inside the sample
-    float4 v[V];
-#pragma unroll
-    for (int u = 0; u < V; ++u) v[u] = __ldg(x4 + tt * V + u);
-#pragma unroll
-    for (int u = 0; u < V; ++u) {
-      const int c = (cv * V + u) * 4;
-      if (d.stats) {
-        const float4 a = *(const float4*)&sAB[c];
-        const float4 b = *(const float4*)&sAB[d.C + c];
-        v[u].x = fmaf(v[u].x, a.x, b.x); v[u].y = fmaf(v[u].y, a.y, b.y); v[u].z = fmaf(v[u].z, a.z, b.z); v[u].w = fmaf(v[u].w, a.w, b.w);
-      } else if (gA) {
-        const float4 a = __ldg((const float4*)(gA + c));
-        const float4 b = __ldg((const float4*)(gB + c));
-        v[u].x = fmaf(v[u].x, a.x, b.x); v[u].y = fmaf(v[u].y, a.y, b.y); v[u].z = fmaf(v[u].z, a.z, b.z); v[u].w = fmaf(v[u].w, a.w, b.w);
-      }
-      if (r4) {
-        float4 r = __ldg(r4 + tt * V + u);
-        if (d.A2) {
-          const float4 a = __ldg((const float4*)(d.A2 + c));
-          const float4 b = __ldg((const float4*)(d.B2 + c));
-          r.x = fmaf(r.x, a.x, b.x); r.y = fmaf(r.y, a.y, b.y); r.z = fmaf(r.z, a.z, b.z); r.w = fmaf(r.w, a.w, b.w);
-        }
-        v[u].x += r.x; v[u].y += r.y; v[u].z += r.z; v[u].w += r.w;
-      }
-      v[u].x = act_apply(v[u].x, d.act); v[u].y = act_apply(v[u].y, d.act);
-      v[u].z = act_apply(v[u].z, d.act); v[u].w = act_apply(v[u].w, d.act);
-    }
-    uint2 hi[V], lo[V], lo2[V];
-    if (d.out_hi) {
-#pragma unroll
-      for (int u = 0; u < V; ++u) {
-        if (d.out_lo2) split4x3(v[u], hi[u], lo[u], lo2[u]);
-        else split4(v[u], hi[u], lo[u]);
-      }
-    }
-    auto store = [&](long long o) {  // o = float4-slot index of the first vector of this thread in the output tensor
-      if (d.out) {
-#pragma unroll
-        for (int u = 0; u < V; ++u) ((float4*)d.out)[o + u] = v[u];
-      }
-      if (d.out_hi) {
-        if (V == 2) {
-          ((uint4*)d.out_hi)[o >> 1] = make_uint4(hi[0].x, hi[0].y, hi[V - 1].x, hi[V - 1].y);
-          ((uint4*)d.out_lo)[o >> 1] = make_uint4(lo[0].x, lo[0].y, lo[V - 1].x, lo[V - 1].y);
-          if (d.out_lo2) ((uint4*)d.out_lo2)[o >> 1] = make_uint4(lo2[0].x, lo2[0].y, lo2[V - 1].x, lo2[V - 1].y);
-        } else {
-          ((uint2*)d.out_hi)[o] = hi[0];
-          ((uint2*)d.out_lo)[o] = lo[0];
-          if (d.out_lo2) ((uint2*)d.out_lo2)[o] = lo2[0];
-        }
-      }
-    };
-    if (UP == 1) {
-      store(((long long)n * per_n + tt) * V);
-    } else {
-      const int w = (int)(s % d.W);
-      const int h = (int)((s / d.W) % d.H);
-      const int dd = (int)(s / ((long long)d.W * d.H));
-      const int H2 = d.H * UP, W2 = d.W * UP;
-#pragma unroll
-      for (int uy = 0; uy < UP; ++uy)
-#pragma unroll
-        for (int ux = 0; ux < UP; ++ux)
-          store((((((long long)n * d.D + dd) * H2 + (h * UP + uy)) * W2 + (w * UP + ux)) * cvn + cv) * V);
-    }
-  }
-}
+#define EMO_APPLY_F16 0
+#define EMO_APPLY_KERNEL_NAME apply_kernel
+#include "apply_kernel.inc"
+#undef EMO_APPLY_F16
+#undef EMO_APPLY_KERNEL_NAME
+#define EMO_APPLY_F16 1
+#define EMO_APPLY_KERNEL_NAME apply_f16_kernel
+#include "apply_kernel.inc"
+#undef EMO_APPLY_F16
+#undef EMO_APPLY_KERNEL_NAME
 
 // Image head (emo_gn_head): one warp handles 8 pixels per step.  Lane l owns channels 4l..4l+3 (+128k): a warp load reads a
 // pixel's whole channel vector (512 B at C = 128); the 8 x 4 per-lane partial dot products are transpose-reduced over the
@@ -262,6 +168,14 @@ __global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* _
   }
 }
 
+__global__ void split_f16_kernel(const float* __restrict__ x, long long n4, float scale, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    uint2 h, l;
+    split4_h(__ldg((const float4*)x + t), scale, h, l);
+    hi[t] = h; lo[t] = l;
+  }
+}
+
 __global__ void flush_kernel(float4* buf, long long n4) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
     buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -312,6 +226,14 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   const dim3 grid((unsigned)blocks, (unsigned)d->N);
   const size_t smem = d->stats ? 2 * (size_t)d->C * sizeof(float) : 0;
   EMO_REQUIRE(smem <= 48 * 1024, "emo_apply: C=%d too large for the fused finalisation", d->C);
+  if (d->plane_fp16) {
+    EMO_REQUIRE(!d->out_lo2 && d->plane_scale > 0.f, "emo_apply: fp16 planes come in pairs and need a positive plane_scale");
+    if (d->up == 1 && V == 2) apply_f16_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
+    else if (d->up == 1) apply_f16_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
+    else if (V == 2) apply_f16_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
+    else apply_f16_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
+    return check_launch("emo_apply");
+  }
   if (d->up == 1 && V == 2) apply_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
   else if (d->up == 1) apply_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
   else if (V == 2) apply_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
@@ -344,6 +266,17 @@ extern "C" int emo_split_bf16(const float* x, long long n, void* hi, void* lo, v
   if (blocks < 1) blocks = 1;
   split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, (uint2*)hi, (uint2*)lo, (uint2*)lo2);
   return check_launch("emo_split_bf16");
+}
+
+extern "C" int emo_split_f16(const float* x, long long n, float scale, void* hi, void* lo, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(x && hi && lo, "emo_split_f16: null pointer");
+  EMO_REQUIRE(n % 4 == 0 && scale > 0.f, "emo_split_f16: n must be a multiple of 4 and scale positive");
+  long long blocks = cdivll(n / 4, 256);
+  if (blocks > 148ll * 32) blocks = 148ll * 32;
+  if (blocks < 1) blocks = 1;
+  split_f16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, scale, (uint2*)hi, (uint2*)lo);
+  return check_launch("emo_split_f16");
 }
 
 extern "C" int emo_l2_flush(void* buf, long long bytes, void* stream_) {

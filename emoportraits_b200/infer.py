@@ -41,6 +41,12 @@ class Model:
         pr.update(precision or {})
         if os.environ.get("EMO_PLANES"):
             pr = {k: int(os.environ["EMO_PLANES"]) for k in pr}
+        # EMO_H2_NETS=warp,expression,...: run these networks with fp16 two-plane operands ("h2": fp32-faithful like three
+        # bf16 planes at half the MMAs; opt-in until measured on the GPU, see ops.H2)
+        for k in filter(None, os.environ.get("EMO_H2_NETS", "").split(",")):
+            if k not in pr:
+                raise ValueError(f"EMO_H2_NETS: unknown network {k!r} (known: {sorted(pr)})")
+            pr[k] = ops.H2
         self.precision = pr
         self.local_encoder_nw = nets.LocalEncoder(sd, cfg, dev, planes=pr["local_encoder"])
         self.idt_embedder_nw = nets.IdtEmbed(sd, cfg, dev, planes=pr["idt"])

@@ -45,7 +45,8 @@ class ApplyDesc(C.Structure):
                 ("A", c_void_p), ("B", c_void_p), ("ab_per_sample", c_int), ("res", c_void_p), ("A2", c_void_p),
                 ("B2", c_void_p), ("act", c_int), ("up", c_int), ("out", c_void_p), ("out_hi", c_void_p),
                 ("out_lo", c_void_p), ("out_lo2", c_void_p), ("stats", c_void_p), ("G", c_int), ("count", c_double),
-                ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p), ("ada_w", c_void_p), ("ada_b", c_void_p)]
+                ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p), ("ada_w", c_void_p), ("ada_b", c_void_p),
+                ("plane_fp16", c_int), ("plane_scale", c_float)]
 
 
 class GnHeadDesc(C.Structure):
@@ -62,7 +63,8 @@ class ConvDesc(C.Structure):
                 ("bias", c_void_p), ("residual", c_void_p), ("res_shift", c_int), ("act", c_int),
                 ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int),
                 ("a_lo2", c_void_p), ("w_lo2", c_void_p), ("acc_chunk_mmas", c_int),
-                ("splitk_ws", c_void_p), ("splitk_ws_elems", c_ll), ("upconv", c_int)]
+                ("splitk_ws", c_void_p), ("splitk_ws_elems", c_ll), ("upconv", c_int),
+                ("operand_fp16", c_int), ("out_scale", c_float)]
 
 
 class ConvDirectDesc(C.Structure):
@@ -110,6 +112,7 @@ SYMBOLS = {
     "emo_global_avgpool": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p]),
     "emo_pose_theta": (c_int, [C.POINTER(PoseDesc), c_void_p]),
     "emo_split_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emo_split_f16": (c_int, [c_void_p, c_ll, c_float, c_void_p, c_void_p, c_void_p]),
     "emo_l2_flush": (c_int, [c_void_p, c_ll, c_void_p]),
 }
 

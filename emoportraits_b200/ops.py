@@ -35,13 +35,27 @@ def _chk(t: torch.Tensor, dtype=torch.float32):
     return t
 
 
+# fp16 two-plane operand mode ("h2"): planes hold (value * power of two) so that both fp16 planes stay in the normal range;
+# the convolution undoes the two scales on its fp32 sums (emo_conv_desc.operand_fp16 / out_scale).  ~2^-22 per operand:
+# fp32-faithful like three bf16 planes, at three MMAs per product instead of six (tools/split_precision_emulation.py).
+H2 = "h2"
+F16_ACT_SCALE = 16.0    # activations: post-GroupNorm / ReLU values are O(1)
+F16_W_SCALE = 256.0     # spectral-norm / weight-standardised weights are O(0.01 .. 1)
+
+
+def _nplanes(planes) -> int:
+    return 2 if planes == H2 else int(planes)
+
+
 @dataclass
 class Split:
-    """bf16 planes of a channels-last activation (N, D, H, W, C): (hi, lo) — or (hi, lo, lo2) in the fp32-faithful
-    three-plane mode used by the numerically sensitive networks."""
+    """operand planes of a channels-last activation (N, D, H, W, C): bf16 (hi, lo) — or (hi, lo, lo2) in the fp32-faithful
+    three-plane mode used by the numerically sensitive networks — or, with f16 = True, fp16 (hi, lo) of value * scale."""
     hi: torch.Tensor
     lo: torch.Tensor
     lo2: Optional[torch.Tensor] = None
+    f16: bool = False
+    scale: float = 1.0
 
     @property
     def shape(self):
@@ -52,16 +66,21 @@ class Split:
         return 3 if self.lo2 is not None else 2
 
     @staticmethod
-    def empty(shape, device, planes: int = 2) -> "Split":
+    def empty(shape, device, planes=2) -> "Split":
+        if planes == H2:
+            buf = torch.empty((2,) + tuple(shape), dtype=torch.float16, device=device)
+            return Split(buf[0], buf[1], None, True, F16_ACT_SCALE)
         buf = torch.empty((planes,) + tuple(shape), dtype=torch.bfloat16, device=device)
         return Split(buf[0], buf[1], buf[2] if planes == 3 else None)
 
     def view(self, *shape) -> "Split":
-        return Split(self.hi.view(*shape), self.lo.view(*shape), self.lo2.view(*shape) if self.lo2 is not None else None)
+        return Split(self.hi.view(*shape), self.lo.view(*shape), self.lo2.view(*shape) if self.lo2 is not None else None,
+                     self.f16, self.scale)
 
     def float(self) -> torch.Tensor:
         f = self.hi.float() + self.lo.float()
-        return f + self.lo2.float() if self.lo2 is not None else f
+        f = f + self.lo2.float() if self.lo2 is not None else f
+        return f / self.scale if self.f16 else f
 
 
 @dataclass
@@ -75,10 +94,17 @@ class PackedConvWeight:
     k: tuple  # (kd, kh, kw)
     lo2: Optional[torch.Tensor] = None
     acc_chunk: int = 0  # MMAs per TMEM accumulation chunk (0 = kernel default: 48 with two planes, 24 with three)
+    f16: bool = False   # fp16 planes of weight * scale (the "h2" operand mode)
+    scale: float = 1.0
 
 
-def split_host(w: torch.Tensor, planes: int = 2):
-    """fp32 -> bf16 planes with torch ops (load-time weight preparation only)."""
+def split_host(w: torch.Tensor, planes=2):
+    """fp32 -> bf16 planes (or, planes == "h2", fp16 planes of w * F16_W_SCALE) with torch ops (load-time weight preparation only)."""
+    if planes == H2:
+        assert float(w.abs().max()) * F16_W_SCALE < 6.0e4, "weight too large for the fp16 plane scale"
+        ws = w * F16_W_SCALE
+        hi = ws.to(torch.float16)
+        return hi, (ws - hi.float()).to(torch.float16)
     hi = w.to(torch.bfloat16)
     r = w - hi.float()
     lo = r.to(torch.bfloat16)
@@ -88,7 +114,7 @@ def split_host(w: torch.Tensor, planes: int = 2):
     return hi, lo, lo2
 
 
-def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tensor] = None, planes: int = 2) -> PackedConvWeight:
+def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tensor] = None, planes=2) -> PackedConvWeight:
     """OIHW / OIDHW fp32 (already SN/WS-folded) -> PackedConvWeight. `in_perm` optionally re-orders input channels."""
     w = w.detach().float()
     if w.dim() == 4:
@@ -101,6 +127,10 @@ def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tenso
     wp[:, :co] = w.permute(2, 3, 4, 0, 1).reshape(kd * kh * kw, co, ci).cpu()
     pl = split_host(wp, planes)
     dev = device or "cuda"
+    if planes == H2:
+        # 24 MMAs per TMEM accumulation chunk, as in the three-plane mode it replaces (the accumulator truncates)
+        return PackedConvWeight(pl[0].contiguous().to(dev), pl[1].contiguous().to(dev), co, co_pad, ci, (kd, kh, kw), None, 24,
+                                True, F16_W_SCALE)
     return PackedConvWeight(pl[0].contiguous().to(dev), pl[1].contiguous().to(dev), co, co_pad, ci, (kd, kh, kw),
                             pl[2].contiguous().to(dev) if planes == 3 else None)
 
@@ -296,7 +326,7 @@ def gn_finalize(stats: torch.Tensor, count: float, gamma, beta, eps: float = 1e-
 
 
 def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
-          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes: int = 2, gn=None):
+          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes=2, gn=None):
     """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W).
     gn = dict(stats, count, gamma, beta[, ada_w, ada_b, eps]) fuses the GroupNorm finalisation (replaces A/B)."""
     _chk(x)
@@ -308,7 +338,8 @@ def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=Non
                     _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, _p(sp.lo2) if sp else None,
                     _p(gn["stats"]) if gn else None, gn["stats"].shape[1] if gn else 0, float(gn["count"]) if gn else 0.0,
                     float(gn.get("eps", 1e-5)) if gn else 0.0, _p(gn["gamma"]) if gn else None, _p(gn["beta"]) if gn else None,
-                    _p(gn.get("ada_w")) if gn else None, _p(gn.get("ada_b")) if gn else None)
+                    _p(gn.get("ada_w")) if gn else None, _p(gn.get("ada_b")) if gn else None,
+                    1 if (sp is not None and sp.f16) else 0, sp.scale if (sp is not None and sp.f16) else 0.0)
     L.call("emo_apply", C.byref(d), _stream())
     if want_f32 and want_split:
         return out, sp
@@ -329,10 +360,14 @@ def gn_head(x: torch.Tensor, gn: dict, w: torch.Tensor, bias: Optional[torch.Ten
     return out
 
 
-def split_bf16(x: torch.Tensor, planes: int = 2) -> Split:
+def split_bf16(x: torch.Tensor, planes=2) -> Split:
+    """fp32 -> operand planes (bf16 x2 / x3, or fp16 x2 of x * F16_ACT_SCALE when planes == "h2")"""
     _chk(x)
     sp = Split.empty(x.shape, x.device, planes)
-    L.call("emo_split_bf16", _p(x), x.numel(), _p(sp.hi), _p(sp.lo), _p(sp.lo2), _stream())
+    if sp.f16:
+        L.call("emo_split_f16", _p(x), x.numel(), C.c_float(sp.scale), _p(sp.hi), _p(sp.lo), _stream())
+    else:
+        L.call("emo_split_bf16", _p(x), x.numel(), _p(sp.hi), _p(sp.lo), _p(sp.lo2), _stream())
     return sp
 
 
@@ -397,6 +432,8 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
     ws = None if (L.DRY_RUN or not split_k) else _splitk_workspace(a.hi.device)
     three = a.lo2 is not None
     assert not three or w.lo2 is not None, "3-plane activations need 3-plane weights (pack_conv_weight(planes=3))"
+    assert a.f16 == w.f16, "fp16-plane activations need fp16-plane weights (pack_conv_weight(planes='h2')) and vice versa"
+    assert not (a.f16 and upconv), "the sub-pixel convolution runs with bf16 planes"
     kd, kh, kw = w.k
     if pad is None:
         pad = (kd // 2, kh // 2, kw // 2)
@@ -411,7 +448,8 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                    stride[0], stride[1], stride[2], pad[0], pad[1], pad[2], Do, Ho, Wo, _p(bias), _p(residual),
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
                    G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None,
-                   acc_chunk_mmas or w.acc_chunk, _p(ws), ws.numel() if ws is not None else 0, 1 if upconv else 0)
+                   acc_chunk_mmas or w.acc_chunk, _p(ws), ws.numel() if ws is not None else 0, 1 if upconv else 0,
+                   1 if a.f16 else 0, 1.0 / (a.scale * w.scale) if a.f16 else 0.0)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -421,7 +459,7 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
         # (sub-pixel mode issues 4 of the 9 taps)
         _conv_profiler.rec.append((e0, e1, 2.0 * N * Do * Ho * Wo * w.cout * Ci * kd * kh * kw,
                                    (6 if three else 3) * (4.0 / 9.0 if upconv else 1.0),
-                                   f"{N}x{Di}x{Hi}x{Wi}x{Ci}->{w.cout} k{kd}{kh}{kw} s{stride[1]} p{3 if three else 2}"
+                                   f"{N}x{Di}x{Hi}x{Wi}x{Ci}->{w.cout} k{kd}{kh}{kw} s{stride[1]} p{'h2' if a.f16 else (3 if three else 2)}"
                                    + (" up2-subpixel" if upconv else "")))
     else:
         L.call("emo_conv_igemm", C.byref(d), _stream())

@@ -145,6 +145,10 @@ typedef struct {
   const float* beta;  /* [C] */
   const float* ada_w; /* [N][C] or NULL */
   const float* ada_b;
+  /* fp16 two-plane operand mode (see emo_conv_desc.operand_fp16): when plane_fp16 != 0, out_hi/out_lo receive the fp16
+   * planes of y * plane_scale (plane_scale a power of two that keeps the planes in fp16's normal range; out_lo2 unused). */
+  int plane_fp16;
+  float plane_scale;
 } emo_apply_desc;
 int emo_apply(const emo_apply_desc* d, void* stream);
 
@@ -216,6 +220,13 @@ typedef struct {
    * a 2x2 conv over the low-resolution map (4/9 of the MMAs, no upsampled operand in HBM).  residual/res_shift/post_add
    * are indexed at the output resolution as usual.  Two-plane operands only. */
   int upconv;
+  /* fp16 two-plane operand mode: a_hi/a_lo and w_hi/w_lo are FP16 planes of (activation * sa) and (weight * sw), sa and sw
+   * powers of two chosen by the caller (emo_apply.plane_scale / the weight packer); the kernel issues the same three MMAs
+   * (hi*hi + hi*lo + lo*hi, kind::f16 with fp16 inputs) and multiplies the fp32 sums by out_scale = 1 / (sa * sw) before
+   * bias / residual.  ~22 mantissa bits per operand: fp32-faithful like the three-plane bf16 mode at half its MMAs.
+   * Not combinable with a_lo2/w_lo2 or upconv. */
+  int operand_fp16;
+  float out_scale;
 } emo_conv_desc;
 int emo_conv_igemm(const emo_conv_desc* d, void* stream);
 
@@ -310,6 +321,8 @@ int emo_pose_theta(const emo_pose_desc* d, void* stream);
 
 /* fp32 -> bf16 hi/lo(/lo2) planes (n elements); lo2 may be NULL. */
 int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* lo2, void* stream);
+/* fp32 -> fp16 hi/lo planes of x * scale (n elements), the operand format of emo_conv_desc.operand_fp16. */
+int emo_split_f16(const float* x, long long n, float scale, void* hi, void* lo, void* stream);
 /* L2 flush helper for benchmarks: writes `bytes` of `buf`. */
 int emo_l2_flush(void* buf, long long bytes, void* stream);
 

@@ -153,9 +153,9 @@ int main(int argc, char** argv) {
     }
     const double bytes = ((double)2 * c.C + (c.affine ? 0 : 3)) * 4.0 * (double)vox;
     const char* variants[] = {"brick", "balanced", "balanced_4perSM", "balanced_5perSM", "balanced_8perSM"};
-    const char* envs[] = {nullptr, "1", "592", "740", "1184"};
+    const char* envs[] = {"0", "1", "592", "740", "1184"};
     for (int v = 0; v < 5; ++v) {
-      if (envs[v]) setenv("EMO_GS3_BALANCED", envs[v], 1); else unsetenv("EMO_GS3_BALANCED");
+      setenv("EMO_GS3_BALANCED", envs[v], 1);
       const int slot = v == 0 ? 0 : 1;
       d.out = out[slot];
       d.out_hi = planes[slot][0]; d.out_lo = planes[slot][1];
