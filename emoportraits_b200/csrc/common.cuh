@@ -84,6 +84,7 @@ __device__ __forceinline__ uint32_t pack_f16x2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -65000.f), 65000.f);  // fp16 has no headroom beyond 65504: saturate instead of producing inf
   hi = __float2half_rn(x);
   lo = __float2half_rn(x - __half2float(hi));
 }

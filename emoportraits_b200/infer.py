@@ -46,6 +46,8 @@ class Model:
         for k in filter(None, os.environ.get("EMO_H2_NETS", "").split(",")):
             if k not in pr:
                 raise ValueError(f"EMO_H2_NETS: unknown network {k!r} (known: {sorted(pr)})")
+            if k == "decoder":
+                raise ValueError("EMO_H2_NETS: the decoder's input planes are written by grid_sample_3d in bf16; it stays at two bf16 planes")
             pr[k] = ops.H2
         self.precision = pr
         self.local_encoder_nw = nets.LocalEncoder(sd, cfg, dev, planes=pr["local_encoder"])

@@ -115,3 +115,40 @@ def test_dry_run_forward_options():
     env = dict(os.environ, EMO_DRY_RUN="1")
     r = subprocess.run([sys.executable, "-c", OPTIONS_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+H2_SCRIPT = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from emoportraits_b200 import lib as L, ops
+assert L.DRY_RUN
+from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
+from emoportraits_b200.config import shipped_config
+from emoportraits_b200.infer import Model
+cfg = shipped_config(256)
+m = Model(cfg, synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0), "cpu")
+assert m.precision["warp"] == ops.H2 and m.precision["expression"] == ops.H2 and m.precision["decoder"] == 2, m.precision
+x = torch.rand(1, 3, 256, 256)
+st = m.source_pass(x)
+img, _, _, _ = m.driver_pass(st, x, mix=True)
+assert img.shape == (1, 3, 256, 256)
+# load-time weight planes: fp16 of w * 256, reproducing w to ~2^-22
+w = torch.randn(32, 64, 3, 3) * 0.05
+pw = ops.pack_conv_weight(w, device="cpu", planes=ops.H2)
+assert pw.f16 and pw.hi.dtype == torch.float16 and pw.scale == ops.F16_W_SCALE and pw.acc_chunk == 24
+rec = (pw.hi.float() + pw.lo.float()) / pw.scale                       # [taps][Cout_pad][Cin]
+ref = w.permute(2, 3, 0, 1).reshape(9, 32, 64)
+assert (rec - ref).abs().max().item() < 2 ** -21 * ref.abs().max().item()
+a = ops.Split.empty((1, 1, 4, 4, 8), "cpu", ops.H2)
+assert a.f16 and a.hi.dtype == torch.float16 and a.scale == ops.F16_ACT_SCALE and a.view(1, 1, 16, 1, 8).f16
+print("ok")
+"""
+
+
+def test_dry_run_fp16_two_plane_networks():
+    env = dict(os.environ, EMO_DRY_RUN="1", EMO_H2_NETS="warp,expression,head_pose")
+    r = subprocess.run([sys.executable, "-c", H2_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+    bad = dict(os.environ, EMO_DRY_RUN="1", EMO_H2_NETS="decoder")
+    r = subprocess.run([sys.executable, "-c", H2_SCRIPT % str(ROOT)], env=bad, capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "decoder" in r.stderr

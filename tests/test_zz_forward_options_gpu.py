@@ -272,3 +272,61 @@ def test_models_with_poolconv_fold_match_reference(ctx, monkeypatch):
     e_img = _sub_err((ffhq * 255).floor().clamp(0, 255).permute(0, 2, 3, 1).contiguous(), gold["ffhq_uint8"])
     print(f"[stage-2 + folded encoder convs vs reference golden] add {e_add:.2e} ffhq(uint8 steps) {e_img:.0f}")
     assert e_add < 1e-3 and e_img <= 1.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp16 two-plane operand mode ("h2", ops.H2; opt-in per network via EMO_H2_NETS / Model(precision=...)): three MMAs per
+# product at fp32-level operand accuracy (tools/split_precision_emulation.py), meant to replace the six-MMA three-plane
+# bf16 mode of the embedding / warp / source networks.  First GPU run pending.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Cin,Cout,sp,k", [(512, 512, (64, 64), 3), (96, 96, (16, 16), 3), (64, 32, (8, 16, 16), 3), (64, 128, (8, 8), 3),
+                                           (256, 128, (8, 8, 8), 1)])
+def test_conv_igemm_fp16_two_planes(Cin, Cout, sp, k):
+    """same cases and bar as tests/test_ops_gpu.py::test_conv_igemm_three_planes: fp32-faithful against an fp64 reference"""
+    import math
+
+    import torch.nn.functional as F
+
+    from emoportraits_b200 import ops
+
+    g = torch.Generator().manual_seed(Cin + Cout)
+    three_d = len(sp) == 3
+    x = torch.randn(1, Cin, *sp, generator=g)
+    w = torch.randn(Cout, Cin, *([k] * len(sp)), generator=g) / math.sqrt(Cin * k ** len(sp))
+    b = torch.randn(Cout, generator=g)
+    ref = (F.conv3d if three_d else F.conv2d)(x.double(), w.double(), b.double(), padding=k // 2)
+    xc = x.permute(0, 2, 3, 4, 1).contiguous() if three_d else x.permute(0, 2, 3, 1)[:, None].contiguous()
+    ops.begin_pass("cuda")
+    a = ops.split_bf16(xc.cuda(), ops.H2)
+    assert a.f16 and a.hi.dtype == torch.float16
+    assert (a.float().cpu() - xc).abs().max().item() < 1e-5                # the planes reproduce the activations
+    out = ops.conv_igemm(a, ops.pack_conv_weight(w, planes=ops.H2), bias=b.cuda())
+    torch.cuda.synchronize()
+    got = out.permute(0, 4, 1, 2, 3).cpu() if three_d else out[:, 0].permute(0, 3, 1, 2).cpu()
+    err = (got.double() - ref).abs().max().item()
+    print(f"\n[conv fp16 two planes vs fp64] {Cin}->{Cout} {sp} k{k}: max-abs {err:.2e} (scale {ref.abs().max().item():.2f})")
+    assert err < 2e-5 * max(1.0, ref.abs().max().item())
+    # GroupNorm + ReLU planes written by the apply pass in the same format
+    st = ops.gn_stats(out, 32)
+    gamma, beta = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    sp_h = ops.apply(out, gn=dict(stats=st, count=out.numel() / 32, gamma=gamma.cuda(), beta=beta.cuda()), act=ops.ACT_RELU, planes=ops.H2)
+    want = torch.relu(F.group_norm(got, 32, gamma, beta, 1e-5))
+    back = sp_h.float().permute(0, 4, 1, 2, 3).cpu() if three_d else sp_h.float()[:, 0].permute(0, 3, 1, 2).cpu()
+    assert (back - want).abs().max().item() < 1e-4
+
+
+def test_model_with_fp16_two_plane_networks_matches_reference(ctx):
+    """the per-frame networks that run with three bf16 planes today (head pose, expression, warp generators) switched to
+    fp16 two planes: same 1e-3 image bar against the reference fixture, and stage outputs close to the default path"""
+    from emoportraits_b200 import ops
+    from emoportraits_b200.infer import Model
+
+    model = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda",
+                  precision=dict(head_pose=ops.H2, expression=ops.H2, warp=ops.H2, idt=ops.H2, local_encoder=ops.H2,
+                                 volume_source=ops.H2, unet3d=ops.H2))
+    st = model.source_pass(ctx["src"])
+    img, _, _, so = model.driver_pass(st, ctx["drv"][0], mix=True)
+    _check(ctx["gold"]["default"], img, so, "default+h2 networks")
+    base, _, _, so0 = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True)
+    print(f"[h2 vs three-plane networks] image max-abs {(img - base).abs().max().item():.2e} "
+          f"pose_embed {(so.target_pose_embed - so0.target_pose_embed).abs().max().item():.2e}")
