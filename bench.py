@@ -185,7 +185,7 @@ def grid_sample_roofline(peaks, reps=20):
     """config 3 microbench: 96ch volume, D=64 (BASELINE's "64^3") and D=16 (model-true), channels-last,
     L2 flushed (256 MB write) between reps.  Variants: `jitter` = identity lattice + 0.1*randn grid tensor (the spec'd
     workload: sigma = 3.2 voxels, i.e. an L2-resident random gather), `affine` = fused theta lattice (30 deg rotation +
-    0.2 translation; no grid tensor; the hot path's rotation warp), batch 1 and 8."""
+    0.2 translation; no grid tensor; the hot path's rotation warp), batch 1, 8 and 32 (BASELINE configs[2]: "batch 1-32")."""
     import math
 
     from emoportraits_b200 import ops
@@ -210,22 +210,31 @@ def grid_sample_roofline(peaks, reps=20):
             ts.append(e0.elapsed_time(e1))
         return float(np.median(ts))
 
-    for name, D, B in (("d64", 64, 1), ("d16", 16, 1), ("d64_b8", 64, 8)):
-        C, S = 96, 64
-        g = torch.Generator(device="cpu").manual_seed(0)
-        vol = torch.randn(B, D, S, S, C, generator=g).to(dev)
-        zs, ys = torch.linspace(-1, 1, D), torch.linspace(-1, 1, S)
-        w, v, u = torch.meshgrid(zs, ys, ys, indexing="ij")
-        grid = (torch.stack([u, v, w], -1)[None] + 0.1 * torch.randn(B, D, S, S, 3, generator=g)).contiguous().to(dev)
-        theta = theta1.repeat(B, 1, 1).contiguous().to(dev)
-        ms = timeit(lambda: ops.grid_sample3d(vol, grid=grid, in_layout="cl"))
-        alg = (2 * C * D * S * S + 3 * D * S * S) * 4 * B
-        out[name] = {"ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / peaks["hbm_gbs"]}
-        ms = timeit(lambda: ops.grid_sample3d(vol, theta=theta, out_size=(D, S, S), in_layout="cl"))
-        alg = (2 * C * D * S * S) * 4 * B
-        out[name + "_affine"] = {"ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6,
-                                 "frac": alg / ms / 1e6 / peaks["hbm_gbs"]}
-        del vol, grid
+    for name, D, B in (("d64", 64, 1), ("d16", 16, 1), ("d64_b8", 64, 8), ("d64_b32", 64, 32)):
+        try:
+            C, S = 96, 64
+            zs, ys = torch.linspace(-1, 1, D), torch.linspace(-1, 1, S)
+            w, v, u = torch.meshgrid(zs, ys, ys, indexing="ij")
+            if B <= 8:
+                g = torch.Generator(device="cpu").manual_seed(0)
+                vol = torch.randn(B, D, S, S, C, generator=g).to(dev)
+                grid = (torch.stack([u, v, w], -1)[None] + 0.1 * torch.randn(B, D, S, S, 3, generator=g)).contiguous().to(dev)
+            else:  # BASELINE configs[2] upper end (25.8 GB in, 25.8 GB out): generate on the device
+                g = torch.Generator(device=dev).manual_seed(0)
+                vol = torch.randn(B, D, S, S, C, generator=g, device=dev)
+                grid = (torch.stack([u, v, w], -1)[None].to(dev) + 0.1 * torch.randn(B, D, S, S, 3, generator=g, device=dev)).contiguous()
+            theta = theta1.repeat(B, 1, 1).contiguous().to(dev)
+            ms = timeit(lambda: ops.grid_sample3d(vol, grid=grid, in_layout="cl"))
+            alg = (2 * C * D * S * S + 3 * D * S * S) * 4 * B
+            out[name] = {"ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "frac": alg / ms / 1e6 / peaks["hbm_gbs"]}
+            ms = timeit(lambda: ops.grid_sample3d(vol, theta=theta, out_size=(D, S, S), in_layout="cl"))
+            alg = (2 * C * D * S * S) * 4 * B
+            out[name + "_affine"] = {"ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6,
+                                     "frac": alg / ms / 1e6 / peaks["hbm_gbs"]}
+            del vol, grid
+        except RuntimeError as e:  # e.g. out of memory on a shared device: report, do not lose the whole bench line
+            out[name] = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
     return out
 
 
