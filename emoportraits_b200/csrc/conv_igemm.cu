@@ -652,11 +652,12 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cuuint32_t wes[3] = {1, 1, 1};
     const void* ap[3] = {d->a_hi, d->a_lo, d->a_lo2};
     const void* wp[3] = {d->w_hi, d->w_lo, d->w_lo2};
+    const CUtensorMapDataType plane_type = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     for (int pl = 0; pl < NP; ++pl) {
       EMO_REQUIRE(((uintptr_t)ap[pl] % 16) == 0 && ((uintptr_t)wp[pl] % 16) == 0, "emo_conv_igemm: planes must be 16-byte aligned");
-      CUresult r1 = encode(&tm.a[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)ap[pl], gdim, gstr, box, estr,
+      CUresult r1 = encode(&tm.a[pl], plane_type, 5, (void*)ap[pl], gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      CUresult r2 = encode(&tm.b[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wp[pl], wdim, wstr, wbox, wes,
+      CUresult r2 = encode(&tm.b[pl], plane_type, 3, (void*)wp[pl], wdim, wstr, wbox, wes,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
         set_error("emo_conv_igemm: cuTensorMapEncodeTiled failed: A %d W %d (Cin=%d W=%d H=%d D=%d N=%d box=%d,%d,%d BN=%d)", (int)r1,
