@@ -1,0 +1,58 @@
+"""CPU test: every ctypes structure of emoportraits_b200/lib.py has exactly the layout of its C counterpart in
+include/emoportraits_b200.h (size and the offset of every field, in declaration order).  A small C program is compiled
+against the header and prints sizeof / offsetof; a mismatch would silently scramble kernel arguments on the GPU."""
+import ctypes as C
+import pathlib
+import subprocess
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+PAIRS = {
+    "GridSample3dDesc": "emo_grid_sample3d_desc", "GridSample2dAffineDesc": "emo_grid_sample2d_affine_desc",
+    "ResizeBilinearDesc": "emo_resize_bilinear_desc", "GnFinalizeDesc": "emo_gn_finalize_desc", "ApplyDesc": "emo_apply_desc",
+    "GnHeadDesc": "emo_gn_head_desc", "ConvDesc": "emo_conv_desc", "ConvDirectDesc": "emo_conv_direct_desc",
+    "LinearDesc": "emo_linear_desc", "ResampleDesc": "emo_resample_desc", "PoseDesc": "emo_pose_desc",
+}
+
+
+def _c_name(f):
+    return f[:-1] if f.endswith("_") and f[:-1] in ("in",) else f
+
+
+def test_ctypes_structures_match_the_header(tmp_path):
+    from emoportraits_b200 import lib as L
+
+    structs = {n: getattr(L, n) for n in PAIRS}
+    # every Structure subclass defined in lib.py is covered
+    defined = {n for n, v in vars(L).items() if isinstance(v, type) and issubclass(v, C.Structure) and v is not C.Structure}
+    assert defined == set(PAIRS), defined ^ set(PAIRS)
+    lines = ['#include <stddef.h>', '#include <stdio.h>', f'#include "{ROOT / "include" / "emoportraits_b200.h"}"', "int main(void) {"]
+    for py, cn in PAIRS.items():
+        lines.append(f'  printf("{py} sizeof %zu\\n", sizeof({cn}));')
+        for fname, _ in structs[py]._fields_:
+            lines.append(f'  printf("{py} {fname} %zu\\n", offsetof({cn}, {_c_name(fname)}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)       # unknown field name -> compile error
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        py, key, val = ln.split()
+        got[(py, key)] = int(val)
+    for py, st in structs.items():
+        assert got[(py, "sizeof")] == C.sizeof(st), (py, got[(py, "sizeof")], C.sizeof(st))
+        for fname, _ in st._fields_:
+            assert got[(py, fname)] == getattr(st, fname).offset, (py, fname, got[(py, fname)], getattr(st, fname).offset)
+    # and the header declares no field the binding lacks: count the members of each C struct
+    import re
+
+    hdr = (ROOT / "include" / "emoportraits_b200.h").read_text()
+    for py, cn in PAIRS.items():
+        body = hdr[:hdr.index("} " + cn + ";")]
+        body = body[body.rindex("typedef struct {"):]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        decls = [d for d in body.split("{", 1)[1].split(";") if d.strip()]
+        n_members = sum(len(d.split(",")) for d in decls)
+        assert n_members == len(structs[py]._fields_), (py, n_members, len(structs[py]._fields_))
