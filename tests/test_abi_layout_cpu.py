@@ -56,3 +56,35 @@ def test_ctypes_structures_match_the_header(tmp_path):
         decls = [d for d in body.split("{", 1)[1].split(";") if d.strip()]
         n_members = sum(len(d.split(",")) for d in decls)
         assert n_members == len(structs[py]._fields_), (py, n_members, len(structs[py]._fields_))
+
+
+def test_ctypes_prototypes_match_the_header():
+    """argument count and kind (pointer / int / long long / float / double) of every prototype in lib.SYMBOLS vs the header"""
+    import re
+
+    from emoportraits_b200 import lib as L
+
+    hdr = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "emoportraits_b200.h").read_text(), flags=re.S)
+    protos = dict(re.findall(r"\n\s*(?:const\s+char\s*\*|int)\s+(emo_\w+)\s*\(([^)]*)\)\s*;", hdr))
+    assert set(protos) == set(L.SYMBOLS), set(protos) ^ set(L.SYMBOLS)
+
+    def kind_c(arg):
+        arg = arg.strip()
+        if arg in ("void", ""):
+            return None
+        if "*" in arg:
+            return "ptr"
+        for k in ("long long", "double", "float", "int"):
+            if re.search(rf"\b{k}\b", arg):
+                return k
+        raise AssertionError(arg)
+
+    def kind_py(t):
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_longlong: "long long", C.c_double: "double", C.c_float: "float", C.c_int: "int"}[t]
+
+    for name, (res, args) in L.SYMBOLS.items():
+        want = [k for k in (kind_c(a) for a in protos[name].split(",")) if k is not None]
+        got = [kind_py(t) for t in args]
+        assert want == got, (name, want, got)
