@@ -3,7 +3,6 @@
 import ast
 import pathlib
 
-import numpy as np
 import pytest
 import torch
 

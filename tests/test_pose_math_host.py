@@ -5,7 +5,6 @@ the oracle (oracle/restatement.py: torch + scipy.linalg.polar, as the reference 
 unmodified reference produced (tests/golden/va256_options.pt).  This is test infrastructure: the product never calls
 the host build (the GPU parity tests call the kernel through the C-ABI)."""
 import ctypes as C
-import math
 import pathlib
 import subprocess
 

@@ -2,7 +2,6 @@
 oracle's output, so an error cannot hide behind (or be blamed on) an upstream stage.  256^2 config, CPU oracle live."""
 import pathlib
 
-import numpy as np
 import pytest
 import torch
 
