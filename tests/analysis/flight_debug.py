@@ -1,6 +1,6 @@
 """scratch: in-flight pipeline against the eager pass, several models / sizes in one process (module-order repro)."""
 import sys, pathlib
-sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[2]))
 import torch
 from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
 from emoportraits_b200.config import shipped_config

@@ -1,7 +1,7 @@
 """CPU what-if: how much do the operand-split schemes of the convolution kernel move the IMAGE when they are applied to
 the per-frame embedding / warp networks (head-pose regressor, expression encoder, predict_embed, uv warp generator)?
 
-    python tools/h2_network_emulation.py [size=256]
+    python tests/analysis/h2_network_emulation.py [size=256]
 
 The oracle restatement (oracle/restatement.py, torch fp32 on the CPU) is run once as is and once per scheme with every
 F.conv2d / F.conv3d of those networks replaced by an emulation of the kernel's arithmetic on OPERANDS: inputs and weights
@@ -15,7 +15,7 @@ import sys
 import torch
 import torch.nn.functional as F
 
-ROOT = pathlib.Path(__file__).resolve().parents[1]
+ROOT = pathlib.Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 
 T3 = [(0, 0), (0, 1), (1, 0)]

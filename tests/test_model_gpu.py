@@ -143,7 +143,7 @@ def test_frames_in_flight_match_sequential(setup):
     """DriverPipeline (CUDA graphs of consecutive frames replayed on alternating streams, separate scratch slots) returns,
     frame by frame, what the plain one-after-the-other driver pass returns.  Two runs of the SAME path already differ by up
     to ~1e-4 at 512^2 (GroupNorm statistics are accumulated with fp32 shared-memory / fp64 global atomics whose order
-    varies, and the warp network amplifies it; tools/flight_debug.py prints eager-vs-eager next to pipeline-vs-eager), so
+    varies, and the warp network amplifies it; tests/analysis/flight_debug.py prints eager-vs-eager next to pipeline-vs-eager), so
     the bound is 5e-4, half the parity tolerance; a scratch-sharing bug between the in-flight frames shows up as 1e-2+."""
     size, cfg, model, gold = setup
     from emoportraits_b200.infer import DriverPipeline
