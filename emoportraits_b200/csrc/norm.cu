@@ -5,6 +5,8 @@
 //     y = (GN(x)*w + b) * (w + dw) + (b + db)
 // ResBlock pre-activation order  utils.py:761-788: [nearest up] -> norm -> ReLU -> conv
 // The apply pass writes what the next tensor-core conv consumes: bf16 (hi, lo) planes, channels-last.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace emo {
@@ -217,7 +219,12 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   EMO_REQUIRE(d->up == 1 || d->up == 2, "emo_apply: up must be 1 or 2");
   EMO_REQUIRE((d->A == nullptr) == (d->B == nullptr) && (d->A2 == nullptr) == (d->B2 == nullptr), "emo_apply: A/B must come in pairs");
   if (d->stats) EMO_REQUIRE(d->G > 0 && d->C % d->G == 0 && d->count > 0, "emo_apply: bad GroupNorm arguments");
-  const int V = (d->C % 8 == 0) ? 2 : 1;
+  // V = 2 gives 16-byte bf16 plane stores but makes every 32-lane LDG.128 span 8 half-used lines (two consecutive float4
+  // per thread); EMO_APPLY_V1=1 forces the one-float4-per-thread instantiation (fully coalesced loads, 8-byte plane stores)
+  // for an A/B on the GPU.  Both instantiations are in use today (V = 1 for C % 8 != 0), results are identical.
+  static int force_v1 = -1;
+  if (force_v1 < 0) { const char* e = getenv("EMO_APPLY_V1"); force_v1 = e ? atoi(e) : 0; }
+  const int V = (d->C % 8 == 0 && !force_v1) ? 2 : 1;
   const long long per_n = (long long)d->D * d->H * d->W * (d->C / (4 * V));
   long long blocks = cdivll(per_n, 256);
   const long long cap = (148ll * 32) / (d->N > 0 ? d->N : 1);
