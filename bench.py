@@ -407,7 +407,7 @@ def run_ours(args):
                    "cuda_graph": runner is not None,
                    "frames_in_flight": depth,
                    "e2e_host_run_ahead": ring,
-                   "experimental": {k: os.environ[k] for k in ("EMO_UPCONV_PS", "EMO_GS3_BALANCED", "EMO_GS3_VEC2", "EMO_H2_NETS", "EMO_APPLY_V1") if os.environ.get(k)},
+                   "experimental": {k: os.environ[k] for k in ("EMO_UPCONV_PS", "EMO_GS3_BALANCED", "EMO_GS3_VEC2", "EMO_H2_NETS", "EMO_APPLY_V1", "EMO_APPLY_OCC", "EMO_APPLY_PF") if os.environ.get(k)},
                    "frames_in_flight_note": "consecutive driver frames replay on alternating streams (infer.DriverPipeline); "
                                             "each frame still runs alone through the same kernels, batch 1"},
         "e2e": {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 3 * SIZE * SIZE * 4,

@@ -77,6 +77,8 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 }
 
 #define EMO_APPLY_F16 0
+#define EMO_APPLY_PF 0
+#define EMO_APPLY_BOUNDS 256
 #define EMO_APPLY_KERNEL_NAME apply_kernel
 #include "apply_kernel.inc"
 #undef EMO_APPLY_F16
@@ -85,6 +87,22 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 #define EMO_APPLY_KERNEL_NAME apply_f16_kernel
 #include "apply_kernel.inc"
 #undef EMO_APPLY_F16
+#undef EMO_APPLY_PF
+#undef EMO_APPLY_KERNEL_NAME
+#define EMO_APPLY_F16 0
+#define EMO_APPLY_PF 1
+#define EMO_APPLY_KERNEL_NAME apply_pf_kernel
+#include "apply_kernel.inc"
+#undef EMO_APPLY_PF
+#undef EMO_APPLY_BOUNDS
+#undef EMO_APPLY_KERNEL_NAME
+#define EMO_APPLY_PF 0
+#define EMO_APPLY_BOUNDS 256, 4
+#define EMO_APPLY_KERNEL_NAME apply_occ_kernel
+#include "apply_kernel.inc"
+#undef EMO_APPLY_F16
+#undef EMO_APPLY_PF
+#undef EMO_APPLY_BOUNDS
 #undef EMO_APPLY_KERNEL_NAME
 
 // Image head (emo_gn_head): one warp handles 8 pixels per step.  Lane l owns channels 4l..4l+3 (+128k): a warp load reads a
@@ -239,6 +257,24 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
     else if (d->up == 1) apply_f16_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
     else if (V == 2) apply_f16_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
     else apply_f16_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
+    return check_launch("emo_apply");
+  }
+  static int prefetch = -1;  // EMO_APPLY_PF=1: the software-prefetching instantiation (A/B on the GPU; same results)
+  if (prefetch < 0) { const char* e = getenv("EMO_APPLY_PF"); prefetch = e ? atoi(e) : 0; }
+  static int occ4 = -1;  // EMO_APPLY_OCC=1: the __launch_bounds__(256, 4) instantiation (A/B on the GPU; same results)
+  if (occ4 < 0) { const char* e = getenv("EMO_APPLY_OCC"); occ4 = e ? atoi(e) : 0; }
+  if (occ4) {
+    if (d->up == 1 && V == 2) apply_occ_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
+    else if (d->up == 1) apply_occ_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
+    else if (V == 2) apply_occ_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
+    else apply_occ_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
+    return check_launch("emo_apply");
+  }
+  if (prefetch) {
+    if (d->up == 1 && V == 2) apply_pf_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
+    else if (d->up == 1) apply_pf_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
+    else if (V == 2) apply_pf_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
+    else apply_pf_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
     return check_launch("emo_apply");
   }
   if (d->up == 1 && V == 2) apply_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);

@@ -21,6 +21,8 @@ timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_default.json" 2>
 EMO_UPCONV_PS=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_upconv_ps.json" 2> "$out/bench_upconv_ps.err"
 EMO_GS3_BALANCED=0 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_gs3_brick.json" 2> "$out/bench_gs3_brick.err"
 EMO_APPLY_V1=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_apply_v1.json" 2> "$out/bench_apply_v1.err"
+EMO_APPLY_OCC=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_apply_occ.json" 2> "$out/bench_apply_occ.err"
+EMO_APPLY_PF=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_apply_pf.json" 2> "$out/bench_apply_pf.err"
 EMO_GS3_VEC2=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_gs3_vec2.json" 2> "$out/bench_gs3_vec2.err"
 EMO_H2_NETS=warp,expression,head_pose timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_h2_nets.json" 2> "$out/bench_h2_nets.err"
 EMO_H2_NETS=warp,expression,head_pose EMO_UPCONV_PS=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_h2_ps.json" 2> "$out/bench_h2_ps.err"
