@@ -18,14 +18,14 @@ grep -E "^\[(upconv|options parity|subpixel|stage-2 \+|4x4 stride-2)" "$out/pyte
 
 # 3. A/B of the opt-in variants on the headline bench (each ~1 min)
 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_default.json" 2> "$out/bench_default.err"
-EMO_UPCONV_PS=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_upconv_ps.json" 2> "$out/bench_upconv_ps.err"
-EMO_GS3_BALANCED=0 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_gs3_brick.json" 2> "$out/bench_gs3_brick.err"
-EMO_APPLY_V1=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_apply_v1.json" 2> "$out/bench_apply_v1.err"
-EMO_APPLY_OCC=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_apply_occ.json" 2> "$out/bench_apply_occ.err"
-EMO_APPLY_PF=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_apply_pf.json" 2> "$out/bench_apply_pf.err"
-EMO_GS3_VEC2=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_gs3_vec2.json" 2> "$out/bench_gs3_vec2.err"
-EMO_H2_NETS=warp,expression,head_pose timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_h2_nets.json" 2> "$out/bench_h2_nets.err"
-EMO_H2_NETS=warp,expression,head_pose EMO_UPCONV_PS=1 timeout 400 python bench.py --steps 30 --warmup 5 > "$out/bench_h2_ps.json" 2> "$out/bench_h2_ps.err"
+EMO_UPCONV_PS=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_upconv_ps.json" 2> "$out/bench_upconv_ps.err"
+EMO_GS3_BALANCED=0 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_gs3_brick.json" 2> "$out/bench_gs3_brick.err"
+EMO_APPLY_V1=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_apply_v1.json" 2> "$out/bench_apply_v1.err"
+EMO_APPLY_OCC=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_apply_occ.json" 2> "$out/bench_apply_occ.err"
+EMO_APPLY_PF=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_apply_pf.json" 2> "$out/bench_apply_pf.err"
+EMO_GS3_VEC2=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_gs3_vec2.json" 2> "$out/bench_gs3_vec2.err"
+EMO_H2_NETS=warp,expression,head_pose timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_h2_nets.json" 2> "$out/bench_h2_nets.err"
+EMO_H2_NETS=warp,expression,head_pose EMO_UPCONV_PS=1 timeout 400 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > "$out/bench_h2_ps.json" 2> "$out/bench_h2_ps.err"
 EMO_UPCONV_PS=1 EMO_POOLCONV_FOLD=1 timeout 600 python bench.py --workload stage2 --steps 10 --warmup 3 > "$out/bench_stage2_folds.json" 2> "$out/bench_stage2_folds.err"
 timeout 600 python bench.py --workload stage2 --steps 10 --warmup 3 > "$out/bench_stage2_default.json" 2> "$out/bench_stage2_default.err"
 for f in "$out"/bench_*.json; do
