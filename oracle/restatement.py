@@ -1,10 +1,12 @@
 """TEST INFRASTRUCTURE ONLY (oracle).  CPU restatement, in plain PyTorch fp32 functional ops, of the reference's
-volumetric-avatar inference hot path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
-`--impl reference` leg may import this module; the product path (emoportraits_b200/) never does.
+volumetric-avatar inference hot path.  Only tests/ (including the analysis scripts under tests/analysis/),
+__graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may import this module; the product path
+(emoportraits_b200/) never does.
 
 Every function cites the reference file:line it restates.  The restatement is PINNED against outputs of the
 unmodified reference run in the build container (oracle/make_golden.py -> tests/golden/*.pt; checked by
-tests/test_oracle_golden.py), because the reference itself has no tests or golden vectors.
+tests/test_oracle_golden.py; the non-default forward() arguments by tests/test_oracle_options.py against
+tests/golden/va256_options.pt), because the reference itself has no tests or golden vectors.
 
 The arithmetic itself lives in third-party PyTorch (reference pins pytorch=1.13.1, environment.yml:173-174; here torch
 2.11 CPU, semantics of conv/group_norm/grid_sample/interpolate unchanged): F.conv2d/3d, F.group_norm, F.grid_sample,
