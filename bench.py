@@ -386,10 +386,10 @@ def run_ours(args):
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         traffic = json.loads(tf.read_text()).get(top_shape)
-    gs = grid_sample_roofline(peaks)
+    gs = grid_sample_roofline(peaks) if not args.quick else {"d64_affine": {"achieved_gbs": 0.0, "frac": 0.0}, "skipped": "--quick"}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
         fps_cpu, dt, threads = cpu_port_fps(4, 1)
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": f"4 driver frames @512^2 after 1 warm-up ({dt:.1f} s), oracle/restatement.py torch-CPU fp32"}
@@ -488,6 +488,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="do not capture the driver frame in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="A/B runs: skip the grid_sample microbench and the CPU baseline (not a bench record)")
     ap.add_argument("--inflight", type=int, default=2, help="driver frames in flight per GPU (1 = strictly one after the other)")
     ap.add_argument("--workload", default="driver", choices=["driver", "stage2"],
                     help="driver = the headline metric (default); stage2 = BASELINE config 5, secondary")

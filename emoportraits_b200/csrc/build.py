@@ -35,14 +35,19 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    stamp = HERE / ".build_stamp"
+def build(force: bool = False, verbose: bool = False, debug: bool = False) -> pathlib.Path:
+    """debug=True: the instrumented build (-DEMO_CONV_DEBUG: parts of the conv kernel can be switched off at run time,
+    tools/conv_bound_probe.py) as libemoport_dbg.so next to the product library; loaded only through EMO_LIB=<path>."""
+    LIB = HERE / ("libemoport_dbg.so" if debug else "libemoport.so")
+    stamp = HERE / (".build_stamp_dbg" if debug else ".build_stamp")
     dig = _digest()
     if LIB.exists() and not force and stamp.exists() and stamp.read_text() == dig:
         return LIB
     cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo"]  # no --use_fast_math: expf/tanhf/division stay IEEE-accurate
     cmd += ["-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
-    cmd += os.environ.get("EMO_NVCC_EXTRA", "").split()  # e.g. -DEMO_CONV_DEBUG for tools/conv_bound_probe.py
+    cmd += os.environ.get("EMO_NVCC_EXTRA", "").split()
+    if debug:
+        cmd += ["-DEMO_CONV_DEBUG"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     tmp = LIB.with_name(LIB.name + ".tmp")  # link into a temporary name, then rename: a reader (or a gpurun snapshot)
@@ -60,5 +65,5 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
 
 
 if __name__ == "__main__":
-    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    p = build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv)
     print(p)

@@ -204,6 +204,7 @@ class DriverPipeline:
 
     def __init__(self, model: "Model", st, depth: int = 2, mix: bool = True, target_theta: bool = True, mix_old: bool = False):
         self.model, self.depth, self.n = model, depth, 0
+        self.st = st  # the captured graphs hold raw pointers into this state's tensors: keep it alive as long as they are
         self.slots = []
         for k in range(depth):
             run = model.make_driver_graph(st, mix=mix, target_theta=target_theta, slot=k, mix_old=mix_old)
@@ -352,6 +353,7 @@ class InferenceWrapper(torch.nn.Module):
             st = self.model.source_pass(src, mask=mask, c_source_latent_volume=c_source_latent_volume,
                                         c_target_latent_volume=c_target_latent_volume)
             self._state = st
+            self._pipeline = None  # captured for the previous identity
             # cached attributes of the reference wrapper (infer.py:405-507)
             self.idt_embed = st.idt_embed
             self.pred_source_theta = st.pred_source_theta
@@ -372,8 +374,8 @@ class InferenceWrapper(torch.nn.Module):
         per_frame = smooth_pose or custom_srt is not None or custome_target_pose_embed is not None
         if drv.shape[0] >= 2 and not per_frame:
             # a list of driver frames: captured frames, two in flight (DriverPipeline); same kernels as the eager pass below
-            key = (id(self._state), bool(mix), bool(target_theta), bool(mix_old))
-            if self._pipeline is None or self._pipeline_key != key:
+            key = (bool(mix), bool(target_theta), bool(mix_old))
+            if self._pipeline is None or self._pipeline.st is not self._state or self._pipeline_key != key:
                 self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=2, mix=mix,
                                                                     target_theta=target_theta, mix_old=mix_old), key
             img = torch.empty_like(drv)

@@ -9,7 +9,9 @@ import os
 import pathlib
 
 _HERE = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _HERE / "csrc" / "libemoport.so"
+# EMO_LIB=<path>: load another build of the same sources instead (tools/conv_bound_probe.py uses the instrumented
+# libemoport_dbg.so that `python -m emoportraits_b200.csrc.build --debug` writes next to the product library)
+LIB_PATH = pathlib.Path(os.environ["EMO_LIB"]).resolve() if os.environ.get("EMO_LIB") else _HERE / "csrc" / "libemoport.so"
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 

@@ -1,17 +1,8 @@
-"""GPU tests of everything that was written AFTER round 1's GPU budget was spent and has therefore never run on a B200.
-They sort last (test_zz_*), carry xfail(strict=False) — an XPASS in the round-end log is the record of their first pass —
-and a hard per-test timeout, so that a defect here cannot take the validated suite down with it.
-
-  1. the non-default InferenceWrapper.forward arguments that reach the hot path (notebooks/infer.py:355-357: mix_old,
-     mix=False, target_theta=False, smooth_pose, custome_target_pose_embed, custome_target_theta_embed, source_mask /
-     driver_mask, c_source_latent_volume, c_target_latent_volume) against fixtures recorded from the UNMODIFIED reference
-     (tests/golden/va256_options.pt, `python -m oracle.make_golden options`); the oracle restatement of the same options is
-     pinned to the same fixtures on the CPU (tests/test_oracle_options.py) and the device pose algebra source is checked on
-     the CPU by tests/test_pose_math_host.py;
-  2. the sub-pixel up-sampling convolution (emo_conv_desc.upconv, EMO_UPCONV_PS=1);
-  3. `conv -> avgpool` folded into one 4x4 stride-2 convolution (EMO_POOLCONV_FOLD=1);
-  4. fp16 two-plane operands for the fp32-faithful networks (EMO_H2_NETS).
-When they have passed once on the GPU, drop the xfail marker (and, for 2-4, flip the defaults if they are faster)."""
+"""GPU parity of the convolution modes beyond the plain two/three-plane implicit GEMM (tests/test_ops_gpu.py):
+  * sub-pixel form of `nearest x2 -> 3x3 conv` (emo_conv_desc.upconv; weight folding checked on the CPU by tests/test_upconv_fold.py),
+  * `3x3 conv -> 2x2 avgpool` folded into one 4x4 stride-2 convolution (ops.fold_poolconv_weight),
+  * fp16 two-plane operands ("h2": fp32-faithful at three MMAs per product),
+each at op level against torch fp64 / the plain kernel, and at model level against the reference fixtures."""
 import pathlib
 
 import pytest
@@ -19,9 +10,7 @@ import torch
 
 from oracle import frames as FR
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU run pending (round-1 GPU budget was spent before these were written)"),
-              pytest.mark.timeout(600, method="thread")]   # never-run kernels: bound a hang instead of blocking the suite
+pytestmark = pytest.mark.gpu
 GOLD = pathlib.Path(__file__).parent / "golden"
 SIZE = 256
 IMG_TOL = 1e-3      # BASELINE.json north_star: max-abs per pixel on the fp32 image
@@ -60,86 +49,9 @@ def _check(case, img, so, name):
     assert e_img < IMG_TOL, (name, e_img)
 
 
-@pytest.mark.parametrize("name,kw", [
-    ("default", {}),
-    ("mix_old", dict(mix_old=True)),
-    ("no_mix", dict(mix=False)),
-    ("target_theta_false", dict(target_theta=False)),
-])
-def test_pose_options(ctx, name, kw):
-    kw = dict(dict(mix=True), **kw)
-    img, _, _, so = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], **kw)
-    _check(ctx["gold"][name], img, so, name)
-
-
-def test_smooth_pose_state_carried_over_frames(ctx):
-    state = torch.zeros((3, 4), device="cuda")
-    for i, d in enumerate(ctx["drv"]):
-        img, _, _, so = ctx["model"].driver_pass(ctx["st"], d, mix=True, smooth_state=state, smooth_momentum=0.5, smooth_init=(i == 0))
-        _check(ctx["gold"][f"smooth_pose_{i}"], img, so, f"smooth_pose_{i}")
-        assert torch.equal(state, so.pred_target_theta[0, :3])
-
-
-def test_custom_embeddings(ctx):
-    X = ctx["X"]
-    img, _, _, so = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True, custom_pose_embed=X["pose_embed"])
-    _check(ctx["gold"]["custome_target_pose_embed"], img, so, "custome_target_pose_embed")
-    img, _, _, so = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True, custom_srt=torch.cat(X["theta_embed"], 1))
-    _check(ctx["gold"]["custome_target_theta_embed"], img, so, "custome_target_theta_embed")
-
-
-def test_source_mask_and_custom_volumes(ctx):
-    m, X = ctx["model"], ctx["X"]
-    g = ctx["gold"]["source_mask"]
-    st = m.source_pass(ctx["src"], mask=X["source_mask"].cuda())
-    assert (st.idt_embed.cpu() - g["idt_embed"]).abs().max().item() < 1e-4
-    assert (st.pred_source_theta.cpu() - g["pred_source_theta"]).abs().max().item() < THETA_TOL   # regressor sees the unmasked image
-    img, _, _, so = m.driver_pass(st, ctx["drv"][0], mix=True)
-    _check(g, img, so, "source_mask")
-    for key in ("c_source_latent_volume", "c_target_latent_volume"):
-        st = m.source_pass(ctx["src"], **{key: X[key]})
-        img, _, _, so = m.driver_pass(st, ctx["drv"][0], mix=True)
-        _check(ctx["gold"][key], img, so, key)
-
-
-def test_wrapper_forward_options(ctx, tmp_path):
-    """the same options through the drop-in InferenceWrapper.forward (PIL in, (list[PIL], tensor) out)"""
-    from emoportraits_b200.infer import InferenceWrapper
-
-    gold, X = ctx["gold"], ctx["X"]
-    exp = tmp_path / "logs" / "exp" / "checkpoints"
-    exp.mkdir(parents=True)
-    (tmp_path / "logs" / "exp" / "args.txt").write_text((GOLD / f"args_{SIZE}.txt").read_text())
-    torch.save(ctx["sd"], exp / "000_model.pth")
-    w = InferenceWrapper(experiment_name="exp", model_file_name="000_model.pth", project_dir=str(tmp_path), folder="logs",
-                         print_params=False, head_pose_state_dict=ctx["hsd"])
-    full = torch.load(GOLD / f"va{SIZE}_options.pt", weights_only=False)
-    src = FR.pil(SIZE, full["src_seed"], full["kind"])
-    drv = [FR.pil(SIZE, s, full["kind"]) for s in full["drv_seeds"]]
-    base = dict(crop=False, mix=True, mix_old=False)
-    _, img = w.forward(src, drv[0], crop=False, mix=True, mix_old=True)
-    assert _img_err(img, gold["mix_old"]["img"]) < IMG_TOL
-    w.forward(src, None, **base)
-    for i, d in enumerate(drv):
-        pil, img = w.forward(None, d, smooth_pose=True, reset_tracking=(i == 0), **base)
-        assert _img_err(img, gold[f"smooth_pose_{i}"]["img"]) < IMG_TOL, i
-        assert (w.pred_target_theta[:, :3].cpu() - gold[f"smooth_pose_{i}"]["pred_target_theta"][:, :3]).abs().max().item() < THETA_TOL
-    assert w.theta.shape == (3, 4)
-    _, img = w.forward(src, drv[0], custome_target_theta_embed=X["theta_embed"], **base)
-    assert _img_err(img, gold["custome_target_theta_embed"]["img"]) < IMG_TOL
-    _, img = w.forward(src, drv[0], custome_target_pose_embed=X["pose_embed"], **base)
-    assert _img_err(img, gold["custome_target_pose_embed"]["img"]) < IMG_TOL
-    _, img = w.forward(src, drv[0], source_mask=X["source_mask"], driver_mask=X["driver_mask"], **base)
-    assert _img_err(img, gold["source_mask"]["img"]) < IMG_TOL
-    assert w.source_img_mask.shape == (1, 1, SIZE, SIZE)
-    _, img = w.forward(src, drv[0], c_target_latent_volume=X["c_target_latent_volume"], **base)
-    assert _img_err(img, gold["c_target_latent_volume"]["img"]) < IMG_TOL
-
-
 # ------------------------------------------------------------------------------------------------------------------
-# sub-pixel up-sampling convolution (emo_conv_desc.upconv; opt-in in the model via EMO_UPCONV_PS=1).  Same status as the
-# tests above: written after the round-1 GPU budget was spent, first GPU run pending.  The weight folding and the
-# kernel's index arithmetic are checked on the CPU by tests/test_upconv_fold.py.
+# sub-pixel up-sampling convolution (emo_conv_desc.upconv).  The weight folding and the kernel's index arithmetic are
+# checked on the CPU by tests/test_upconv_fold.py.
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Cin,Cout,S,residual", [(192, 128, 64, False), (320, 192, 32, True), (512, 320, 32, False),
                                                  (192, 128, 256, True)])
@@ -169,7 +81,17 @@ def test_upconv_subpixel_matches_conv_on_upsampled_planes(Cin, Cout, S, residual
     err = (out - ref).abs().max().item()
     print(f"\n[upconv sub-pixel vs upsampled planes] {Cin}->{Cout} @{S}^2: max-abs {err:.2e} (scale {scale:.2f})")
     assert err < scale * 2 ** -13
-    assert ((st_ps - st_ref).abs() / st_ref.abs().clamp_min(1.0)).max().item() < 1e-5
+    # statistics, in the terms GroupNorm consumes them: per-group mean and mean square.  (The raw sums of the two kernels
+    # differ by the sum of ~N independent 2^-17-relative operand roundings, i.e. by ~sqrt(N) * 3e-5 * scale in absolute terms,
+    # which is 1e-4 of a near-zero sum but 1e-7 of the mean; the round-1 form of this check compared raw sums at 1e-5.)
+    count = ref.numel() / 32
+    d_mean = ((st_ps[..., 0] - st_ref[..., 0]).abs() / count).max().item()
+    d_msq = ((st_ps[..., 1] - st_ref[..., 1]).abs() / st_ref[..., 1].abs()).max().item()
+    want_st = torch.stack([ref.view(1, -1, 32, Cout // 32).double().sum((1, 3)), (ref.view(1, -1, 32, Cout // 32).double() ** 2).sum((1, 3))], -1)
+    d_own = ((st_ref - want_st).abs() / want_st.abs().clamp_min(1.0)).max().item()
+    print(f"[upconv statistics] group mean differs by {d_mean:.2e}, mean square by {d_msq:.2e} (relative); plain kernel's statistics vs "
+          f"fp64 sums of its own output {d_own:.2e}")
+    assert d_mean < 1e-6 * max(1.0, scale) and d_msq < 1e-5
     if S <= 64:   # and against torch fp32 on the CPU
         xr = torch.relu(x[0, 0].permute(2, 0, 1)[None].cpu())
         want = F_conv_up(xr, w, b.cpu(), res)
@@ -223,7 +145,7 @@ def test_stage2_with_subpixel_up_convolutions_matches_reference(fixture, monkeyp
 
 # ------------------------------------------------------------------------------------------------------------------
 # `3x3 conv -> 2x2 average pool` folded into one 4x4 stride-2 convolution (ops.fold_poolconv_weight; opt-in in the models
-# via EMO_POOLCONV_FOLD=1).  No kernel change: the implicit-GEMM kernel is generic in the tap count.  First GPU run pending.
+# via EMO_POOLCONV_FOLD=1).  No kernel change: the implicit-GEMM kernel is generic in the tap count.
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Cin,Cout,S,planes", [(128, 128, 64, 2), (256, 256, 128, 2), (128, 256, 32, 3)])
 def test_poolconv_fold_matches_conv_then_avgpool(Cin, Cout, S, planes):
@@ -282,7 +204,7 @@ def test_models_with_poolconv_fold_match_reference(ctx, monkeypatch):
 # ------------------------------------------------------------------------------------------------------------------
 # fp16 two-plane operand mode ("h2", ops.H2; opt-in per network via EMO_H2_NETS / Model(precision=...)): three MMAs per
 # product at fp32-level operand accuracy (tools/split_precision_emulation.py), meant to replace the six-MMA three-plane
-# bf16 mode of the embedding / warp / source networks.  First GPU run pending.
+# bf16 mode of the embedding / warp / source networks.
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Cin,Cout,sp,k", [(512, 512, (64, 64), 3), (96, 96, (16, 16), 3), (64, 32, (8, 16, 16), 3), (64, 128, (8, 8), 3),
                                            (256, 128, (8, 8, 8), 1)])
@@ -335,62 +257,5 @@ def test_model_with_fp16_two_plane_networks_matches_reference(ctx):
     base, _, _, so0 = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True)
     print(f"[h2 vs three-plane networks] image max-abs {(img - base).abs().max().item():.2e} "
           f"pose_embed {(so.target_pose_embed - so0.target_pose_embed).abs().max().item():.2e}")
-
-
-# ------------------------------------------------------------------------------------------------------------------
-# grid_sample_3d at BASELINE's largest size and its edge cases (validated kernels, new tests)
-# ------------------------------------------------------------------------------------------------------------------
-def test_grid_sample3d_full_size_batch32_properties():
-    """BASELINE configs[2] at its largest size (96ch x 64^3 volume, 64^3 lattice, batch 32: 25.8 GB in, 25.8 GB out), where a
-    CPU reference would take minutes: size-independent properties instead, all bit-exact.
-      * batch independence: sample n of the batched call == the single-sample call on (x[n], theta[n] / grid[n]);
-      * linearity in the volume for a power-of-two factor: gs(0.5 x) == 0.5 gs(x);
-      * zeros padding: a lattice entirely outside the volume samples exactly 0;
-      * channel equivariance: permuting the channels of the volume permutes the channels of the result."""
-    from emoportraits_b200 import ops
-    from test_ops_gpu import _grid
-
-    N, C, S = 32, 96, 64
-    g = torch.Generator(device="cuda").manual_seed(5)
-    x = torch.randn((N, S, S, S, C), generator=g, device="cuda")
-    ang = torch.linspace(-0.6, 0.6, N)
-    th = torch.zeros(N, 3, 4)
-    th[:, 0, 0], th[:, 0, 1], th[:, 1, 0], th[:, 1, 1], th[:, 2, 2] = ang.cos(), -ang.sin(), ang.sin(), ang.cos(), 0.9
-    th[:, :, 3] = torch.tensor([0.2, -0.1, 0.05])
-    th = th.cuda().contiguous()
-    out = ops.grid_sample3d(x, theta=th, out_size=(S, S, S), in_layout="cl")
-    assert out.shape == (N, S, S, S, C)
-    for n in (0, 17, 31):
-        one = ops.grid_sample3d(x[n:n + 1].contiguous(), theta=th[n:n + 1].contiguous(), out_size=(S, S, S), in_layout="cl")
-        assert torch.equal(one[0], out[n]), n
-    assert (out[31] != 0).float().mean().item() > 0.5            # a rotated, shifted lattice still lands mostly inside
-    half = ops.grid_sample3d((x[:2] * 0.5).contiguous(), theta=th[:2].contiguous(), out_size=(S, S, S), in_layout="cl")
-    assert torch.equal(half, out[:2] * 0.5)
-    perm = torch.randperm(C, generator=torch.Generator().manual_seed(6)).cuda()
-    pc = ops.grid_sample3d(x[:1, ..., perm].contiguous(), theta=th[:1].contiguous(), out_size=(S, S, S), in_layout="cl")
-    assert torch.equal(pc, out[:1, ..., perm])
-    far = th[:1].clone()
-    far[:, :, 3] = 4.0
-    assert ops.grid_sample3d(x[:1].contiguous(), theta=far.contiguous(), out_size=(S, S, S), in_layout="cl").abs().max().item() == 0.0
-    del out, half, pc
-    # explicit grid tensor (jittered identity lattice), batch 32
-    grid = (_grid(1, S, S, S, 9).cuda() + 0.02 * torch.arange(N, device="cuda").view(N, 1, 1, 1, 1)).contiguous()
-    outg = ops.grid_sample3d(x, grid=grid, in_layout="cl")
-    for n in (0, 31):
-        one = ops.grid_sample3d(x[n:n + 1].contiguous(), grid=grid[n:n + 1].contiguous(), in_layout="cl")
-        assert torch.equal(one[0], outg[n]), n
-
-
-def test_grid_sample3d_empty_and_invalid_inputs():
-    """edge cases: an empty batch returns an empty tensor (as F.grid_sample does) without launching; malformed arguments
-    are refused by the C-ABI with a message (EMO_ERR_INVALID -> RuntimeError), never launched."""
-    from emoportraits_b200 import ops
-
-    e = ops.grid_sample3d(torch.empty((0, 4, 4, 4, 8), device="cuda"), theta=torch.empty((0, 3, 4), device="cuda"),
-                          out_size=(4, 4, 4), in_layout="cl")
-    assert e.shape == (0, 4, 4, 4, 8)
-    x = torch.randn((1, 4, 4, 4, 6), device="cuda")          # channels-last path needs C % 4 == 0
-    with pytest.raises(RuntimeError, match="C % 4"):
-        ops.grid_sample3d(x, theta=torch.eye(4, device="cuda")[None, :3].contiguous(), out_size=(4, 4, 4), in_layout="cl")
 
 

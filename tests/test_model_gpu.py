@@ -23,6 +23,9 @@ from oracle import frames as FR
 pytestmark = pytest.mark.gpu
 GOLD = pathlib.Path(__file__).parent / "golden"
 IMG_TOL = 1e-3
+# white-noise frames, pose algebra on the device: bounded by the REFERENCE's own sensitivity to a 1-ulp change of its fp32 LU
+# inverse (measured per size by tests/test_oracle_golden.py::test_reference_noise_floor_of_white_noise_frames; see module doc)
+NOISE_DEVICE_TOL = {256: 5e-3, 512: 5e-3}
 
 
 def _sub_err(got, ref):
@@ -47,20 +50,53 @@ def setup(request):
     return size, cfg, model, gold
 
 
+def _scale(ref):
+    return float((ref if isinstance(ref, torch.Tensor) else ref[0]).abs().max())
+
+
+# Stage taps, asserted at BOTH sizes so that the sigmoid cannot hide an error: bound = TAP_TOL[key] * max(1, max|reference tap|).
+# The numbers are the stage-isolated bounds of tests/test_stage_parity_gpu.py widened for the chain upstream of each tap
+# (an embedding error e moves the warp by ~10 e and the sampled volumes by ~100 e); measured values are printed and written
+# to gpurun_out/parity_<case>.txt, and committed per round under profiles/.
+TAP_TOL = {"idt_embed": 5e-5, "source_theta": 1e-5, "source_pose_embed": 5e-5, "xy_warp": 1e-4, "source_latent_volume": 1e-4,
+           "target_latent_volume_1": 5e-4, "target_latent_volume": 5e-4, "theta": 1e-5, "pose_embed": 5e-5, "uv_warp": 1e-4,
+           "aligned_feat2d": 5e-4, "dec_feat": 5e-4, "logits": 4e-3, "img": IMG_TOL}
+# taps that sit downstream of the reference's fp32 LU inverse of the pose matrix (the 1-ulp-fragile step, module docstring):
+# not asserted in the all-on-device white-noise case
+POSE_NOISE_LIMITED = ("source_pose_embed", "xy_warp", "target_latent_volume_1", "target_latent_volume", "pose_embed", "uv_warp",
+                      "aligned_feat2d", "dec_feat", "logits", "img")
+
+
+def _assert_taps(errs, scales, skip=()):
+    bad = []
+    for k, v in errs.items():
+        name = k.split(".")[-1]
+        if name in skip:
+            continue
+        bound = TAP_TOL[name] * (1.0 if name in ("img", "logits") else max(1.0, scales[k]))
+        if not v < bound:
+            bad.append((k, v, bound))
+    assert not bad, bad
+
+
 def _run_case(size, cfg, model, case, inject_pose: bool):
     kind = case["kind"]
     s = case["source"]
     po = (s["pred_source_theta"], s["inv_warp"], s["align2d"]) if inject_pose else None
     st = model.source_pass(FR.frame(size, case["src_seed"], kind).cuda(), pose_override=po)
-    errs = {}
-    errs["idt_embed"] = _sub_err(st.idt_embed, s["idt_embed"])
-    errs["source_theta"] = _sub_err(st.pred_source_theta, s["pred_source_theta"])
-    errs["source_pose_embed"] = _sub_err(st.pred_source_pose_embed, s["pred_source_pose_embed"])
-    errs["xy_warp"] = _sub_err(st.source_xy_warp_resize, s["xy_warp"])
+    errs, scales = {}, {}
+
+    def rec(key, got, ref):
+        errs[key], scales[key] = _sub_err(got, ref), _scale(ref)
+
+    rec("idt_embed", st.idt_embed, s["idt_embed"])
+    rec("source_theta", st.pred_source_theta, s["pred_source_theta"])
+    rec("source_pose_embed", st.pred_source_pose_embed, s["pred_source_pose_embed"])
+    rec("xy_warp", st.source_xy_warp_resize, s["xy_warp"])
     ncdhw = lambda t: t.permute(0, 4, 1, 2, 3).contiguous()
-    errs["source_latent_volume"] = _sub_err(ncdhw(st.source_latent_volume), s["source_latent_volume"])
-    errs["target_latent_volume_1"] = _sub_err(ncdhw(st.target_latent_volume_1), s["target_latent_volume_1"])
-    errs["target_latent_volume"] = _sub_err(ncdhw(st.target_latent_volume), s["target_latent_volume"])
+    rec("source_latent_volume", ncdhw(st.source_latent_volume), s["source_latent_volume"])
+    rec("target_latent_volume_1", ncdhw(st.target_latent_volume_1), s["target_latent_volume_1"])
+    rec("target_latent_volume", ncdhw(st.target_latent_volume), s["target_latent_volume"])
     for fr in case["frames"]:
         drv = FR.frame(size, fr["seed"], kind).cuda()
         th = fr["pred_target_theta"]
@@ -70,20 +106,20 @@ def _run_case(size, cfg, model, case, inject_pose: bool):
         logits, _, _, so = model.driver_pass(st, drv, mix=True, taps=taps, want_logits=True, pose_override=po)
         img, deep_f, img_f, so = model.driver_pass(st, drv, mix=True, pose_override=po)
         k = f"f{fr['seed']}."
-        errs[k + "theta"] = _sub_err(so.pred_target_theta[:, :3], th[:, :3])
-        errs[k + "pose_embed"] = _sub_err(so.target_pose_embed, fr["target_pose_embed"])
-        errs[k + "uv_warp"] = _sub_err(taps["uv_warp"], fr["uv_warp"])
+        rec(k + "theta", so.pred_target_theta[:, :3], th[:, :3])
+        rec(k + "pose_embed", so.target_pose_embed, fr["target_pose_embed"])
+        rec(k + "uv_warp", taps["uv_warp"], fr["uv_warp"])
         # reference (b, c*D+d, h, w)  <->  ours (h, w, d, c)
         av = taps["aligned_volume_hwdc"].view(1, cfg.S, cfg.S, cfg.D, cfg.C).permute(0, 4, 3, 1, 2).reshape(1, cfg.C * cfg.D, cfg.S, cfg.S)
-        errs[k + "aligned_feat2d"] = _sub_err(av.contiguous(), fr["aligned_feat2d"])
-        errs[k + "dec_feat"] = _sub_err(deep_f[:, 0].permute(0, 3, 1, 2).contiguous(), fr["dec_feat"])
-        errs[k + "logits"] = _sub_err(logits, fr["logits"])
-        errs[k + "img"] = _sub_err(img, fr["img"])
+        rec(k + "aligned_feat2d", av.contiguous(), fr["aligned_feat2d"])
+        rec(k + "dec_feat", deep_f[:, 0].permute(0, 3, 1, 2).contiguous(), fr["dec_feat"])
+        rec(k + "logits", logits, fr["logits"])
+        rec(k + "img", img, fr["img"])
     tag = f"{size}_{kind}_{'refpose' if inject_pose else 'device'}"
     print(f"\n[parity vs reference golden @ {tag}] " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
     out = pathlib.Path("gpurun_out"); out.mkdir(exist_ok=True)
-    (out / f"parity_{tag}.txt").write_text("\n".join(f"{k} {v:.3e}" for k, v in errs.items()) + "\n")
-    return errs
+    (out / f"parity_{tag}.txt").write_text("\n".join(f"{k} err {v:.3e} ref_max {scales[k]:.3e}" for k, v in errs.items()) + "\n")
+    return errs, scales
 
 
 def _case(gold, kind):
@@ -92,30 +128,23 @@ def _case(gold, kind):
 
 def test_noise_frames_with_reference_pose_matrices(setup):
     size, cfg, model, gold = setup
-    errs = _run_case(size, cfg, model, _case(gold, "noise"), inject_pose=True)
-    for k, v in errs.items():
-        if k.endswith("img"):
-            assert v < IMG_TOL, (k, v)
-        elif k.endswith("logits"):
-            assert v < 4e-3, (k, v)
+    errs, scales = _run_case(size, cfg, model, _case(gold, "noise"), inject_pose=True)
+    _assert_taps(errs, scales)
 
 
 def test_smooth_frames_all_on_device(setup):
     size, cfg, model, gold = setup
-    errs = _run_case(size, cfg, model, _case(gold, "smooth"), inject_pose=False)
-    for k, v in errs.items():
-        if k.endswith("img"):
-            assert v < IMG_TOL, (k, v)
-        elif k.endswith("logits"):
-            assert v < 4e-3, (k, v)
+    errs, scales = _run_case(size, cfg, model, _case(gold, "smooth"), inject_pose=False)
+    _assert_taps(errs, scales)
 
 
 def test_noise_frames_all_on_device_reference_noise_limited(setup):
     size, cfg, model, gold = setup
-    errs = _run_case(size, cfg, model, _case(gold, "noise"), inject_pose=False)
+    errs, scales = _run_case(size, cfg, model, _case(gold, "noise"), inject_pose=False)
+    _assert_taps(errs, scales, skip=POSE_NOISE_LIMITED)   # everything upstream of the fragile inverse holds its bound
     for k, v in errs.items():
         if k.endswith("img"):
-            assert v < 5e-3, (k, v)
+            assert v < NOISE_DEVICE_TOL[size], (k, v)
 
 
 def test_driver_pass_matches_cpu_oracle_on_fresh_inputs(setup):

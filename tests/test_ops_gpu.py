@@ -314,3 +314,61 @@ def test_gn_head(ops, C, Cout, S, act):
     assert out.shape == (N, Cout, 1, *S)
     err = (out[:, :, 0].double() - ref).abs().max().item()
     assert err < 2e-5, err
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# grid_sample_3d at BASELINE's largest size and its edge cases (validated kernels, new tests)
+# ------------------------------------------------------------------------------------------------------------------
+def test_grid_sample3d_full_size_batch32_properties():
+    """BASELINE configs[2] at its largest size (96ch x 64^3 volume, 64^3 lattice, batch 32: 25.8 GB in, 25.8 GB out), where a
+    CPU reference would take minutes: size-independent properties instead, all bit-exact.
+      * batch independence: sample n of the batched call == the single-sample call on (x[n], theta[n] / grid[n]);
+      * linearity in the volume for a power-of-two factor: gs(0.5 x) == 0.5 gs(x);
+      * zeros padding: a lattice entirely outside the volume samples exactly 0;
+      * channel equivariance: permuting the channels of the volume permutes the channels of the result."""
+    from emoportraits_b200 import ops
+
+    N, C, S = 32, 96, 64
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((N, S, S, S, C), generator=g, device="cuda")
+    ang = torch.linspace(-0.6, 0.6, N)
+    th = torch.zeros(N, 3, 4)
+    th[:, 0, 0], th[:, 0, 1], th[:, 1, 0], th[:, 1, 1], th[:, 2, 2] = ang.cos(), -ang.sin(), ang.sin(), ang.cos(), 0.9
+    th[:, :, 3] = torch.tensor([0.2, -0.1, 0.05])
+    th = th.cuda().contiguous()
+    out = ops.grid_sample3d(x, theta=th, out_size=(S, S, S), in_layout="cl")
+    assert out.shape == (N, S, S, S, C)
+    for n in (0, 17, 31):
+        one = ops.grid_sample3d(x[n:n + 1].contiguous(), theta=th[n:n + 1].contiguous(), out_size=(S, S, S), in_layout="cl")
+        assert torch.equal(one[0], out[n]), n
+    assert (out[31] != 0).float().mean().item() > 0.5            # a rotated, shifted lattice still lands mostly inside
+    half = ops.grid_sample3d((x[:2] * 0.5).contiguous(), theta=th[:2].contiguous(), out_size=(S, S, S), in_layout="cl")
+    assert torch.equal(half, out[:2] * 0.5)
+    perm = torch.randperm(C, generator=torch.Generator().manual_seed(6)).cuda()
+    pc = ops.grid_sample3d(x[:1, ..., perm].contiguous(), theta=th[:1].contiguous(), out_size=(S, S, S), in_layout="cl")
+    assert torch.equal(pc, out[:1, ..., perm])
+    far = th[:1].clone()
+    far[:, :, 3] = 4.0
+    assert ops.grid_sample3d(x[:1].contiguous(), theta=far.contiguous(), out_size=(S, S, S), in_layout="cl").abs().max().item() == 0.0
+    del out, half, pc
+    # explicit grid tensor (jittered identity lattice), batch 32
+    grid = (_grid(1, S, S, S, 9).cuda() + 0.02 * torch.arange(N, device="cuda").view(N, 1, 1, 1, 1)).contiguous()
+    outg = ops.grid_sample3d(x, grid=grid, in_layout="cl")
+    for n in (0, 31):
+        one = ops.grid_sample3d(x[n:n + 1].contiguous(), grid=grid[n:n + 1].contiguous(), in_layout="cl")
+        assert torch.equal(one[0], outg[n]), n
+
+
+def test_grid_sample3d_empty_and_invalid_inputs():
+    """edge cases: an empty batch returns an empty tensor (as F.grid_sample does) without launching; malformed arguments
+    are refused by the C-ABI with a message (EMO_ERR_INVALID -> RuntimeError), never launched."""
+    from emoportraits_b200 import ops
+
+    e = ops.grid_sample3d(torch.empty((0, 4, 4, 4, 8), device="cuda"), theta=torch.empty((0, 3, 4), device="cuda"),
+                          out_size=(4, 4, 4), in_layout="cl")
+    assert e.shape == (0, 4, 4, 4, 8)
+    x = torch.randn((1, 4, 4, 4, 6), device="cuda")          # channels-last path needs C % 4 == 0
+    with pytest.raises(RuntimeError, match="C % 4"):
+        ops.grid_sample3d(x, theta=torch.eye(4, device="cuda")[None, :3].contiguous(), out_size=(4, 4, 4), in_layout="cl")
+
+

@@ -1,5 +1,6 @@
 """Stage-isolated GPU parity: every network of the path is fed the ORACLE's input for that stage and compared with the
-oracle's output, so an error cannot hide behind (or be blamed on) an upstream stage.  256^2 config, CPU oracle live."""
+oracle's output, so an error cannot hide behind (or be blamed on) an upstream stage.  CPU oracle run live, at 256^2 and at
+512^2 (the shipped size: third LocalEncoder block, 512^2 decoder level)."""
 import pathlib
 
 import pytest
@@ -23,14 +24,14 @@ def uncl(x):
     return x.permute(0, 4, 1, 2, 3).contiguous()
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=[256, 512])
+def ctx(request):
     from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
     from emoportraits_b200.config import shipped_config
     from emoportraits_b200.infer import Model
     from oracle import restatement as R
 
-    size = 256
+    size = request.param
     cfg = shipped_config(size)
     sd, hsd = synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0)
     model = Model(cfg, sd, hsd, "cuda")
@@ -50,8 +51,8 @@ def _rec(ctx, name, got, ref, tol):
     ctx["report"][name] = (err, scale)
     out = pathlib.Path("gpurun_out"); out.mkdir(exist_ok=True)
     with open(out / "stage_parity.txt", "a") as f:
-        f.write(f"{name} err={err:.3e} scale={scale:.3e} rel={err / max(scale, 1e-30):.3e}\n")
-    print(f"\n[stage] {name}: max-abs err {err:.3e} (ref max {scale:.3e})")
+        f.write(f"{ctx['size']} {name} err={err:.3e} scale={scale:.3e} rel={err / max(scale, 1e-30):.3e}\n")
+    print(f"\n[stage @{ctx['size']}] {name}: max-abs err {err:.3e} (ref max {scale:.3e})")
     assert err < tol * max(scale, 1.0), (name, err, scale)
 
 

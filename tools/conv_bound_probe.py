@@ -1,11 +1,13 @@
-"""Which resource bounds the conv main loop?  (GPU box; needs a debug build:
-   EMO_NVCC_EXTRA=-DEMO_CONV_DEBUG python -m emoportraits_b200.csrc.build --force)
+"""Which resource bounds the conv main loop?  (GPU box; runs on the instrumented build libemoport_dbg.so that
+   `python -m emoportraits_b200.csrc.build --debug` writes next to the product library)
 
 Times CUDA-graph replays of back-to-back launches with parts of the kernel switched off (EMO_CONV_DBG bits:
 1 no TMA loads, 2 no MMAs, 4 no tile-epilogue global traffic, 8 no TMEM chunk reads).  Outputs are garbage in those
-modes; only the time matters.  Rebuild without the flag afterwards."""
+modes; only the time matters."""
 import math, os, sys, pathlib
-sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("EMO_LIB", str(ROOT / "emoportraits_b200" / "csrc" / "libemoport_dbg.so"))
 import torch
 from emoportraits_b200 import ops
 dev = "cuda"
