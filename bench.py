@@ -407,7 +407,6 @@ def run_ours(args):
                    "cuda_graph": runner is not None,
                    "frames_in_flight": depth,
                    "e2e_host_run_ahead": ring,
-                   "experimental": {k: os.environ[k] for k in ("EMO_UPCONV_PS", "EMO_GS3_BALANCED", "EMO_GS3_VEC2", "EMO_H2_NETS", "EMO_APPLY_V1", "EMO_APPLY_OCC", "EMO_APPLY_PF") if os.environ.get(k)},
                    "frames_in_flight_note": "consecutive driver frames replay on alternating streams (infer.DriverPipeline); "
                                             "each frame still runs alone through the same kernels, batch 1"},
         "e2e": {"value": world * K / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": 3 * SIZE * SIZE * 4,
@@ -471,8 +470,7 @@ def run_stage2(args):
     line = {"metric": "stage-2 refinement images/s @1024^2, batch 4 (BASELINE configs[4])", "value": B * 1000.0 / ms, "unit": "images/s",
             "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x2-split operands, fp32 accumulate", "data": "synthetic",
-            "config": {"workload": "stage-2 LocalEncoderOld + Decoder_stage2, output_size_s2 1024, batch 4, default stage-2 args",
-                       "experimental": {k: os.environ[k] for k in ("EMO_UPCONV_PS", "EMO_POOLCONV_FOLD") if os.environ.get(k)}},
+            "config": {"workload": "stage-2 LocalEncoderOld + Decoder_stage2, output_size_s2 1024, batch 4, default stage-2 args"},
             "gpu_launches": launches * K,
             "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv layers of one step)", "achieved": conv_flops / conv_ms / 1e9,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": conv_flops / conv_ms / 1e9 / peaks["bf16_tflops_sustained"],

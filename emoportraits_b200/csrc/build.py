@@ -43,20 +43,37 @@ def build(force: bool = False, verbose: bool = False, debug: bool = False) -> pa
     dig = _digest()
     if LIB.exists() and not force and stamp.exists() and stamp.read_text() == dig:
         return LIB
-    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo"]  # no --use_fast_math: expf/tanhf/division stay IEEE-accurate
-    cmd += ["-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]
-    cmd += os.environ.get("EMO_NVCC_EXTRA", "").split()
+    flags = [*ARCH_FLAGS, "-O3", "-std=c++17", "-lineinfo"]  # no --use_fast_math: expf/tanhf/division stay IEEE-accurate
+    flags += ["-Xcompiler", "-fPIC", "-cudart", "shared"]
+    flags += os.environ.get("EMO_NVCC_EXTRA", "").split()
     if debug:
-        cmd += ["-DEMO_CONV_DEBUG"]
+        flags += ["-DEMO_CONV_DEBUG"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
+        flags += ["-Xptxas", "-v"]
+    # one nvcc per source, side by side (conv_igemm.cu alone is most of the wall time), then one link
+    objdir = HERE / ("_obj_dbg" if debug else "_obj")
+    objdir.mkdir(exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = objdir / (pathlib.Path(src).stem + ".o")
+        procs.append((src, obj, subprocess.Popen([_nvcc(), *flags, "-c", str(HERE / src), "-o", str(obj)], stdout=subprocess.PIPE,
+                                                 stderr=subprocess.STDOUT, text=True)))
+    log, failed = "", False
+    for src, obj, pr in procs:
+        out, _ = pr.communicate()
+        log += out
+        failed |= pr.returncode != 0
+    if failed:
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed building libemoport.so")
     tmp = LIB.with_name(LIB.name + ".tmp")  # link into a temporary name, then rename: a reader (or a gpurun snapshot)
-    cmd += ["-o", str(tmp)] + [str(HERE / s) for s in SOURCES]  # never sees a half-written library
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    r = subprocess.run([_nvcc(), *ARCH_FLAGS, "-shared", "-cudart", "shared", "-o", str(tmp)] + [str(o) for _, o, _ in procs],
+                       capture_output=True, text=True)  # never sees a half-written library
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         tmp.unlink(missing_ok=True)
-        raise RuntimeError("nvcc failed building libemoport.so")
+        raise RuntimeError("nvcc failed linking libemoport.so")
+    r.stdout = log + r.stdout
     os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)

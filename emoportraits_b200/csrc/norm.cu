@@ -77,8 +77,6 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 }
 
 #define EMO_APPLY_F16 0
-#define EMO_APPLY_PF 0
-#define EMO_APPLY_BOUNDS 256
 #define EMO_APPLY_KERNEL_NAME apply_kernel
 #include "apply_kernel.inc"
 #undef EMO_APPLY_F16
@@ -87,22 +85,6 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 #define EMO_APPLY_KERNEL_NAME apply_f16_kernel
 #include "apply_kernel.inc"
 #undef EMO_APPLY_F16
-#undef EMO_APPLY_PF
-#undef EMO_APPLY_KERNEL_NAME
-#define EMO_APPLY_F16 0
-#define EMO_APPLY_PF 1
-#define EMO_APPLY_KERNEL_NAME apply_pf_kernel
-#include "apply_kernel.inc"
-#undef EMO_APPLY_PF
-#undef EMO_APPLY_BOUNDS
-#undef EMO_APPLY_KERNEL_NAME
-#define EMO_APPLY_PF 0
-#define EMO_APPLY_BOUNDS 256, 4
-#define EMO_APPLY_KERNEL_NAME apply_occ_kernel
-#include "apply_kernel.inc"
-#undef EMO_APPLY_F16
-#undef EMO_APPLY_PF
-#undef EMO_APPLY_BOUNDS
 #undef EMO_APPLY_KERNEL_NAME
 
 // Image head (emo_gn_head): one warp handles 8 pixels per step.  Lane l owns channels 4l..4l+3 (+128k): a warp load reads a
@@ -237,12 +219,9 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   EMO_REQUIRE(d->up == 1 || d->up == 2, "emo_apply: up must be 1 or 2");
   EMO_REQUIRE((d->A == nullptr) == (d->B == nullptr) && (d->A2 == nullptr) == (d->B2 == nullptr), "emo_apply: A/B must come in pairs");
   if (d->stats) EMO_REQUIRE(d->G > 0 && d->C % d->G == 0 && d->count > 0, "emo_apply: bad GroupNorm arguments");
-  // V = 2 gives 16-byte bf16 plane stores but makes every 32-lane LDG.128 span 8 half-used lines (two consecutive float4
-  // per thread); EMO_APPLY_V1=1 forces the one-float4-per-thread instantiation (fully coalesced loads, 8-byte plane stores)
-  // for an A/B on the GPU.  Both instantiations are in use today (V = 1 for C % 8 != 0), results are identical.
-  static int force_v1 = -1;
-  if (force_v1 < 0) { const char* e = getenv("EMO_APPLY_V1"); force_v1 = e ? atoi(e) : 0; }
-  const int V = (d->C % 8 == 0 && !force_v1) ? 2 : 1;
+  // V = 2 (two consecutive float4 per thread, 16-byte plane stores) whenever C % 8 == 0; one float4 per thread otherwise
+  // (measured round 2: forcing V = 1 everywhere costs 3% of the frame)
+  const int V = (d->C % 8 == 0) ? 2 : 1;
   const long long per_n = (long long)d->D * d->H * d->W * (d->C / (4 * V));
   long long blocks = cdivll(per_n, 256);
   const long long cap = (148ll * 32) / (d->N > 0 ? d->N : 1);
@@ -257,24 +236,6 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
     else if (d->up == 1) apply_f16_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
     else if (V == 2) apply_f16_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
     else apply_f16_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
-    return check_launch("emo_apply");
-  }
-  static int prefetch = -1;  // EMO_APPLY_PF=1: the software-prefetching instantiation (A/B on the GPU; same results)
-  if (prefetch < 0) { const char* e = getenv("EMO_APPLY_PF"); prefetch = e ? atoi(e) : 0; }
-  static int occ4 = -1;  // EMO_APPLY_OCC=1: the __launch_bounds__(256, 4) instantiation (A/B on the GPU; same results)
-  if (occ4 < 0) { const char* e = getenv("EMO_APPLY_OCC"); occ4 = e ? atoi(e) : 0; }
-  if (occ4) {
-    if (d->up == 1 && V == 2) apply_occ_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
-    else if (d->up == 1) apply_occ_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
-    else if (V == 2) apply_occ_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
-    else apply_occ_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
-    return check_launch("emo_apply");
-  }
-  if (prefetch) {
-    if (d->up == 1 && V == 2) apply_pf_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
-    else if (d->up == 1) apply_pf_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
-    else if (V == 2) apply_pf_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
-    else apply_pf_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
     return check_launch("emo_apply");
   }
   if (d->up == 1 && V == 2) apply_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);

@@ -11,7 +11,6 @@ ones (what the stubbed reference oracle uses too).
 """
 from __future__ import annotations
 
-import os
 import pathlib
 from types import SimpleNamespace
 from typing import Optional
@@ -27,11 +26,14 @@ from .config import HotPathConfig, hot_path_config, parse_args
 class Model:
     """Inference-only counterpart of models/stage_1/volumetric_avatar/va.py:39 Model (attribute names kept)."""
 
-    # bf16 planes per tensor-core operand, per network: 2 -> 3 MMAs/product (~2^-16 relative), 3 -> 6 MMAs/product
-    # (~2^-24, fp32-faithful).  The embedding / warp networks are tiny but the warp they produce is differentiated by
-    # the sampler (an error of 1e-4 in the embedding moves the image by 1e-2), so they run fp32-faithful; measured
-    # stage by stage in tests/test_stage_parity_gpu.py.  EMO_PLANES=<n> overrides every entry (experiments only).
-    PRECISION = dict(head_pose=3, expression=3, idt=3, warp=3, local_encoder=3, volume_source=3, unet3d=3, decoder=2)
+    # Operand planes per network (ops.conv_igemm): 2 = two bf16 planes, 3 MMAs per product, ~2^-16 relative (decoder: isolated
+    # stage error 2e-4 on logits of magnitude 4); ops.H2 = two fp16 planes of (value x power of two), 3 MMAs per product,
+    # ~2^-22 relative, i.e. fp32-faithful — for the embedding / warp networks, whose output the sampler differentiates (an
+    # error of 1e-4 in the embedding moves the image by 1e-2), and for the source-pass networks.  Three bf16 planes (6 MMAs,
+    # the round-1 setting of those networks) give the same accuracy at twice the MMAs (tests/test_conv_modes_gpu.py) and
+    # remain available through `precision=`.  The decoder's input planes are written by grid_sample_3d in bf16.
+    PRECISION = dict(head_pose=ops.H2, expression=ops.H2, idt=ops.H2, warp=ops.H2, local_encoder=ops.H2, volume_source=ops.H2,
+                     unet3d=ops.H2, decoder=2)
 
     def __init__(self, cfg: HotPathConfig, state_dict, head_pose_state_dict, device="cuda", precision: Optional[dict] = None):
         self.cfg = cfg
@@ -39,16 +41,8 @@ class Model:
         sd = state_dict
         pr = dict(self.PRECISION)
         pr.update(precision or {})
-        if os.environ.get("EMO_PLANES"):
-            pr = {k: int(os.environ["EMO_PLANES"]) for k in pr}
-        # EMO_H2_NETS=warp,expression,...: run these networks with fp16 two-plane operands ("h2": fp32-faithful like three
-        # bf16 planes at half the MMAs; opt-in until measured on the GPU, see ops.H2)
-        for k in filter(None, os.environ.get("EMO_H2_NETS", "").split(",")):
-            if k not in pr:
-                raise ValueError(f"EMO_H2_NETS: unknown network {k!r} (known: {sorted(pr)})")
-            if k == "decoder":
-                raise ValueError("EMO_H2_NETS: the decoder's input planes are written by grid_sample_3d in bf16; it stays at two bf16 planes")
-            pr[k] = ops.H2
+        if pr["decoder"] == ops.H2:
+            raise ValueError("the decoder's input planes are written by grid_sample_3d in bf16; it runs with 2 or 3 bf16 planes")
         self.precision = pr
         self.local_encoder_nw = nets.LocalEncoder(sd, cfg, dev, planes=pr["local_encoder"])
         self.idt_embedder_nw = nets.IdtEmbed(sd, cfg, dev, planes=pr["idt"])

@@ -17,8 +17,6 @@ tensor (double (N,32,2)), produced by the epilogue of whichever kernel wrote it.
 """
 from __future__ import annotations
 
-import os
-
 import math
 
 import torch
@@ -28,8 +26,6 @@ from .checkpoint import fold_conv
 from .config import HotPathConfig
 
 G = 32
-SUBPIXEL_UP = os.environ.get("EMO_UPCONV_PS") == "1"  # sub-pixel up-sampling convolutions in the image decoder (opt-in)
-POOLCONV_FOLD = os.environ.get("EMO_POOLCONV_FOLD") == "1"  # `3x3 conv -> 2x2 avgpool` as one 4x4 stride-2 conv (opt-in)
 
 
 class ConvW:
@@ -78,8 +74,8 @@ class ResBlock:
         self.n1 = Norm(sd, p + ".block_feats.0", dev)
         self.c1 = ConvW(sd, p + ".block_feats.2", dev, ws=ws_first, planes=planes)
         # sub-pixel form of `nearest x2 -> norm -> relu -> 3x3 conv` for blocks called with up=2 (ops.pack_upconv_weight):
-        # the conv then reads the LOW-resolution planes (4/9 of the MMAs, no upsampled operand).  Opt-in (EMO_UPCONV_PS=1)
-        # until it has been measured on the GPU.
+        # the conv then reads the LOW-resolution planes (4/9 of the MMAs, no upsampled operand; measured round 2: 229 -> 244
+        # frames/s).  Shapes the sub-pixel kernel does not take (Cout % 32, Cin % 64, odd pixel-tile count) use the plain form.
         self.c1_ps = None
         if subpixel_up and planes == 2:
             w, _ = fold_conv(sd, p + ".block_feats.2", ws=ws_first)
@@ -89,8 +85,8 @@ class ResBlock:
         self.c2 = ConvW(sd, p + ".block.0", dev, planes=planes)
         self.skip = ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
         # `conv -> avgpool (1,2,2)` of down-sampling blocks folded into one 4x4 stride-2 conv (ops.fold_poolconv_weight):
-        # 16 taps per pooled output instead of 36 and no full-resolution conv output.  Opt-in (EMO_POOLCONV_FOLD=1) until
-        # it has been measured on the GPU.
+        # 16 taps per pooled output instead of 36 and no full-resolution conv output (stage-2 @1024^2: 37.5 -> 44.4 images/s
+        # together with the sub-pixel form).
         self.c2_pool = None
         if pool_fold:
             w, _ = fold_conv(sd, p + ".block.0")
@@ -135,7 +131,7 @@ class LocalEncoder:
         self.stem_w, self.stem_b = wc.to(dev).contiguous(), b.to(dev).contiguous()
         self.blocks = []
         for i in range(len(cfg.enc_channels) - 1):
-            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev, planes=planes, pool_fold=POOLCONV_FOLD))
+            self.blocks.append(ResBlock(sd, f"{p}.enc_{i}_block={s}px", dev, planes=planes, pool_fold=True))
             s //= 2
         self.fin_norm = Norm(sd, p + ".finale_layers.0", dev)
         # output channel o = c*D + d in the reference (infer.py:485 view(1,c,d,s,s)); emit d*C + c so the map is (h,w,d,c)
@@ -487,7 +483,7 @@ class Decoder:
         j = 0
         while f"{p}.img_decoder.dec_img_blocks.{j}.block.0.weight_orig" in sd:
             self.img.append(ResBlock(sd, f"{p}.img_decoder.dec_img_blocks.{j}", dev, planes=planes,
-                                     subpixel_up=SUBPIXEL_UP and (j % cfg.im_dec_lrs == 0)))
+                                     subpixel_up=(j % cfg.im_dec_lrs == 0)))
             j += 1
         self.lrs = cfg.im_dec_lrs
         self.head_norm = Norm(sd, p + ".img_decoder.dec_img_head.0", dev)

@@ -160,7 +160,7 @@ class ResBlockBN:
         self.planes = planes
         self.n1 = _BN(sd, p + ".block_feats.0", dev)
         self.c1 = nets.ConvW(sd, p + ".block_feats.2", dev, planes=planes)
-        self.c1_ps = None  # sub-pixel form of `nearest x2 -> bn -> relu -> 3x3 conv` (see nets.ResBlock; opt-in EMO_UPCONV_PS=1)
+        self.c1_ps = None  # sub-pixel form of `nearest x2 -> bn -> relu -> 3x3 conv` (see nets.ResBlock)
         if subpixel_up and planes == 2:
             w, _ = fold_conv(sd, p + ".block_feats.2")
             if tuple(w.shape[2:]) == (3, 3) and w.shape[0] % 32 == 0 and w.shape[1] % 64 == 0:
@@ -168,7 +168,7 @@ class ResBlockBN:
         self.n2 = _BN(sd, p + ".block_feats.3", dev)
         self.c2 = nets.ConvW(sd, p + ".block.0", dev, planes=planes)
         self.skip = nets.ConvW(sd, p + ".skip.0", dev, planes=planes) if (p + ".skip.0.weight_orig") in sd else None
-        self.c2_pool = None  # `conv -> avgpool (1,2,2)` as one 4x4 stride-2 conv (see nets.ResBlock; opt-in EMO_POOLCONV_FOLD=1)
+        self.c2_pool = None  # `conv -> avgpool (1,2,2)` as one 4x4 stride-2 conv (see nets.ResBlock)
         if pool_fold:
             w, _ = fold_conv(sd, p + ".block.0")
             if tuple(w.shape[2:]) == (3, 3):
@@ -211,14 +211,14 @@ class Stage2Model:
         self.stem_w, self.stem_b = wc.to(dev).contiguous(), b.to(dev).contiguous()
         self.enc = []
         for i in range(len(cfg.enc_channels) - 1):
-            self.enc.append(ResBlockBN(sd, f"{p}.enc_{i}_block={s}px", dev, planes, pool_fold=nets.POOLCONV_FOLD))
+            self.enc.append(ResBlockBN(sd, f"{p}.enc_{i}_block={s}px", dev, planes, pool_fold=True))
             s //= 2
         self.fin_norm = _BN(sd, p + ".finale_layers.0", dev)
         self.fin = nets.ConvW(sd, p + ".finale_layers.2", dev, planes=planes)
         p = "decoder"
         self.inp = nets.ConvW(sd, p + ".res_decoder.0", dev, planes=planes)
         self.res = [ResBlockBN(sd, f"{p}.res_decoder.{i + 1}", dev, planes) for i in range(cfg.dec_num_blocks)]
-        ps = nets.SUBPIXEL_UP
+        ps = True
         self.up = [ResBlockBN(sd, f"{p}.img_decoder.dec_img_blocks.{i}", dev, planes, subpixel_up=ps) for i in range(len(cfg.up_channels) - 1)]
         self.feat = [ResBlockBN(sd, f"{p}.img_decoder.dec_img_feat_blocks.{i}", dev, planes, subpixel_up=ps and i == 0) for i in range(4)]
         self.head_norm = _BN(sd, p + ".img_decoder.dec_img_head.0", dev)

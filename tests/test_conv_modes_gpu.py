@@ -107,45 +107,34 @@ def F_conv_up(xr, w, b, res):
     return y.float()
 
 
-def test_model_with_subpixel_up_convolutions_matches_reference(ctx, monkeypatch):
-    """whole driver pass with the three up-sampling convolutions of the image decoder in sub-pixel form vs the reference
-    fixture (same 1e-3 bar as the default path)"""
-    from emoportraits_b200 import nets
+def test_default_model_uses_the_folded_forms_and_agrees_with_the_plain_ones(ctx):
+    """The shipped path runs the sub-pixel up-convolutions, the 4x4 stride-2 down-convolutions and fp16 two-plane networks
+    (parity vs the reference: tests/test_model_gpu.py).  The plain forms they replace (nearest-x2 planes + 3x3 conv,
+    conv + avgpool, three bf16 planes) stay reachable for shapes the folded kernels do not take; built explicitly here,
+    they must give the same image up to the documented operand rounding."""
+    from emoportraits_b200 import nets, ops
     from emoportraits_b200.infer import Model
 
-    monkeypatch.setattr(nets, "SUBPIXEL_UP", True)
-    model = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda")
-    assert any(b.c1_ps is not None for b in model.decoder_nw.img)
-    st = model.source_pass(ctx["src"])
-    img, _, _, so = model.driver_pass(st, ctx["drv"][0], mix=True)
-    _check(ctx["gold"]["default"], img, so, "default+subpixel_up")
-    base, _, _, _ = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True)
-    print(f"[subpixel vs plain decoder] image max-abs {(img - base).abs().max().item():.2e}")
-
-
-@pytest.mark.parametrize("fixture", ["s2_512_b1.pt", "s2_1024_b4.pt"])
-def test_stage2_with_subpixel_up_convolutions_matches_reference(fixture, monkeypatch):
-    """stage-2 refinement decoder (four nearest-x2 up blocks, batch 1 and 4) with the sub-pixel convolutions vs the
-    reference fixtures; same bars as tests/test_stage2.py"""
-    from emoportraits_b200 import nets
-    from emoportraits_b200.stage2 import Stage2Config, Stage2Model, synthetic_state_dict_s2
-    from test_stage2 import _inputs, _sub_err   # tests/ is on sys.path under pytest (rootdir conftest)
-
-    monkeypatch.setattr(nets, "SUBPIXEL_UP", True)
-    gold = torch.load(GOLD / fixture, weights_only=False)
-    cfg = Stage2Config(output_size=gold["output_size"])
-    model = Stage2Model(cfg, synthetic_state_dict_s2(cfg, 0), "cuda")
-    assert sum(b.c1_ps is not None for b in model.up + model.feat) >= 3
-    resized, add, ffhq = model.forward(_inputs(gold).cuda())
-    e_add = _sub_err(add, gold["add"])
-    e_img = _sub_err((ffhq * 255).floor().clamp(0, 255).permute(0, 2, 3, 1).contiguous(), gold["ffhq_uint8"])
-    print(f"\n[stage-2 + sub-pixel up convs vs reference golden {fixture}] add {e_add:.2e} ffhq(uint8 steps) {e_img:.0f}")
-    assert e_add < 1e-3 and e_img <= 1.0
+    m = ctx["model"]
+    assert m.decoder_nw.img[0].c1_ps is not None      # (the 160 -> 96 up block of the 256^2 config keeps the plain form: Cin % 64)
+    assert all(b.c2_pool is not None for b in m.local_encoder_nw.blocks)
+    assert m.precision["warp"] == ops.H2 and m.precision["decoder"] == 2
+    plain = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda", precision={k: 3 for k in m.precision if k != "decoder"})
+    for b in plain.decoder_nw.img:
+        b.c1_ps = None
+    for b in plain.local_encoder_nw.blocks:
+        b.c2_pool = None
+    st = plain.source_pass(ctx["src"])
+    img, _, _, so = plain.driver_pass(st, ctx["drv"][0], mix=True)
+    _check(ctx["gold"]["default"], img, so, "plain forms (three bf16 planes, unfolded convolutions)")
+    base, _, _, so0 = m.driver_pass(ctx["st"], ctx["drv"][0], mix=True)
+    print(f"[default vs plain forms] image max-abs {(img - base).abs().max().item():.2e} "
+          f"pose_embed {(so.target_pose_embed - so0.target_pose_embed).abs().max().item():.2e}")
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# `3x3 conv -> 2x2 average pool` folded into one 4x4 stride-2 convolution (ops.fold_poolconv_weight; opt-in in the models
-# via EMO_POOLCONV_FOLD=1).  No kernel change: the implicit-GEMM kernel is generic in the tap count.
+# `3x3 conv -> 2x2 average pool` folded into one 4x4 stride-2 convolution (ops.fold_poolconv_weight; the form the
+# down-sampling blocks run).  No kernel change: the implicit-GEMM kernel is generic in the tap count.
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("Cin,Cout,S,planes", [(128, 128, 64, 2), (256, 256, 128, 2), (128, 256, 32, 3)])
 def test_poolconv_fold_matches_conv_then_avgpool(Cin, Cout, S, planes):
@@ -177,32 +166,8 @@ def test_poolconv_fold_matches_conv_then_avgpool(Cin, Cout, S, planes):
     assert ((st.cpu() - ref_st).abs() / ref_st.abs().clamp_min(1.0)).max().item() < 1e-3
 
 
-def test_models_with_poolconv_fold_match_reference(ctx, monkeypatch):
-    """LocalEncoder (source pass) and the stage-2 encoder with the folded down-sampling convolutions vs the fixtures"""
-    from emoportraits_b200 import nets
-    from emoportraits_b200.infer import Model
-    from emoportraits_b200.stage2 import Stage2Config, Stage2Model, synthetic_state_dict_s2
-    from test_stage2 import _inputs, _sub_err
-
-    monkeypatch.setattr(nets, "POOLCONV_FOLD", True)
-    model = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda")
-    assert all(b.c2_pool is not None for b in model.local_encoder_nw.blocks)
-    st = model.source_pass(ctx["src"])
-    img, _, _, so = model.driver_pass(st, ctx["drv"][0], mix=True)
-    _check(ctx["gold"]["default"], img, so, "default+poolconv_fold")
-    gold = torch.load(GOLD / "s2_512_b1.pt", weights_only=False)
-    cfg = Stage2Config(output_size=gold["output_size"])
-    s2 = Stage2Model(cfg, synthetic_state_dict_s2(cfg, 0), "cuda")
-    assert all(b.c2_pool is not None for b in s2.enc)
-    resized, add, ffhq = s2.forward(_inputs(gold).cuda())
-    e_add = _sub_err(add, gold["add"])
-    e_img = _sub_err((ffhq * 255).floor().clamp(0, 255).permute(0, 2, 3, 1).contiguous(), gold["ffhq_uint8"])
-    print(f"[stage-2 + folded encoder convs vs reference golden] add {e_add:.2e} ffhq(uint8 steps) {e_img:.0f}")
-    assert e_add < 1e-3 and e_img <= 1.0
-
-
 # ------------------------------------------------------------------------------------------------------------------
-# fp16 two-plane operand mode ("h2", ops.H2; opt-in per network via EMO_H2_NETS / Model(precision=...)): three MMAs per
+# fp16 two-plane operand mode ("h2", ops.H2; the default of every network but the decoder, infer.Model.PRECISION): three MMAs per
 # product at fp32-level operand accuracy (tools/split_precision_emulation.py), meant to replace the six-MMA three-plane
 # bf16 mode of the embedding / warp / source networks.
 # ------------------------------------------------------------------------------------------------------------------
@@ -240,22 +205,3 @@ def test_conv_igemm_fp16_two_planes(Cin, Cout, sp, k):
     want = torch.relu(F.group_norm(got, 32, gamma, beta, 1e-5))
     back = sp_h.float().permute(0, 4, 1, 2, 3).cpu() if three_d else sp_h.float()[:, 0].permute(0, 3, 1, 2).cpu()
     assert (back - want).abs().max().item() < 1e-4
-
-
-def test_model_with_fp16_two_plane_networks_matches_reference(ctx):
-    """the per-frame networks that run with three bf16 planes today (head pose, expression, warp generators) switched to
-    fp16 two planes: same 1e-3 image bar against the reference fixture, and stage outputs close to the default path"""
-    from emoportraits_b200 import ops
-    from emoportraits_b200.infer import Model
-
-    model = Model(ctx["cfg"], ctx["sd"], ctx["hsd"], "cuda",
-                  precision=dict(head_pose=ops.H2, expression=ops.H2, warp=ops.H2, idt=ops.H2, local_encoder=ops.H2,
-                                 volume_source=ops.H2, unet3d=ops.H2))
-    st = model.source_pass(ctx["src"])
-    img, _, _, so = model.driver_pass(st, ctx["drv"][0], mix=True)
-    _check(ctx["gold"]["default"], img, so, "default+h2 networks")
-    base, _, _, so0 = ctx["model"].driver_pass(ctx["st"], ctx["drv"][0], mix=True)
-    print(f"[h2 vs three-plane networks] image max-abs {(img - base).abs().max().item():.2e} "
-          f"pose_embed {(so.target_pose_embed - so0.target_pose_embed).abs().max().item():.2e}")
-
-

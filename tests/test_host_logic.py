@@ -99,14 +99,12 @@ img2, _, _, so2 = model.driver_pass(st, x, mix=True, custom_pose_embed=torch.ran
 assert img.shape == img2.shape == (1, 3, size, size)
 assert L.launch_count - n0 < full        # the expression encoder is skipped when its output is replaced
 assert so2.target_pose_embed.shape == (1, 128)
-# sub-pixel up-sampling convolutions (opt-in): same shapes, one conv reads the low-resolution planes
-from emoportraits_b200 import nets
-nets.SUBPIXEL_UP = True
-m2 = Model(cfg, synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0), "cpu")
-ps = [b.c1_ps for b in m2.decoder_nw.img if b.c1_ps is not None]
-assert ps and ps[0].hi.shape[0] == 16 and ps[0].hi.shape[1] == ps[0].cout
-img3, deep_f, img_f, _ = m2.driver_pass(st, x, mix=True)
-assert img3.shape == (1, 3, size, size) and img_f.shape == (1, 1, size, size, cfg.dec_channels[-1])
+# sub-pixel up-sampling convolutions: the first conv of every up block reads the low-resolution planes
+ps = [b.c1_ps for b in model.decoder_nw.img if b.c1_ps is not None]
+assert ps and ps[0].hi.shape[0] == 16 and ps[0].hi.shape[1] == ps[0].cout   # (the 160 -> 96 block of the 256^2 config keeps the plain form)
+assert all(b.c2_pool is not None for b in model.local_encoder_nw.blocks)      # conv -> avgpool folded into 4x4 stride-2 convs
+_, deep_f, img_f, _ = model.driver_pass(st, x, mix=True)
+assert img_f.shape == (1, 1, size, size, cfg.dec_channels[-1])
 print("ok")
 """
 
@@ -141,14 +139,16 @@ ref = w.permute(2, 3, 0, 1).reshape(9, 32, 64)
 assert (rec - ref).abs().max().item() < 2 ** -21 * ref.abs().max().item()
 a = ops.Split.empty((1, 1, 4, 4, 8), "cpu", ops.H2)
 assert a.f16 and a.hi.dtype == torch.float16 and a.scale == ops.F16_ACT_SCALE and a.view(1, 1, 16, 1, 8).f16
+try:
+    Model(cfg, synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0), "cpu", precision=dict(decoder=ops.H2))
+    raise SystemExit("decoder=h2 must be refused")
+except ValueError as e:
+    assert "decoder" in str(e)
 print("ok")
 """
 
 
 def test_dry_run_fp16_two_plane_networks():
-    env = dict(os.environ, EMO_DRY_RUN="1", EMO_H2_NETS="warp,expression,head_pose")
+    env = dict(os.environ, EMO_DRY_RUN="1")
     r = subprocess.run([sys.executable, "-c", H2_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
-    bad = dict(os.environ, EMO_DRY_RUN="1", EMO_H2_NETS="decoder")
-    r = subprocess.run([sys.executable, "-c", H2_SCRIPT % str(ROOT)], env=bad, capture_output=True, text=True, timeout=600)
-    assert r.returncode != 0 and "decoder" in r.stderr
