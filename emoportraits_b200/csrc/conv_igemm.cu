@@ -409,6 +409,8 @@ struct FinParams {
 };
 
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sstat[];
   const int n = blockIdx.y;
   if (f.stats) {
@@ -687,13 +689,15 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cfg.blockDim = dim3(EPI_ ? kThreadsEpi1 : kThreads);                                                                                        \
     cfg.dynamicSmemBytes = smem_bytes;                                                                                    \
     cfg.stream = stream;                                                                                                  \
-    cudaLaunchAttribute attr[1];                                                                                          \
+    cudaLaunchAttribute attr[2];                                                                                          \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
     attr[0].val.clusterDim.x = (unsigned)csz;                                                                             \
     attr[0].val.clusterDim.y = 1;                                                                                         \
     attr[0].val.clusterDim.z = 1;                                                                                         \
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; /* common.cuh: programmatic dependent launch */      \
+    attr[1].val.programmaticStreamSerializationAllowed = 1;                                                               \
     cfg.attrs = attr;                                                                                                     \
-    cfg.numAttrs = 1;                                                                                                     \
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;                                                                                 \
     e = cudaLaunchKernelEx(&cfg, KERNEL_<KC_, NP_, CG_, EPI_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
@@ -740,7 +744,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     if (bx > 148 * 4) bx = 148 * 4;
     if (bx < 1) bx = 1;
     dim3 fg((unsigned)bx, (unsigned)d->N);
-    splitk_finalize_kernel<<<fg, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(f);
+    launch_kernel(splitk_finalize_kernel, fg, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, f);
   }
   return check_launch("emo_conv_igemm");
 }

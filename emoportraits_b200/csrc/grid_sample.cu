@@ -163,6 +163,8 @@ __device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int 
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) int s_off[kBrickVox][8];
   __shared__ __align__(16) float s_wgt[kBrickVox][8];
   __shared__ long long s_out[kBrickVox];  // output element offset of the voxel (or -1)
@@ -256,6 +258,8 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
 // arithmetic as the brick kernel (shared device functions), so the outputs are bit-identical.
 template <bool SPLIT>
 __global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const GS3Params p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) int s_off[kBrickVox][8];
   __shared__ __align__(16) float s_wgt[kBrickVox][8];
   __shared__ long long s_out[kBrickVox];
@@ -289,6 +293,8 @@ __global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const GS3Params
 // corner offsets/weights held in registers; lanes run along W so both the gathers and the stores coalesce.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gs3_nc_kernel(const GS3Params p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)p.N * p.Dout * p.Hout * p.Wout;
   const long long plane_in = (long long)p.Din * p.Hin * p.Win;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -344,6 +350,8 @@ struct GS2Params {
 };
 
 __global__ void gs2_affine_kernel(const GS2Params p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)p.N * p.Hout * p.Wout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx;
@@ -394,6 +402,8 @@ struct ResizeParams {
 };
 
 __global__ void resize_bilinear_kernel(const ResizeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)p.N * p.Hout * p.Wout;
   const float sh = (float)p.Hin / (float)p.Hout, sw = (float)p.Win / (float)p.Wout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -484,20 +494,20 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
       // at least 64 voxels per CTA
       long long ctas = force > 1 ? force : slots[k];
       if (ctas > cdivll(total, 64)) ctas = cdivll(total, 64);
-      if (d->out_hi) gs3_cl_balanced_kernel<true><<<(unsigned)ctas, 256, 0, stream>>>(p);
-      else gs3_cl_balanced_kernel<false><<<(unsigned)ctas, 256, 0, stream>>>(p);
+      if (d->out_hi) launch_kernel(gs3_cl_balanced_kernel<true>, (unsigned)ctas, 256, 0, stream, p);
+      else launch_kernel(gs3_cl_balanced_kernel<false>, (unsigned)ctas, 256, 0, stream, p);
       return check_launch("emo_grid_sample3d");
     }
     p.bh = bh_brick;
     p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
-    if (d->out_hi) gs3_cl_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(p);
-    else gs3_cl_kernel<false><<<(unsigned)blocks, 256, 0, stream>>>(p);
+    if (d->out_hi) launch_kernel(gs3_cl_kernel<true>, (unsigned)blocks, 256, 0, stream, p);
+    else launch_kernel(gs3_cl_kernel<false>, (unsigned)blocks, 256, 0, stream, p);
   } else {
     p.bw = p.bh = p.bd = p.bricks_w = p.bricks_h = p.bricks_d = 1;
     const long long total = (long long)d->N * d->Dout * d->Hout * d->Wout;
     long long blocks = cdivll(total, 256);
     if (blocks > 148ll * 64) blocks = 148ll * 64;
-    gs3_nc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p);
+    launch_kernel(gs3_nc_kernel, (unsigned)blocks, 256, 0, stream, p);
   }
   return check_launch("emo_grid_sample3d");
 }
@@ -508,7 +518,7 @@ extern "C" int emo_grid_sample2d_affine(const emo_grid_sample2d_affine_desc* d, 
   EMO_REQUIRE(d->C_pad >= d->C, "emo_grid_sample2d_affine: C_pad < C");
   GS2Params p{d->in, d->N, d->C, d->Hin, d->Win, d->Hout, d->Wout, d->C_pad, d->theta, d->mean, d->std, d->out, d->out_nchw};
   const long long total = (long long)d->N * d->Hout * d->Wout;
-  gs2_affine_kernel<<<(unsigned)cdivll(total, 128), 128, 0, stream>>>(p);
+  launch_kernel(gs2_affine_kernel, (unsigned)cdivll(total, 128), 128, 0, stream, p);
   return check_launch("emo_grid_sample2d_affine");
 }
 
@@ -518,6 +528,6 @@ extern "C" int emo_resize_bilinear(const emo_resize_bilinear_desc* d, void* stre
   EMO_REQUIRE(d->C_pad >= d->C, "emo_resize_bilinear: C_pad < C");
   ResizeParams p{d->in, d->N, d->C, d->Hin, d->Win, d->Hout, d->Wout, d->C_pad, d->mean, d->std, d->out};
   const long long total = (long long)d->N * d->Hout * d->Wout;
-  resize_bilinear_kernel<<<(unsigned)cdivll(total, 128), 128, 0, stream>>>(p);
+  launch_kernel(resize_bilinear_kernel, (unsigned)cdivll(total, 128), 128, 0, stream, p);
   return check_launch("emo_resize_bilinear");
 }

@@ -3,6 +3,7 @@
 #include "pose_math.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace emo {
 
@@ -13,6 +14,12 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("EMO_PDL"); on = e ? (atoi(e) != 0) : 1; }
+  return on != 0;
 }
 
 int check_launch(const char* what) {
@@ -28,6 +35,8 @@ int check_launch(const char* what) {
 // linear: one warp per output element (m, n), lanes stride over K.  Sizes are tiny (<= 20 MFLOP).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_kernel(const emo_linear_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= d.M * d.N) return;
@@ -51,6 +60,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const emo_linear_desc d) {
 // the activation load is a warp broadcast.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_direct_kernel(const emo_conv_direct_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int co4n = d.Cout >> 2;
   const long long total = (long long)d.N * d.Hout * d.Wout * co4n;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -123,6 +134,8 @@ __device__ __forceinline__ void up_coord(int o, int f, int n_in, int& i0, int& i
 }
 
 __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resample_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = d.C >> 2;
   const int Do = d.D * d.fd, Ho = d.H * d.fh, Wo = d.W * d.fw;
   const long long So = (long long)Do * Ho * Wo;
@@ -186,6 +199,8 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resam
 
 // avgpool with kernel == stride == (fd, fh, fw), channels-last; optional add + stats of the result
 __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = d.C >> 2;
   const int Do = d.D / d.fd, Ho = d.H / d.fh, Wo = d.W / d.fw;
   const long long per_n = (long long)Do * Ho * Wo * c4n;
@@ -238,6 +253,8 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d)
 }
 
 __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int N, int H, int W, int C, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = C >> 2;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * c4n;
@@ -263,6 +280,8 @@ __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int N, int H, i
 }
 
 __global__ void global_avgpool_kernel(const float* __restrict__ x, int N, long long S, int C, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * C) return;
   const int n = idx / C, c = idx % C;
@@ -275,6 +294,8 @@ __global__ void global_avgpool_kernel(const float* __restrict__ x, int N, long l
 // pose algebra: pose_math.cuh (host+device source, also compiled for the CPU by tests/test_pose_math_host.py)
 // ------------------------------------------------------------------------------------------------
 __global__ void pose_theta_kernel(const emo_pose_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (d.smooth_state) {
     // exponential smoothing carries state from sample to sample: one thread walks the samples in order
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -310,7 +331,7 @@ extern "C" int emo_linear(const emo_linear_desc* d, void* stream_) {
   EMO_REQUIRE(d && d->x && d->w && d->out, "emo_linear: null pointer");
   EMO_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0, "emo_linear: bad shape");
   const long long warps = (long long)d->M * d->N;
-  linear_kernel<<<(unsigned)cdivll(warps * 32, 256), 256, 0, stream>>>(*d);
+  launch_kernel(linear_kernel, (unsigned)cdivll(warps * 32, 256), 256, 0, stream, *d);
   return check_launch("emo_linear");
 }
 
@@ -321,7 +342,7 @@ extern "C" int emo_conv_direct(const emo_conv_direct_desc* d, void* stream_) {
   const long long per_n = (long long)d->Hout * d->Wout * (d->Cout / 4);
   if (d->stats) EMO_REQUIRE(per_n % 256 == 0 && d->G > 0 && d->Cout % d->G == 0, "emo_conv_direct: stats need Hout*Wout*Cout/4 %% 256 == 0");
   const long long total = per_n * d->N;
-  conv_direct_kernel<<<(unsigned)cdivll(total, 256), 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(*d);
+  launch_kernel(conv_direct_kernel, (unsigned)cdivll(total, 256), 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, *d);
   return check_launch("emo_conv_direct");
 }
 
@@ -342,7 +363,7 @@ extern "C" int emo_upsample_trilinear(const emo_resample_desc* d, void* stream_)
   if (bx > 148 * 16) bx = 148 * 16;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)d->N);
-  upsample_trilinear_kernel<<<grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(*d);
+  launch_kernel(upsample_trilinear_kernel, grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, *d);
   return check_launch("emo_upsample_trilinear");
 }
 
@@ -356,7 +377,7 @@ extern "C" int emo_avgpool(const emo_resample_desc* d, void* stream_) {
   if (bx > 148 * 16) bx = 148 * 16;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)d->N);
-  avgpool_kernel<<<grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream>>>(*d);
+  launch_kernel(avgpool_kernel, grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, *d);
   return check_launch("emo_avgpool");
 }
 
@@ -365,14 +386,14 @@ extern "C" int emo_maxpool2d_3x3s2(const float* x, int N, int H, int W, int C, f
   EMO_REQUIRE(x && out && C % 4 == 0, "emo_maxpool2d_3x3s2: bad arguments");
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * (C / 4);
-  maxpool3x3s2_kernel<<<(unsigned)cdivll(total, 256), 256, 0, stream>>>(x, N, H, W, C, out);
+  launch_kernel(maxpool3x3s2_kernel, (unsigned)cdivll(total, 256), 256, 0, stream, x, N, H, W, C, out);
   return check_launch("emo_maxpool2d_3x3s2");
 }
 
 extern "C" int emo_global_avgpool(const float* x, int N, long long S, int C, float* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EMO_REQUIRE(x && out, "emo_global_avgpool: null pointer");
-  global_avgpool_kernel<<<cdiv(N * C, 128), 128, 0, stream>>>(x, N, S, C, out);
+  launch_kernel(global_avgpool_kernel, cdiv(N * C, 128), 128, 0, stream, x, N, S, C, out);
   return check_launch("emo_global_avgpool");
 }
 
@@ -383,6 +404,6 @@ extern "C" int emo_pose_theta(const emo_pose_desc* d, void* stream_) {
   EMO_REQUIRE(!d->mix || d->source_theta, "emo_pose_theta: mix needs source_theta");
   EMO_REQUIRE(!d->smooth_state || (d->smooth_momentum >= 0.f && d->smooth_momentum <= 1.f),
               "emo_pose_theta: smooth_momentum must be in [0,1]");
-  pose_theta_kernel<<<cdiv(d->N, 32), 32, 0, stream>>>(*d);
+  launch_kernel(pose_theta_kernel, cdiv(d->N, 32), 32, 0, stream, *d);
   return check_launch("emo_pose_theta");
 }

@@ -14,6 +14,8 @@ namespace emo {
 // ---- statistics: x [N][S][C] fp32, per (n, g) sum and sum of squares, double accumulation across CTAs ----
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int N, long long S, int C, int G,
                                                        double* __restrict__ stats, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   // grid = N * chunks; each CTA reduces a slab of spatial positions for all channels
   const int n = blockIdx.x / chunks, ch = blockIdx.x % chunks;
   const long long s_per = (S + chunks - 1) / chunks;
@@ -56,6 +58,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 
 // ---- finalize: stats -> per-(n,c) scale/shift ----
 __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= d.N * d.C) return;
   const int n = idx / d.C, c = idx % d.C;
@@ -91,6 +95,8 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 // pixel's whole channel vector (512 B at C = 128); the 8 x 4 per-lane partial dot products are transpose-reduced over the
 // warp with 31 shuffles, after which lane l = 4u + o holds output o of pixel u.
 __global__ void __launch_bounds__(256) gn_head_kernel(const emo_gn_head_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sAB[];  // A[C], B[C] of this CTA's sample, then w[4][C] (rows >= Cout are zero)
   const int n = blockIdx.y;
   const int C = d.C;
@@ -158,6 +164,8 @@ __global__ void __launch_bounds__(256) gn_head_kernel(const emo_gn_head_desc d) 
 
 __global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
                              uint2* __restrict__ lo2) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
     uint2 h, l, l2;
     if (lo2) {
@@ -171,6 +179,8 @@ __global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* _
 }
 
 __global__ void split_f16_kernel(const float* __restrict__ x, long long n4, float scale, uint2* __restrict__ hi, uint2* __restrict__ lo) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
     uint2 h, l;
     split4_h(__ldg((const float4*)x + t), scale, h, l);
@@ -179,6 +189,8 @@ __global__ void split_f16_kernel(const float* __restrict__ x, long long n4, floa
 }
 
 __global__ void flush_kernel(float4* buf, long long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
     buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
@@ -197,7 +209,7 @@ extern "C" int emo_gn_stats(const float* x, int N, long long spatial, int C, int
   if (chunks < 1) chunks = 1;
   const int max_chunks = (148 * 8) / (N > 0 ? N : 1) > 0 ? (148 * 8) / N : 1;
   if (chunks > max_chunks) chunks = max_chunks;
-  gn_stats_kernel<<<N * chunks, 256, 2 * G * sizeof(float), stream>>>(x, N, spatial, C, G, stats, chunks);
+  launch_kernel(gn_stats_kernel, N * chunks, 256, 2 * G * sizeof(float), stream, x, N, spatial, C, G, stats, chunks);
   return check_launch("emo_gn_stats");
 }
 
@@ -207,7 +219,7 @@ extern "C" int emo_gn_finalize(const emo_gn_finalize_desc* d, void* stream_) {
   EMO_REQUIRE(d->G > 0 && d->C % d->G == 0, "emo_gn_finalize: C=%d not divisible by G=%d", d->C, d->G);
   EMO_REQUIRE((d->ada_w == nullptr) == (d->ada_b == nullptr), "emo_gn_finalize: ada_w/ada_b must come together");
   const int total = d->N * d->C;
-  gn_finalize_kernel<<<cdiv(total, 128), 128, 0, stream>>>(*d);
+  launch_kernel(gn_finalize_kernel, cdiv(total, 128), 128, 0, stream, *d);
   return check_launch("emo_gn_finalize");
 }
 
@@ -232,16 +244,16 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   EMO_REQUIRE(smem <= 48 * 1024, "emo_apply: C=%d too large for the fused finalisation", d->C);
   if (d->plane_fp16) {
     EMO_REQUIRE(!d->out_lo2 && d->plane_scale > 0.f, "emo_apply: fp16 planes come in pairs and need a positive plane_scale");
-    if (d->up == 1 && V == 2) apply_f16_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
-    else if (d->up == 1) apply_f16_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
-    else if (V == 2) apply_f16_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
-    else apply_f16_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
+    if (d->up == 1 && V == 2) launch_kernel(apply_f16_kernel<1, 2>, grid, 256, smem, stream, *d);
+    else if (d->up == 1) launch_kernel(apply_f16_kernel<1, 1>, grid, 256, smem, stream, *d);
+    else if (V == 2) launch_kernel(apply_f16_kernel<2, 2>, grid, 256, smem, stream, *d);
+    else launch_kernel(apply_f16_kernel<2, 1>, grid, 256, smem, stream, *d);
     return check_launch("emo_apply");
   }
-  if (d->up == 1 && V == 2) apply_kernel<1, 2><<<grid, 256, smem, stream>>>(*d);
-  else if (d->up == 1) apply_kernel<1, 1><<<grid, 256, smem, stream>>>(*d);
-  else if (V == 2) apply_kernel<2, 2><<<grid, 256, smem, stream>>>(*d);
-  else apply_kernel<2, 1><<<grid, 256, smem, stream>>>(*d);
+  if (d->up == 1 && V == 2) launch_kernel(apply_kernel<1, 2>, grid, 256, smem, stream, *d);
+  else if (d->up == 1) launch_kernel(apply_kernel<1, 1>, grid, 256, smem, stream, *d);
+  else if (V == 2) launch_kernel(apply_kernel<2, 2>, grid, 256, smem, stream, *d);
+  else launch_kernel(apply_kernel<2, 1>, grid, 256, smem, stream, *d);
   return check_launch("emo_apply");
 }
 
@@ -257,7 +269,7 @@ extern "C" int emo_gn_head(const emo_gn_head_desc* d, void* stream_) {
   long long blocks = cdivll(d->S, 8 * 8);  // 8 warps x 8 pixels per step
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  gn_head_kernel<<<dim3((unsigned)blocks, (unsigned)d->N), 256, smem, stream>>>(*d);
+  launch_kernel(gn_head_kernel, dim3((unsigned)blocks, (unsigned)d->N), 256, smem, stream, *d);
   return check_launch("emo_gn_head");
 }
 
@@ -268,7 +280,7 @@ extern "C" int emo_split_bf16(const float* x, long long n, void* hi, void* lo, v
   long long blocks = cdivll(n / 4, 256);
   if (blocks > 148ll * 32) blocks = 148ll * 32;
   if (blocks < 1) blocks = 1;
-  split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, (uint2*)hi, (uint2*)lo, (uint2*)lo2);
+  launch_kernel(split_kernel, (unsigned)blocks, 256, 0, stream, x, n / 4, (uint2*)hi, (uint2*)lo, (uint2*)lo2);
   return check_launch("emo_split_bf16");
 }
 
@@ -279,13 +291,13 @@ extern "C" int emo_split_f16(const float* x, long long n, float scale, void* hi,
   long long blocks = cdivll(n / 4, 256);
   if (blocks > 148ll * 32) blocks = 148ll * 32;
   if (blocks < 1) blocks = 1;
-  split_f16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, n / 4, scale, (uint2*)hi, (uint2*)lo);
+  launch_kernel(split_f16_kernel, (unsigned)blocks, 256, 0, stream, x, n / 4, scale, (uint2*)hi, (uint2*)lo);
   return check_launch("emo_split_f16");
 }
 
 extern "C" int emo_l2_flush(void* buf, long long bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EMO_REQUIRE(buf && bytes >= 16, "emo_l2_flush: bad buffer");
-  flush_kernel<<<148 * 8, 256, 0, stream>>>((float4*)buf, bytes / 16);
+  launch_kernel(flush_kernel, 148 * 8, 256, 0, stream, (float4*)buf, bytes / 16);
   return check_launch("emo_l2_flush");
 }

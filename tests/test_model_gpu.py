@@ -25,7 +25,9 @@ GOLD = pathlib.Path(__file__).parent / "golden"
 IMG_TOL = 1e-3
 # white-noise frames, pose algebra on the device: bounded by the REFERENCE's own sensitivity to a 1-ulp change of its fp32 LU
 # inverse (measured per size by tests/test_oracle_golden.py::test_reference_noise_floor_of_white_noise_frames; see module doc)
-NOISE_DEVICE_TOL = {256: 5e-3, 512: 5e-3}
+# measured here (round 2): 1.6e-3 at 256^2, 3.8e-3 at 512^2; the reference's own floor from that one-ulp change: 1.2e-3 / see the
+# CPU test's printout for 512^2.  Bound = measured maximum x 1.2 + the 1e-4 run-to-run spread.
+NOISE_DEVICE_TOL = {256: 2.0e-3, 512: 4.6e-3}
 
 
 def _sub_err(got, ref):
@@ -56,10 +58,12 @@ def _scale(ref):
 
 # Stage taps, asserted at BOTH sizes so that the sigmoid cannot hide an error: bound = TAP_TOL[key] * max(1, max|reference tap|).
 # The numbers are the stage-isolated bounds of tests/test_stage_parity_gpu.py widened for the chain upstream of each tap
-# (an embedding error e moves the warp by ~10 e and the sampled volumes by ~100 e); measured values are printed and written
-# to gpurun_out/parity_<case>.txt, and committed per round under profiles/.
+# (an embedding error e moves the warp by ~10 e and the sampled volumes by ~100 e; target_latent_volume_1 is the raw encoder
+# volume sampled through xy_warp, whose 5e-5 error in normalised coordinates is 1.6e-3 voxel of a volume that changes by its
+# own magnitude from voxel to voxel: measured 2e-4 .. 8e-4 of the volume's maximum).  Measured values are printed, written to
+# gpurun_out/parity_<case>.txt and committed per round under profiles/.
 TAP_TOL = {"idt_embed": 5e-5, "source_theta": 1e-5, "source_pose_embed": 5e-5, "xy_warp": 1e-4, "source_latent_volume": 1e-4,
-           "target_latent_volume_1": 5e-4, "target_latent_volume": 5e-4, "theta": 1e-5, "pose_embed": 5e-5, "uv_warp": 1e-4,
+           "target_latent_volume_1": 1.5e-3, "target_latent_volume": 5e-4, "theta": 1e-5, "pose_embed": 5e-5, "uv_warp": 1e-4,
            "aligned_feat2d": 5e-4, "dec_feat": 5e-4, "logits": 4e-3, "img": IMG_TOL}
 # taps that sit downstream of the reference's fp32 LU inverse of the pose matrix (the 1-ulp-fragile step, module docstring):
 # not asserted in the all-on-device white-noise case
@@ -145,6 +149,37 @@ def test_noise_frames_all_on_device_reference_noise_limited(setup):
     for k, v in errs.items():
         if k.endswith("img"):
             assert v < NOISE_DEVICE_TOL[size], (k, v)
+
+
+def test_noise_frames_all_on_device_match_the_reference_arithmetic_with_a_correctly_rounded_inverse(setup):
+    """What the white-noise exception above amounts to, stated as a parity check: the device computes the 4x4 pose inverse in
+    fp64 and rounds once (pose_math.cuh: mat4_inv).  Run the oracle (= the reference's arithmetic, tests/test_oracle_golden.py)
+    live on the CPU on the fixture's white-noise frames with ONLY torch.inverse replaced by the correctly rounded inverse:
+    the device image is within the 1e-3 budget of that.  The remaining 1.6e-3 .. 3.8e-3 to the recorded fixtures is therefore
+    the reference's own fp32 LU rounding of a 4x4 matrix, amplified by the white-noise frames (CPU test:
+    test_reference_noise_floor_of_white_noise_frames, 1.2e-3 / 1.5e-3 from that one change)."""
+    size, cfg, model, gold = setup
+    from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
+    from oracle import restatement as R
+
+    case = _case(gold, "noise")
+    sd, hsd = synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0)
+    ocfg = R.config_from_state_dict(sd, size)
+    src, drv = FR.frame(size, case["src_seed"], "noise"), FR.frame(size, case["frames"][0]["seed"], "noise")
+    orig = torch.Tensor.inverse
+    torch.Tensor.inverse = lambda self: orig(self.double()).float()
+    try:
+        with torch.no_grad():
+            ost = R.source_pass(sd, hsd, src, ocfg)
+            oimg = R.driver_pass(sd, hsd, ost, drv, ocfg)
+    finally:
+        torch.Tensor.inverse = orig
+    st = model.source_pass(src.cuda())
+    img, _, _, _ = model.driver_pass(st, drv.cuda(), mix=True)
+    err = (img.cpu() - oimg).abs().max().item()
+    ref = _sub_err(img, case["frames"][0]["img"])
+    print(f"\n[white-noise frames @ {size}, all on device] vs oracle with correctly rounded 4x4 inverse: {err:.3e}; vs the recorded reference: {ref:.3e}")
+    assert err < IMG_TOL, err
 
 
 def test_driver_pass_matches_cpu_oracle_on_fresh_inputs(setup):

@@ -82,7 +82,8 @@ def test_restatement_matches_reference_golden(size, kind):
             _cmp_sub("img", img, fr["img"], 1e-3)
 
 
-def test_reference_noise_floor_of_white_noise_frames():
+@pytest.mark.parametrize("size", [256, 512])
+def test_reference_noise_floor_of_white_noise_frames(size):
     """How reproducible is the REFERENCE's own arithmetic on the BASELINE white-noise frames?  Replace only its fp32 LU
     4x4 inverse (torch.inverse; infer.py:443, expression_embedder.py:168) by the exactly rounded inverse (fp64, rounded
     to fp32 - a <= 1-ulp change of the pose matrices) and the image moves by more than the 1e-3 parity budget; with
@@ -90,7 +91,6 @@ def test_reference_noise_floor_of_white_noise_frames():
     white-noise case and runs the fully-on-device check on smooth frames."""
     from oracle import frames as FR
 
-    size = 256
     sd, hsd, ocfg, R = _setup(size)
 
     def run(kind, exact_inverse):
@@ -105,7 +105,9 @@ def test_reference_noise_floor_of_white_noise_frames():
             torch.Tensor.inverse = orig
 
     d_noise = (run("noise", False) - run("noise", True)).abs().max().item()
-    d_smooth = (run("smooth", False) - run("smooth", True)).abs().max().item()
-    print(f"reference self-noise from a 1-ulp pose-matrix change: noise frames {d_noise:.2e}, smooth frames {d_smooth:.2e}")
-    assert d_noise > 3e-4, d_noise          # same order as the 1e-3 budget (measured 1.2e-3 in the build container)
-    assert d_smooth < 3e-4, d_smooth
+    print(f"reference self-noise from a 1-ulp pose-matrix change @{size}^2: noise frames {d_noise:.2e}")
+    assert d_noise > 3e-4, d_noise          # same order as the 1e-3 budget (measured 1.2e-3 @256^2 in the build container)
+    if size == 256:                         # (the smooth-frame control runs once: the 512^2 oracle passes take ~15 s each)
+        d_smooth = (run("smooth", False) - run("smooth", True)).abs().max().item()
+        print(f"smooth frames {d_smooth:.2e}")
+        assert d_smooth < 3e-4, d_smooth
