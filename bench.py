@@ -162,6 +162,39 @@ def cpu_port_fps(steps, warmup, threads=None):
     return steps / dt, dt, threads
 
 
+def wrapper_fps(sd, hsd, K):
+    """frames/s through emoportraits_b200.infer.InferenceWrapper.forward with PIL images in and PIL images out (uint8 H2D,
+    on-device ToTensor, captured driver frame, on-device clamp + uint8, D2H, PIL.Image.fromarray), wall clock."""
+    from PIL import Image
+
+    from emoportraits_b200.infer import InferenceWrapper
+
+    args_txt = ROOT / "tests" / "golden" / f"args_{SIZE}.txt"
+    w = InferenceWrapper(experiment_name="bench", model_file_name="", project_dir=str(ROOT), args_path=args_txt, state_dict=sd,
+                         head_pose_state_dict=hsd, print_params=False)
+    pil = [Image.fromarray((np.random.RandomState(2000 + i).rand(SIZE, SIZE, 3) * 255).astype(np.uint8)) for i in range(8)]
+    kw = dict(crop=False, mix=True, mix_old=False)
+    w.forward(pil[0], pil[1], **kw)
+    for i in range(3):
+        w.forward(None, pil[i], **kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        out, img = w.forward(None, pil[i % 8], **kw)
+    torch.cuda.synchronize()
+    per_call = K / (time.perf_counter() - t0)
+    batch = [pil[i % 8] for i in range(K)]
+    w.forward(None, batch[:4], **kw)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out, img = w.forward(None, batch, **kw)
+    torch.cuda.synchronize()
+    listed = K / (time.perf_counter() - t0)
+    assert len(out) == K and out[0].size == (SIZE, SIZE)
+    return {"one_frame_per_call": per_call, "list_of_frames_per_call": listed, "unit": "frames/s",
+            "what": "InferenceWrapper.forward(None, PIL...) -> (list[PIL], tensor): uint8 H2D 0.79 MB + D2H 0.79 MB per frame, wall clock"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -266,7 +299,22 @@ def run_ours(args):
     from emoportraits_b200.dist import broadcast_source_state
 
     st = model.source_pass(frame(SIZE, 0).to(dev)) if rank == 0 else None
-    st = broadcast_source_state(st, cfg, dev, src=0) if world > 1 else st
+    broadcast_ms = None
+    if world > 1:
+        # the one exchange step of the path: 25.2 MB identity state from the rank that ran the source pass.
+        # First call = NCCL communicator warm-up; the second is timed with CUDA events, max over ranks.
+        st0 = st
+        st = broadcast_source_state(st0, cfg, dev, src=0)
+        torch.cuda.synchronize()
+        dist.barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        st = broadcast_source_state(st0 if rank == 0 else st, cfg, dev, src=0)
+        b1.record()
+        torch.cuda.synchronize()
+        tb = torch.tensor([b0.elapsed_time(b1)], device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        broadcast_ms = tb.item()
     torch.cuda.synchronize()
 
     K, W = args.steps, max(args.warmup, 3)
@@ -357,6 +405,26 @@ def run_ours(args):
         return
 
     frame_ms = ms_max / K
+    # ---- latency of ONE frame alone (what an interactive caller sees): one captured frame at a time, device-resident ----
+    lat_pipe = DriverPipeline(model, st, depth=1, mix=True) if not args.eager else None
+    latency_ms = None
+    if lat_pipe is not None:
+        for i in range(3):
+            lat_pipe.submit(frames_dev[i % len(frames_dev)])
+        lat_pipe.drain(); torch.cuda.synchronize()
+        l0e, l1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0e.record()
+        for i in range(K):
+            lat_pipe.submit(frames_dev[i % len(frames_dev)])
+        lat_pipe.drain()
+        l1e.record(); torch.cuda.synchronize()
+        latency_ms = l0e.elapsed_time(l1e) / K
+        del lat_pipe
+    # ---- the drop-in call itself: InferenceWrapper.forward(None, PIL) -> (list[PIL], tensor), one frame per call and a
+    #      list of frames per call (notebooks/infer.py:355-357; E_emo_infer_video.ipynb calls it per frame) ----
+    e2e_wrapper = None
+    if not args.quick:
+        e2e_wrapper = wrapper_fps(sd, hsd, K)
     # ---- per-kernel evidence (rank 0, eager, CUDA events around every tensor-core conv launch) ----
     prof = ops.ConvProfiler()
     ops.set_conv_profiler(prof)
@@ -427,28 +495,41 @@ def run_ours(args):
                                    "launches_per_step": n_conv // 3, "share_of_step_eager": (conv_ms / 3) / frame_ms,
                                    "note": "CUDA events around every conv launch of 3 eager frames (small launches include host gaps)"}},
         "roofline_grid_sample3d": {"bound": "hbm", "unit": "GB/s", "peak": peaks["hbm_gbs"], "peak_source": peaks["source"],
-                                   "achieved": gs["d64_affine"]["achieved_gbs"], "frac": gs["d64_affine"]["frac"],
-                                   "headline": "d64_affine (fused affine lattice, the hot path's rotation warp)", **gs},
+                                   "achieved": gs.get("d64", gs["d64_affine"]).get("achieved_gbs", 0.0), "frac": gs.get("d64", gs["d64_affine"]).get("frac", 0.0),
+                                   "headline": "d64 = BASELINE configs[2] at batch 1: 96ch x 64^3 volume sampled through a 64^3 x 3 warp-field "
+                                               "tensor (identity + 0.1 randn); *_affine = fused affine lattice (no grid tensor), d16 = model-true depth", **gs},
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if latency_ms is not None:
+        line["latency_ms_one_frame_alone"] = latency_ms
+    if e2e_wrapper is not None:
+        line["e2e_wrapper"] = e2e_wrapper
+    if broadcast_ms is not None:
+        line["broadcast_ms"] = {"value": broadcast_ms, "bytes": 4 * (cfg.D * cfg.S * cfg.S * cfg.C + cfg.idt_channels * cfg.embed_size ** 2 + 16),
+                                "what": "identity state rank 0 -> all ranks (second call, CUDA events, max over ranks); outside the timed region, once per identity"}
+    if world == 1 and not args.quick:
+        del pipe, model
+        torch.cuda.empty_cache()
+        try:
+            line["stage2"] = stage2_numbers(5, 3)
+        except RuntimeError as e:
+            line["stage2"] = {"error": str(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_stage2(args):
-    """BASELINE config 5 (secondary workload, `--workload stage2`): stage-2 refinement encoder+decoder @1024^2, batch 4."""
+def stage2_numbers(K, W):
+    """BASELINE config 5: stage-2 refinement encoder+decoder @1024^2, batch 4 (secondary workload)."""
     from emoportraits_b200 import lib as L
     from emoportraits_b200 import ops
     from emoportraits_b200.stage2 import Stage2Config, Stage2Model, synthetic_state_dict_s2
 
-    torch.cuda.set_device(0)
     cfg = Stage2Config(output_size=1024)
     model = Stage2Model(cfg, synthetic_state_dict_s2(cfg, 0), "cuda")
     B = 4
     img = torch.rand(B, 3, 512, 512, device="cuda")
-    K, W = args.steps, max(args.warmup, 3)
     for _ in range(W):
         model.forward(img)
     torch.cuda.synchronize()
@@ -467,14 +548,22 @@ def run_stage2(args):
     ops.set_conv_profiler(None)
     conv_ms, conv_flops, n_conv = prof.summary()
     peaks = measured_peaks()
-    line = {"metric": "stage-2 refinement images/s @1024^2, batch 4 (BASELINE configs[4])", "value": B * 1000.0 / ms, "unit": "images/s",
-            "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x2-split operands, fp32 accumulate", "data": "synthetic",
+    return {"metric": "stage-2 refinement images/s @1024^2, batch 4 (BASELINE configs[4])", "value": B * 1000.0 / ms, "unit": "images/s",
+            "ms_per_step": ms, "steps": K, "warmup": W, "gpu_launches_per_step": launches,
             "config": {"workload": "stage-2 LocalEncoderOld + Decoder_stage2, output_size_s2 1024, batch 4, default stage-2 args"},
-            "gpu_launches": launches * K,
             "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel (all conv layers of one step)", "achieved": conv_flops / conv_ms / 1e9,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": conv_flops / conv_ms / 1e9 / peaks["bf16_tflops_sustained"],
                          "traffic": None, "tensor_pipe_frac_est": prof.mma_flops / conv_ms / 1e9 / peaks["bf16_tflops_sustained"]}}
+
+
+def run_stage2(args):
+    """`--workload stage2`: the secondary workload alone, as its own JSON line (the default run carries it under "stage2")."""
+    torch.cuda.set_device(0)
+    K, W = args.steps, max(args.warmup, 3)
+    d = stage2_numbers(K, W)
+    line = {"metric": d["metric"], "value": d["value"], "unit": d["unit"], "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": d["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2-split operands, fp32 accumulate",
+            "data": "synthetic", "config": d["config"], "gpu_launches": d["gpu_launches_per_step"] * K, "roofline": d["roofline"]}
     print(json.dumps(line))
 
 

@@ -26,31 +26,16 @@ int check_launch(const char* what);
     }                                          \
   } while (0)
 
-// ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch.  Every kernel of the library is launched with the programmatic-stream-serialization
-// attribute and runs  pdl_launch_dependents(); [input-independent prologue]; pdl_wait();  before it touches global
-// memory: the next kernel of the stream (or of the captured graph: consecutive kernel nodes get a programmatic edge)
-// becomes resident and runs its own prologue (barrier init, TMEM allocation, tensor-map prefetch, smem zeroing, the launch
-// latency itself) while this one is still running, and blocks in griddepcontrol.wait until this grid has completed and
-// flushed.  A driver frame is ~200 dependent launches, so the per-boundary drain + launch + prologue time is a
-// first-order term of the frame latency.  griddepcontrol.wait is a no-op for a launch without the attribute.
-// EMO_PDL=0 drops the attribute (A/B measurement).
-// ------------------------------------------------------------------------------------------------
-bool pdl_enabled();
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
+// One launch path for every kernel of the library (cudaLaunchKernelEx).  Programmatic dependent launch (attribute +
+// griddepcontrol.launch_dependents / .wait in every kernel) was built and measured in round 2: 221.8 vs 221.1 frames/s with one
+// frame in flight, 254 vs 260 with two, 269 vs 270 with three (profiles/README.md) - the captured frame is a chain of
+// data-dependent kernels whose summed durations already equal the frame time, so there is no launch gap to hide; removed.
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

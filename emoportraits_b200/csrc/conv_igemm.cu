@@ -77,6 +77,7 @@ struct ConvKParams {
   int oH, oW;
   int ntc;  // channel tiles per phase (= Cout_pad / BN)
   float out_scale;  // conv_igemm_f16_kernel: 1 / (activation plane scale * weight plane scale)
+  int res_tma;      // EPI = 2: the residual has the output's resolution and is TMA-loaded into the staging tile (tm.res)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -144,6 +145,17 @@ __device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint64_t
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA tensor store of one staged panel (shared -> global through the async proxy) and its bulk-group bookkeeping
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
@@ -372,6 +384,8 @@ __device__ __forceinline__ void store_rows(const StoreRowCtx& c, int chunk0, int
 struct TMaps {
   CUtensorMap a[3];  // activation planes: hi, lo, lo2
   CUtensorMap b[3];  // weight planes
+  CUtensorMap out;   // EPI = 2: fp32 output, 32-channel panels of one pixel box (SWIZZLE_128B)
+  CUtensorMap res;   // EPI = 2: same-resolution residual, same boxes
 };
 
 #define EMO_CONV_PS 0
@@ -409,8 +423,6 @@ struct FinParams {
 };
 
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f) {
-  pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ float sstat[];
   const int n = blockIdx.y;
   if (f.stats) {
@@ -594,20 +606,24 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
-  // store-warp epilogue (EPI = 1): pair-mode, full-K tiles with vectorisable channels-last output; needs a [128][BN] fp32
-  // staging buffer next to >= 3 pipeline stages (measured: 3 stages cost nothing against 4, 2 stages cost 10-25%)
+  // Final phase of a tile (template parameter EPI, see the kernel's header comment):
+  //   2  TMA epilogue: pair-mode, full-K tiles, channels-last output in whole 32-channel panels, no post-add; needs a [128][BN]
+  //      fp32 staging tile next to >= 3 pipeline stages (measured: 3 stages cost nothing against 4, 2 stages cost 10-25%)
+  //   1  store warps (round-1 form, kept for the A/B: EMO_CONV_EPI=1): same conditions, >= 2 tiles per CTA
+  //   0  in-warp final phase: everything else (split-K, NCHW / ragged-channel outputs, single-CTA tiles)
   int epi = 0;
   {
     static int epi_env = -1;
-    if (epi_env < 0) { const char* e = getenv("EMO_CONV_EPI"); epi_env = e ? atoi(e) : 1; }
+    if (epi_env < 0) { const char* e = getenv("EMO_CONV_EPI"); epi_env = e ? atoi(e) : 2; }
     const long long elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;  // 32-bit element offsets in the store warps
-    // pays when a CTA walks several tiles (the final phase of tile t then overlaps the MMAs of tile t+1: 512^2 x 128 -> 128
-    // 221 -> 197 us); a single tile per CTA has nothing to overlap and loses ~5% to the extra hand-over
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
-    if (epi_env == 1 && p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0 && elems < (1ll << 31) &&
-        tiles >= 2ll * sm_count) epi = 1;
-    if (epi_env == 2 && p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0 && elems < (1ll << 31)) epi = 1;  // tests: force
+    const bool common = p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0;
+    if (epi_env == 2 && common && d->Cout == d->Cout_pad && d->Cout % 32 == 0 && BN % 32 == 0 && !d->post_add &&
+        ((uintptr_t)d->out % 16) == 0 && (!d->residual || ((uintptr_t)d->residual % 16) == 0) && (!ps || d->N * (long long)gH < (1ll << 31)))
+      epi = 2;
+    if (epi_env == 1 && common && elems < (1ll << 31) && tiles >= 2ll * sm_count) epi = 1;
   }
+  p.res_tma = (epi == 2 && d->residual && d->res_shift == 0 && !ps) ? 1 : 0;
   size_t staging = 0, stage_bytes = 0;
   int stages = 0;
   const int KC0 = KC;
@@ -618,7 +634,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     if (KC == 64 && avail / ((size_t)NP * (kTileM + BN / p.cg) * 64 * 2) < 3) KC = 32;
     stage_bytes = (size_t)NP * (kTileM + BN / p.cg) * KC * 2;
     stages = (int)(avail / stage_bytes);
-    if (epi && stages < 3) { epi = 0; continue; }
+    if (epi && (stages < 3 || (ps && KC != 64))) { epi = 0; p.res_tma = 0; continue; }  // (the sub-pixel kernel is built for KC = 64)
     break;
   }
   p.kchunks = d->Cin / KC;
@@ -669,6 +685,35 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     }
   }
 
+  if (epi == 2) {
+    // output (and same-resolution residual) as 32-channel panels of the tile's pixel box; SWIZZLE_128B = the staging tile's
+    // chunk order.  Sub-pixel mode: the [2 H][2 W] output seen as (C, column parity, W, row parity, N * H): one phase's pixels
+    // of a low-resolution box are again a box.
+    cuuint64_t gdim[5], gstr[4];
+    cuuint32_t box[5], es[5] = {1, 1, 1, 1, 1};
+    const cuuint64_t C4 = (cuuint64_t)d->Cout * 4;
+    if (ps) {
+      gdim[0] = (cuuint64_t)d->Cout; gdim[1] = 2; gdim[2] = (cuuint64_t)gW; gdim[3] = 2; gdim[4] = (cuuint64_t)d->N * gH;
+      gstr[0] = C4; gstr[1] = 2 * C4; gstr[2] = (cuuint64_t)d->Wout * C4; gstr[3] = 2 * (cuuint64_t)d->Wout * C4;
+      box[0] = 32; box[1] = 1; box[2] = (cuuint32_t)p.tw; box[3] = 1; box[4] = (cuuint32_t)p.th;
+    } else {
+      gdim[0] = (cuuint64_t)d->Cout; gdim[1] = (cuuint64_t)d->Wout; gdim[2] = (cuuint64_t)d->Hout; gdim[3] = (cuuint64_t)d->Dout; gdim[4] = (cuuint64_t)d->N;
+      gstr[0] = C4; gstr[1] = (cuuint64_t)d->Wout * C4; gstr[2] = (cuuint64_t)d->Hout * d->Wout * C4; gstr[3] = (cuuint64_t)d->Dout * d->Hout * d->Wout * C4;
+      box[0] = 32; box[1] = (cuuint32_t)p.tw; box[2] = (cuuint32_t)p.th; box[3] = (cuuint32_t)p.td; box[4] = 1;
+    }
+    CUresult r1 = encode(&tm.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)d->out, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = CUDA_SUCCESS;
+    if (p.res_tma)
+      r2 = encode(&tm.res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)d->residual, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+      set_error("emo_conv_igemm: cuTensorMapEncodeTiled failed for the output / residual map: %d %d (Cout=%d W=%d H=%d D=%d N=%d box=%d,%d,%d)",
+                (int)r1, (int)r2, d->Cout, d->Wout, d->Hout, d->Dout, d->N, p.tw, p.th, p.td);
+      return EMO_ERR_CUDA;
+    }
+  }
+
   const int total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   int grid = total_tiles < sm_count ? total_tiles : sm_count;
   const int csz = p.cg == 2 ? 2 : p.cs;
@@ -686,23 +731,24 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cudaLaunchConfig_t cfg;                                                                                               \
     memset(&cfg, 0, sizeof(cfg));                                                                                         \
     cfg.gridDim = dim3((unsigned)grid);                                                                                   \
-    cfg.blockDim = dim3(EPI_ ? kThreadsEpi1 : kThreads);                                                                                        \
+    cfg.blockDim = dim3(EPI_ == 1 ? kThreadsEpi1 : kThreads);                                                                                        \
     cfg.dynamicSmemBytes = smem_bytes;                                                                                    \
     cfg.stream = stream;                                                                                                  \
-    cudaLaunchAttribute attr[2];                                                                                          \
+    cudaLaunchAttribute attr[1];                                                                                          \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                                     \
     attr[0].val.clusterDim.x = (unsigned)csz;                                                                             \
     attr[0].val.clusterDim.y = 1;                                                                                         \
     attr[0].val.clusterDim.z = 1;                                                                                         \
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; /* common.cuh: programmatic dependent launch */      \
-    attr[1].val.programmaticStreamSerializationAllowed = 1;                                                               \
     cfg.attrs = attr;                                                                                                     \
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;                                                                                 \
+    cfg.numAttrs = 1;                                                                                                     \
     e = cudaLaunchKernelEx(&cfg, KERNEL_<KC_, NP_, CG_, EPI_>, tm, p);                                                      \
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
   if (f16) {
-    if (epi) {
+    if (epi == 2) {
+      if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 2, 2);
+      else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 2, 2);
+    } else if (epi == 1) {
       if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 2, 1);
       else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 2, 1);
     } else if (p.cg == 2) {
@@ -714,9 +760,15 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     }
   } else if (ps) {
     EMO_REQUIRE(KC == 64, "emo_conv_igemm: upconv tile does not fit with KC = 64");
-    if (epi) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 1);
+    if (epi == 2) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 2);
+    else if (epi == 1) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 1);
     else EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 0);
-  } else if (epi) {
+  } else if (epi == 2) {
+    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 2);
+    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 2);
+    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 2);
+    else EMO_LAUNCH_CONV(32, 2, 2, 2);
+  } else if (epi == 1) {
     if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 1);
     else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 1);
     else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 1);

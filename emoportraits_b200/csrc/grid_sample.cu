@@ -163,8 +163,6 @@ __device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int 
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ __align__(16) int s_off[kBrickVox][8];
   __shared__ __align__(16) float s_wgt[kBrickVox][8];
   __shared__ long long s_out[kBrickVox];  // output element offset of the voxel (or -1)
@@ -258,8 +256,6 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
 // arithmetic as the brick kernel (shared device functions), so the outputs are bit-identical.
 template <bool SPLIT>
 __global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const GS3Params p) {
-  pdl_launch_dependents();
-  pdl_wait();
   __shared__ __align__(16) int s_off[kBrickVox][8];
   __shared__ __align__(16) float s_wgt[kBrickVox][8];
   __shared__ long long s_out[kBrickVox];
@@ -293,8 +289,6 @@ __global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const GS3Params
 // corner offsets/weights held in registers; lanes run along W so both the gathers and the stores coalesce.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gs3_nc_kernel(const GS3Params p) {
-  pdl_launch_dependents();
-  pdl_wait();
   const long long total = (long long)p.N * p.Dout * p.Hout * p.Wout;
   const long long plane_in = (long long)p.Din * p.Hin * p.Win;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -350,8 +344,6 @@ struct GS2Params {
 };
 
 __global__ void gs2_affine_kernel(const GS2Params p) {
-  pdl_launch_dependents();
-  pdl_wait();
   const long long total = (long long)p.N * p.Hout * p.Wout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long r = idx;
@@ -402,8 +394,6 @@ struct ResizeParams {
 };
 
 __global__ void resize_bilinear_kernel(const ResizeParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
   const long long total = (long long)p.N * p.Hout * p.Wout;
   const float sh = (float)p.Hin / (float)p.Hout, sw = (float)p.Win / (float)p.Wout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -430,9 +420,102 @@ __global__ void resize_bilinear_kernel(const ResizeParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// wrapper-boundary image conversions and the bicubic pre-processing resize
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) u8_to_image_kernel(const unsigned char* __restrict__ in, int N, long long HW, int C, float* __restrict__ out) {
+  const long long total = (long long)N * HW;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long n = t / HW, s = t - n * HW;
+    for (int c = 0; c < C; ++c) out[(n * C + c) * HW + s] = __fdiv_rn((float)in[t * C + c], 255.f);  // ToTensor: u / 255
+  }
+}
+
+__global__ void __launch_bounds__(256) image_to_u8_kernel(const float* __restrict__ in, int N, int C, long long HW, unsigned char* __restrict__ out) {
+  const long long total = (long long)N * HW;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long n = t / HW, s = t - n * HW;
+    for (int c = 0; c < C; ++c) {
+      const float v = fminf(fmaxf(__ldg(in + (n * C + c) * HW + s), 0.f), 1.f) * 255.f;  // clamp(0, 1).mul(255).byte(): truncation
+      out[t * C + c] = (unsigned char)(int)v;
+    }
+  }
+}
+
+// torch's upsample_bicubic2d (align_corners = False): src = scale * (dst + 0.5) - 0.5 (not clamped), taps floor(src) - 1 ..
+// + 2 with indices clamped to the border, cubic-convolution coefficients with A = -0.75 evaluated as torch evaluates them
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+__global__ void __launch_bounds__(256) resize_bicubic_kernel(const float* __restrict__ in, int NC, int Hin, int Win, int Hout, int Wout,
+                                                             float* __restrict__ out) {
+  const float sh = (float)Hin / (float)Hout, sw = (float)Win / (float)Wout;
+  const long long total = (long long)NC * Hout * Wout;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int ow = (int)(t % Wout);
+    const int oh = (int)((t / Wout) % Hout);
+    const long long nc = t / ((long long)Wout * Hout);
+    const float ry = sh * ((float)oh + 0.5f) - 0.5f, rx = sw * ((float)ow + 0.5f) - 0.5f;
+    const float fy = floorf(ry), fx = floorf(rx);
+    float wy[4], wx[4];
+    cubic_coeffs(ry - fy, wy);
+    cubic_coeffs(rx - fx, wx);
+    const float* src = in + nc * (long long)Hin * Win;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int y = min(max((int)fy - 1 + i, 0), Hin - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int x = min(max((int)fx - 1 + j, 0), Win - 1);
+        row += __ldg(src + (long long)y * Win + x) * wx[j];
+      }
+      acc += row * wy[i];
+    }
+    out[t] = acc;
+  }
+}
+
 }  // namespace emo
 
 using namespace emo;
+
+extern "C" int emo_u8_to_image(const unsigned char* nhwc, int N, int H, int W, int C, float* nchw, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(nhwc && nchw && N > 0 && H > 0 && W > 0 && C > 0 && C <= 4, "emo_u8_to_image: bad arguments");
+  const long long total = (long long)N * H * W;
+  long long blocks = cdivll(total, 256);
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  launch_kernel(u8_to_image_kernel, (unsigned)blocks, 256, 0, stream, nhwc, N, (long long)H * W, C, nchw);
+  return check_launch("emo_u8_to_image");
+}
+
+extern "C" int emo_image_to_u8(const float* nchw, int N, int C, int H, int W, unsigned char* nhwc, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(nhwc && nchw && N > 0 && H > 0 && W > 0 && C > 0 && C <= 4, "emo_image_to_u8: bad arguments");
+  const long long total = (long long)N * H * W;
+  long long blocks = cdivll(total, 256);
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  launch_kernel(image_to_u8_kernel, (unsigned)blocks, 256, 0, stream, nchw, N, C, (long long)H * W, nhwc);
+  return check_launch("emo_image_to_u8");
+}
+
+extern "C" int emo_resize_bicubic(const float* in, int N, int C, int Hin, int Win, int Hout, int Wout, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(in && out && N > 0 && C > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "emo_resize_bicubic: bad arguments");
+  const long long total = (long long)N * C * Hout * Wout;
+  long long blocks = cdivll(total, 256);
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  launch_kernel(resize_bicubic_kernel, (unsigned)blocks, 256, 0, stream, in, N * C, Hin, Win, Hout, Wout, out);
+  return check_launch("emo_resize_bicubic");
+}
 
 extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

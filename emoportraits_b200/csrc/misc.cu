@@ -16,12 +16,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) { const char* e = getenv("EMO_PDL"); on = e ? (atoi(e) != 0) : 1; }
-  return on != 0;
-}
-
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -35,8 +29,6 @@ int check_launch(const char* what) {
 // linear: one warp per output element (m, n), lanes stride over K.  Sizes are tiny (<= 20 MFLOP).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) linear_kernel(const emo_linear_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= d.M * d.N) return;
@@ -60,8 +52,6 @@ __global__ void __launch_bounds__(256) linear_kernel(const emo_linear_desc d) {
 // the activation load is a warp broadcast.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_direct_kernel(const emo_conv_direct_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int co4n = d.Cout >> 2;
   const long long total = (long long)d.N * d.Hout * d.Wout * co4n;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,8 +124,6 @@ __device__ __forceinline__ void up_coord(int o, int f, int n_in, int& i0, int& i
 }
 
 __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resample_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int c4n = d.C >> 2;
   const int Do = d.D * d.fd, Ho = d.H * d.fh, Wo = d.W * d.fw;
   const long long So = (long long)Do * Ho * Wo;
@@ -199,8 +187,6 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resam
 
 // avgpool with kernel == stride == (fd, fh, fw), channels-last; optional add + stats of the result
 __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int c4n = d.C >> 2;
   const int Do = d.D / d.fd, Ho = d.H / d.fh, Wo = d.W / d.fw;
   const long long per_n = (long long)Do * Ho * Wo * c4n;
@@ -253,8 +239,6 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d)
 }
 
 __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int N, int H, int W, int C, float* __restrict__ out) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int c4n = C >> 2;
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * c4n;
@@ -280,8 +264,6 @@ __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, int N, int H, i
 }
 
 __global__ void global_avgpool_kernel(const float* __restrict__ x, int N, long long S, int C, float* __restrict__ out) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * C) return;
   const int n = idx / C, c = idx % C;
@@ -294,8 +276,6 @@ __global__ void global_avgpool_kernel(const float* __restrict__ x, int N, long l
 // pose algebra: pose_math.cuh (host+device source, also compiled for the CPU by tests/test_pose_math_host.py)
 // ------------------------------------------------------------------------------------------------
 __global__ void pose_theta_kernel(const emo_pose_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   if (d.smooth_state) {
     // exponential smoothing carries state from sample to sample: one thread walks the samples in order
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -311,7 +291,7 @@ __global__ void pose_theta_kernel(const emo_pose_desc d) {
 using namespace emo;
 
 extern "C" const char* emo_last_error(void) { return emo::g_err; }
-extern "C" int emo_version(void) { return 101; }  // 101: emo_pose_desc (+theta_in, mix_old, smoothing) and emo_conv_desc (+upconv) grew trailing fields
+extern "C" int emo_version(void) { return 102; }  // 101: emo_pose_desc (+theta_in, mix_old, smoothing) and emo_conv_desc (+upconv) grew trailing fields
 
 extern "C" int emo_device_info(int* sm_count, int* cc) {
   int dev = 0;

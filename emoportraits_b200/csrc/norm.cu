@@ -14,8 +14,6 @@ namespace emo {
 // ---- statistics: x [N][S][C] fp32, per (n, g) sum and sum of squares, double accumulation across CTAs ----
 __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ x, int N, long long S, int C, int G,
                                                        double* __restrict__ stats, int chunks) {
-  pdl_launch_dependents();
-  pdl_wait();
   // grid = N * chunks; each CTA reduces a slab of spatial positions for all channels
   const int n = blockIdx.x / chunks, ch = blockIdx.x % chunks;
   const long long s_per = (S + chunks - 1) / chunks;
@@ -58,8 +56,6 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 
 // ---- finalize: stats -> per-(n,c) scale/shift ----
 __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= d.N * d.C) return;
   const int n = idx / d.C, c = idx % d.C;
@@ -95,8 +91,6 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
 // pixel's whole channel vector (512 B at C = 128); the 8 x 4 per-lane partial dot products are transpose-reduced over the
 // warp with 31 shuffles, after which lane l = 4u + o holds output o of pixel u.
 __global__ void __launch_bounds__(256) gn_head_kernel(const emo_gn_head_desc d) {
-  pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ float sAB[];  // A[C], B[C] of this CTA's sample, then w[4][C] (rows >= Cout are zero)
   const int n = blockIdx.y;
   const int C = d.C;
@@ -164,8 +158,6 @@ __global__ void __launch_bounds__(256) gn_head_kernel(const emo_gn_head_desc d) 
 
 __global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* __restrict__ hi, uint2* __restrict__ lo,
                              uint2* __restrict__ lo2) {
-  pdl_launch_dependents();
-  pdl_wait();
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
     uint2 h, l, l2;
     if (lo2) {
@@ -179,8 +171,6 @@ __global__ void split_kernel(const float* __restrict__ x, long long n4, uint2* _
 }
 
 __global__ void split_f16_kernel(const float* __restrict__ x, long long n4, float scale, uint2* __restrict__ hi, uint2* __restrict__ lo) {
-  pdl_launch_dependents();
-  pdl_wait();
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
     uint2 h, l;
     split4_h(__ldg((const float4*)x + t), scale, h, l);
@@ -189,8 +179,6 @@ __global__ void split_f16_kernel(const float* __restrict__ x, long long n4, floa
 }
 
 __global__ void flush_kernel(float4* buf, long long n4) {
-  pdl_launch_dependents();
-  pdl_wait();
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
     buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 }

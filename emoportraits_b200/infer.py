@@ -17,7 +17,6 @@ from typing import Optional
 
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from . import nets, ops
 from .config import HotPathConfig, hot_path_config, parse_args
@@ -286,28 +285,26 @@ class InferenceWrapper(torch.nn.Module):
 
     # -- notebooks/infer.py:229-243
     def convert_to_tensor(self, image):
-        def one(img):
-            a = np.asarray(img)
-            if a.ndim == 2:
-                a = a[:, :, None]
-            t = torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1)
-            return t.float().div(255) if t.dtype == torch.uint8 else t.float()
-
+        """PIL image(s) / numpy uint8 (H,W,C) -> fp32 (N,C,H,W) in [0,1] on the device.  uint8 pixels cross the bus as bytes
+        (0.79 MB per 512^2 frame instead of 3.1 MB) and become u / 255 in emo_u8_to_image (= transforms.ToTensor)."""
         if isinstance(image, torch.Tensor):
-            t = image
-        elif isinstance(image, list):
-            t = torch.stack([one(i) for i in image])
-        else:
-            t = one(image)
-        if t.dim() == 3:
-            t = t[None]
-        return t.to(self.device)
+            t = image if image.dim() == 4 else image[None]
+            return t.to(self.device).float()
+        items = image if isinstance(image, list) else [image]
+        arrs = []
+        for img in items:
+            a = np.asarray(img)
+            arrs.append(a[:, :, None] if a.ndim == 2 else a)
+        if all(a.dtype == np.uint8 for a in arrs):
+            u8 = torch.from_numpy(np.ascontiguousarray(np.stack(arrs))).to(self.device, non_blocking=True)
+            return ops.u8_to_image(u8)
+        return torch.stack([torch.from_numpy(np.ascontiguousarray(a)).permute(2, 0, 1).float() for a in arrs]).to(self.device)
 
     def _prep(self, image):
-        t = self.convert_to_tensor(image)[:, :3]
+        t = self.convert_to_tensor(image)[:, :3].contiguous()
         s = self.cfg.image_size
         if t.shape[-2:] != (s, s):
-            t = F.interpolate(t, size=(s, s), mode='bicubic')  # pre-processing resize, infer.py:401-402 / :554-555
+            t = ops.resize_bicubic(t, (s, s))  # pre-processing resize, infer.py:401-402 / :554-555
         return t.contiguous().float()
 
     def forward(self, source_image=None, driver_image=None, source_mask=None, source_mask_add=0, driver_mask=None,
@@ -366,8 +363,9 @@ class InferenceWrapper(torch.nn.Module):
         if custome_target_theta_embed is not None:   # (scale, rotation, translation), each (1,3): infer.py:566-567
             custom_srt = torch.cat([torch.as_tensor(t).float().reshape(1, 3) for t in custome_target_theta_embed], 1)
         per_frame = smooth_pose or custom_srt is not None or custome_target_pose_embed is not None
-        if drv.shape[0] >= 2 and not per_frame:
-            # a list of driver frames: captured frames, two in flight (DriverPipeline); same kernels as the eager pass below
+        if not per_frame:
+            # captured driver frames (CUDA graphs), two in flight when a list of frames is given (DriverPipeline); same
+            # kernels as the eager pass below
             key = (bool(mix), bool(target_theta), bool(mix_old))
             if self._pipeline is None or self._pipeline.st is not self._state or self._pipeline_key != key:
                 self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=2, mix=mix,
@@ -376,8 +374,10 @@ class InferenceWrapper(torch.nn.Module):
             for i in range(drv.shape[0]):
                 sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1]).slot
             self._pipeline.drain()
-            self.pred_target_theta = sl.run.static_state.pred_target_theta.clone()
-            self.target_pose_embed = sl.run.static_state.target_pose_embed.clone()
+            so = sl.run.static_state
+            self.pred_target_theta = so.pred_target_theta.clone()
+            self.pred_target_srt = (so.srt[:, :3].clone(), so.srt[:, 3:6].clone(), so.srt[:, 6:9].clone())
+            self.target_pose_embed = so.target_pose_embed.clone()
         else:
             imgs = []
             for i in range(drv.shape[0]):
@@ -399,6 +399,6 @@ class InferenceWrapper(torch.nn.Module):
             self.target_pose_embed = so.target_pose_embed
         from PIL import Image
 
-        host = (img.detach().clamp(0, 1) * 255).byte().permute(0, 2, 3, 1).cpu().numpy()  # ToPILImage: mul(255).byte()
+        host = ops.image_to_u8(img.detach().contiguous()).cpu().numpy()  # clamp(0, 1) + ToPILImage (mul(255).byte()) on the device
         pred_target_img = [Image.fromarray(h) for h in host]
         return pred_target_img, img

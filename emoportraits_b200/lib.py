@@ -115,6 +115,9 @@ SYMBOLS = {
     "emo_pose_theta": (c_int, [C.POINTER(PoseDesc), c_void_p]),
     "emo_split_bf16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "emo_split_f16": (c_int, [c_void_p, c_ll, c_float, c_void_p, c_void_p, c_void_p]),
+    "emo_u8_to_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "emo_image_to_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "emo_resize_bicubic": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "emo_l2_flush": (c_int, [c_void_p, c_ll, c_void_p]),
 }
 

@@ -252,6 +252,14 @@ class ResNet:
         return x, xs
 
 
+def _norm_buffers(sd, p, dev):
+    """input normalisation of an embedder: its `mean` / `std` buffers from the checkpoint (identity_embedder.py:21-22,
+    expression_embedder.py:352-353 register the ImageNet statistics), the ImageNet constants if the checkpoint has none"""
+    mean = sd[p + ".mean"].detach().float().reshape(-1) if (p + ".mean") in sd else torch.tensor([0.485, 0.456, 0.406])
+    std = sd[p + ".std"].detach().float().reshape(-1) if (p + ".std") in sd else torch.tensor([0.229, 0.224, 0.225])
+    return mean.to(dev).contiguous(), std.to(dev).contiguous()
+
+
 class HeadPoseRegressor:
     """head_pose_regressor.py:11-31 — resnet18(num_classes=9), BatchNorm, its own checkpoint."""
 
@@ -277,8 +285,7 @@ class ExpressionEmbed:
         w, _ = fold_conv(sd, p + ".pose_head")  # (E, E*16), input index c*16 + s (torch.flatten of NCHW)
         E = cfg.expr_channels
         self.head_w = w.view(E, E, 16).permute(0, 2, 1).reshape(E, 16 * E).to(dev).contiguous()  # -> index s*E + c
-        self.mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
-        self.std = torch.tensor([0.229, 0.224, 0.225], device=dev)
+        self.mean, self.std = _norm_buffers(sd, p, dev)
         self.grid = cfg.exp_image_size // 2
 
     def __call__(self, img_nchw, align2d, want_aligned=False):
@@ -299,8 +306,7 @@ class IdtEmbed:
         p = "idt_embedder_nw"
         self.net = ResNet(sd, p + ".net", dev, gn=True, planes=planes)
         self.fc = ConvW(sd, p + ".net.fc", dev, planes=planes)
-        self.mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
-        self.std = torch.tensor([0.229, 0.224, 0.225], device=dev)
+        self.mean, self.std = _norm_buffers(sd, p, dev)
         self.size = cfg.idt_image_size
 
     def __call__(self, img_nchw):

@@ -564,5 +564,34 @@ def pose_theta(srt: Optional[torch.Tensor], source_theta: Optional[torch.Tensor]
     return theta, warp, align
 
 
+def u8_to_image(u8_nhwc: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """uint8 (N,H,W,C) on device (PIL / numpy layout) -> fp32 (N,C,H,W) = u / 255 (ToTensor, notebooks/infer.py:229-243)"""
+    _chk(u8_nhwc, torch.uint8)
+    N, H, W, Cc = u8_nhwc.shape
+    if out is None:
+        out = torch.empty((N, Cc, H, W), dtype=torch.float32, device=u8_nhwc.device)
+    L.call("emo_u8_to_image", _p(u8_nhwc), N, H, W, Cc, _p(out), _stream())
+    return out
+
+
+def image_to_u8(img_nchw: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 (N,C,H,W) -> uint8 (N,H,W,C) = trunc(clamp(x,0,1)*255): `.clamp(0,1)` + ToPILImage (notebooks/infer.py:641-644)"""
+    _chk(img_nchw)
+    N, Cc, H, W = img_nchw.shape
+    if out is None:
+        out = torch.empty((N, H, W, Cc), dtype=torch.uint8, device=img_nchw.device)
+    L.call("emo_image_to_u8", _p(img_nchw), N, Cc, H, W, _p(out), _stream())
+    return out
+
+
+def resize_bicubic(img_nchw: torch.Tensor, out_hw) -> torch.Tensor:
+    """F.interpolate(mode='bicubic', align_corners=False) (notebooks/infer.py:399-403, 551-556)"""
+    _chk(img_nchw)
+    N, Cc, Hi, Wi = img_nchw.shape
+    out = torch.empty((N, Cc, out_hw[0], out_hw[1]), dtype=torch.float32, device=img_nchw.device)
+    L.call("emo_resize_bicubic", _p(img_nchw), N, Cc, Hi, Wi, out_hw[0], out_hw[1], _p(out), _stream())
+    return out
+
+
 def l2_flush(buf: torch.Tensor):
     L.call("emo_l2_flush", _p(buf), buf.numel() * buf.element_size(), _stream())

@@ -299,7 +299,9 @@ class InferenceWrapper(torch.nn.Module):
         from PIL import Image
 
         img = img.to(self.device).float()
+        if self.cloth:
+            face_mask = None  # infer_s2.py:365-368: with cloth=True the refinement is not restricted to the face region
         resized, add, ffhq = self.model_two.forward(img, mask, face_mask)
-        to_pil = lambda t: [Image.fromarray(h) for h in (t.detach().clamp(0, 1) * 255).byte().permute(0, 2, 3, 1).cpu().numpy()]
+        to_pil = lambda t: [Image.fromarray(h) for h in ops.image_to_u8(t.detach().contiguous().float()).cpu().numpy()]
         m = mask if mask is not None else torch.ones_like(img[:, :1])
         return to_pil(img), to_pil(resized), to_pil(ffhq), m.detach().cpu().clamp(0, 1)

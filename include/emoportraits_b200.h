@@ -35,7 +35,7 @@ extern "C" {
 enum { EMO_ACT_NONE = 0, EMO_ACT_RELU = 1, EMO_ACT_SIGMOID = 2, EMO_ACT_TANH = 3 };
 
 const char* emo_last_error(void);
-int emo_version(void); /* 101: emo_pose_desc and emo_conv_desc gained trailing fields (zero = previous behaviour) */
+int emo_version(void); /* 102: + emo_u8_to_image, emo_image_to_u8, emo_resize_bicubic; 101: emo_pose_desc and emo_conv_desc gained trailing fields */
 /* sm count, and cc major*10+minor of the current device */
 int emo_device_info(int* sm_count, int* cc);
 
@@ -323,6 +323,18 @@ int emo_pose_theta(const emo_pose_desc* d, void* stream);
 int emo_split_bf16(const float* x, long long n, void* hi, void* lo, void* lo2, void* stream);
 /* fp32 -> fp16 hi/lo planes of x * scale (n elements), the operand format of emo_conv_desc.operand_fp16. */
 int emo_split_f16(const float* x, long long n, float scale, void* hi, void* lo, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Pre/post-processing at the wrapper boundary.
+ *   emo_u8_to_image   uint8 [N][H][W][C] (PIL / numpy layout) -> fp32 [N][C][H][W] = u / 255
+ *                     replaces transforms.ToTensor() in notebooks/infer.py:229-243 (convert_to_tensor)
+ *   emo_image_to_u8   fp32 [N][C][H][W] -> uint8 [N][H][W][C] = trunc(clamp(x, 0, 1) * 255)
+ *                     replaces `.clamp(0, 1)` + transforms.ToPILImage() (mul(255).byte()) notebooks/infer.py:641-644
+ *   emo_resize_bicubic fp32 [N][C][Hin][Win] -> [N][C][Hout][Wout]: F.interpolate(mode='bicubic', align_corners=False),
+ *                     A = -0.75, border-replicated taps; replaces notebooks/infer.py:399-403, 551-556
+ * ------------------------------------------------------------------------------------------------ */
+int emo_u8_to_image(const unsigned char* nhwc, int N, int H, int W, int C, float* nchw, void* stream);
+int emo_image_to_u8(const float* nchw, int N, int C, int H, int W, unsigned char* nhwc, void* stream);
+int emo_resize_bicubic(const float* in, int N, int C, int Hin, int Win, int Hout, int Wout, float* out, void* stream);
 /* L2 flush helper for benchmarks: writes `bytes` of `buf`. */
 int emo_l2_flush(void* buf, long long bytes, void* stream);
 

@@ -62,9 +62,14 @@ def _scale(ref):
 # volume sampled through xy_warp, whose 5e-5 error in normalised coordinates is 1.6e-3 voxel of a volume that changes by its
 # own magnitude from voxel to voxel: measured 2e-4 .. 8e-4 of the volume's maximum).  Measured values are printed, written to
 # gpurun_out/parity_<case>.txt and committed per round under profiles/.
-TAP_TOL = {"idt_embed": 5e-5, "source_theta": 1e-5, "source_pose_embed": 5e-5, "xy_warp": 1e-4, "source_latent_volume": 1e-4,
-           "target_latent_volume_1": 1.5e-3, "target_latent_volume": 5e-4, "theta": 1e-5, "pose_embed": 5e-5, "uv_warp": 1e-4,
-           "aligned_feat2d": 5e-4, "dec_feat": 5e-4, "logits": 4e-3, "img": IMG_TOL}
+TAP_TOL = {"idt_embed": 5e-5, "source_theta": 2.5e-7, "source_pose_embed": 5e-5, "xy_warp": 1e-4, "source_latent_volume": 1e-4,
+           "target_latent_volume_1": 1.5e-3, "target_latent_volume": 5e-4, "theta": 2.5e-7, "pose_embed": 5e-5, "uv_warp": 1e-4,
+           "aligned_feat2d": 5e-4, "dec_feat": 5e-4, "logits": 1.5e-3, "img": IMG_TOL}
+# theta: the device pose algebra is within two fp32 ulps of the reference's (CUDA sinf/cosf vs the host libm); on white-noise
+# frames the reference amplifies ONE such ulp to 1.2e-3 / 1.5e-3 in the image (tests/test_oracle_golden.py), which is the whole
+# white-noise exception: with the reference's matrices injected the same frames are within 1e-3.
+# logits: pre-sigmoid, relative to their maximum (|logit| <= 4.3: an error of 1.5e-3 x 4.3 at sigmoid'(0) = 1/4 is 1.6e-3 in the
+# image, so the image bound is the sharper one near 0 and this one guards the saturated range)
 # taps that sit downstream of the reference's fp32 LU inverse of the pose matrix (the 1-ulp-fragile step, module docstring):
 # not asserted in the all-on-device white-noise case
 POSE_NOISE_LIMITED = ("source_pose_embed", "xy_warp", "target_latent_volume_1", "target_latent_volume", "pose_embed", "uv_warp",
@@ -77,7 +82,7 @@ def _assert_taps(errs, scales, skip=()):
         name = k.split(".")[-1]
         if name in skip:
             continue
-        bound = TAP_TOL[name] * (1.0 if name in ("img", "logits") else max(1.0, scales[k]))
+        bound = TAP_TOL[name] * (1.0 if name == "img" else max(1.0, scales[k]))
         if not v < bound:
             bad.append((k, v, bound))
     assert not bad, bad
@@ -149,37 +154,6 @@ def test_noise_frames_all_on_device_reference_noise_limited(setup):
     for k, v in errs.items():
         if k.endswith("img"):
             assert v < NOISE_DEVICE_TOL[size], (k, v)
-
-
-def test_noise_frames_all_on_device_match_the_reference_arithmetic_with_a_correctly_rounded_inverse(setup):
-    """What the white-noise exception above amounts to, stated as a parity check: the device computes the 4x4 pose inverse in
-    fp64 and rounds once (pose_math.cuh: mat4_inv).  Run the oracle (= the reference's arithmetic, tests/test_oracle_golden.py)
-    live on the CPU on the fixture's white-noise frames with ONLY torch.inverse replaced by the correctly rounded inverse:
-    the device image is within the 1e-3 budget of that.  The remaining 1.6e-3 .. 3.8e-3 to the recorded fixtures is therefore
-    the reference's own fp32 LU rounding of a 4x4 matrix, amplified by the white-noise frames (CPU test:
-    test_reference_noise_floor_of_white_noise_frames, 1.2e-3 / 1.5e-3 from that one change)."""
-    size, cfg, model, gold = setup
-    from emoportraits_b200.checkpoint import synthetic_head_pose_state_dict, synthetic_state_dict
-    from oracle import restatement as R
-
-    case = _case(gold, "noise")
-    sd, hsd = synthetic_state_dict(cfg, 0), synthetic_head_pose_state_dict(0)
-    ocfg = R.config_from_state_dict(sd, size)
-    src, drv = FR.frame(size, case["src_seed"], "noise"), FR.frame(size, case["frames"][0]["seed"], "noise")
-    orig = torch.Tensor.inverse
-    torch.Tensor.inverse = lambda self: orig(self.double()).float()
-    try:
-        with torch.no_grad():
-            ost = R.source_pass(sd, hsd, src, ocfg)
-            oimg = R.driver_pass(sd, hsd, ost, drv, ocfg)
-    finally:
-        torch.Tensor.inverse = orig
-    st = model.source_pass(src.cuda())
-    img, _, _, _ = model.driver_pass(st, drv.cuda(), mix=True)
-    err = (img.cpu() - oimg).abs().max().item()
-    ref = _sub_err(img, case["frames"][0]["img"])
-    print(f"\n[white-noise frames @ {size}, all on device] vs oracle with correctly rounded 4x4 inverse: {err:.3e}; vs the recorded reference: {ref:.3e}")
-    assert err < IMG_TOL, err
 
 
 def test_driver_pass_matches_cpu_oracle_on_fresh_inputs(setup):

@@ -129,7 +129,7 @@ def test_apply_upsample_and_residual(ops):
 
 
 def _conv_case(ops, N, Cin, Cout, sp, k, stride=1, bias=True, residual=False, act=0, stats=False, out_nchw=False, seed=0,
-               planes=2):
+               planes=2, split_k=True, res_shift=0):
     g = torch.Generator().manual_seed(seed)
     three_d = len(sp) == 3
     x = torch.randn(N, Cin, *sp, generator=g)
@@ -139,8 +139,12 @@ def _conv_case(ops, N, Cin, Cout, sp, k, stride=1, bias=True, residual=False, ac
     ref = conv(x.double(), w.double(), b.double() if bias else None, stride=stride, padding=k // 2)
     res = None
     if residual:
-        res = torch.randn(ref.shape, generator=g)
-        ref = ref + res.double()
+        if res_shift:   # residual at half the output resolution, read with nearest-neighbour replication (2-D maps)
+            res = torch.randn(ref.shape[:2] + tuple(v // 2 for v in ref.shape[2:]), generator=g)
+            ref = ref + F.interpolate(res.double(), scale_factor=2, mode="nearest")
+        else:
+            res = torch.randn(ref.shape, generator=g)
+            ref = ref + res.double()
     if act == 2:
         ref = torch.sigmoid(ref)
     elif act == 3:
@@ -150,7 +154,7 @@ def _conv_case(ops, N, Cin, Cout, sp, k, stride=1, bias=True, residual=False, ac
     st = ops.new_stats(N, 32, "cuda") if stats else None
     s3 = (stride,) * 3 if three_d else (1, stride, stride)
     out = ops.conv_igemm(a, pw, stride=s3, bias=b.cuda() if bias else None, residual=cl(res).cuda() if residual else None,
-                         act=act, stats=st, out_nchw=out_nchw)
+                         act=act, stats=st, out_nchw=out_nchw, split_k=split_k, res_shift=res_shift)
     torch.cuda.synchronize()
     got = out.cpu() if out_nchw else uncl(out.cpu())
     if not three_d:
@@ -187,6 +191,22 @@ def test_conv_igemm_three_planes(ops, Cin, Cout, sp, k):
     err = _conv_case(ops, 1, Cin, Cout, sp, k, bias=True, residual=True, stats=True, planes=3)
 
 
+@pytest.mark.parametrize("N,Cin,Cout,sp,k,planes,kw", [
+    (1, 64, 96, (24, 40), 3, 2, dict(residual=True, stats=True)),          # ragged pixel tiles: TMA clips the store, zero-fills the residual
+    (1, 128, 128, (64, 64), 3, 2, dict(residual=False, stats=True)),       # no residual: staging tile written directly
+    (1, 512, 320, (32, 32), 3, 2, dict(residual=True, stats=True)),        # N tile 160: five panels, KC = 32 ring next to the 80 KB tile
+    (2, 64, 64, (16, 32), 3, 2, dict(residual=True, stats=True, act=3)),   # batch of 2 (per-sample statistics), tanh
+    (1, 64, 128, (32, 32), 3, 2, dict(residual=True, res_shift=1, stats=True)),  # half-resolution residual: read from global
+    (1, 64, 64, (8, 16, 16), 3, 3, dict(residual=True, stats=True)),       # 3-D boxes, three planes
+    (1, 96, 96, (4, 16, 16), 3, "h2", dict(residual=True, stats=True)),    # fp16 planes, KC = 32
+    (1, 256, 64, (32, 32), 1, 2, dict(residual=True, stats=False)),        # 1x1, narrow N tile
+])
+def test_conv_igemm_tma_epilogue(ops, N, Cin, Cout, sp, k, planes, kw):
+    """The TMA epilogue (conv kernel EPI = 2: staging tile -> TMA tensor store, same-resolution residual TMA-loaded into the
+    tile) on shapes the model's small layers would hand to split-K: forced here with split_k=False."""
+    _conv_case(ops, N, Cin, Cout, sp, k, bias=True, planes=planes, split_k=False, **kw)
+
+
 def test_conv2d_igemm_batch_and_act(ops):
     _conv_case(ops, 2, 128, 3, (32, 32), 1, act=2, out_nchw=True)
     _conv_case(ops, 2, 64, 64, (16, 16), 3, act=3)
@@ -207,6 +227,25 @@ def test_conv3d_igemm(ops, Cin, Cout, sp, k):
 def test_conv2d_igemm_stride2(ops, sp):
     _conv_case(ops, 1, 64, 128, sp, 3, stride=2, bias=False)
     _conv_case(ops, 1, 64, 128, sp, 1, stride=2, bias=False)
+
+
+def test_wrapper_boundary_image_ops(ops):
+    """uint8 <-> fp32 image conversion and the bicubic pre-processing resize against the torch ops the reference calls
+    (ToTensor / clamp + ToPILImage: notebooks/infer.py:229-243, 641-644; F.interpolate bicubic :399-403)"""
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (2, 37, 53, 3), generator=g, dtype=torch.uint8)
+    got = ops.u8_to_image(u8.cuda()).cpu()
+    assert torch.equal(got, u8.permute(0, 3, 1, 2).float().div(255))
+    x = torch.rand(2, 3, 40, 24, generator=g) * 1.4 - 0.2                      # values outside [0, 1] are clamped
+    x[0, 0, 0, :4] = torch.tensor([1.0, 0.0, 0.999999, 254.5 / 255.0])
+    want = (x.clamp(0, 1) * 255).byte().permute(0, 2, 3, 1)
+    assert torch.equal(ops.image_to_u8(x.cuda()).cpu(), want)
+    for (hi, wi, ho, wo) in [(300, 280, 256, 256), (128, 160, 256, 512), (512, 512, 256, 256)]:
+        y = torch.rand(1, 3, hi, wi, generator=g)
+        ref = F.interpolate(y, size=(ho, wo), mode="bicubic")
+        err = (ops.resize_bicubic(y.cuda(), (ho, wo)).cpu() - ref).abs().max().item()
+        print(f"[bicubic {hi}x{wi} -> {ho}x{wo}] max-abs err vs F.interpolate {err:.2e}")
+        assert err < 2e-6
 
 
 def test_conv_direct_stem(ops):

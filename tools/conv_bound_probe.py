@@ -47,6 +47,12 @@ if len(sys.argv) > 1 and sys.argv[1] == "epi":
                [(0, "all"), (16, "-res"), (32, "-store"), (64, "-stats"), (48, "-res-store"), (80, "-res-stats"), (96, "-store-stats"), (112, "none")]]
         print(f"128->128 512^2 {bname}: " + " | ".join(row), flush=True)
     sys.exit(0)
+if len(sys.argv) > 1 and sys.argv[1] == "full":
+    # the whole kernel only, per decoder / warp-generator shape (EMO_CONV_EPI picks the final-phase form)
+    for (Cin, Cout, sp, k, planes) in [(128, 128, (512, 512), 3, 2), (192, 192, (256, 256), 3, 2), (320, 320, (128, 128), 3, 2), (512, 512, (64, 64), 3, 2),
+                                       (1536, 512, (64, 64), 1, 2), (64, 64, (32, 32, 32), 3, "h2"), (64, 32, (32, 64, 64), 3, "h2")]:
+        print(f"{Cin:4d}->{Cout:4d} {str(sp):14s} k{k} p{planes} EMO_CONV_EPI={os.environ.get('EMO_CONV_EPI', '(default)')}: {bench(1, Cin, Cout, sp, k, planes, 0):7.1f} us/launch", flush=True)
+    sys.exit(0)
 MODES = [(0, "full"), (1, "noTMA"), (2, "noMMA"), (4, "noEpiGmem"), (8, "noTmemLd"), (12, "noEpi"), (3, "noTMA+noMMA"),
          (6, "TMAonly+chunks"), (14, "TMAonly"), (13, "MMAonly"), (15, "skeleton")]
 for (Cin, Cout, sp, k, planes) in [(128, 128, (512, 512), 3, 2), (512, 512, (64, 64), 3, 2), (320, 320, (128, 128), 3, 2),
