@@ -52,8 +52,9 @@ struct ConvKParams {
   int stages;
   int flush;  // k-steps per TMEM accumulation chunk
   int nbuf;   // depth of the TMEM chunk ring = min(4, 512 / BN)
-  int ksplit;   // split-K factor: work item = (tile, K part); partial sums are red.add'ed into `ws`
-  float* ws;    // split-K fp32 workspace [N][Dout][Hout][Wout][Cout], zero on entry (the finalize kernel re-zeroes it)
+  int ksplit;   // split-K factor: work item = (tile, K part); part `k` writes its partial sums to ws + k * ws_part_elems
+  float* ws;    // split-K fp32 workspace [ksplit][N][Dout][Hout][Wout][Cout] (no initial state needed)
+  long long ws_part_elems;
   int dbg;    // EMO_CONV_DEBUG builds only (tools/conv_bound_probe.py): 1 skip TMA loads, 2 skip MMAs, 4 skip the tile epilogue's
               // global traffic, 8 skip the TMEM chunk reads, 16 / 32 / 64 skip the residual reads / output stores / statistics.  Results are garbage; only the timing is of interest.
   int cg;     // 1, or 2: CTA pairs issue cta_group::2 MMAs (M = 256: two pixel tiles; the weight tile is split across the
@@ -381,6 +382,24 @@ __device__ __forceinline__ void store_rows(const StoreRowCtx& c, int chunk0, int
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+// Instrumented build only (-DEMO_CONV_DEBUG, tools/conv_timeline.py): per-CTA time stamps (%globaltimer, ns) of the phases of
+// the LAST stamped launch: 0 entry, 1 prologue done, 2 / 3 producer first / last issue, 4 first operands landed, 5 last MMA
+// issued, 6 last accumulation chunk consumed (per tile: last tile wins), 7 final-phase stores issued, 8 statistics done,
+// 9 teardown barrier passed, 10 TMEM freed.
+#ifdef EMO_CONV_DEBUG
+__device__ unsigned long long g_conv_stamps[160 * 16];
+__device__ __forceinline__ unsigned long long emo_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define EMO_STAMP(k, cond) do { if ((p.dbg & 256) && (cond) && blockIdx.x < 160) g_conv_stamps[blockIdx.x * 16 + (k)] = emo_gtime(); } while (0)
+#define EMO_STAMP_ONCE(k, cond) EMO_STAMP(k, cond)
+#else
+#define EMO_STAMP(k, cond) do { } while (0)
+#define EMO_STAMP_ONCE(k, cond) do { } while (0)
+#endif
+
 struct TMaps {
   CUtensorMap a[3];  // activation planes: hi, lo, lo2
   CUtensorMap b[3];  // weight planes
@@ -408,9 +427,12 @@ struct TMaps {
 #undef EMO_CONV_F16
 #undef EMO_CONV_KERNEL_NAME
 
-// split-K finalize: out = act(ws + bias + residual) + post_add, statistics, and the workspace is zeroed for the next user
+// split-K finalize: out = act(sum_parts ws[part] + bias + residual) + post_add, statistics.  The parts are summed in part
+// order (fixed), so the output is reproducible run to run.
 struct FinParams {
-  float* ws;
+  const float* ws;
+  int ksplit;
+  long long part_elems;
   float* out;
   int N, C;
   long long S;  // spatial positions per sample
@@ -435,8 +457,8 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f)
     const long long i = (long long)n * per_n + t;
     const int c = (int)(t % f.C);
     const long long sp = t / f.C;
-    float v = f.ws[i];
-    f.ws[i] = 0.f;
+    float v = 0.f;
+    for (int k = 0; k < f.ksplit; ++k) v += f.ws[(long long)k * f.part_elems + i];
     if (f.bias) v += __ldg(f.bias + c);
     if (f.residual) v += __ldg(f.residual + i);
     v = act_apply(v, f.act);
@@ -453,6 +475,139 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f)
     for (int g = threadIdx.x; g < f.G; g += blockDim.x) {
       atomicAdd(&f.stats[((long long)n * f.G + g) * 2], (double)sstat[g]);
       atomicAdd(&f.stats[((long long)n * f.G + g) * 2 + 1], (double)sstat[f.G + g]);
+    }
+  }
+}
+
+// Fused finalize + normalisation + activation + plane split for SMALL split-K layers (emo_conv_desc.post): one 8-CTA
+// cluster per sample does what splitk_finalize_kernel + gn statistics + emo_apply do in three launches for the ResNet
+// tails and the first warp-generator blocks (<= 64 Ki elements per sample, 4x4 .. 32x32 maps), whose time is launch
+// latency, not work.  Thread -> elements e = rank * 512 + tid + k * 4096: C divides 512, so a thread owns ONE channel.
+// GroupNorm statistics: per-thread sums in element order -> per-CTA group sums in thread order -> cluster totals in rank
+// order over distributed shared memory: fixed orders throughout, bit-reproducible.
+static constexpr int kPostCluster = 8;
+static constexpr int kPostThreads = 512;
+static constexpr int kPostMaxV = 16;  // elements per thread: <= 65536 elements per sample
+struct PostParams {
+  const float* ws;
+  int ksplit;
+  long long part_elems;
+  int N, C;
+  long long S;
+  const float* bias;      // the convolution's own bias / same-resolution residual / activation (before the norm)
+  const float* residual;
+  int conv_act;
+  emo_apply_desc ap;      // the post-op: x ignored (= the convolution's output), up == 1
+};
+
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ double ld_dsmem_f64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kPostThreads, 1) splitk_post_kernel(const PostParams f) {
+  __shared__ float s_sum[kPostThreads], s_sq[kPostThreads];
+  __shared__ double s_part[2 * 64];  // this CTA's (sum, sum of squares) per group
+  __shared__ double s_tot[2 * 64];   // cluster totals
+  const emo_apply_desc& a = f.ap;
+  const int tid = threadIdx.x;
+  const uint32_t rank = (uint32_t)blockIdx.x % kPostCluster;
+  const int n = (int)blockIdx.x / kPostCluster;
+  const long long per_n = f.S * f.C;
+  const int c = tid % f.C;  // this thread's channel (512 % C == 0 and 4096 % C == 0)
+  float v[kPostMaxV];
+  float ts = 0.f, tq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kPostMaxV; ++k) {
+    const long long e = (long long)rank * kPostThreads + tid + (long long)k * (kPostCluster * kPostThreads);
+    v[k] = 0.f;
+    if (e < per_n) {
+      const long long i = (long long)n * per_n + e;
+      float x = 0.f;
+      for (int part = 0; part < f.ksplit; ++part) x += f.ws[(long long)part * f.part_elems + i];
+      if (f.bias) x += __ldg(f.bias + c);
+      if (f.residual) x += __ldg(f.residual + i);
+      x = act_apply(x, f.conv_act);
+      v[k] = x;
+      ts += x; tq = fmaf(x, x, tq);
+    }
+  }
+  float A = 1.f, B = 0.f;
+  if (a.stats) {
+    // GroupNorm of the convolution's output
+    const int G = a.G, cpg = f.C / G;
+    s_sum[tid] = ts; s_sq[tid] = tq;
+    __syncthreads();
+    if (tid < G) {
+      double sg = 0.0, qg = 0.0;
+      for (int m = 0; m < kPostThreads / f.C; ++m)
+        for (int cc = tid * cpg; cc < (tid + 1) * cpg; ++cc) { sg += (double)s_sum[cc + m * f.C]; qg += (double)s_sq[cc + m * f.C]; }
+      s_part[tid] = sg; s_part[64 + tid] = qg;
+    }
+    cluster_sync_all();  // every CTA's group sums are in its shared memory
+    if (tid < G) {
+      double sg = 0.0, qg = 0.0;
+      for (uint32_t r = 0; r < (uint32_t)kPostCluster; ++r) {
+        sg += ld_dsmem_f64(dsmem_addr(&s_part[tid], r));
+        qg += ld_dsmem_f64(dsmem_addr(&s_part[64 + tid], r));
+      }
+      s_tot[tid] = sg; s_tot[64 + tid] = qg;
+      if (rank == 0) {  // publish the statistics too (same layout as every other producer)
+        double* st = const_cast<double*>(a.stats);  // == the convolution's `stats` output (checked by the host)
+        st[((long long)n * G + tid) * 2] = sg;
+        st[((long long)n * G + tid) * 2 + 1] = qg;
+      }
+    }
+    cluster_sync_all();  // nobody retires (or overwrites s_part) while a peer may still read it
+    const int g = c / cpg;
+    const double mean = s_tot[g] / a.count;
+    double var = s_tot[64 + g] / a.count - mean * mean;
+    if (var < 0) var = 0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    float gam = a.gamma ? a.gamma[c] : 1.f, bet = a.beta ? a.beta[c] : 0.f;
+    if (a.ada_w) {
+      const float aw = a.ada_w[(long long)n * f.C + c], ab = a.ada_b[(long long)n * f.C + c];
+      bet = bet * aw + ab;
+      gam = gam * aw;
+    }
+    A = rstd * gam;
+    B = bet - (float)mean * A;
+  } else if (a.A) {
+    A = a.A[(a.ab_per_sample ? (long long)n * f.C : 0) + c];
+    B = a.B[(a.ab_per_sample ? (long long)n * f.C : 0) + c];
+  }
+  float A2 = 1.f, B2 = 0.f;
+  if (a.A2) { A2 = a.A2[c]; B2 = a.B2[c]; }
+#pragma unroll
+  for (int k = 0; k < kPostMaxV; ++k) {
+    const long long e = (long long)rank * kPostThreads + tid + (long long)k * (kPostCluster * kPostThreads);
+    if (e < per_n) {
+      const long long i = (long long)n * per_n + e;
+      float y = fmaf(v[k], A, B);
+      if (a.res) y += fmaf(__ldg(a.res + i), A2, B2);
+      y = act_apply(y, a.act);
+      if (a.out) a.out[i] = y;
+      if (a.out_hi) {
+        if (a.plane_fp16) {
+          __half h, l;
+          split_f16(y * a.plane_scale, h, l);
+          ((__half*)a.out_hi)[i] = h; ((__half*)a.out_lo)[i] = l;
+        } else if (a.out_lo2) {
+          __nv_bfloat16 h, l, l2;
+          split_bf16x3(y, h, l, l2);
+          ((__nv_bfloat16*)a.out_hi)[i] = h; ((__nv_bfloat16*)a.out_lo)[i] = l; ((__nv_bfloat16*)a.out_lo2)[i] = l2;
+        } else {
+          __nv_bfloat16 h, l;
+          split_bf16(y, h, l);
+          ((__nv_bfloat16*)a.out_hi)[i] = h; ((__nv_bfloat16*)a.out_lo)[i] = l;
+        }
+      }
     }
   }
 }
@@ -481,6 +636,12 @@ static int pick_box(int dim, int want) {
 
 using namespace emo;
 
+#ifdef EMO_CONV_DEBUG
+extern "C" int emo_debug_conv_stamps(unsigned long long* host160x16) {
+  return cudaMemcpyFromSymbol(host160x16, g_conv_stamps, sizeof(unsigned long long) * 160 * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   EMO_REQUIRE(d && d->a_hi && d->a_lo && d->w_hi && d->w_lo && d->out, "emo_conv_igemm: null pointer");
@@ -491,6 +652,11 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
                   ((uintptr_t)d->w_lo % 16) == 0 && ((uintptr_t)d->out % 16) == 0,
               "emo_conv_igemm: pointers must be 16-byte aligned");
   if (d->stats) EMO_REQUIRE(d->G > 0 && d->Cout % d->G == 0, "emo_conv_igemm: Cout=%d not divisible by G=%d", d->Cout, d->G);
+  if (d->post) {
+    EMO_REQUIRE(!d->out_nchw && d->post->N == d->N && d->post->C == d->Cout && d->post->D == d->Dout && d->post->H == d->Hout && d->post->W == d->Wout,
+                "emo_conv_igemm: post-op shape must be the convolution's channels-last output shape");
+    EMO_REQUIRE(!d->post->stats || d->post->stats == d->stats, "emo_conv_igemm: a GroupNorm post-op normalises with the convolution's own statistics (post->stats == stats)");
+  }
   const bool vec_ok = (d->Cout % 4 == 0);
   EMO_REQUIRE(vec_ok || d->Cout < 16, "emo_conv_igemm: Cout=%d must be a multiple of 4 (or < 16)", d->Cout);
 
@@ -555,9 +721,10 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   {
     const long long tiles = (long long)p.m_tiles * (d->Cout_pad / BN) * nt_mult;
     const long long out_elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;
-    if (!ps && d->splitk_ws && out_elems <= d->splitk_ws_elems && d->res_shift == 0 && tiles * 2 <= sm_count) {
+    if (!ps && d->splitk_ws && 2 * out_elems <= d->splitk_ws_elems && d->res_shift == 0 && tiles * 2 <= sm_count) {
       long long parts = (2ll * sm_count) / tiles;
       if (parts > ksteps_total / 4) parts = ksteps_total / 4;
+      if (parts * out_elems > d->splitk_ws_elems) parts = d->splitk_ws_elems / out_elems;  // one workspace slice per part
       if (parts >= 2) ksplit = (int)parts;
     }
   }
@@ -573,6 +740,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   p.n_tiles = p.ntc * nt_mult;
   p.ksplit = ksplit;
   p.ws = d->splitk_ws;
+  p.ws_part_elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;
   p.dbg = 0;
 #ifdef EMO_CONV_DEBUG
   { const char* e = getenv("EMO_CONV_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -786,9 +954,34 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   }
 #undef EMO_LAUNCH_CONV
 #undef EMO_LAUNCH_CONV5
+  const long long per_n = (long long)d->Dout * d->Hout * d->Wout * d->Cout;
+  const emo_apply_desc* post = d->post;
+  if (ksplit > 1 && post && post->up == 1 && !d->out_nchw && !d->post_add && per_n <= (long long)kPostCluster * kPostThreads * kPostMaxV &&
+      d->Cout <= kPostThreads && kPostThreads % d->Cout == 0 && (!post->stats || (post->G <= 64 && d->Cout % post->G == 0))) {
+    // small split-K layer with a post-op: one cluster per sample finishes the convolution, normalises, activates and writes the
+    // next convolution's operand planes (splitk_post_kernel)
+    PostParams f;
+    memset(&f, 0, sizeof(f));
+    f.ws = d->splitk_ws; f.ksplit = ksplit; f.part_elems = p.ws_part_elems;
+    f.N = d->N; f.C = d->Cout; f.S = (long long)d->Dout * d->Hout * d->Wout;
+    f.bias = d->bias; f.residual = d->residual; f.conv_act = d->act;
+    f.ap = *post;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(kPostCluster * d->N));
+    cfg.blockDim = dim3(kPostThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kPostCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, splitk_post_kernel, f);
+    if (e != cudaSuccess) { set_error("emo_conv_igemm: post launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }
+    return check_launch("emo_conv_igemm");
+  }
   if (ksplit > 1) {
     FinParams f;
-    f.ws = d->splitk_ws; f.out = d->out; f.N = d->N; f.C = d->Cout;
+    f.ws = d->splitk_ws; f.ksplit = ksplit; f.part_elems = p.ws_part_elems; f.out = d->out; f.N = d->N; f.C = d->Cout;
     f.S = (long long)d->Dout * d->Hout * d->Wout;
     f.bias = d->bias; f.residual = d->residual; f.post_add = d->post_add; f.act = d->act; f.out_nchw = d->out_nchw;
     f.stats = d->stats; f.G = d->G;
@@ -797,6 +990,14 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     if (bx < 1) bx = 1;
     dim3 fg((unsigned)bx, (unsigned)d->N);
     launch_kernel(splitk_finalize_kernel, fg, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, f);
+  }
+  if (post) {
+    // every other layer: the post-op is the ordinary elementwise pass over the convolution's output
+    int rc = check_launch("emo_conv_igemm");
+    if (rc) return rc;
+    emo_apply_desc ap = *post;
+    ap.x = d->out;
+    return emo_apply(&ap, stream_);
   }
   return check_launch("emo_conv_igemm");
 }

@@ -66,7 +66,7 @@ class ConvDesc(C.Structure):
                 ("post_add", c_void_p), ("out", c_void_p), ("out_nchw", c_int), ("stats", c_void_p), ("G", c_int),
                 ("a_lo2", c_void_p), ("w_lo2", c_void_p), ("acc_chunk_mmas", c_int),
                 ("splitk_ws", c_void_p), ("splitk_ws_elems", c_ll), ("upconv", c_int),
-                ("operand_fp16", c_int), ("out_scale", c_float)]
+                ("operand_fp16", c_int), ("out_scale", c_float), ("post", c_void_p)]
 
 
 class ConvDirectDesc(C.Structure):

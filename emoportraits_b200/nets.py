@@ -100,10 +100,13 @@ class ResBlock:
         if up == 2 and self.c1_ps is not None and x.shape[1] == 1 and (x.shape[2] * x.shape[3]) % 256 == 0:
             a = ops.apply(x, gn=self.n1.gn(sx, _count(x), ada[0] if ada else None), act=ops.ACT_RELU, up=1, planes=self.planes)
             y = ops.conv_igemm(a, self.c1_ps, bias=self.c1.b, stats=st1, upconv=True)
+            b = ops.apply(y, gn=self.n2.gn(st1, _count(y), ada[1] if ada else None), act=ops.ACT_RELU, planes=self.planes)
         else:
             a = ops.apply(x, gn=self.n1.gn(sx, _count(x), ada[0] if ada else None), act=ops.ACT_RELU, up=up, planes=self.planes)
-            y = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1)
-        b = ops.apply(y, gn=self.n2.gn(st1, _count(y), ada[1] if ada else None), act=ops.ACT_RELU, planes=self.planes)
+            # conv -> norm -> relu: the second norm's pass is the convolution's post-op (one launch for the small split-K layers)
+            cnt = a.shape[1] * a.shape[2] * a.shape[3] * self.c1.cout / G
+            b = ops.conv_igemm(a, self.c1.w, bias=self.c1.b, stats=st1,
+                               post=dict(gn=self.n2.gn(st1, cnt, ada[1] if ada else None), act=ops.ACT_RELU, planes=self.planes))
         # skip path: the 1x1 conv commutes with nearest-upsampling and with average pooling, so it runs at the smaller size
         s = ops.avgpool(x, down) if down else x
         if self.skip is not None:
@@ -211,6 +214,20 @@ class ResNet:
         y = ops.conv_igemm(a, cw.w, stride=(1, stride, stride), bias=cw.b, stats=st)
         return y, st
 
+    def _conv_norm(self, a, cw, norm, stride=1, **kw):
+        """conv -> norm (-> + residual) -> relu as one call: the norm pass is the convolution's post-op (emo_conv_desc.post; the
+        ResNet layers are small split-K layers, so this is one finalize launch instead of finalize + apply).  eval-BatchNorm is
+        a per-channel affine; GroupNorm is finalised from the convolution's own statistics."""
+        kw.setdefault("planes", self.planes)
+        N, _, Hi, Wi, _ = a.shape
+        if norm.is_bn:
+            return ops.conv_igemm(a, cw.w, stride=(1, stride, stride), bias=cw.b, post=dict(A=norm.A, B=norm.B, per_sample=False, **kw))
+        st = ops.new_stats(N, G, a.hi.device)
+        k = cw.w.k[1]
+        Ho, Wo = (Hi + 2 * (k // 2) - k) // stride + 1, (Wi + 2 * (k // 2) - k) // stride + 1
+        return ops.conv_igemm(a, cw.w, stride=(1, stride, stride), bias=cw.b, stats=st,
+                              post=dict(gn=norm.n.gn(st, Ho * Wo * cw.cout / G), **kw))
+
     @staticmethod
     def _napply(norm, y, st, **kw):
         """norm + activation pass: eval-BatchNorm is a per-channel affine; GroupNorm is finalised inside the apply kernel"""
@@ -226,38 +243,25 @@ class ResNet:
         y = self._napply(self.bn1, y, st, act=ops.ACT_RELU, want_f32=True, want_split=False)
         x = ops.maxpool2d_3x3s2(y)
         xs = ops.split_bf16(x, self.planes)
-        P = self.planes
+        relu = dict(act=ops.ACT_RELU)
         for blk in self.blocks:
             s = blk["stride"]
             if blk["bottleneck"]:
-                y, st = self._conv(xs, blk["c1"])
-                a = self._napply(blk["n1"], y, st, act=ops.ACT_RELU, planes=P)
-                y, st = self._conv(a, blk["c2"], s)
-                a = self._napply(blk["n2"], y, st, act=ops.ACT_RELU, planes=P)
-                y, st = self._conv(a, blk["c3"])
-                last = blk["n3"]
+                a = self._conv_norm(xs, blk["c1"], blk["n1"], **relu)
+                a = self._conv_norm(a, blk["c2"], blk["n2"], s, **relu)
+                last_c, last_n, last_s = blk["c3"], blk["n3"], 1
             else:
-                y, st = self._conv(xs, blk["c1"], s)
-                a = self._napply(blk["n1"], y, st, act=ops.ACT_RELU, planes=P)
-                y, st = self._conv(a, blk["c2"])
-                last = blk["n2"]
+                a = self._conv_norm(xs, blk["c1"], blk["n1"], s, **relu)
+                last_c, last_n, last_s = blk["c2"], blk["n2"], 1
             if "cd" in blk:
                 r, std = self._conv(xs, blk["cd"], s)
                 A2, B2 = blk["nd"].affine(std, _count(r))
                 # residual affine is per-channel in the kernel; with GN and N == 1 the per-sample row is that vector
-                assert last.is_bn or N == 1, "GN ResNet path runs one image at a time"
-                x, xs = self._napply(last, y, st, act=ops.ACT_RELU, res=r, A2=A2, B2=B2, want_f32=True, want_split=True, planes=P)
+                assert last_n.is_bn or N == 1, "GN ResNet path runs one image at a time"
+                x, xs = self._conv_norm(a, last_c, last_n, last_s, res=r, A2=A2, B2=B2, want_f32=True, want_split=True, **relu)
             else:
-                x, xs = self._napply(last, y, st, act=ops.ACT_RELU, res=x, want_f32=True, want_split=True, planes=P)
+                x, xs = self._conv_norm(a, last_c, last_n, last_s, res=x, want_f32=True, want_split=True, **relu)
         return x, xs
-
-
-def _norm_buffers(sd, p, dev):
-    """input normalisation of an embedder: its `mean` / `std` buffers from the checkpoint (identity_embedder.py:21-22,
-    expression_embedder.py:352-353 register the ImageNet statistics), the ImageNet constants if the checkpoint has none"""
-    mean = sd[p + ".mean"].detach().float().reshape(-1) if (p + ".mean") in sd else torch.tensor([0.485, 0.456, 0.406])
-    std = sd[p + ".std"].detach().float().reshape(-1) if (p + ".std") in sd else torch.tensor([0.229, 0.224, 0.225])
-    return mean.to(dev).contiguous(), std.to(dev).contiguous()
 
 
 class HeadPoseRegressor:

@@ -325,21 +325,28 @@ def gn_finalize(stats: torch.Tensor, count: float, gamma, beta, eps: float = 1e-
     return A, B
 
 
-def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
-          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes=2, gn=None):
-    """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W).
-    gn = dict(stats, count, gamma, beta[, ada_w, ada_b, eps]) fuses the GroupNorm finalisation (replaces A/B)."""
-    _chk(x)
-    N, D, H, W, Cc = x.shape
-    shape = (N, D, H * up, W * up, Cc)
-    out = torch.empty(shape, dtype=torch.float32, device=x.device) if want_f32 else None
-    sp = Split.empty(shape, x.device, planes) if want_split else None
-    d = L.ApplyDesc(_p(x), N, Cc, D, H, W, _p(A), _p(B), 1 if per_sample else 0, _p(res), _p(A2), _p(B2), act, up,
+def _apply_desc(x_ptr, shape, device, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
+                want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes=2, gn=None):
+    """emo_apply_desc + its freshly allocated outputs for a channels-last (N,D,H,W,C) input at `x_ptr`"""
+    N, D, H, W, Cc = shape
+    oshape = (N, D, H * up, W * up, Cc)
+    out = torch.empty(oshape, dtype=torch.float32, device=device) if want_f32 else None
+    sp = Split.empty(oshape, device, planes) if want_split else None
+    d = L.ApplyDesc(x_ptr, N, Cc, D, H, W, _p(A), _p(B), 1 if per_sample else 0, _p(res), _p(A2), _p(B2), act, up,
                     _p(out), _p(sp.hi) if sp else None, _p(sp.lo) if sp else None, _p(sp.lo2) if sp else None,
                     _p(gn["stats"]) if gn else None, gn["stats"].shape[1] if gn else 0, float(gn["count"]) if gn else 0.0,
                     float(gn.get("eps", 1e-5)) if gn else 0.0, _p(gn["gamma"]) if gn else None, _p(gn["beta"]) if gn else None,
                     _p(gn.get("ada_w")) if gn else None, _p(gn.get("ada_b")) if gn else None,
                     1 if (sp is not None and sp.f16) else 0, sp.scale if (sp is not None and sp.f16) else 0.0)
+    return d, out, sp
+
+
+def apply(x: torch.Tensor, A=None, B=None, act: int = ACT_NONE, res=None, A2=None, B2=None, up: int = 1,
+          want_f32: bool = False, want_split: bool = True, per_sample: bool = True, planes=2, gn=None):
+    """y = act(x*A + B [+ res*A2 + B2]) on a channels-last (N,D,H,W,C) tensor; optional nearest x2 on (H, W).
+    gn = dict(stats, count, gamma, beta[, ada_w, ada_b, eps]) fuses the GroupNorm finalisation (replaces A/B)."""
+    _chk(x)
+    d, out, sp = _apply_desc(_p(x), x.shape, x.device, A, B, act, res, A2, B2, up, want_f32, want_split, per_sample, planes, gn)
     L.call("emo_apply", C.byref(d), _stream())
     if want_f32 and want_split:
         return out, sp
@@ -424,9 +431,13 @@ def set_conv_profiler(p: Optional[ConvProfiler]):
 def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=None, residual=None, res_shift: int = 0,
                act: int = ACT_NONE, post_add=None, out_nchw: bool = False, stats: Optional[torch.Tensor] = None,
                G: int = 32, out: Optional[torch.Tensor] = None, acc_chunk_mmas: int = 0, split_k: bool = True,
-               upconv: bool = False) -> torch.Tensor:
+               upconv: bool = False, post: Optional[dict] = None):
     """upconv=True: `a` holds the LOW-resolution planes and `w` a pack_upconv_weight(): the result is
-    conv3x3(pad 1)(nearest_x2(a)) at (2H, 2W), evaluated in sub-pixel form (see emo_conv_desc.upconv)."""
+    conv3x3(pad 1)(nearest_x2(a)) at (2H, 2W), evaluated in sub-pixel form (see emo_conv_desc.upconv).
+    post = dict(<arguments of apply()>): the elementwise pass that follows the convolution (GroupNorm / affine + residual +
+    activation -> fp32 and/or operand planes; a `gn` post-op normalises with this convolution's `stats`).  Small split-K layers
+    run it inside the finalize step (one launch instead of three, emo_conv_desc.post).  With `post` the call returns what
+    apply() would return for it; the raw convolution output is then an internal scratch tensor."""
     N, Di, Hi, Wi, Ci = a.shape
     assert Ci == w.cin, (Ci, w.cin)
     ws = None if (L.DRY_RUN or not split_k) else _splitk_workspace(a.hi.device)
@@ -449,7 +460,17 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                    res_shift, act, _p(post_add), _p(out), 1 if out_nchw else 0, _p(stats),
                    G if stats is not None else 0, _p(a.lo2) if three else None, _p(w.lo2) if three else None,
                    acc_chunk_mmas or w.acc_chunk, _p(ws), ws.numel() if ws is not None else 0, 1 if upconv else 0,
-                   1 if a.f16 else 0, 1.0 / (a.scale * w.scale) if a.f16 else 0.0)
+                   1 if a.f16 else 0, 1.0 / (a.scale * w.scale) if a.f16 else 0.0, None)
+    post_ret = None
+    if post is not None:
+        assert not out_nchw and not upconv, "post-op: channels-last output of a plain convolution"
+        kw = dict(post)
+        if kw.get("gn") is not None:
+            assert stats is not None and kw["gn"]["stats"] is stats, "a GroupNorm post-op uses the convolution's own statistics"
+        pd, pout, psp = _apply_desc(None, (N, Do, Ho, Wo, w.cout), a.hi.device, **kw)
+        d.post = C.cast(C.pointer(pd), C.c_void_p)
+        wf, wsp = kw.get("want_f32", False), kw.get("want_split", True)
+        post_ret = (pout, psp) if (wf and wsp) else (pout if wf else psp)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -463,7 +484,7 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
                                    + (" up2-subpixel" if upconv else "")))
     else:
         L.call("emo_conv_igemm", C.byref(d), _stream())
-    return out
+    return out if post is None else post_ret
 
 
 def conv_direct(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, bias=None, stats=None, G: int = 32):

@@ -35,7 +35,7 @@ extern "C" {
 enum { EMO_ACT_NONE = 0, EMO_ACT_RELU = 1, EMO_ACT_SIGMOID = 2, EMO_ACT_TANH = 3 };
 
 const char* emo_last_error(void);
-int emo_version(void); /* 102: + emo_u8_to_image, emo_image_to_u8, emo_resize_bicubic; 101: emo_pose_desc and emo_conv_desc gained trailing fields */
+int emo_version(void); /* 103: emo_conv_desc.post; 102: + emo_u8_to_image, emo_image_to_u8, emo_resize_bicubic; 101: emo_pose_desc and emo_conv_desc gained trailing fields */
 /* sm count, and cc major*10+minor of the current device */
 int emo_device_info(int* sm_count, int* cc);
 
@@ -119,7 +119,7 @@ typedef struct {
 } emo_gn_finalize_desc;
 int emo_gn_finalize(const emo_gn_finalize_desc* d, void* stream);
 
-typedef struct {
+typedef struct emo_apply_desc_s {
   const float* x; /* [N][S][C] fp32 channels-last, S = D*H*W */
   int N, C;
   int D, H, W;
@@ -227,6 +227,12 @@ typedef struct {
    * Not combinable with a_lo2/w_lo2 or upconv. */
   int operand_fp16;
   float out_scale;
+  /* optional post-op on the convolution's output: y = act(GN-or-affine(out) [+ res*A2 + B2]) -> fp32 and/or operand planes,
+   * exactly emo_apply with x = out (post->x is ignored; a GroupNorm post-op must name the convolution's own statistics:
+   * post->stats == stats; up must be 1).  Small split-K layers (<= 64 Ki elements per sample) run it inside the finalize
+   * step - one launch instead of finalize + emo_apply, `out` is then NOT written - every other layer runs emo_apply after
+   * the convolution.  NULL: none. */
+  const struct emo_apply_desc_s* post;
 } emo_conv_desc;
 int emo_conv_igemm(const emo_conv_desc* d, void* stream);
 

@@ -51,7 +51,7 @@ def test_ctypes_structures_match_the_header(tmp_path):
     hdr = (ROOT / "include" / "emoportraits_b200.h").read_text()
     for py, cn in PAIRS.items():
         body = hdr[:hdr.index("} " + cn + ";")]
-        body = body[body.rindex("typedef struct {"):]
+        body = body[body.rindex("typedef struct"):]   # (emo_apply_desc carries a struct tag: emo_conv_desc.post points to it)
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         decls = [d for d in body.split("{", 1)[1].split(";") if d.strip()]
         n_members = sum(len(d.split(",")) for d in decls)
