@@ -782,7 +782,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   int epi = 0;
   {
     static int epi_env = -1;
-    if (epi_env < 0) { const char* e = getenv("EMO_CONV_EPI"); epi_env = e ? atoi(e) : 2; }
+    if (epi_env < 0) { const char* e = getenv("EMO_CONV_EPI"); epi_env = e ? atoi(e) : 1; }
     const long long elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;  // 32-bit element offsets in the store warps
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     const bool common = p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0;

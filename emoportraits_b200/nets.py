@@ -264,6 +264,14 @@ class ResNet:
         return x, xs
 
 
+def _norm_buffers(sd, p, dev):
+    """input normalisation of an embedder: its `mean` / `std` buffers from the checkpoint (identity_embedder.py:21-22,
+    expression_embedder.py:352-353 register the ImageNet statistics), the ImageNet constants if the checkpoint has none"""
+    mean = sd[p + ".mean"].detach().float().reshape(-1) if (p + ".mean") in sd else torch.tensor([0.485, 0.456, 0.406])
+    std = sd[p + ".std"].detach().float().reshape(-1) if (p + ".std") in sd else torch.tensor([0.229, 0.224, 0.225])
+    return mean.to(dev).contiguous(), std.to(dev).contiguous()
+
+
 class HeadPoseRegressor:
     """head_pose_regressor.py:11-31 — resnet18(num_classes=9), BatchNorm, its own checkpoint."""
 

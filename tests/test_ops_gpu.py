@@ -207,6 +207,61 @@ def test_conv_igemm_tma_epilogue(ops, N, Cin, Cout, sp, k, planes, kw):
     _conv_case(ops, N, Cin, Cout, sp, k, bias=True, planes=planes, split_k=False, **kw)
 
 
+@pytest.mark.parametrize("N,Cin,Cout,sp,mode,planes", [
+    (1, 64, 64, (32, 32), "gn", "h2"),        # ResNet-18 layer1 shape: split-K, fused finalize + GroupNorm + ReLU + fp16 planes
+    (1, 256, 512, (4, 4), "gn_res", "h2"),    # layer4: 16 pixels, 18 K parts; residual + fp32 + planes out
+    (2, 128, 128, (16, 16), "bn_res", 2),     # eval-BatchNorm affine, batch of 2, bf16 planes
+    (1, 64, 64, (8, 8, 8), "gn", 3),          # small 3-D layer, three planes
+    (1, 128, 128, (64, 64), "gn", 2),         # too large for the fused finalize: convolution + elementwise pass (same result)
+])
+def test_conv_post_op(ops, N, Cin, Cout, sp, mode, planes):
+    """conv_igemm(..., post=...) == conv -> norm -> (+ residual) -> ReLU of torch in fp64, whichever way the library runs it
+    (emo_conv_desc.post), and the fused split-K path is bit-reproducible run to run (fixed summation orders)."""
+    g = torch.Generator().manual_seed(Cin + Cout)
+    three_d = len(sp) == 3
+    x = torch.randn(N, Cin, *sp, generator=g)
+    w = torch.randn(Cout, Cin, *([3] * len(sp)), generator=g) / math.sqrt(Cin * 3 ** len(sp))
+    b = torch.randn(Cout, generator=g)
+    conv = F.conv3d if three_d else F.conv2d
+    y = conv(x.double(), w.double(), b.double(), padding=1)
+    gamma, beta = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    res = torch.randn(y.shape, generator=g) if mode.endswith("res") else None
+    bshape = (1, Cout) + (1,) * len(sp)
+    if mode.startswith("gn"):
+        z = F.group_norm(y, 32, gamma.double(), beta.double(), 1e-5)
+    else:
+        z = y * gamma.double().view(bshape) + beta.double().view(bshape)
+    if res is not None:
+        z = z + res.double()
+    ref = torch.relu(z).float()
+    a = ops.split_bf16(cl(x).cuda(), planes)
+    pw = ops.pack_conv_weight(w, planes=planes)
+
+    def run():
+        ops.begin_pass("cuda")
+        st = ops.new_stats(N, 32, "cuda") if mode.startswith("gn") else None
+        post = dict(act=ops.ACT_RELU, planes=planes, want_f32=True, want_split=True, res=cl(res).cuda() if res is not None else None)
+        if mode.startswith("gn"):
+            post["gn"] = dict(stats=st, count=y.numel() / N / 32, gamma=gamma.cuda(), beta=beta.cuda())
+        else:
+            post.update(A=gamma[None].cuda().contiguous(), B=beta[None].cuda().contiguous(), per_sample=False)
+        out, sp_ = ops.conv_igemm(a, pw, bias=b.cuda(), stats=st, post=post)
+        torch.cuda.synchronize()
+        return out, sp_
+
+    out, planes_out = run()
+    got = uncl(out.cpu())
+    got = got if three_d else got[:, :, 0]
+    err = (got - ref).abs().max().item()
+    perr = ((uncl(planes_out.float().cpu()) if three_d else uncl(planes_out.float().cpu())[:, :, 0]) - ref).abs().max().item()
+    print(f"\n[conv post-op {mode} {N}x{Cin}->{Cout} {sp} planes {planes}] fp32 out err {err:.2e}, planes err {perr:.2e} (ref max {ref.abs().max().item():.2f})")
+    assert err < 5e-5 * max(1.0, ref.abs().max().item())
+    assert perr < (2e-4 if planes == 2 else 5e-5) * max(1.0, ref.abs().max().item())
+    out2, planes2 = run()
+    if y.numel() // N <= 65536:      # the fused split-K path: fixed summation orders
+        assert torch.equal(out, out2) and torch.equal(planes_out.hi, planes2.hi) and torch.equal(planes_out.lo, planes2.lo)
+
+
 def test_conv2d_igemm_batch_and_act(ops):
     _conv_case(ops, 2, 128, 3, (32, 32), 1, act=2, out_nchw=True)
     _conv_case(ops, 2, 64, 64, (16, 16), 3, act=3)

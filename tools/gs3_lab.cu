@@ -1,0 +1,286 @@
+// grid_sample_3d laboratory (GPU box, native): experiments that decide what the product kernel looks like, kept out of
+// the library.  Compiles the product source (emoportraits_b200/csrc/grid_sample.cu) into this binary and adds
+//   * the memory-system denominators the kernel is measured against: DRAM read stream, L2-resident read stream (LDG.128
+//     from a 48 MB buffer: what the L2 -> SM fabric delivers), both in TB/s;
+//   * variants of the balanced kernel's gather loop: L2 eviction-priority hints (volume evict_last, output evict_first),
+//     one warp per voxel row (3 aligned lines per load instruction instead of 4-5), two items in flight per thread;
+// every variant is checked bit for bit against the product kernel and timed like bench.py times it (L2 flushed before
+// every launch, CUDA events, median of 15).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o tools/gs3_lab tools/gs3_lab.cu
+#include <stdarg.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../emoportraits_b200/csrc/grid_sample.cu"
+
+namespace emo {
+static char g_err[512];
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return EMO_ERR_CUDA; }
+  return EMO_OK;
+}
+}  // namespace emo
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
+
+using namespace emo;
+
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void read_stream_kernel(const float4* __restrict__ p, long long n4, int passes, float* sink) {
+  float acc = 0.f;
+  for (int k = 0; k < passes; ++k)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(p + i);
+      acc += v.x + v.y + v.z + v.w;
+    }
+  if (acc == 123.456f) *sink = acc;
+}
+__global__ void flush_k(float4* buf, long long n4) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ unsigned hash32(unsigned x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+__global__ void fill_uniform(float* p, long long n, unsigned seed, float lo, float hi) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = lo + (hi - lo) * (hash32((unsigned)i * 2654435761u + seed) >> 8) * (1.0f / 16777216.0f);
+}
+// identity lattice + gaussian-ish jitter (sum of 4 uniforms, sigma = `sigma`), as bench.py's 0.1 * randn
+__global__ void fill_grid(float* g, int N, int D, int H, int W, float sigma, unsigned seed) {
+  const long long total = (long long)N * D * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D);
+    const float base[3] = {-1.f + 2.f * w / (W - 1), -1.f + 2.f * h / (H - 1), D > 1 ? -1.f + 2.f * d / (D - 1) : 0.f};
+    for (int k = 0; k < 3; ++k) {
+      float s = 0.f;
+      for (int q = 0; q < 4; ++q) s += (hash32((unsigned)(i * 12 + k * 4 + q) + seed) >> 8) * (1.0f / 16777216.0f) - 0.5f;
+      g[i * 3 + k] = base[k] + sigma * s * 1.7320508f;  // var of the sum = 4/12 -> x sqrt(3)
+    }
+  }
+}
+__global__ void count_diff(const unsigned* a, const unsigned* b, long long n, unsigned long long* cnt) {
+  unsigned long long c = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += a[i] != b[i];
+  if (c) atomicAdd(cnt, c);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gather-loop variants.  MODE bit 0: L2 hints, bit 1: two items in flight per thread, bit 2: one warp per voxel (24 lanes)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void st_hint(float4* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+#define GS_ACC(f) acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, fmaf(v3.f, w0.w, fmaf(v2.f, w0.z, fmaf(v1.f, w0.y, v0.f * w0.x)))))));
+
+template <int MODE>
+__device__ __forceinline__ void one_item(const GS3Params& p, const float4* in4, int vox, int c4, const int (*s_off)[8], const float (*s_wgt)[8],
+                                         const long long* s_out, uint64_t pol_in, uint64_t pol_out) {
+  const long long ob = s_out[vox];
+  if (ob < 0) return;
+  const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
+  const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
+  const float4* base = in4 + c4;
+  float4 v0, v1, v2, v3, v4, v5, v6, v7;
+  if (MODE & 1) {
+    v0 = ld_hint(base + o0.x, pol_in); v1 = ld_hint(base + o0.y, pol_in); v2 = ld_hint(base + o0.z, pol_in); v3 = ld_hint(base + o0.w, pol_in);
+    v4 = ld_hint(base + o1.x, pol_in); v5 = ld_hint(base + o1.y, pol_in); v6 = ld_hint(base + o1.z, pol_in); v7 = ld_hint(base + o1.w, pol_in);
+  } else {
+    v0 = __ldg(base + o0.x); v1 = __ldg(base + o0.y); v2 = __ldg(base + o0.z); v3 = __ldg(base + o0.w);
+    v4 = __ldg(base + o1.x); v5 = __ldg(base + o1.y); v6 = __ldg(base + o1.z); v7 = __ldg(base + o1.w);
+  }
+  float4 acc;
+  GS_ACC(x) GS_ACC(y) GS_ACC(z) GS_ACC(w)
+  float4* dst = (float4*)(p.out + ob + (long long)(c4 * 4));
+  if (MODE & 1) st_hint(dst, acc, pol_out);
+  else __stcs(dst, acc);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 6) gs3_lab_kernel(const GS3Params p) {
+  __shared__ __align__(16) int s_off[kBrickVox][8];
+  __shared__ __align__(16) float s_wgt[kBrickVox][8];
+  __shared__ long long s_out[kBrickVox];
+  uint64_t pol_in = 0, pol_out = 0;
+  if (MODE & 1) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_in));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_out));
+  }
+  const int c4n = p.C >> 2;
+  const int brick_vox = p.bw * p.bh * p.bd;
+  const int per_sample = p.bricks_w * p.bricks_h * p.bricks_d * brick_vox;
+  const long long total = (long long)per_sample * p.N;
+  const int v_begin = (int)(total * blockIdx.x / gridDim.x), v_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  for (int base = v_begin; base < v_end;) {
+    const int n = base / per_sample;
+    const int stop = min(min(base + kBrickVox, v_end), (n + 1) * per_sample);
+    const int nvox = stop - base;
+    if ((int)threadIdx.x < nvox) {
+      const int v = base + (int)threadIdx.x - n * per_sample;
+      int b = v / brick_vox;
+      const int l = v - b * brick_vox;
+      const int bwi = b % p.bricks_w; b /= p.bricks_w;
+      const int bhi = b % p.bricks_h; b /= p.bricks_h;
+      const int bdi = b;
+      const int lw = l % p.bw, lh = (l / p.bw) % p.bh, ld = l / (p.bw * p.bh);
+      gs3_setup_voxel(p, n, bdi * p.bd + ld, bhi * p.bh + lh, bwi * p.bw + lw, threadIdx.x, s_off, s_wgt, s_out);
+    }
+    __syncthreads();
+    const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
+    if (MODE & 4) {
+      // one warp per voxel: lanes 0..c4n-1 each own one float4 of the voxel's channel row (three aligned 128-byte lines at C = 96)
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      for (int vox = warp; vox < nvox; vox += 8)
+        for (int c4 = lane; c4 < c4n; c4 += 32) one_item<MODE>(p, in4, vox, c4, s_off, s_wgt, s_out, pol_in, pol_out);
+    } else if (MODE & 2) {
+      const int work = nvox * c4n;
+      for (int t = threadIdx.x; t < work; t += 2 * blockDim.x) {
+        // both items' loads are issued before either item's arithmetic (the compiler keeps the two chains independent)
+        const int t2 = t + blockDim.x;
+        const int va = t / c4n, ca = t - va * c4n;
+        if (t2 < work) {
+          const int vb = t2 / c4n, cb = t2 - vb * c4n;
+          const long long oa = s_out[va], obb = s_out[vb];
+          if (oa >= 0 && obb >= 0) {
+            const int4 a0 = *(const int4*)&s_off[va][0], a1 = *(const int4*)&s_off[va][4], b0 = *(const int4*)&s_off[vb][0], b1 = *(const int4*)&s_off[vb][4];
+            const float4* pa = in4 + ca; const float4* pb = in4 + cb;
+            const float4 x0 = __ldg(pa + a0.x), x1 = __ldg(pa + a0.y), x2 = __ldg(pa + a0.z), x3 = __ldg(pa + a0.w), x4 = __ldg(pa + a1.x), x5 = __ldg(pa + a1.y), x6 = __ldg(pa + a1.z), x7 = __ldg(pa + a1.w);
+            const float4 y0 = __ldg(pb + b0.x), y1 = __ldg(pb + b0.y), y2 = __ldg(pb + b0.z), y3 = __ldg(pb + b0.w), y4 = __ldg(pb + b1.x), y5 = __ldg(pb + b1.y), y6 = __ldg(pb + b1.z), y7 = __ldg(pb + b1.w);
+            {
+              const float4 w0 = *(const float4*)&s_wgt[va][0], w1 = *(const float4*)&s_wgt[va][4];
+              const float4 v0 = x0, v1 = x1, v2 = x2, v3 = x3, v4 = x4, v5 = x5, v6 = x6, v7 = x7;
+              float4 acc; GS_ACC(x) GS_ACC(y) GS_ACC(z) GS_ACC(w)
+              __stcs((float4*)(p.out + oa + (long long)(ca * 4)), acc);
+            }
+            {
+              const float4 w0 = *(const float4*)&s_wgt[vb][0], w1 = *(const float4*)&s_wgt[vb][4];
+              const float4 v0 = y0, v1 = y1, v2 = y2, v3 = y3, v4 = y4, v5 = y5, v6 = y6, v7 = y7;
+              float4 acc; GS_ACC(x) GS_ACC(y) GS_ACC(z) GS_ACC(w)
+              __stcs((float4*)(p.out + obb + (long long)(cb * 4)), acc);
+            }
+            continue;
+          }
+          one_item<MODE>(p, in4, vb, cb, s_off, s_wgt, s_out, pol_in, pol_out);
+        }
+        one_item<MODE>(p, in4, va, ca, s_off, s_wgt, s_out, pol_in, pol_out);
+      }
+    } else {
+      const int work = nvox * c4n;
+      for (int t = threadIdx.x; t < work; t += blockDim.x) {
+        const int vox = t / c4n;
+        one_item<MODE>(p, in4, vox, t - vox * c4n, s_off, s_wgt, s_out, pol_in, pol_out);
+      }
+    }
+    __syncthreads();
+    base = stop;
+  }
+}
+
+struct Case { const char* name; int N, C, D, S; bool affine; };
+
+int main() {
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const long long flush_bytes = 256ll << 20;
+  float4* flush_buf; CK(cudaMalloc(&flush_buf, flush_bytes));
+  float* sink; CK(cudaMalloc(&sink, 4));
+  // ---- denominators ----
+  {
+    const long long big = 1ll << 30, small = 48ll << 20;
+    float4* buf; CK(cudaMalloc(&buf, big));
+    fill_uniform<<<592, 256, 0, st>>>((float*)buf, big / 4, 1u, 0.f, 1.f);
+    for (int which = 0; which < 2; ++which) {
+      const long long bytes = which ? small : big;
+      const int passes = which ? 20 : 1;
+      float best = 1e9f;
+      for (int r = 0; r < 5; ++r) {
+        if (which) read_stream_kernel<<<148 * 8, 256, 0, st>>>(buf, bytes / 16, 1, sink);  // warm L2
+        CK(cudaEventRecord(e0, st));
+        read_stream_kernel<<<148 * 8, 256, 0, st>>>(buf, bytes / 16, passes, sink);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        best = std::min(best, t);
+      }
+      printf("%s read stream (LDG.128, %lld MB x %d): %.2f TB/s\n", which ? "L2-resident" : "DRAM", bytes >> 20, passes, bytes * (double)passes / (best * 1e-3) * 1e-12);
+    }
+    CK(cudaFree(buf));
+  }
+  unsigned long long* d_cnt; CK(cudaMalloc(&d_cnt, 8));
+  const Case cases[] = {{"d64_affine", 1, 96, 64, 64, true}, {"d64_grid", 1, 96, 64, 64, false}, {"d16_affine", 1, 96, 16, 64, true},
+                        {"d16_grid", 1, 96, 16, 64, false}, {"d64_b8_grid", 8, 96, 64, 64, false}};
+  int bad = 0;
+  for (const Case& c : cases) {
+    const long long vox = (long long)c.N * c.D * c.S * c.S, n = vox * c.C;
+    float *in, *grid = nullptr, *theta = nullptr, *out[2];
+    CK(cudaMalloc(&in, n * 4)); CK(cudaMalloc(&out[0], n * 4)); CK(cudaMalloc(&out[1], n * 4));
+    fill_uniform<<<592, 256, 0, st>>>(in, n, 17u, -1.f, 1.f);
+    if (c.affine) {
+      std::vector<float> t(12 * c.N);
+      for (int k = 0; k < c.N; ++k) {
+        const float a = 0.5236f;
+        const float m[12] = {cosf(a), -sinf(a), 0, 0.2f, sinf(a), cosf(a), 0, 0.2f, 0, 0, 1.f, 0.2f};
+        for (int i = 0; i < 12; ++i) t[k * 12 + i] = m[i];
+      }
+      CK(cudaMalloc(&theta, t.size() * 4));
+      CK(cudaMemcpy(theta, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      CK(cudaMalloc(&grid, vox * 3 * 4));
+      fill_grid<<<592, 256, 0, st>>>(grid, c.N, c.D, c.S, c.S, 0.1f, 99u);
+    }
+    GS3Params p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.grid = grid; p.theta = theta; p.N = c.N; p.C = c.C; p.Din = c.D; p.Hin = c.S; p.Win = c.S; p.Dout = c.D; p.Hout = c.S; p.Wout = c.S;
+    p.os_c = 1; p.os_w = c.C; p.os_h = (long long)c.S * c.C; p.os_d = p.os_h * c.S; p.os_n = p.os_d * c.D;
+    p.bw = 8; p.bh = 8; p.bd = 4; p.bricks_w = c.S / 8; p.bricks_h = c.S / 8; p.bricks_d = c.D / 4;
+    const double bytes = ((double)2 * c.C + (c.affine ? 0 : 3)) * 4.0 * (double)vox;
+    const char* names[] = {"product (balanced)", "L2 hints", "2 items in flight", "warp per voxel", "warp per voxel + hints"};
+    for (int v = 0; v < 5; ++v) {
+      const int slot = v == 0 ? 0 : 1;
+      p.out = out[slot];
+      std::vector<float> ms;
+      for (int r = 0; r < 15; ++r) {
+        flush_k<<<148 * 8, 256, 0, st>>>(flush_buf, flush_bytes / 16);
+        CK(cudaEventRecord(e0, st));
+        const unsigned ctas = 888;
+        if (v == 0) gs3_cl_balanced_kernel<false><<<ctas, 256, 0, st>>>(p);
+        else if (v == 1) gs3_lab_kernel<1><<<ctas, 256, 0, st>>>(p);
+        else if (v == 2) gs3_lab_kernel<2><<<ctas, 256, 0, st>>>(p);
+        else if (v == 3) gs3_lab_kernel<4><<<ctas, 256, 0, st>>>(p);
+        else gs3_lab_kernel<5><<<ctas, 256, 0, st>>>(p);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        ms.push_back(t);
+      }
+      std::sort(ms.begin(), ms.end());
+      unsigned long long diff = 0;
+      if (v > 0) {
+        CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+        count_diff<<<592, 256, 0, st>>>((const unsigned*)out[0], (const unsigned*)out[1], n, d_cnt);
+        CK(cudaMemcpyAsync(&diff, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (diff) ++bad;
+        CK(cudaMemsetAsync(out[1], 0xff, n * 4, st));
+      }
+      printf("%-12s %-24s median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic  diff_words %llu\n", c.name, names[v], ms[7] * 1e3, ms[0] * 1e3,
+             bytes / (ms[7] * 1e-3) * 1e-9, diff);
+      fflush(stdout);
+    }
+    CK(cudaFree(in)); CK(cudaFree(out[0])); CK(cudaFree(out[1]));
+    if (grid) CK(cudaFree(grid));
+    if (theta) CK(cudaFree(theta));
+  }
+  printf(bad ? "FAIL: %d variants differ\n" : "OK: all variants bit-identical to the product kernel\n", bad);
+  return bad ? 1 : 0;
+}
