@@ -37,6 +37,7 @@ static constexpr int kEpiThreads = 256;
 static constexpr int kThreadsEpi1 = 512;  // EPI = 1 layout: warps 0..3 TMA / MMA / idle, 4..11 accumulators, 12..15 store warps
 static constexpr int kStoreThreads = 128;
 static constexpr int kMaxStages = 8;
+static constexpr int kMaxAStages = 4;  // row-reuse mode: depth cap of the A (halo tile) ring
 static constexpr int kTileM = 128;
 static constexpr int kMaxBN = 160;  // N tile cap: each epilogue thread keeps half a row of accumulators in registers
 static constexpr int kAccBufs = 4;  // max depth of the TMEM accumulation-chunk ring (512 columns / BN, at most 4)
@@ -79,6 +80,10 @@ struct ConvKParams {
   int ntc;  // channel tiles per phase (= Cout_pad / BN)
   float out_scale;  // conv_igemm_f16_kernel: 1 / (activation plane scale * weight plane scale)
   int res_tma;      // EPI = 2: the residual has the output's resolution and is TMA-loaded into the staging tile (tm.res)
+  // row-reuse mode (stride-1 convolutions with kh > 1 on tiles of one depth slice): the A operand of a (kernel column,
+  // k-chunk) group is ONE halo tile of a_rows = tw * (th + kh - 1) pixels serving all kh tap rows; A ring of `sa` halo tiles,
+  // B ring of `sb` weight tiles (see the kernel's producer role)
+  int yreuse, sa, sb, a_rows;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -772,7 +777,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
               "emo_conv_igemm: residual shift does not divide the output size");
   EMO_REQUIRE(!ps || p.cg == 2, "emo_conv_igemm: upconv needs an even number of pixel tiles and BN %% 32 == 0 (pair mode)");
 
-  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2) * 8 + 16 + 4 * 256 * sizeof(float);
+  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2 + 2 * kMaxAStages) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
   // Final phase of a tile (template parameter EPI, see the kernel's header comment):
   //   2  TMA epilogue: pair-mode, full-K tiles, channels-last output in whole 32-channel panels, no post-add; needs a [128][BN]
@@ -795,6 +800,13 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   size_t staging = 0, stage_bytes = 0;
   int stages = 0;
   const int KC0 = KC;
+  // row reuse needs: more than one tap row, unit stride along H, tiles inside one depth slice (a row shift is then one uniform
+  // offset of the whole tile), whole swizzle atoms per image row of the tile, the full K loop in one CTA, no weight multicast
+  const int kh_eff = ps ? 2 : d->kh;
+  static int yr_env = -1;
+  if (yr_env < 0) { const char* e = getenv("EMO_CONV_YREUSE"); yr_env = e ? atoi(e) : 1; }
+  bool want_yreuse = yr_env != 0 && kh_eff > 1 && d->sh == 1 && d->sw == 1 && d->sd == 1 && p.td == 1 && p.tw >= 8 && ksplit == 1 && p.cs == 1 && p.th + kh_eff - 1 <= 256;
+  size_t ring_bytes = 0;
   for (;;) {
     staging = epi ? (size_t)kTileM * BN * sizeof(float) : 0;
     const size_t avail = smem_limit - tail_bytes - 1024 - staging;
@@ -803,6 +815,23 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     stage_bytes = (size_t)NP * (kTileM + BN / p.cg) * KC * 2;
     stages = (int)(avail / stage_bytes);
     if (epi && (stages < 3 || (ps && KC != 64))) { epi = 0; p.res_tma = 0; continue; }  // (the sub-pixel kernel is built for KC = 64)
+    p.yreuse = 0;
+    if (want_yreuse) {
+      // A ring of 2-3 halo tiles, the rest of the operand area as B ring (>= 3 tiles: one group's kh taps in flight)
+      for (int KCy = KC0; KCy >= 32 && !p.yreuse; KCy >>= 1) {
+        if (ps && KCy != 64) break;
+        const size_t a_tile = (size_t)NP * p.tw * (p.th + kh_eff - 1) * KCy * 2, b_tile = (size_t)NP * (BN / p.cg) * KCy * 2;
+        if (2 * a_tile + 3 * b_tile > avail || (p.tw * KCy * 2) % 1024 != 0) continue;
+        const int sa = (3 * a_tile + 4 * b_tile <= avail) ? 3 : 2;
+        int sb = (int)((avail - sa * a_tile) / b_tile);
+        if (sb > kMaxStages) sb = kMaxStages;
+        p.yreuse = 1; p.sa = sa; p.sb = sb; p.a_rows = p.tw * (p.th + kh_eff - 1);
+        KC = KCy;
+        ring_bytes = sa * a_tile + sb * b_tile;
+        stages = sb;
+      }
+    }
+    if (!p.yreuse) ring_bytes = (size_t)(stages > kMaxStages ? kMaxStages : stages) * stage_bytes;
     break;
   }
   p.kchunks = d->Cin / KC;
@@ -819,7 +848,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     const int target = d->acc_chunk_mmas > 0 ? d->acc_chunk_mmas : (NP == 3 ? 24 : 48);
     p.flush = target / mmas_per_kstep < 1 ? 1 : target / mmas_per_kstep;
   }
-  const size_t smem_bytes = stages * stage_bytes + tail_bytes + staging + 1024;
+  const size_t smem_bytes = ring_bytes + tail_bytes + staging + 1024;
 
   // ---- tensor maps ----
   TMaps tm;
@@ -828,7 +857,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cuuint64_t gdim[5] = {(cuuint64_t)d->Cin, (cuuint64_t)d->Win, (cuuint64_t)d->Hin, (cuuint64_t)d->Din, (cuuint64_t)d->N};
     cuuint64_t gstr[4] = {(cuuint64_t)d->Cin * 2, (cuuint64_t)d->Win * d->Cin * 2, (cuuint64_t)d->Hin * d->Win * d->Cin * 2,
                           (cuuint64_t)d->Din * d->Hin * d->Win * d->Cin * 2};
-    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(p.tw * d->sw), (cuuint32_t)(p.th * d->sh), (cuuint32_t)(p.td * d->sd), 1};
+    cuuint32_t box[5] = {(cuuint32_t)KC, (cuuint32_t)(p.tw * d->sw), (cuuint32_t)(p.yreuse ? p.th + kh_eff - 1 : p.th * d->sh), (cuuint32_t)(p.td * d->sd), 1};
     cuuint32_t estr[5] = {1, (cuuint32_t)d->sw, (cuuint32_t)d->sh, (cuuint32_t)d->sd, 1};
     const CUtensorMapSwizzle sw = (KC == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const int taps = ps ? 16 : d->kd * d->kh * d->kw;  // sub-pixel mode: [4 phases][2x2 taps]

@@ -464,12 +464,12 @@ def conv_igemm(a: Split, w: PackedConvWeight, stride=(1, 1, 1), pad=None, bias=N
     post_ret = None
     if post is not None:
         assert not out_nchw and not upconv, "post-op: channels-last output of a plain convolution"
-        kw = dict(post)
-        if kw.get("gn") is not None:
-            assert stats is not None and kw["gn"]["stats"] is stats, "a GroupNorm post-op uses the convolution's own statistics"
-        pd, pout, psp = _apply_desc(None, (N, Do, Ho, Wo, w.cout), a.hi.device, **kw)
+        pkw = dict(post)
+        if pkw.get("gn") is not None:
+            assert stats is not None and pkw["gn"]["stats"] is stats, "a GroupNorm post-op uses the convolution's own statistics"
+        pd, pout, psp = _apply_desc(None, (N, Do, Ho, Wo, w.cout), a.hi.device, **pkw)
         d.post = C.cast(C.pointer(pd), C.c_void_p)
-        wf, wsp = kw.get("want_f32", False), kw.get("want_split", True)
+        wf, wsp = pkw.get("want_f32", False), pkw.get("want_split", True)
         post_ret = (pout, psp) if (wf and wsp) else (pout if wf else psp)
     if _conv_profiler is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
