@@ -51,6 +51,28 @@ __device__ __forceinline__ void sample_coord(const GS3Params& p, int n, int od, 
   }
 }
 
+// L2 eviction-priority hints: the volume is re-read by neighbouring voxels' corner fetches (evict_last), the output is
+// written once and not read by this kernel (evict_first).  Measured with tools/gs3_lab (round 2, bit-identical output):
+// 16 x 64 x 64 warp-field case 22.6 -> 20.6 us, 64^3 cases unchanged or 2% better.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_hint(float4* p, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 struct Corner8 {
   int x0, y0, z0;
   float fx, fy, fz;
@@ -114,6 +136,7 @@ __device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int 
   const int c4n = p.C >> 2;
   const int work = nvox * c4n;
   const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
+  const uint64_t pol_in = l2_policy_evict_last(), pol_out = l2_policy_evict_first();
   for (int t = threadIdx.x; t < work; t += blockDim.x) {
     const int vox = t / c4n, c4 = t - vox * c4n;
     const long long ob = s_out[vox];
@@ -121,8 +144,8 @@ __device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int 
     const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
     const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
     const float4* base = in4 + c4;
-    const float4 v0 = __ldg(base + o0.x), v1 = __ldg(base + o0.y), v2 = __ldg(base + o0.z), v3 = __ldg(base + o0.w);
-    const float4 v4 = __ldg(base + o1.x), v5 = __ldg(base + o1.y), v6 = __ldg(base + o1.z), v7 = __ldg(base + o1.w);
+    const float4 v0 = ldg_hint(base + o0.x, pol_in), v1 = ldg_hint(base + o0.y, pol_in), v2 = ldg_hint(base + o0.z, pol_in), v3 = ldg_hint(base + o0.w, pol_in);
+    const float4 v4 = ldg_hint(base + o1.x, pol_in), v5 = ldg_hint(base + o1.y, pol_in), v6 = ldg_hint(base + o1.z, pol_in), v7 = ldg_hint(base + o1.w, pol_in);
     float4 acc;
 #define EMO_GS_ACC(f) \
   acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
@@ -131,7 +154,7 @@ __device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int 
 #undef EMO_GS_ACC
     const long long o = ob + (long long)(c4 * 4) * p.os_c;
     if (p.os_c == 1) {
-      if (p.out) __stcs((float4*)(p.out + o), acc);  // streaming store: the output is not re-read by this kernel
+      if (p.out) stg_hint((float4*)(p.out + o), acc, pol_out);  // the output is not re-read by this kernel
       if (SPLIT) {
         uint2 hi, lo, lo2;
         if (p.out_lo2) {
@@ -200,6 +223,7 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
   __syncthreads();
   const int work = brick_vox * c4n;
   const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
+  const uint64_t pol_in = l2_policy_evict_last(), pol_out = l2_policy_evict_first();
   for (int t = threadIdx.x; t < work; t += blockDim.x) {
     const int vox = t / c4n, c4 = t - vox * c4n;
     const long long ob = s_out[vox];
@@ -207,8 +231,8 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
     const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
     const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
     const float4* base = in4 + c4;
-    const float4 v0 = __ldg(base + o0.x), v1 = __ldg(base + o0.y), v2 = __ldg(base + o0.z), v3 = __ldg(base + o0.w);
-    const float4 v4 = __ldg(base + o1.x), v5 = __ldg(base + o1.y), v6 = __ldg(base + o1.z), v7 = __ldg(base + o1.w);
+    const float4 v0 = ldg_hint(base + o0.x, pol_in), v1 = ldg_hint(base + o0.y, pol_in), v2 = ldg_hint(base + o0.z, pol_in), v3 = ldg_hint(base + o0.w, pol_in);
+    const float4 v4 = ldg_hint(base + o1.x, pol_in), v5 = ldg_hint(base + o1.y, pol_in), v6 = ldg_hint(base + o1.z, pol_in), v7 = ldg_hint(base + o1.w, pol_in);
     float4 acc;
 #define EMO_GS_ACC(f) \
   acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
@@ -217,7 +241,7 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
 #undef EMO_GS_ACC
     const long long o = ob + (long long)(c4 * 4) * p.os_c;
     if (p.os_c == 1) {
-      if (p.out) __stcs((float4*)(p.out + o), acc);  // streaming store: the output is not re-read by this kernel
+      if (p.out) stg_hint((float4*)(p.out + o), acc, pol_out);  // the output is not re-read by this kernel
       if (SPLIT) {
         uint2 hi, lo, lo2;
         if (p.out_lo2) {

@@ -184,6 +184,95 @@ __global__ void __launch_bounds__(256, 6) gs3_lab_kernel(const GS3Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// TMA-staged variant (what BASELINE.json's north_star sketches: "TMA-staged feature tiles"), affine lattice only.  One CTA per
+// 8 x 8 x 4 output brick: the brick's samples fall into a box of the volume (the bounding box of its eight corner samples,
+// +1 for the trilinear footprint); the box is staged into shared memory with TMA, 16 channels at a time (double buffered,
+// [z][y][x][16 floats]), zero-filled outside the volume (= zeros padding), and the eight corners of every sample are read
+// with LDS.128.  The box extent is fixed by the tensor map: 14 x 14 x 6 voxels covers the 30-degree test lattice.
+// L2 -> SM traffic = box / brick = 14*14*6 / 256 = 4.6 x the volume (the gather kernel moves 8 x (1 - L1 hit rate) = 3.2 x).
+// ---------------------------------------------------------------------------------------------------------------
+#include <cudaTypedefs.h>
+static constexpr int SBX = 14, SBY = 14, SBZ = 6, SCH = 16;
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(c)); }
+__device__ __forceinline__ void mb_expect(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mb_wait(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(s_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma5(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(s_u32(dst)), "l"(m), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1) gs3_staged_kernel(const __grid_constant__ CUtensorMap tmap, const GS3Params p) {
+  extern __shared__ __align__(128) uint8_t sraw[];
+  float* buf[2] = {(float*)sraw, (float*)(sraw + SBX * SBY * SBZ * SCH * 4)};
+  __shared__ uint64_t bar[2];
+  __shared__ int s_org[3];
+  __shared__ int s_loc[256];          // corner (x0,y0,z0) relative to the box, packed 10 bits each
+  __shared__ float s_frac[256][3];
+  __shared__ int s_bad;
+  int b = blockIdx.x;
+  const int bwi = b % p.bricks_w; b /= p.bricks_w;
+  const int bhi = b % p.bricks_h; b /= p.bricks_h;
+  const int bdi = b % p.bricks_d; b /= p.bricks_d;
+  const int n = b;
+  const int tid = threadIdx.x;
+  if (tid == 0) { mb_init(&bar[0], 1); mb_init(&bar[1], 1); s_bad = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  // sample position of this thread's voxel
+  const int lw = tid % 8, lh = (tid / 8) % 8, ld = tid / 64;
+  const int ow = bwi * 8 + lw, oh = bhi * 8 + lh, od = bdi * 4 + ld;
+  float gx, gy, gz;
+  sample_coord(p, n, od, oh, ow, gx, gy, gz);
+  const float ix = ((gx + 1.f) * (float)p.Win - 1.f) * 0.5f, iy = ((gy + 1.f) * (float)p.Hin - 1.f) * 0.5f, iz = ((gz + 1.f) * (float)p.Din - 1.f) * 0.5f;
+  const int x0 = (int)floorf(ix), y0 = (int)floorf(iy), z0 = (int)floorf(iz);
+  // box origin = minimum corner over the brick (block reduction through shared memory atomics)
+  if (tid == 0) { s_org[0] = 1 << 30; s_org[1] = 1 << 30; s_org[2] = 1 << 30; }
+  __syncthreads();
+  atomicMin(&s_org[0], x0); atomicMin(&s_org[1], y0); atomicMin(&s_org[2], z0);
+  __syncthreads();
+  const int bx = s_org[0], by = s_org[1], bz = s_org[2];
+  const int rx = x0 - bx, ry = y0 - by, rz = z0 - bz;
+  if (rx + 1 >= SBX || ry + 1 >= SBY || rz + 1 >= SBZ) s_bad = 1;  // the lattice does not fit the fixed box: results invalid
+  s_loc[tid] = rx | (ry << 10) | (rz << 20);
+  s_frac[tid][0] = ix - (float)x0; s_frac[tid][1] = iy - (float)y0; s_frac[tid][2] = iz - (float)z0;
+  const int nsl = p.C / SCH;
+  const uint32_t slice_bytes = SBX * SBY * SBZ * SCH * 4;
+  if (tid == 0) {
+    mb_expect(&bar[0], slice_bytes);
+    tma5(&tmap, &bar[0], buf[0], 0, bx, by, bz, n);
+  }
+  __syncthreads();
+  for (int s = 0; s < nsl; ++s) {
+    if (tid == 0 && s + 1 < nsl) {  // next slice into the other buffer (its readers finished at the barrier below)
+      mb_expect(&bar[(s + 1) & 1], slice_bytes);
+      tma5(&tmap, &bar[(s + 1) & 1], buf[(s + 1) & 1], (s + 1) * SCH, bx, by, bz, n);
+    }
+    mb_wait(&bar[s & 1], (s >> 1) & 1);
+    const float4* src = (const float4*)buf[s & 1];
+    for (int t = tid; t < 256 * (SCH / 4); t += 256) {
+      const int vox = t / (SCH / 4), q = t % (SCH / 4);
+      const int loc = s_loc[vox];
+      const int cx = loc & 1023, cy = (loc >> 10) & 1023, cz = loc >> 20;
+      const float fx = s_frac[vox][0], fy = s_frac[vox][1], fz = s_frac[vox][2];
+      const int base = ((cz * SBY + cy) * SBX + cx) * (SCH / 4) + q;
+      const int dxo = SCH / 4, dyo = SBX * (SCH / 4), dzo = SBY * SBX * (SCH / 4);
+      const float4 v0 = src[base], v1 = src[base + dxo], v2 = src[base + dyo], v3 = src[base + dyo + dxo];
+      const float4 v4 = src[base + dzo], v5 = src[base + dzo + dxo], v6 = src[base + dzo + dyo], v7 = src[base + dzo + dyo + dxo];
+      const float4 w0 = make_float4((1 - fx) * (1 - fy) * (1 - fz), fx * (1 - fy) * (1 - fz), (1 - fx) * fy * (1 - fz), fx * fy * (1 - fz));
+      const float4 w1 = make_float4((1 - fx) * (1 - fy) * fz, fx * (1 - fy) * fz, (1 - fx) * fy * fz, fx * fy * fz);
+      float4 acc;
+      GS_ACC(x) GS_ACC(y) GS_ACC(z) GS_ACC(w)
+      const int vw = vox % 8, vh = (vox / 8) % 8, vd = vox / 64;
+      const long long o = (long long)n * p.os_n + (long long)(bdi * 4 + vd) * p.os_d + (long long)(bhi * 8 + vh) * p.os_h + (long long)(bwi * 8 + vw) * p.os_w + s * SCH + q * 4;
+      __stcs((float4*)(p.out + o), acc);
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && s_bad) p.out[0] = __int_as_float(0x7fc00000);
+}
+
 struct Case { const char* name; int N, C, D, S; bool affine; };
 
 int main() {
@@ -276,6 +365,43 @@ int main() {
       printf("%-12s %-24s median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic  diff_words %llu\n", c.name, names[v], ms[7] * 1e3, ms[0] * 1e3,
              bytes / (ms[7] * 1e-3) * 1e-9, diff);
       fflush(stdout);
+    }
+    if (c.affine) {
+      // TMA-staged variant: tensor map over the channels-last volume, box {16 ch, 14, 14, 6, 1}
+      PFN_cuTensorMapEncodeTiled encode = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&encode, cudaEnableDefault, &qres));
+      CUtensorMap tmap;
+      cuuint64_t gdim[5] = {(cuuint64_t)c.C, (cuuint64_t)c.S, (cuuint64_t)c.S, (cuuint64_t)c.D, (cuuint64_t)c.N};
+      cuuint64_t gstr[4] = {(cuuint64_t)c.C * 4, (cuuint64_t)c.S * c.C * 4, (cuuint64_t)c.S * c.S * c.C * 4, (cuuint64_t)c.D * c.S * c.S * c.C * 4};
+      cuuint32_t box[5] = {SCH, SBX, SBY, SBZ, 1}, es[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, in, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { fprintf(stderr, "tensor map encode failed %d\n", (int)r); return 2; }
+      const size_t smem = 2 * (size_t)SBX * SBY * SBZ * SCH * 4;
+      CK(cudaFuncSetAttribute(gs3_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      p.out = out[1];
+      std::vector<float> ms;
+      const unsigned bricks = (unsigned)(c.N * (c.D / 4) * (c.S / 8) * (c.S / 8));
+      for (int r2 = 0; r2 < 15; ++r2) {
+        flush_k<<<148 * 8, 256, 0, st>>>(flush_buf, flush_bytes / 16);
+        CK(cudaEventRecord(e0, st));
+        gs3_staged_kernel<<<bricks, 256, smem, st>>>(tmap, p);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        ms.push_back(t);
+      }
+      std::sort(ms.begin(), ms.end());
+      // same trilinear sample with another (exact) weight / summation order: compare by value
+      std::vector<float> h0(4096), h1(4096);
+      CK(cudaMemcpy(h0.data(), out[0] + n / 2, 4096 * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(h1.data(), out[1] + n / 2, 4096 * 4, cudaMemcpyDeviceToHost));
+      float maxerr = 0.f, first = 0.f;
+      CK(cudaMemcpy(&first, out[1], 4, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < 4096; ++i) maxerr = fmaxf(maxerr, fabsf(h0[i] - h1[i]));
+      printf("%-12s %-24s median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic  max |diff| on a 4096-element sample %.2e%s\n", c.name,
+             "TMA-staged box", ms[7] * 1e3, ms[0] * 1e3, bytes / (ms[7] * 1e-3) * 1e-9, maxerr, first != first ? "  (BOX TOO SMALL)" : "");
     }
     CK(cudaFree(in)); CK(cudaFree(out[0])); CK(cudaFree(out[1]));
     if (grid) CK(cudaFree(grid));
