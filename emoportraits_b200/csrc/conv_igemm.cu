@@ -18,9 +18,13 @@
 //   4-deep TMEM chunk ring.  Plain bf16/tf32 operands, or one long accumulation chain, do not hold the 1e-3 budget.
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (both issue behind elect.sync),
 //   8 accumulator warps, two per TMEM lane quadrant, each owning half of the tile's columns (chunk promotion during
-//   the main loop).  EPI = 0 (320 threads): the accumulator warps also run the tile's final phase (bias / residual /
-//   activation -> global, GN statistics).  EPI = 1 (512 threads, setmaxnreg budgets): they hand the finished tile to
-//   four store warps through a swizzled shared-memory staging tile.  See the template comment at the kernel.
+//   the main loop) and running the tile's final phase: EPI = 0 straight from registers to global memory, EPI = 1 through a
+//   swizzled shared-memory staging tile and TMA tensor stores / residual loads.  See the template comment at the kernel.
+// Main loop: stride-1 convolutions load ONE halo A tile per (kernel column, k-chunk) and serve its kh tap rows through
+//   descriptor row offsets (A ring + B ring, "row reuse"); other layers load an {A, B} stage per (tap, k-chunk).  On the
+//   instrumented build (tools/conv_timeline.py) the main loop of the dominant layer runs at the tensor pipe's pace for the
+//   clock the power cap allows (72 k-steps x 12 MMAs in 35.6 us); what is left of a launch is prologue (2.8 us) and the
+//   last tile's final phase.
 // CG = 2: CTA pairs (2-CTA clusters) issue cta_group::2 M = 256 MMAs; each CTA stages its own 128 pixels and half of
 //   the weight tile, which halves the weight ingest and brings the shared-memory operand reads per MMA under the
 //   tensor floor (measured in tools/mma_probe.cu).
@@ -34,8 +38,6 @@ namespace emo {
 
 static constexpr int kThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 static constexpr int kEpiThreads = 256;
-static constexpr int kThreadsEpi1 = 512;  // EPI = 1 layout: warps 0..3 TMA / MMA / idle, 4..11 accumulators, 12..15 store warps
-static constexpr int kStoreThreads = 128;
 static constexpr int kMaxStages = 8;
 static constexpr int kMaxAStages = 4;  // row-reuse mode: depth cap of the A (halo tile) ring
 static constexpr int kTileM = 128;
@@ -79,7 +81,8 @@ struct ConvKParams {
   int oH, oW;
   int ntc;  // channel tiles per phase (= Cout_pad / BN)
   float out_scale;  // conv_igemm_f16_kernel: 1 / (activation plane scale * weight plane scale)
-  int res_tma;      // EPI = 2: the residual has the output's resolution and is TMA-loaded into the staging tile (tm.res)
+  int res_tma;      // EPI = 1: 1 = same-resolution residual TMA-loaded into the staging tile, 2 = half-resolution residual
+                    // (res_shift == 1) TMA-loaded into a quarter-size tile next to it (tm.res); 0 = read from global by the warps
   // row-reuse mode (stride-1 convolutions with kh > 1 on tiles of one depth slice): the A operand of a (kernel column,
   // k-chunk) group is ONE halo tile of a_rows = tw * (th + kh - 1) pixels serving all kh tap rows; A ring of `sa` halo tiles,
   // B ring of `sb` weight tiles (see the kernel's producer role)
@@ -298,7 +301,7 @@ __device__ __forceinline__ void tile_stats(const float (&acc)[kMaxBN / 2], int n
   }
 }
 
-// Second half of the tile statistics: the CTA's column accumulators (filled by tile_stats / the store warps, then a named
+// Second half of the tile statistics: the CTA's column accumulators (filled by tile_stats, then a named
 // barrier) are folded per GroupNorm group and added to the fp64 global sums; the accumulators are left zeroed.
 __device__ __forceinline__ void tile_group_stats(const ConvKParams& p, float* cs, float* cq, int n, int n0, int BN, int et, int nthreads) {
   const int cpg = p.cpg;
@@ -329,61 +332,6 @@ __device__ __forceinline__ void tile_group_stats(const ConvKParams& p, float* cs
   }
 }
 
-// Store-warp row loop (EPI = 1).  `chunk0` = 0 or 32: which 16-byte chunk of every staged row this lane owns in this pass;
-// `cg` = first global channel of that chunk.  PLAIN = no activation, no post-add, residual at the output resolution.
-struct StoreRowCtx {
-  int off, roff, poff;  // this lane's row: element offsets of the pixel in out / residual / post_add (-1: no pixel)
-  const float* stg;     // first staged row of this warp
-  int BN, lane, row0;
-  float* out;
-  const float* residual;
-  const float* post_add;
-  int act;
-};
-template <bool PLAIN>
-__device__ __forceinline__ void store_rows(const StoreRowCtx& c, int chunk0, int cg, bool ok, const float4 bias, float4& s, float4& q) {
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int r0 = 0; r0 < 32; r0 += 8) {
-    float4 v[8], e[8];
-    int off[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int r = r0 + u;
-      off[u] = __shfl_sync(0xffffffffu, c.off, r);
-      const bool live = ok && off[u] >= 0;
-      // staged rows are [BN] floats; chunk q of row r sits at q ^ (r & 7) (row0 is a multiple of 8)
-      v[u] = ok ? *((const float4*)(c.stg + (size_t)r * c.BN) + ((chunk0 + c.lane) ^ (r & 7))) : zero;
-      e[u] = zero;
-      if (c.residual) {
-        const int ro = PLAIN ? off[u] : __shfl_sync(0xffffffffu, c.roff, r);
-        if (live) e[u] = __ldg((const float4*)(c.residual + ro + cg));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const bool live = ok && off[u] >= 0;
-      float4 a = v[u];
-      a.x += bias.x + e[u].x; a.y += bias.y + e[u].y; a.z += bias.z + e[u].z; a.w += bias.w + e[u].w;
-      if (!PLAIN) {
-        a.x = act_apply(a.x, c.act); a.y = act_apply(a.y, c.act); a.z = act_apply(a.z, c.act); a.w = act_apply(a.w, c.act);
-        if (c.post_add) {
-          const int po = __shfl_sync(0xffffffffu, c.poff, r0 + u);
-          if (live) {
-            const float4 t = __ldg((const float4*)(c.post_add + po + cg));
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-          }
-        }
-      }
-      if (live) {
-        *(float4*)(c.out + off[u] + cg) = a;
-        s.x += a.x; s.y += a.y; s.z += a.z; s.w += a.w;
-        q.x = fmaf(a.x, a.x, q.x); q.y = fmaf(a.y, a.y, q.y); q.z = fmaf(a.z, a.z, q.z); q.w = fmaf(a.w, a.w, q.w);
-      }
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
@@ -408,8 +356,8 @@ __device__ __forceinline__ unsigned long long emo_gtime() {
 struct TMaps {
   CUtensorMap a[3];  // activation planes: hi, lo, lo2
   CUtensorMap b[3];  // weight planes
-  CUtensorMap out;   // EPI = 2: fp32 output, 32-channel panels of one pixel box (SWIZZLE_128B)
-  CUtensorMap res;   // EPI = 2: same-resolution residual, same boxes
+  CUtensorMap out;   // EPI = 1: fp32 output, 32-channel panels of one pixel box (SWIZZLE_128B)
+  CUtensorMap res;   // EPI = 1: residual, same panels (half-size boxes for a half-resolution residual)
 };
 
 #define EMO_CONV_PS 0
@@ -779,36 +727,39 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 
   const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2 + 2 * kMaxAStages) * 8 + 16 + 4 * 256 * sizeof(float);
   const size_t smem_limit = 227 * 1024;
-  // Final phase of a tile (template parameter EPI, see the kernel's header comment):
-  //   2  TMA epilogue: pair-mode, full-K tiles, channels-last output in whole 32-channel panels, no post-add; needs a [128][BN]
-  //      fp32 staging tile next to >= 3 pipeline stages (measured: 3 stages cost nothing against 4, 2 stages cost 10-25%)
-  //   1  store warps (round-1 form, kept for the A/B: EMO_CONV_EPI=1): same conditions, >= 2 tiles per CTA
-  //   0  in-warp final phase: everything else (split-K, NCHW / ragged-channel outputs, single-CTA tiles)
+  // Final phase of a tile (template parameter EPI, see the kernel's header comment).  TMA epilogue when the layer qualifies
+  // (pair mode, full K loop, channels-last output in whole 32-channel panels, no post-add) and pays: per-layer CUDA-graph timings
+  // of every shape of the driver frame (tools/conv_layer_bench.py, profiles/conv_layers_r2.md) put it ahead for N tiles of
+  // >= 96 channels when either a residual rides in through TMA or the CTA walks >= 2 tiles; narrow-N 3-D layers and
+  // single-wave layers without a residual stay with the in-warp form.
   int epi = 0;
   {
-    static int epi_env = -1;
-    if (epi_env < 0) { const char* e = getenv("EMO_CONV_EPI"); epi_env = e ? atoi(e) : 1; }
-    const long long elems = (long long)d->N * d->Dout * d->Hout * d->Wout * d->Cout;  // 32-bit element offsets in the store warps
+    int want = -1;
+#ifdef EMO_CONV_DEBUG
+    { const char* e = getenv("EMO_CONV_EPI"); if (e) want = atoi(e); }  // instrumented build: force 0 / 1 for the A/B tools
+#endif
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
-    const bool common = p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout % 4 == 0;
-    if (epi_env == 2 && common && d->Cout == d->Cout_pad && d->Cout % 32 == 0 && BN % 32 == 0 && !d->post_add &&
-        ((uintptr_t)d->out % 16) == 0 && (!d->residual || ((uintptr_t)d->residual % 16) == 0) && (!ps || d->N * (long long)gH < (1ll << 31)))
-      epi = 2;
-    if (epi_env == 1 && common && elems < (1ll << 31) && tiles >= 2ll * sm_count) epi = 1;
+    const bool eligible = p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout == d->Cout_pad && d->Cout % 32 == 0 && BN % 32 == 0 && !d->post_add &&
+                          ((uintptr_t)d->out % 16) == 0 && (!d->residual || ((uintptr_t)d->residual % 16) == 0) && (!ps || d->N * (long long)gH < (1ll << 31));
+    const bool res_ok = !d->residual || d->res_shift == 0 || (d->res_shift == 1 && !ps && p.td == 1 && p.tw % 2 == 0 && p.th % 2 == 0 && p.tw * p.th == kTileM);
+    const bool pays = BN >= 96 && (d->residual || tiles >= 2ll * sm_count);
+    if (eligible && res_ok && (want < 0 ? pays : want == 1)) epi = 1;
   }
-  p.res_tma = (epi == 2 && d->residual && d->res_shift == 0 && !ps) ? 1 : 0;
+  p.res_tma = (epi == 1 && d->residual && !ps) ? (d->res_shift == 0 ? 1 : 2) : 0;
   size_t staging = 0, stage_bytes = 0;
   int stages = 0;
   const int KC0 = KC;
   // row reuse needs: more than one tap row, unit stride along H, tiles inside one depth slice (a row shift is then one uniform
   // offset of the whole tile), whole swizzle atoms per image row of the tile, the full K loop in one CTA, no weight multicast
   const int kh_eff = ps ? 2 : d->kh;
-  static int yr_env = -1;
-  if (yr_env < 0) { const char* e = getenv("EMO_CONV_YREUSE"); yr_env = e ? atoi(e) : 1; }
+  int yr_env = 1;
+#ifdef EMO_CONV_DEBUG
+  { const char* e = getenv("EMO_CONV_YREUSE"); if (e) yr_env = atoi(e); }  // instrumented build: per-tap form for the A/B tools
+#endif
   bool want_yreuse = yr_env != 0 && kh_eff > 1 && d->sh == 1 && d->sw == 1 && d->sd == 1 && p.td == 1 && p.tw >= 8 && ksplit == 1 && p.cs == 1 && p.th + kh_eff - 1 <= 256;
   size_t ring_bytes = 0;
   for (;;) {
-    staging = epi ? (size_t)kTileM * BN * sizeof(float) : 0;
+    staging = epi ? (size_t)(kTileM + (p.res_tma == 2 ? kTileM / 4 : 0)) * BN * sizeof(float) : 0;
     const size_t avail = smem_limit - tail_bytes - 1024 - staging;
     KC = KC0;
     if (KC == 64 && avail / ((size_t)NP * (kTileM + BN / p.cg) * 64 * 2) < 3) KC = 32;
@@ -882,7 +833,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     }
   }
 
-  if (epi == 2) {
+  if (epi == 1) {
     // output (and same-resolution residual) as 32-channel panels of the tile's pixel box; SWIZZLE_128B = the staging tile's
     // chunk order.  Sub-pixel mode: the [2 H][2 W] output seen as (C, column parity, W, row parity, N * H): one phase's pixels
     // of a low-resolution box are again a box.
@@ -901,6 +852,11 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     CUresult r1 = encode(&tm.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)d->out, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     CUresult r2 = CUDA_SUCCESS;
+    if (p.res_tma == 2) {  // half-resolution residual [N][D][H/2][W/2][C], boxes of (tw/2) x (th/2) pixels
+      gdim[1] = (cuuint64_t)(d->Wout >> 1); gdim[2] = (cuuint64_t)(d->Hout >> 1);
+      gstr[1] = gdim[1] * C4; gstr[2] = gdim[2] * gstr[1]; gstr[3] = (cuuint64_t)d->Dout * gstr[2];
+      box[1] = (cuuint32_t)(p.tw >> 1); box[2] = (cuuint32_t)(p.th >> 1);
+    }
     if (p.res_tma)
       r2 = encode(&tm.res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)d->residual, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -928,7 +884,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     cudaLaunchConfig_t cfg;                                                                                               \
     memset(&cfg, 0, sizeof(cfg));                                                                                         \
     cfg.gridDim = dim3((unsigned)grid);                                                                                   \
-    cfg.blockDim = dim3(EPI_ == 1 ? kThreadsEpi1 : kThreads);                                                                                        \
+    cfg.blockDim = dim3(kThreads);                                                                                        \
     cfg.dynamicSmemBytes = smem_bytes;                                                                                    \
     cfg.stream = stream;                                                                                                  \
     cudaLaunchAttribute attr[1];                                                                                          \
@@ -942,10 +898,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     if (e != cudaSuccess) { set_error("emo_conv_igemm: launch: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; }         \
   } while (0)
   if (f16) {
-    if (epi == 2) {
-      if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 2, 2);
-      else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 2, 2);
-    } else if (epi == 1) {
+    if (epi) {
       if (KC == 64) EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 64, 2, 2, 1);
       else EMO_LAUNCH_CONV5(conv_igemm_f16_kernel, 32, 2, 2, 1);
     } else if (p.cg == 2) {
@@ -957,15 +910,9 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     }
   } else if (ps) {
     EMO_REQUIRE(KC == 64, "emo_conv_igemm: upconv tile does not fit with KC = 64");
-    if (epi == 2) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 2);
-    else if (epi == 1) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 1);
+    if (epi) EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 1);
     else EMO_LAUNCH_CONV5(conv_igemm_ps_kernel, 64, 2, 2, 0);
-  } else if (epi == 2) {
-    if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 2);
-    else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 2);
-    else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 2);
-    else EMO_LAUNCH_CONV(32, 2, 2, 2);
-  } else if (epi == 1) {
+  } else if (epi) {
     if (NP == 3 && KC == 64) EMO_LAUNCH_CONV(64, 3, 2, 1);
     else if (NP == 3) EMO_LAUNCH_CONV(32, 3, 2, 1);
     else if (KC == 64) EMO_LAUNCH_CONV(64, 2, 2, 1);

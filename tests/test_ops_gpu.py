@@ -193,17 +193,19 @@ def test_conv_igemm_three_planes(ops, Cin, Cout, sp, k):
 
 @pytest.mark.parametrize("N,Cin,Cout,sp,k,planes,kw", [
     (1, 64, 96, (24, 40), 3, 2, dict(residual=True, stats=True)),          # ragged pixel tiles: TMA clips the store, zero-fills the residual
-    (1, 128, 128, (64, 64), 3, 2, dict(residual=False, stats=True)),       # no residual: staging tile written directly
-    (1, 512, 320, (32, 32), 3, 2, dict(residual=True, stats=True)),        # N tile 160: five panels, KC = 32 ring next to the 80 KB tile
-    (2, 64, 64, (16, 32), 3, 2, dict(residual=True, stats=True, act=3)),   # batch of 2 (per-sample statistics), tanh
-    (1, 64, 128, (32, 32), 3, 2, dict(residual=True, res_shift=1, stats=True)),  # half-resolution residual: read from global
-    (1, 64, 64, (8, 16, 16), 3, 3, dict(residual=True, stats=True)),       # 3-D boxes, three planes
+    (1, 64, 128, (256, 256), 3, 2, dict(residual=False, stats=True)),      # no residual, several tiles per CTA: staging tile written directly
+    (1, 512, 320, (32, 32), 3, 2, dict(residual=True, stats=True)),        # N tile 160: five panels
+    (2, 64, 96, (16, 32), 3, 2, dict(residual=True, stats=True, act=3)),   # batch of 2 (per-sample statistics), tanh
+    (1, 64, 128, (32, 32), 3, 2, dict(residual=True, res_shift=1, stats=True)),  # half-resolution residual: quarter-size TMA tile
+    (1, 64, 128, (24, 40), 3, 2, dict(residual=True, res_shift=1, stats=True)),  # the same on ragged tiles
+    (1, 64, 96, (4, 16, 16), 3, 3, dict(residual=True, stats=True)),       # 3-D volume (tiles inside one depth slice), three planes
     (1, 96, 96, (4, 16, 16), 3, "h2", dict(residual=True, stats=True)),    # fp16 planes, KC = 32
-    (1, 256, 64, (32, 32), 1, 2, dict(residual=True, stats=False)),        # 1x1, narrow N tile
+    (1, 256, 128, (32, 32), 1, 2, dict(residual=True, stats=False)),       # 1x1 (per-tap main loop)
 ])
 def test_conv_igemm_tma_epilogue(ops, N, Cin, Cout, sp, k, planes, kw):
-    """The TMA epilogue (conv kernel EPI = 2: staging tile -> TMA tensor store, same-resolution residual TMA-loaded into the
-    tile) on shapes the model's small layers would hand to split-K: forced here with split_k=False."""
+    """The TMA epilogue (conv kernel EPI = 1: staging tile -> TMA tensor store, residual TMA-loaded) and the row-reuse main loop
+    on small shapes the model would hand to split-K: forced here with split_k=False (N tiles of >= 96 channels with a residual,
+    or >= 2 tiles per CTA, take the TMA epilogue: emo_conv_igemm's selection rule)."""
     _conv_case(ops, N, Cin, Cout, sp, k, bias=True, planes=planes, split_k=False, **kw)
 
 

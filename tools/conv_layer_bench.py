@@ -1,9 +1,13 @@
 """Per-layer device time of the driver frame's convolution shapes (GPU box): CUDA-graph replays of 10 back-to-back launches,
 so neither host launch cost nor tensor-map encoding is in the number (bench.py's per-layer table is taken in eager mode and
-carries both).  EMO_CONV_EPI / EMO_CONV_YREUSE select the kernel form; one setting per process."""
+carries both).  With EMO_CONV_EPI (0 in-warp final phase / 1 TMA epilogue) or EMO_CONV_YREUSE (0 per-tap main loop) set, the
+instrumented build libemoport_dbg.so is loaded, which honours them (the product library selects per layer by itself); one
+setting per process."""
 import math, os, pathlib, sys
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+if os.environ.get("EMO_CONV_EPI") or os.environ.get("EMO_CONV_YREUSE"):
+    os.environ.setdefault("EMO_LIB", str(ROOT / "emoportraits_b200" / "csrc" / "libemoport_dbg.so"))
 import torch
 from emoportraits_b200 import ops
 

@@ -59,9 +59,9 @@ def run(Cin, Cout, sp, k, planes, residual=True):
     return
 
 
-for epi in sys.argv[1:] or ["0"]:
-    os.environ["EMO_CONV_EPI"] = epi
-    # the library reads EMO_CONV_EPI once per process: run one setting per invocation
+for epi in sys.argv[1:] or ["auto"]:
+    if epi != "auto":
+        os.environ["EMO_CONV_EPI"] = epi   # 0 in-warp final phase, 1 TMA epilogue; "auto" = the library's per-layer choice
     run(512, 512, (64, 64), 3, 2)
     run(128, 128, (512, 512), 3, 2)
     run(320, 320, (128, 128), 3, 2)
