@@ -733,11 +733,12 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   // >= 96 channels when either a residual rides in through TMA or the CTA walks >= 2 tiles; narrow-N 3-D layers and
   // single-wave layers without a residual stay with the in-warp form.
   int epi = 0;
-  {
-    int want = -1;
+  int want_epi = -1;
 #ifdef EMO_CONV_DEBUG
-    { const char* e = getenv("EMO_CONV_EPI"); if (e) want = atoi(e); }  // instrumented build: force 0 / 1 for the A/B tools
+  { const char* e = getenv("EMO_CONV_EPI"); if (e) want_epi = atoi(e); }  // instrumented build: force 0 / 1 for the A/B tools
 #endif
+  {
+    const int want = want_epi;
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     const bool eligible = p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout == d->Cout_pad && d->Cout % 32 == 0 && BN % 32 == 0 && !d->post_add &&
                           ((uintptr_t)d->out % 16) == 0 && (!d->residual || ((uintptr_t)d->residual % 16) == 0) && (!ps || d->N * (long long)gH < (1ll << 31));
@@ -767,6 +768,12 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     stages = (int)(avail / stage_bytes);
     if (epi && (stages < 3 || (ps && KC != 64))) { epi = 0; p.res_tma = 0; continue; }  // (the sub-pixel kernel is built for KC = 64)
     p.yreuse = 0;
+    if (epi && want_yreuse && want_epi < 0 && KC0 == 64 &&
+        2 * (size_t)NP * p.tw * (p.th + kh_eff - 1) * 64 * 2 + 3 * (size_t)NP * (BN / p.cg) * 64 * 2 > avail) {
+      // the staging tile(s) would push the row-reuse rings down to 32-channel k-steps (N tile 160 with a half-resolution
+      // residual: measured 84 us against 74 us in-warp): the in-warp final phase keeps the full-width rings
+      epi = 0; p.res_tma = 0; continue;
+    }
     if (want_yreuse) {
       // A ring of 2-3 halo tiles, the rest of the operand area as B ring (>= 3 tiles: one group's kh taps in flight)
       for (int KCy = KC0; KCy >= 32 && !p.yreuse; KCy >>= 1) {

@@ -52,7 +52,7 @@ def launches():
         if gs and rs:
             lin = [i for i, (n, _) in enumerate(seq) if "linear_kernel" in n and i < gs[0]]
             marks = [("pose_theta + expression encoder (aligned 224^2 crop, ResNet)", 0, lin[0] if lin else gs[0]),
-                     ("embedding MLPs + warp generator (3-D convs, three planes)", lin[0] if lin else gs[0], gs[0]),
+                     ("embedding MLPs + warp generator (3-D convs, fp16 two-plane operands)", lin[0] if lin else gs[0], gs[0]),
                      ("grid_sample_3d x2", gs[0], gs[-1] + 1),
                      ("decoder (two planes)", gs[-1] + 1, rs[0]),
                      ("head-pose regressor of the next frame (ResNet18)", rs[0], len(seq))]
@@ -95,4 +95,5 @@ def rep(name):
 
 launches()
 rep("prof_conv")
+rep("prof_elem")
 rep("prof_gs3")
