@@ -296,23 +296,22 @@ __device__ __forceinline__ void tile_stats(const float (&acc)[kMaxBN / 2], int n
       }
       const int bl = lane / VPB, kind = (lane % VPB) / GPB, gi = lane % GPB;
       const int col = (b0 + bl) * 16 + gi * R;
-      if (bl < BPP && col < ncols) atomicAdd(kind ? &cq[col] : &cs[col], val[0]);
+      if (bl < BPP && col < ncols) (kind ? cq : cs)[col] = val[0];  // this warp is the only writer of (quadrant, column)
     }
   }
 }
 
-// Second half of the tile statistics: the CTA's column accumulators (filled by tile_stats, then a named
-// barrier) are folded per GroupNorm group and added to the fp64 global sums; the accumulators are left zeroed.
-__device__ __forceinline__ void tile_group_stats(const ConvKParams& p, float* cs, float* cq, int n, int n0, int BN, int et, int nthreads) {
+// Second half of the tile statistics: the per-quadrant column slots (filled by tile_stats, then a named barrier) are summed in
+// a fixed order - quadrant 0..3, then the columns of a GroupNorm group - and added to the fp64 global sums.  (Slots of columns
+// that never receive data - all but the first of every R-group - stay zero from the kernel's start.)
+__device__ __forceinline__ void tile_group_stats(const ConvKParams& p, const float* cs, const float* cq, int n, int n0, int BN, int et, int nthreads) {
   const int cpg = p.cpg;
   if (BN % cpg == 0 && (n0 % cpg) == 0) {
     const int ng = BN / cpg;
     for (int g = et; g < ng; g += nthreads) {
       float a = 0.f, b = 0.f;
-      for (int j = 0; j < cpg; ++j) {
-        a += cs[g * cpg + j]; b += cq[g * cpg + j];
-        cs[g * cpg + j] = 0.f; cq[g * cpg + j] = 0.f;
-      }
+      for (int q = 0; q < 4; ++q)
+        for (int j = 0; j < cpg; ++j) { a += cs[q * kMaxBN + g * cpg + j]; b += cq[q * kMaxBN + g * cpg + j]; }
       const int gi = (n0 / cpg) + g;
       if (gi < p.G) {
         atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)a);
@@ -324,10 +323,11 @@ __device__ __forceinline__ void tile_group_stats(const ConvKParams& p, float* cs
       const int c = n0 + j;
       if (c < p.Cout) {
         const int gi = c / cpg;
-        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)cs[j]);
-        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)cq[j]);
+        const float a = (cs[j] + cs[kMaxBN + j]) + (cs[2 * kMaxBN + j] + cs[3 * kMaxBN + j]);
+        const float b = (cq[j] + cq[kMaxBN + j]) + (cq[2 * kMaxBN + j] + cq[3 * kMaxBN + j]);
+        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)a);
+        atomicAdd(&p.stats[((long long)n * p.G + gi) * 2 + 1], (double)b);
       }
-      cs[j] = 0.f; cq[j] = 0.f;
     }
   }
 }
@@ -725,7 +725,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
               "emo_conv_igemm: residual shift does not divide the output size");
   EMO_REQUIRE(!ps || p.cg == 2, "emo_conv_igemm: upconv needs an even number of pixel tiles and BN %% 32 == 0 (pair mode)");
 
-  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2 + 2 * kMaxAStages) * 8 + 16 + 4 * 256 * sizeof(float);
+  const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2 + 2 * kMaxAStages) * 8 + 16 + 8 * kMaxBN * sizeof(float);
   const size_t smem_limit = 227 * 1024;
   // Final phase of a tile (template parameter EPI, see the kernel's header comment).  TMA epilogue when the layer qualifies
   // (pair mode, full K loop, channels-last output in whole 32-channel panels, no post-add) and pays: per-layer CUDA-graph timings

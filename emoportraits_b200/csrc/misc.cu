@@ -286,12 +286,38 @@ __global__ void pose_theta_kernel(const emo_pose_desc d) {
   if (n < d.N) pose::pose_sample(d, n);
 }
 
+// video-loop compositing (E_emo_infer_video.ipynb cell 41): out = m^8 * img + (1 - m^8) * bg with m zeroed below the threshold
+__global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ img, const float* __restrict__ mask, const float* __restrict__ bg,
+                                                       int N, int C, long long HW, float thr, float* __restrict__ out) {
+  const long long total = (long long)N * C * HW;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long s = t % HW;
+    const long long nc = t / HW;
+    const int c = (int)(nc % C);
+    const long long n = nc / C;
+    float m = __ldg(mask + n * HW + s);
+    m = m > thr ? m : 0.f;
+    const float m2 = m * m, m4 = m2 * m2, m8 = m4 * m4;
+    out[t] = m8 * __ldg(img + t) + (1.f - m8) * __ldg(bg + (long long)c * HW + s);
+  }
+}
+
 }  // namespace emo
 
 using namespace emo;
 
+extern "C" int emo_composite(const float* img, const float* mask, const float* bg, int N, int C, int H, int W, float threshold, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(img && mask && bg && out && N > 0 && C > 0 && H > 0 && W > 0, "emo_composite: bad arguments");
+  const long long total = (long long)N * C * H * W;
+  long long blocks = cdivll(total, 256);
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  launch_kernel(composite_kernel, (unsigned)blocks, 256, 0, stream, img, mask, bg, N, C, (long long)H * W, threshold, out);
+  return check_launch("emo_composite");
+}
+
 extern "C" const char* emo_last_error(void) { return emo::g_err; }
-extern "C" int emo_version(void) { return 103; }  // 101: emo_pose_desc (+theta_in, mix_old, smoothing) and emo_conv_desc (+upconv) grew trailing fields
+extern "C" int emo_version(void) { return 104; }  // 101: emo_pose_desc (+theta_in, mix_old, smoothing) and emo_conv_desc (+upconv) grew trailing fields
 
 extern "C" int emo_device_info(int* sm_count, int* cc) {
   int dev = 0;

@@ -118,6 +118,7 @@ SYMBOLS = {
     "emo_u8_to_image": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "emo_image_to_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "emo_resize_bicubic": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "emo_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "emo_l2_flush": (c_int, [c_void_p, c_ll, c_void_p]),
 }
 

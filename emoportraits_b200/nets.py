@@ -370,17 +370,42 @@ class WarpGenerator:
         self.head = ConvW(sd, p + ".head.0.0", dev, planes=planes)
         idg = sd[p + ".identity_grid"].detach().float()  # (1,3,D,S,S) -> (D,S,S,3)
         self.idg = idg[0].permute(1, 2, 3, 0).contiguous().to(dev)
+        self._prepare_ada()
 
-    def _ada(self, E, j, norm: Norm):
-        """ProjectorNorm utils.py:1140-1151 + assign_adaptive_norm_params :994-995 for one AdaptiveGroupNorm:
-        (gamma + (u.E.v)[:,0], beta + (u.E.v)[:,1]) as a (2, C) tensor."""
-        u, vT = self.pu[j], self.pvT[j]
-        Cc = u.shape[0]
-        T = torch.empty((Cc, 16), dtype=torch.float32, device=E.device)
-        ops.linear(E, u, x_strides=(1, 16), M=16, K=u.shape[1], out=T, out_strides=(1, 16))  # T[c][s] = sum_k u[c][k] E[k][s]
-        out = torch.empty((2, Cc), dtype=torch.float32, device=E.device)
-        ops.linear(T, vT, add=norm.gb, x_strides=(16, 1), M=Cc, K=16, out=out, out_strides=(1, Cc))
-        return out[0:1], out[1:2]
+    def _prepare_ada(self):
+        """ProjectorNorm (utils.py:1140-1151) for ALL AdaptiveGroupNorm layers in two launches instead of two per layer:
+        (u_j . E . v_j) = u_j . (E . v_j), so  EV = E . [v_0 | v_1 | ...]  (512 x 2L, one small GEMM) and then
+        OUT = [u_0; u_1; ...] . EV + [gamma_j, beta_j in layer j's two columns]  (sum C_j x 2L, one GEMM: every layer reads only
+        its own column pair; the other columns are wasted flops of a 8 MFLOP product).  OUT is written transposed, so that
+        (gamma + dgamma, beta + dbeta) of layer j are two contiguous rows slices."""
+        norms = []
+        for blk in self.blocks:
+            norms += [blk.n1, blk.n2]
+        L = len(self.pu)
+        assert L == len(norms)
+        dev = self.pu[0].device
+        self.ada_rows = [0]
+        for u in self.pu:
+            self.ada_rows.append(self.ada_rows[-1] + u.shape[0])
+        Ctot = self.ada_rows[-1]
+        self.ada_U = torch.cat(self.pu, 0).contiguous()                                            # (Ctot, 512)
+        self.ada_V = torch.cat(self.pvT, 0).contiguous()                                           # (2L, 16): row 2j+i = v_j[:, i]
+        add = torch.zeros((2 * L, Ctot), dtype=torch.float32, device=dev)
+        for j, nrm in enumerate(norms):
+            add[2 * j, self.ada_rows[j]:self.ada_rows[j + 1]] = nrm.gamma
+            add[2 * j + 1, self.ada_rows[j]:self.ada_rows[j + 1]] = nrm.beta
+        self.ada_add = add.contiguous()
+        self.ada_L = L
+
+    def _ada_all(self, E):
+        """E (512,16) -> list over layers of (ada_w (1,C_j), ada_b (1,C_j))"""
+        L, Ctot, K = self.ada_L, self.ada_rows[-1], E.shape[0]
+        EVt = torch.empty((2 * L, K), dtype=torch.float32, device=E.device)                        # EVt[q][k] = sum_s E[k][s] V[q][s]
+        ops.linear(E, self.ada_V, x_strides=(16, 1), M=K, K=16, out=EVt, out_strides=(1, K))
+        out = torch.empty((2 * L, Ctot), dtype=torch.float32, device=E.device)                     # out[q][c] = sum_k U[c][k] EVt[q][k] + add[q][c]
+        ops.linear(self.ada_U, EVt, add=self.ada_add, x_strides=(K, 1), M=Ctot, K=K, out=out, out_strides=(1, Ctot))
+        return [(out[2 * j:2 * j + 1, self.ada_rows[j]:self.ada_rows[j + 1]], out[2 * j + 1:2 * j + 2, self.ada_rows[j]:self.ada_rows[j + 1]])
+                for j in range(L)]
 
     def __call__(self, E):
         """E (1,512,16) -> warp (1,D,S,S,3) fp32 channels-last == the (b,D,H,W,3) grid of the reference."""
@@ -397,6 +422,7 @@ class WarpGenerator:
         ndr = int(math.log2(cfg.S // isz))
         nblk = len(self.blocks)
         st = None
+        adas = self._ada_all(Em)
         for i in range(1, nblk + 1):
             size[1] *= 2
             size[2] *= 2
@@ -406,7 +432,7 @@ class WarpGenerator:
             st = ops.new_stats(1, G, dev)
             x = ops.upsample_trilinear(x, (2, 2, 2) if up_depth else (1, 2, 2), stats=st)
             blk = self.blocks[i - 1]
-            ada = (self._ada(Em, 2 * (i - 1), blk.n1), self._ada(Em, 2 * (i - 1) + 1, blk.n2))
+            ada = (adas[2 * (i - 1)], adas[2 * (i - 1) + 1])
             x, st = blk(x, st, ada=ada, want_stats=not down_depth)
             if down_depth:
                 st = ops.new_stats(1, G, dev)

@@ -614,5 +614,16 @@ def resize_bicubic(img_nchw: torch.Tensor, out_hw) -> torch.Tensor:
     return out
 
 
+def composite(img: torch.Tensor, mask: torch.Tensor, bg: torch.Tensor, threshold: float = 0.3) -> torch.Tensor:
+    """m' = where(mask > threshold, mask, 0) ** 8;  m' * img + (1 - m') * bg   (E_emo_infer_video.ipynb cell 41)
+    img (N,C,H,W), mask (N,1,H,W), bg (C,H,W) fp32 on device."""
+    _chk(img); _chk(mask); _chk(bg)
+    N, Cc, H, W = img.shape
+    assert mask.shape == (N, 1, H, W) and bg.shape == (Cc, H, W), (mask.shape, bg.shape)
+    out = torch.empty_like(img)
+    L.call("emo_composite", _p(img), _p(mask), _p(bg), N, Cc, H, W, C.c_float(threshold), _p(out), _stream())
+    return out
+
+
 def l2_flush(buf: torch.Tensor):
     L.call("emo_l2_flush", _p(buf), buf.numel() * buf.element_size(), _stream())

@@ -297,6 +297,10 @@ def test_wrapper_boundary_image_ops(ops):
     x[0, 0, 0, :4] = torch.tensor([1.0, 0.0, 0.999999, 254.5 / 255.0])
     want = (x.clamp(0, 1) * 255).byte().permute(0, 2, 3, 1)
     assert torch.equal(ops.image_to_u8(x.cuda()).cpu(), want)
+    img, mask, bg = torch.rand(2, 3, 20, 28, generator=g), torch.rand(2, 1, 20, 28, generator=g), torch.rand(3, 20, 28, generator=g)
+    m8 = torch.where(mask > 0.3, mask, mask * 0) ** 8          # E_emo_infer_video.ipynb cell 41
+    got = ops.composite(img.cuda(), mask.cuda(), bg.cuda()).cpu()
+    assert (got - (m8 * img + (1 - m8) * bg[None])).abs().max().item() < 1e-6
     for (hi, wi, ho, wo) in [(300, 280, 256, 256), (128, 160, 256, 512), (512, 512, 256, 256)]:
         y = torch.rand(1, 3, hi, wi, generator=g)
         ref = F.interpolate(y, size=(ho, wo), mode="bicubic")

@@ -58,7 +58,8 @@ def bench(Cin, Cout, sp, k, planes, residual, upconv, reps=10):
     ops.begin_pass(dev)
     st = ops.new_stats(1, 32, dev)
     bias = torch.zeros(Cout, device=dev)
-    run = lambda: ops.conv_igemm(a, pw, out=out, bias=bias, residual=res, res_shift=rs, stats=st, upconv=upconv)
+    chunk = int(os.environ.get("EMO_ACC_CHUNK", "0"))  # MMAs per TMEM accumulation chunk (0 = the library's default: 48 / 24)
+    run = lambda: ops.conv_igemm(a, pw, out=out, bias=bias, residual=res, res_shift=rs, stats=st, upconv=upconv, acc_chunk_mmas=chunk)
     for _ in range(2):
         run()
     torch.cuda.synchronize()
@@ -76,7 +77,7 @@ def bench(Cin, Cout, sp, k, planes, residual, upconv, reps=10):
 
 
 tot = 0.0
-tag = f"EPI={os.environ.get('EMO_CONV_EPI', 'default')} YREUSE={os.environ.get('EMO_CONV_YREUSE', 'default')}"
+tag = f"EPI={os.environ.get('EMO_CONV_EPI', 'default')} YREUSE={os.environ.get('EMO_CONV_YREUSE', 'default')} CHUNK={os.environ.get('EMO_ACC_CHUNK', 'default')}"
 for (label, Cin, Cout, sp, k, planes, residual, upconv, n) in LAYERS:
     us = bench(Cin, Cout, sp, k, planes, residual, upconv)
     fl = 2.0 * Cout * Cin * k ** len(sp) * math.prod(sp) * (4 if upconv else 1)
