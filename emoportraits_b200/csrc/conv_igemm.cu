@@ -642,10 +642,10 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     if (d->Cout_pad % cand == 0 && cand % bn_step_ok == 0) { BN = cand; break; }
   EMO_REQUIRE(BN > 0, "emo_conv_igemm: no N tile for Cout_pad=%d", d->Cout_pad);
   // prefer 128-wide tiles when that fills the machine better (more tiles than SMs matters more than tile width)
-  int sm_count = 148;
+  int sm_count = 148, cur_dev = 0;
   {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaGetDevice(&cur_dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cur_dev);
   }
 
   ConvKParams p;
@@ -882,7 +882,8 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
 #define EMO_LAUNCH_CONV(KC_, NP_, CG_, EPI_) EMO_LAUNCH_CONV5(conv_igemm_kernel, KC_, NP_, CG_, EPI_)
 #define EMO_LAUNCH_CONV5(KERNEL_, KC_, NP_, CG_, EPI_)                                                                                        \
   do {                                                                                                                    \
-    static bool attr_set = false; /* the opt-in is per function, set once (227 KB covers every configuration) */           \
+    static bool attr_set_dev[64] = {false}; /* the opt-in is per function AND per device (227 KB covers every configuration) */ \
+    bool& attr_set = attr_set_dev[cur_dev & 63];                                                                          \
     if (!attr_set) {                                                                                                      \
       e = cudaFuncSetAttribute(KERNEL_<KC_, NP_, CG_, EPI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      \
       if (e != cudaSuccess) { set_error("emo_conv_igemm: smem attribute: %s", cudaGetErrorString(e)); return EMO_ERR_CUDA; } \

@@ -568,12 +568,17 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     EMO_REQUIRE((long long)d->Din * d->Hin * d->Win * (d->C / 4) < (1ll << 31), "emo_grid_sample3d: volume too large for 32-bit offsets");
     // SMs x resident CTAs of the two instantiations (brick and balanced kernels have the same footprint: 40 registers,
     // 18 KB of shared memory -> 6 CTAs of 256 threads per SM)
-    static int slots[2] = {0, 0};
+    static int slots_dev[64][2] = {{0, 0}};  // per device ordinal: a process may drive several GPUs
     const int k = d->out_hi ? 1 : 0;
+    int dev = 0;
+    {
+      cudaError_t e0 = cudaGetDevice(&dev);
+      EMO_REQUIRE(e0 == cudaSuccess, "emo_grid_sample3d: cudaGetDevice failed (%s)", cudaGetErrorString(e0));
+    }
+    int* slots = slots_dev[dev & 63];
     if (!slots[k]) {
-      int dev = 0, sms = 0, occ = 0;
-      cudaError_t e = cudaGetDevice(&dev);
-      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int sms = 0, occ = 0;
+      cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (e == cudaSuccess)
         e = k ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<true>, 256, 0)
               : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<false>, 256, 0);
