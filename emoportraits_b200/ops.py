@@ -43,6 +43,13 @@ F16_ACT_SCALE = 16.0    # activations: post-GroupNorm / ReLU values are O(1)
 F16_W_SCALE = 256.0     # spectral-norm / weight-standardised weights are O(0.01 .. 1)
 
 
+# MMAs per TMEM accumulation chunk (the tensor core accumulates with truncation: DESIGN.md section 2).  bf16 two-plane operands
+# (decoder, stage 2): 96 - measured round 2 with tools/conv_layer_bench.py: the frame's conv shapes take 2.29 ms at 48, 2.20 ms
+# at 96, 2.17 ms at 192, 2.16 ms unchunked; parity of the decoder stage is unchanged at 96 (tests/test_stage_parity_gpu.py).
+# fp16 two-plane / bf16 three-plane operands keep 24 (fp32-faithful networks).
+ACC_CHUNK_BF16 = 96
+
+
 def _nplanes(planes) -> int:
     return 2 if planes == H2 else int(planes)
 
@@ -132,7 +139,7 @@ def pack_conv_weight(w: torch.Tensor, device=None, in_perm: Optional[torch.Tenso
         return PackedConvWeight(pl[0].contiguous().to(dev), pl[1].contiguous().to(dev), co, co_pad, ci, (kd, kh, kw), None, 24,
                                 True, F16_W_SCALE)
     return PackedConvWeight(pl[0].contiguous().to(dev), pl[1].contiguous().to(dev), co, co_pad, ci, (kd, kh, kw),
-                            pl[2].contiguous().to(dev) if planes == 3 else None)
+                            pl[2].contiguous().to(dev) if planes == 3 else None, ACC_CHUNK_BF16 if planes == 2 else 0)
 
 
 def fold_upconv_weight(w: torch.Tensor) -> torch.Tensor:
@@ -178,7 +185,7 @@ def pack_upconv_weight(w: torch.Tensor, device=None, planes: int = 2) -> PackedC
     wp = fold_upconv_weight(w).reshape(16, co, ci).contiguous()
     hi, lo = split_host(wp, 2)
     dev = device or "cuda"
-    return PackedConvWeight(hi.contiguous().to(dev), lo.contiguous().to(dev), co, co, ci, (1, 3, 3))
+    return PackedConvWeight(hi.contiguous().to(dev), lo.contiguous().to(dev), co, co, ci, (1, 3, 3), None, ACC_CHUNK_BF16)
 
 
 # ------------------------------------------------------------------------------------------------

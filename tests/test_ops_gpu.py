@@ -264,6 +264,29 @@ def test_conv_post_op(ops, N, Cin, Cout, sp, mode, planes):
         assert torch.equal(out, out2) and torch.equal(planes_out.hi, planes2.hi) and torch.equal(planes_out.lo, planes2.lo)
 
 
+def test_conv_statistics_are_reproducible(ops):
+    """GroupNorm statistics of a multi-tile layer: per-tile column sums go through per-quadrant slots (one writer each, fixed
+    summation order), the per-tile group sums are added to the global fp64 sums with atomics - fp64 sums of fp32-sized terms,
+    whose order can only move the last bits of a double: two runs agree to 1e-13 relative (the shared-memory fp32 atomics of
+    round 1 left 1e-7)."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 1, 128, 128, 128, generator=g).cuda()
+    w = torch.randn(128, 128, 3, 3, generator=g) / math.sqrt(9 * 128)
+    a, pw = ops.split_bf16(x, 2), ops.pack_conv_weight(w)
+    res = torch.randn(1, 1, 128, 128, 128, generator=g).cuda()
+    outs = []
+    for _ in range(3):
+        ops.begin_pass("cuda")
+        st = ops.new_stats(1, 32, "cuda")
+        y = ops.conv_igemm(a, pw, residual=res, stats=st)
+        torch.cuda.synchronize()
+        outs.append((y.clone(), st.clone()))
+    for y, st in outs[1:]:
+        assert torch.equal(y, outs[0][0])
+        rel = ((st - outs[0][1]).abs() / outs[0][1].abs().clamp_min(1e-30)).max().item()
+        assert rel < 1e-13, rel
+
+
 def test_conv2d_igemm_batch_and_act(ops):
     _conv_case(ops, 2, 128, 3, (32, 32), 1, act=2, out_nchw=True)
     _conv_case(ops, 2, 64, 64, (16, 16), 3, act=3)

@@ -72,13 +72,16 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def rep(name):
-    f = GO / f"{name}_{tag}.ncu-rep"
-    if not f.exists():
+    f, fcsv = GO / f"{name}_{tag}.ncu-rep", GO / f"{name}_{tag}.raw.csv"
+    if fcsv.exists():       # exported on the GPU box (tools/profile.sh): the report itself is too large to travel
+        text = fcsv.read_text()
+    elif f.exists():
+        text = subprocess.run(["ncu", "-i", str(f), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    r = subprocess.run(["ncu", "-i", str(f), "--page", "raw", "--csv"], capture_output=True, text=True)
-    rows = list(csv.reader(io.StringIO(r.stdout)))
+    rows = list(csv.reader(io.StringIO(text)))
     if len(rows) < 3:
-        print("could not read", f, r.stderr[:300]); return
+        print("could not read", f); return
     hdr, units = rows[0], rows[1]
     out = [f"# ncu --set full --clock-control none: {name}_{tag}.ncu-rep", ""]
     idx = {h: i for i, h in enumerate(hdr)}
