@@ -476,19 +476,41 @@ __global__ void __launch_bounds__(kPostThreads, 1) splitk_post_kernel(const Post
   const int c = tid % f.C;  // this thread's channel (512 % C == 0 and 4096 % C == 0)
   float v[kPostMaxV];
   float ts = 0.f, tq = 0.f;
+  const long long e0 = (long long)rank * kPostThreads + tid;               // this thread's elements: e0 + k * 4096
+  const long long base = (long long)n * per_n;
+#pragma unroll
+  for (int k = 0; k < kPostMaxV; ++k) v[k] = 0.f;
+  // K parts summed in part order; four parts x all of the thread's elements are loaded before they are added, so up to 64
+  // independent L2 loads are in flight per thread instead of one (ncu, round 2: 26 us per launch with the serial loop)
+  for (int part = 0; part < f.ksplit; part += 4) {
+    float t[4][kPostMaxV];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* w = f.ws + (long long)(part + q) * f.part_elems + base;
+#pragma unroll
+      for (int k = 0; k < kPostMaxV; ++k) {
+        const long long e = e0 + (long long)k * (kPostCluster * kPostThreads);
+        t[q][k] = (part + q < f.ksplit && e < per_n) ? __ldcg(w + e) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < kPostMaxV; ++k) v[k] += t[q][k];
+  }
 #pragma unroll
   for (int k = 0; k < kPostMaxV; ++k) {
-    const long long e = (long long)rank * kPostThreads + tid + (long long)k * (kPostCluster * kPostThreads);
-    v[k] = 0.f;
+    const long long e = e0 + (long long)k * (kPostCluster * kPostThreads);
     if (e < per_n) {
-      const long long i = (long long)n * per_n + e;
-      float x = 0.f;
-      for (int part = 0; part < f.ksplit; ++part) x += f.ws[(long long)part * f.part_elems + i];
+      const long long i = base + e;
+      float x = v[k];
       if (f.bias) x += __ldg(f.bias + c);
       if (f.residual) x += __ldg(f.residual + i);
       x = act_apply(x, f.conv_act);
       v[k] = x;
       ts += x; tq = fmaf(x, x, tq);
+    } else {
+      v[k] = 0.f;
     }
   }
   float A = 1.f, B = 0.f;

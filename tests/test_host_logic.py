@@ -133,7 +133,7 @@ assert img.shape == (1, 3, 256, 256)
 # load-time weight planes: fp16 of w * 256, reproducing w to ~2^-22
 w = torch.randn(32, 64, 3, 3) * 0.05
 pw = ops.pack_conv_weight(w, device="cpu", planes=ops.H2)
-assert pw.f16 and pw.hi.dtype == torch.float16 and pw.scale == ops.F16_W_SCALE and pw.acc_chunk == 24
+assert pw.f16 and pw.hi.dtype == torch.float16 and pw.scale == ops.F16_W_SCALE and pw.acc_chunk == ops.ACC_CHUNK_F16
 rec = (pw.hi.float() + pw.lo.float()) / pw.scale                       # [taps][Cout_pad][Cin]
 ref = w.permute(2, 3, 0, 1).reshape(9, 32, 64)
 assert (rec - ref).abs().max().item() < 2 ** -21 * ref.abs().max().item()
