@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f)
     const int c = (int)(t % f.C);
     const long long sp = t / f.C;
     float v = 0.f;
-    for (int k = 0; k < f.ksplit; ++k) v += f.ws[(long long)k * f.part_elems + i];
+#pragma unroll 8
+    for (int k = 0; k < f.ksplit; ++k) v += __ldcg(f.ws + (long long)k * f.part_elems + i);  // part order: reproducible
     if (f.bias) v += __ldg(f.bias + c);
     if (f.residual) v += __ldg(f.residual + i);
     v = act_apply(v, f.act);

@@ -46,10 +46,11 @@ F16_W_SCALE = 256.0     # spectral-norm / weight-standardised weights are O(0.01
 # MMAs per TMEM accumulation chunk (the tensor core accumulates with truncation: DESIGN.md section 2).  bf16 two-plane operands
 # (decoder, stage 2): 96 - measured round 2 with tools/conv_layer_bench.py: the frame's conv shapes take 2.29 ms at 48, 2.20 ms
 # at 96, 2.17 ms at 192, 2.16 ms unchunked; parity of the decoder stage is unchanged at 96 (tests/test_stage_parity_gpu.py).
-# fp16 two-plane operands (the fp32-faithful networks): 48 (warp-generator 3-D layers 8-12 % faster than at 24; stage parity
-# unchanged, measured in the same call); bf16 three-plane operands keep the kernel default 24.
+# fp16 two-plane operands (the fp32-faithful networks) stay at 24: at 48 the frame is 1.5 % faster (285.7 -> 290.1 frames/s) but the
+# truncation bias shows - stage errors of the embedders / warp generator grow 1.5-2x (expression embedding 5e-6 -> 1.2e-5) and one
+# end-to-end tap leaves its bound; bf16 three-plane operands keep the kernel default 24 as well.
 ACC_CHUNK_BF16 = 96
-ACC_CHUNK_F16 = 48
+ACC_CHUNK_F16 = 24
 
 
 def _nplanes(planes) -> int:

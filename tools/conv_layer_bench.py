@@ -37,6 +37,11 @@ LAYERS = [
     ("warp 32^3 64->64+res", 64, 64, (32, 32, 32), 3, "h2", 1, False, 1),
     ("warp 32x64x64 64->32", 64, 32, (32, 64, 64), 3, "h2", 0, False, 1),
     ("warp 32x64x64 32->32+res", 32, 32, (32, 64, 64), 3, "h2", 1, False, 1),
+    # ResNet-18 tails (two networks per frame): split-K convolution + fused finalize / GroupNorm / ReLU / plane split (residual = 3)
+    ("resnet 32^2 64->64 conv+post", 64, 64, (32, 32), 3, "h2", 3, False, 8),
+    ("resnet 16^2 128->128 conv+post", 128, 128, (16, 16), 3, "h2", 3, False, 6),
+    ("resnet 8^2 256->256 conv+post", 256, 256, (8, 8), 3, "h2", 3, False, 6),
+    ("resnet 4^2 512->512 conv+post", 512, 512, (4, 4), 3, "h2", 3, False, 6),
 ]
 
 
@@ -51,7 +56,10 @@ def bench(Cin, Cout, sp, k, planes, residual, upconv, reps=10):
     pw = ops.pack_upconv_weight(w) if upconv else ops.pack_conv_weight(w, planes=planes)
     out = torch.empty(oshape, device=dev)
     res, rs = None, 0
-    if residual == 1:
+    post = None
+    if residual == 3:
+        post = True
+    elif residual == 1:
         res = torch.randn(oshape, generator=g).to(dev)
     elif residual == 2:
         res, rs = torch.randn((1, 1, osp[0] // 2, osp[1] // 2, Cout), generator=g).to(dev), 1
@@ -59,7 +67,11 @@ def bench(Cin, Cout, sp, k, planes, residual, upconv, reps=10):
     st = ops.new_stats(1, 32, dev)
     bias = torch.zeros(Cout, device=dev)
     chunk = int(os.environ.get("EMO_ACC_CHUNK", "0"))  # MMAs per TMEM accumulation chunk (0 = the library's default: 48 / 24)
-    run = lambda: ops.conv_igemm(a, pw, out=out, bias=bias, residual=res, res_shift=rs, stats=st, upconv=upconv, acc_chunk_mmas=chunk)
+    if post:
+        gn = dict(stats=st, count=math.prod(osp) * Cout / 32, gamma=torch.ones(Cout, device=dev), beta=torch.zeros(Cout, device=dev))
+        run = lambda: ops.conv_igemm(a, pw, bias=bias, stats=st, acc_chunk_mmas=chunk, post=dict(gn=gn, act=ops.ACT_RELU, planes=planes))
+    else:
+        run = lambda: ops.conv_igemm(a, pw, out=out, bias=bias, residual=res, res_shift=rs, stats=st, upconv=upconv, acc_chunk_mmas=chunk)
     for _ in range(2):
         run()
     torch.cuda.synchronize()
