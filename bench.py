@@ -533,7 +533,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16x2-split operands (3 tcgen05 MMAs per product), fp32 accumulate / fp32 elsewhere",
+        "dtype": "two 16-bit operand planes per fp32 operand, 3 tcgen05 MMAs per product (bf16 x2 in the decoder, fp16 x2 elsewhere), fp32 accumulate / fp32 elsewhere",
         "data": "synthetic",
         "config": {"workload": f"driver frame @{SIZE}^2, shipped model C96 D16 S64, batch 1 (BASELINE configs[1]); "
                                "BASELINE's '64^3' volume is the grid_sample microbench shape, reported in roofline_grid_sample3d",
@@ -558,7 +558,7 @@ def run_ours(args):
                      "launch_us_detail": top_graph, "launch_us_eager_incl_host": top_ms_per_launch * 1000.0,
                      "tensor_pipe_frac_est_graph": 3.0 * top_alg_tf_graph / peaks["bf16_tflops_sustained"],
                      "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                     "mma_passes": "3 bf16 MMAs per algorithmic product (two-plane split operands)",
+                     "mma_passes": "3 MMAs per algorithmic product (two-plane split operands)",
                      "tensor_pipe_frac_est": top_mma_tf / peaks["bf16_tflops_sustained"],
                      "all_convs": {"achieved": conv_tflops, "frac": conv_tflops / peaks["bf16_tflops_sustained"],
                                    "tensor_pipe_frac_est": (prof.mma_flops / conv_ms / 1e9) / peaks["bf16_tflops_sustained"],
