@@ -724,16 +724,21 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   {
     // pair mode (cta_group::2, M = 256): an SS-mode 128 x 128 x 16 MMA of a single CTA reads 8 KB of operands from shared
     // memory and takes 82 clk against the 64 clk tensor floor (tools/mma_probe.cu: ~100 B/clk of operand bandwidth); in a pair
-    // each CTA supplies half of the weight tile (6 KB per MMA) and the floor is reached.  EMO_CONV_CG2=0 turns it off.
-    static int cg_env = -1;
-    if (cg_env < 0) { const char* e = getenv("EMO_CONV_CG2"); cg_env = e ? atoi(e) : 1; }
+    // each CTA supplies half of the weight tile (6 KB per MMA) and the floor is reached.
+    int cg_env = 1;
+#ifdef EMO_CONV_DEBUG
+    { const char* e = getenv("EMO_CONV_CG2"); if (e) cg_env = atoi(e); }  // instrumented build: single-CTA MMAs for the probes
+#endif
     p.cg = (cg_env == 1 && ksplit == 1 && (p.m_tiles % 2) == 0 && BN % 32 == 0) ? 2 : 1;
   }
   {
-    // cluster size (single-CTA MMAs only): weight-tile multicast across consecutive pixel tiles.  Experiment switch:
-    // measured no gain at 2 and a loss at 4 (multicast does not lower the per-SM fill; pair mode above does)
-    static int forced = -1;
-    if (forced < 0) { const char* e = getenv("EMO_CONV_CLUSTER"); forced = e ? atoi(e) : 0; }
+    // cluster size (single-CTA MMAs only): weight-tile multicast across consecutive pixel tiles.  Measured round 1: no gain at 2
+    // and a loss at 4 (multicast does not lower the per-SM fill; pair mode above does): off in the product, reachable in the
+    // instrumented build only
+    int forced = 0;
+#ifdef EMO_CONV_DEBUG
+    { const char* e = getenv("EMO_CONV_CLUSTER"); if (e) forced = atoi(e); }
+#endif
     int cs = (forced > 0 && ksplit == 1 && p.cg == 1) ? forced : 1;
     while (cs > 1 && (p.m_tiles % cs != 0 || (BN / cs) % 8 != 0 || BN % cs != 0 ||
                       (long long)p.m_tiles * p.n_tiles < 2ll * cs)) cs >>= 1;

@@ -594,10 +594,12 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     // when the brick kernel needs more CTAs than fit at once but at most twice as many, its second wave is a nearly
     // empty tail of lone latency-bound CTAs and the balanced kernel wins (64^3 x 96ch: 69.8 -> 61.4 us, 16x64x64: 24.5 ->
     // 22.5 us); with many waves the tail is negligible and the brick kernel is faster (batch 8 of 64^3: 373 vs 433 us).
-    // EMO_GS3_BALANCED=0 / 1 forces the brick / balanced kernel, > 1 also sets the balanced kernel's CTA count (read per
-    // call so that one process can compare them).
-    const char* bal = getenv("EMO_GS3_BALANCED");
-    const int force = bal ? atoi(bal) : -1;
+    // Instrumented build (tools/gs3_check): EMO_GS3_BALANCED=0 / 1 forces the brick / balanced kernel, > 1 also sets the
+    // balanced kernel's CTA count (read per call so that one process can compare them).
+    int force = -1;
+#ifdef EMO_CONV_DEBUG
+    { const char* bal = getenv("EMO_GS3_BALANCED"); if (bal) force = atoi(bal); }
+#endif
     const bool balanced = force > 0 || (force < 0 && blocks > slots[k] && blocks <= 2ll * slots[k]);
     if (balanced) {
       p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);

@@ -2,7 +2,8 @@
 // the brick kernel (default) against the balanced persistent variant (EMO_GS3_BALANCED), bit for bit, plus timings.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/gs3_check tools/gs3_check.cu -ldl
-//   tools/gs3_check [path/to/libemoport.so]        (default: emoportraits_b200/csrc/libemoport.so)
+//   tools/gs3_check [path/to/libemoport_dbg.so]    (default: emoportraits_b200/csrc/libemoport_dbg.so, the instrumented build:
+//                                                   `python -m emoportraits_b200.csrc.build --debug`; the product library has no switches)
 //
 // For every case: run both kernels on the same seeded input, count differing output words on the device (must be 0:
 // the two kernels share the per-voxel and per-item arithmetic), then time each over REPS launches with an L2 flush
@@ -73,7 +74,7 @@ struct Case {
 };
 
 int main(int argc, char** argv) {
-  const char* libpath = argc > 1 ? argv[1] : "emoportraits_b200/csrc/libemoport.so";
+  const char* libpath = argc > 1 ? argv[1] : "emoportraits_b200/csrc/libemoport_dbg.so";  // the instrumented build honours EMO_GS3_BALANCED
   void* h = dlopen(libpath, RTLD_NOW);
   if (!h) { fprintf(stderr, "dlopen(%s): %s\n", libpath, dlerror()); return 2; }
   gs3_fn gs3 = (gs3_fn)dlsym(h, "emo_grid_sample3d");
