@@ -47,7 +47,7 @@ if rows:
     out = [f"# Convolution shapes of one driver frame, device time per launch ({tag})", "",
            "`tools/conv_layer_bench.py`: CUDA-graph replays of 10 back-to-back launches (no host launch cost, no tensor-map encoding in the",
            "number).  `auto` = the product library's per-layer choice; `epi0` / `epi1` = instrumented build forced to the in-warp final phase /",
-           "the TMA epilogue; `chunkN` = N MMAs per TMEM accumulation chunk (default 48 bf16 / 24 fp16).  TFLOP/s = algorithmic (one product = one",
+           "the TMA epilogue; `chunkN` = N MMAs per TMEM accumulation chunk for every layer (product default: 96 bf16 planes / 24 fp16 planes).  TFLOP/s = algorithmic (one product = one",
            "flop pair; three MMAs are issued per product).", "",
            "| layer | x per frame | " + " | ".join(f"{n} us" for n in names) + " | auto TFLOP/s |", "|---|---:|" + "---:|" * (len(names) + 1)]
     tot = {n: 0.0 for n in names}
