@@ -59,6 +59,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -101,88 +106,6 @@ __device__ __forceinline__ Corner8 corners(const GS3Params& p, float gx, float g
 // Every corner fetch is a 16-byte load inside a contiguous C*4-byte run.
 // ------------------------------------------------------------------------------------------------
 static constexpr int kBrickVox = 256;
-
-// The two device functions below restate the brick kernel's two phases for the balanced variant further down (the
-// brick kernel keeps its own inline copy: routing it through these functions changed its register allocation, 40 -> 44,
-// i.e. 6 -> 5 resident CTAs per SM).
-// phase 1 for one output voxel: sample position -> eight clamped corner offsets (in float4 units) and trilinear
-// weights (0 for corners outside the volume: zeros padding) -> shared memory slot `vox`
-__device__ __forceinline__ void gs3_setup_voxel(const GS3Params& p, int n, int od, int oh, int ow, int vox,
-                                                int (*s_off)[8], float (*s_wgt)[8], long long* s_out) {
-  const int c4n = p.C >> 2;
-  long long o = -1;
-  if (ow < p.Wout && oh < p.Hout && od < p.Dout) {
-    float gx, gy, gz;
-    sample_coord(p, n, od, oh, ow, gx, gy, gz);
-    const Corner8 k = corners(p, gx, gy, gz);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
-      const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
-      const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
-      const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
-      s_wgt[vox][j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
-      s_off[vox][j] = ((zc * p.Hin + yc) * p.Win + xc) * c4n;
-    }
-    o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
-  }
-  s_out[vox] = o;
-}
-
-// phase 2: the CTA's threads sweep (voxel, float4-of-channels) items of `nvox` voxels set up in shared memory
-template <bool SPLIT>
-__device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int nvox, const int (*s_off)[8],
-                                                 const float (*s_wgt)[8], const long long* s_out) {
-  const int c4n = p.C >> 2;
-  const int work = nvox * c4n;
-  const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
-  const uint64_t pol_in = l2_policy_evict_last(), pol_out = l2_policy_evict_first();
-  for (int t = threadIdx.x; t < work; t += blockDim.x) {
-    const int vox = t / c4n, c4 = t - vox * c4n;
-    const long long ob = s_out[vox];
-    if (ob < 0) continue;
-    const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
-    const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
-    const float4* base = in4 + c4;
-    const float4 v0 = ldg_hint(base + o0.x, pol_in), v1 = ldg_hint(base + o0.y, pol_in), v2 = ldg_hint(base + o0.z, pol_in), v3 = ldg_hint(base + o0.w, pol_in);
-    const float4 v4 = ldg_hint(base + o1.x, pol_in), v5 = ldg_hint(base + o1.y, pol_in), v6 = ldg_hint(base + o1.z, pol_in), v7 = ldg_hint(base + o1.w, pol_in);
-    float4 acc;
-#define EMO_GS_ACC(f) \
-  acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
-          fmaf(v3.f, w0.w, fmaf(v2.f, w0.z, fmaf(v1.f, w0.y, v0.f * w0.x)))))));
-    EMO_GS_ACC(x) EMO_GS_ACC(y) EMO_GS_ACC(z) EMO_GS_ACC(w)
-#undef EMO_GS_ACC
-    const long long o = ob + (long long)(c4 * 4) * p.os_c;
-    if (p.os_c == 1) {
-      if (p.out) stg_hint((float4*)(p.out + o), acc, pol_out);  // the output is not re-read by this kernel
-      if (SPLIT) {
-        uint2 hi, lo, lo2;
-        if (p.out_lo2) {
-          split4x3(acc, hi, lo, lo2);
-          *(uint2*)(p.out_lo2 + o) = lo2;
-        } else {
-          split4(acc, hi, lo);
-        }
-        *(uint2*)(p.out_hi + o) = hi;
-        *(uint2*)(p.out_lo + o) = lo;
-      }
-    } else {
-      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (p.out) p.out[o + j * p.os_c] = a[j];
-        if (SPLIT) {
-          __nv_bfloat16 h, l, l2;
-          split_bf16x3(a[j], h, l, l2);
-          if (!p.out_lo2) split_bf16(a[j], h, l);
-          p.out_hi[o + j * p.os_c] = h;
-          p.out_lo[o + j * p.os_c] = l;
-          if (p.out_lo2) p.out_lo2[o + j * p.os_c] = l2;
-        }
-      }
-    }
-  }
-}
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
@@ -268,43 +191,6 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
         }
       }
     }
-  }
-}
-
-// Balanced variant (chosen by emo_grid_sample3d when the brick kernel would run a partial second wave, see there; measured
-// in profiles/gs3_check_r1.txt).  The brick kernel above launches one CTA
-// per 256-voxel brick: 1024 CTAs for a 64^3 lattice against 148 SMs x 6 resident CTAs = 888 slots, so 136 bricks run
-// in a second, nearly empty wave whose lone CTA per SM is latency-bound (24 dependent gather rounds).  Here the grid
-// is exactly (SMs x resident CTAs) and every CTA takes an equal contiguous share of the brick-ordered voxel
-// enumeration, processed in chunks of <= 256 voxels; a chunk never straddles two samples.  Same per-voxel and per-item
-// arithmetic as the brick kernel (shared device functions), so the outputs are bit-identical.
-template <bool SPLIT>
-__global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const GS3Params p) {
-  __shared__ __align__(16) int s_off[kBrickVox][8];
-  __shared__ __align__(16) float s_wgt[kBrickVox][8];
-  __shared__ long long s_out[kBrickVox];
-  const int brick_vox = p.bw * p.bh * p.bd;
-  const int per_sample = p.bricks_w * p.bricks_h * p.bricks_d * brick_vox;  // padded lattice; N * per_sample < 2^31 (host)
-  const long long total = (long long)per_sample * p.N;
-  const int v_begin = (int)(total * blockIdx.x / gridDim.x), v_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
-  for (int base = v_begin; base < v_end;) {
-    const int n = base / per_sample;
-    const int stop = min(min(base + kBrickVox, v_end), (n + 1) * per_sample);
-    const int nvox = stop - base;
-    if ((int)threadIdx.x < nvox) {
-      const int v = base + (int)threadIdx.x - n * per_sample;
-      int b = v / brick_vox;
-      const int l = v - b * brick_vox;
-      const int bwi = b % p.bricks_w; b /= p.bricks_w;
-      const int bhi = b % p.bricks_h; b /= p.bricks_h;
-      const int bdi = b;
-      const int lw = l % p.bw, lh = (l / p.bw) % p.bh, ld = l / (p.bw * p.bh);
-      gs3_setup_voxel(p, n, bdi * p.bd + ld, bhi * p.bh + lh, bwi * p.bw + lw, threadIdx.x, s_off, s_wgt, s_out);
-    }
-    __syncthreads();
-    gs3_gather_items<SPLIT>(p, n, nvox, s_off, s_wgt, s_out);
-    __syncthreads();  // the next chunk overwrites the shared-memory slots
-    base = stop;
   }
 }
 
@@ -561,14 +447,10 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     if (d->os_c == 1)
       EMO_REQUIRE(d->os_n % 4 == 0 && d->os_d % 4 == 0 && d->os_h % 4 == 0 && d->os_w % 4 == 0,
                   "emo_grid_sample3d: vectorised output needs strides that are multiples of 4");
-    // brick: 8 x 8 x 4 voxels (w,h,d) = 256 voxels per CTA (one setup thread per voxel)
-    p.bw = d->Wout >= 8 ? 8 : d->Wout;
-    p.bh = d->Hout >= 8 ? 8 : d->Hout;
-    p.bd = d->Dout >= 4 ? 4 : d->Dout;
     EMO_REQUIRE((long long)d->Din * d->Hin * d->Win * (d->C / 4) < (1ll << 31), "emo_grid_sample3d: volume too large for 32-bit offsets");
-    // SMs x resident CTAs of the two instantiations (brick and balanced kernels have the same footprint: 40 registers,
-    // 18 KB of shared memory -> 6 CTAs of 256 threads per SM)
-    static int slots_dev[64][2] = {{0, 0}};  // per device ordinal: a process may drive several GPUs
+    // SMs x resident CTAs (40 registers, 18 KB of shared memory -> 6 CTAs of 256 threads per SM), per device ordinal
+    static int slots_dev[64][2] = {{0, 0}};
+    static int sms_dev[64] = {0};
     const int k = d->out_hi ? 1 : 0;
     int dev = 0;
     {
@@ -580,42 +462,43 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
       int sms = 0, occ = 0;
       cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (e == cudaSuccess)
-        e = k ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<true>, 256, 0)
-              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_balanced_kernel<false>, 256, 0);
+        e = k ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_kernel<true>, 256, 0)
+              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_kernel<false>, 256, 0);
       EMO_REQUIRE(e == cudaSuccess && sms > 0 && occ > 0, "emo_grid_sample3d: occupancy query failed (%s)", cudaGetErrorString(e));
       slots[k] = sms * occ;
+      sms_dev[dev & 63] = sms;
     }
-    // brick decomposition of the brick kernel: small lattices shrink the brick until there are >= 4 CTAs per SM
-    int bh_brick = p.bh;
-    while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, bh_brick) * cdiv(d->Dout, p.bd) < 4 * 148 && bh_brick > 2) bh_brick >>= 1;
-    const long long blocks = (long long)d->N * cdiv(d->Dout, p.bd) * cdiv(d->Hout, bh_brick) * cdiv(d->Wout, p.bw);
-    EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");
-    // Kernel choice (measured with tools/gs3_check on a B200, profiles/gs3_check_r1.txt; outputs are bit-identical):
-    // when the brick kernel needs more CTAs than fit at once but at most twice as many, its second wave is a nearly
-    // empty tail of lone latency-bound CTAs and the balanced kernel wins (64^3 x 96ch: 69.8 -> 61.4 us, 16x64x64: 24.5 ->
-    // 22.5 us); with many waves the tail is negligible and the brick kernel is faster (batch 8 of 64^3: 373 vs 433 us).
-    // Instrumented build (tools/gs3_check): EMO_GS3_BALANCED=0 / 1 forces the brick / balanced kernel, > 1 also sets the
-    // balanced kernel's CTA count (read per call so that one process can compare them).
-    int force = -1;
+    // Brick shape = processing ORDER (measured with tools/gs3_lab, profiles/gs3_lab_r2b.txt; every shape gives bit-identical
+    // output).  CTAs are dispatched in blockIdx order (w fastest, then h, d, n), so the resident CTAs form a slab that sweeps
+    // through the lattice along d.  With the round-1 brick of 8 x 8 x 4 = 256 voxels a 64^3 lattice is 1024 CTAs against 888
+    // resident ones: the whole lattice is in flight at once, and a warp-field tensor whose samples scatter over +-10 slices
+    // re-reads the 100 MB volume 2.5 times from DRAM (ncu, profiles/prof_gs3_r2.txt) because the lines do not survive in L2
+    // between their ~8 uses.  Flat bricks keep the in-flight slab thin (8 x 8 x 1: 4096 CTAs, ~14 slices in flight):
+    // 64^3 warp-field 90.2 -> 65.5 us, batch 8 474 -> 403 us (8 x 8 x 2).  A persistent kernel walking the same order with
+    // a barrier per chunk was slower than letting the hardware dispatch small CTAs (96-131 us; tools/gs3_lab.cu keeps it).
+    //   depth 2 bricks (128 voxels) when that still gives >= 4 waves of CTAs, else depth 1 (64 voxels);
+    //   small lattices then halve the brick height until there are >= 4 CTAs per SM.
+    p.bw = d->Wout >= 8 ? 8 : d->Wout;
+    p.bh = d->Hout >= 8 ? 8 : d->Hout;
+    p.bd = d->Dout >= 2 ? 2 : d->Dout;
+    if ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4ll * slots[k]) p.bd = 1;
+    while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4ll * sms_dev[dev & 63] && p.bh > 2) p.bh >>= 1;
+    unsigned threads = 256;
 #ifdef EMO_CONV_DEBUG
-    { const char* bal = getenv("EMO_GS3_BALANCED"); if (bal) force = atoi(bal); }
-#endif
-    const bool balanced = force > 0 || (force < 0 && blocks > slots[k] && blocks <= 2ll * slots[k]);
-    if (balanced) {
-      p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
-      const long long total = (long long)d->N * p.bricks_w * p.bricks_h * p.bricks_d * (p.bw * p.bh * p.bd);
-      EMO_REQUIRE(total < (1ll << 31) - kBrickVox, "emo_grid_sample3d: lattice too large for the balanced kernel");
-      // at least 64 voxels per CTA
-      long long ctas = force > 1 ? force : slots[k];
-      if (ctas > cdivll(total, 64)) ctas = cdivll(total, 64);
-      if (d->out_hi) launch_kernel(gs3_cl_balanced_kernel<true>, (unsigned)ctas, 256, 0, stream, p);
-      else launch_kernel(gs3_cl_balanced_kernel<false>, (unsigned)ctas, 256, 0, stream, p);
-      return check_launch("emo_grid_sample3d");
+    {  // instrumented build (tools/gs3_check): EMO_GS3_BRICK="bw,bh,bd[,threads]" forces the brick shape, read per call
+      const char* bs = getenv("EMO_GS3_BRICK");
+      int fw = 0, fh = 0, fd = 0, ft = 0;
+      if (bs && sscanf(bs, "%d,%d,%d,%d", &fw, &fh, &fd, &ft) >= 3 && fw > 0 && fh > 0 && fd > 0 && fw * fh * fd <= kBrickVox) {
+        p.bw = fw < d->Wout ? fw : d->Wout; p.bh = fh < d->Hout ? fh : d->Hout; p.bd = fd < d->Dout ? fd : d->Dout;
+        if (ft >= p.bw * p.bh * p.bd && ft <= 256 && ft % 32 == 0) threads = (unsigned)ft;
+      }
     }
-    p.bh = bh_brick;
+#endif
     p.bricks_w = cdiv(d->Wout, p.bw); p.bricks_h = cdiv(d->Hout, p.bh); p.bricks_d = cdiv(d->Dout, p.bd);
-    if (d->out_hi) launch_kernel(gs3_cl_kernel<true>, (unsigned)blocks, 256, 0, stream, p);
-    else launch_kernel(gs3_cl_kernel<false>, (unsigned)blocks, 256, 0, stream, p);
+    const long long blocks = (long long)d->N * p.bricks_w * p.bricks_h * p.bricks_d;
+    EMO_REQUIRE(blocks < (1ll << 31), "emo_grid_sample3d: grid too large");
+    if (d->out_hi) launch_kernel(gs3_cl_kernel<true>, (unsigned)blocks, threads, 0, stream, p);
+    else launch_kernel(gs3_cl_kernel<false>, (unsigned)blocks, threads, 0, stream, p);
   } else {
     p.bw = p.bh = p.bd = p.bricks_w = p.bricks_h = p.bricks_d = 1;
     const long long total = (long long)d->N * d->Dout * d->Hout * d->Wout;

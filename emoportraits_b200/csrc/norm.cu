@@ -182,6 +182,16 @@ __global__ void flush_kernel(float4* buf, long long n4) {
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x)
     buf[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
+// read the flush buffer back: the dirty lines the write pass left in L2 are written out and replaced by CLEAN lines of the
+// same buffer, so that the kernel under test does not pay for write-backs of the flush itself
+__global__ void flush_read_kernel(const float4* buf, long long n4, float* sink) {
+  float acc = 0.f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldcg(buf + t);
+    acc += v.x + v.y + v.z + v.w;
+  }
+  if (acc == 123.456f) *sink = acc;  // never true (the buffer holds zeros): keeps the loads alive
+}
 
 }  // namespace emo
 
@@ -288,4 +298,12 @@ extern "C" int emo_l2_flush(void* buf, long long bytes, void* stream_) {
   EMO_REQUIRE(buf && bytes >= 16, "emo_l2_flush: bad buffer");
   launch_kernel(flush_kernel, 148 * 8, 256, 0, stream, (float4*)buf, bytes / 16);
   return check_launch("emo_l2_flush");
+}
+
+extern "C" int emo_l2_flush_clean(void* buf, long long bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  EMO_REQUIRE(buf && bytes >= 32, "emo_l2_flush_clean: bad buffer");
+  launch_kernel(flush_kernel, 148 * 8, 256, 0, stream, (float4*)buf, bytes / 16);
+  launch_kernel(flush_read_kernel, 148 * 8, 256, 0, stream, (const float4*)buf, bytes / 16, (float*)buf);
+  return check_launch("emo_l2_flush_clean");
 }

@@ -634,5 +634,7 @@ def composite(img: torch.Tensor, mask: torch.Tensor, bg: torch.Tensor, threshold
     return out
 
 
-def l2_flush(buf: torch.Tensor):
-    L.call("emo_l2_flush", _p(buf), buf.numel() * buf.element_size(), _stream())
+def l2_flush(buf: torch.Tensor, clean: bool = False):
+    """Benchmark helper: evict L2 by writing `buf` (>= 2x the L2 size).  clean=True also reads it back, so that L2 holds clean
+    foreign lines and the kernel under test does not pay for the write-back of the flush's own dirty lines."""
+    L.call("emo_l2_flush_clean" if clean else "emo_l2_flush", _p(buf), buf.numel() * buf.element_size(), _stream())

@@ -345,8 +345,11 @@ int emo_resize_bicubic(const float* in, int N, int C, int Hin, int Win, int Hout
  *   m' = (mask > threshold ? mask : 0)^8;  out = m' * img + (1 - m') * bg
  * img, out fp32 [N][C][H][W]; mask fp32 [N][1][H][W]; bg fp32 [C][H][W] (one background for the whole clip). */
 int emo_composite(const float* img, const float* mask, const float* bg, int N, int C, int H, int W, float threshold, float* out, void* stream);
-/* L2 flush helper for benchmarks: writes `bytes` of `buf`. */
+/* L2 flush helpers for benchmarks: emo_l2_flush writes `bytes` of `buf` (L2 is left full of DIRTY foreign lines: the next
+ * kernel also pays for their write-back); emo_l2_flush_clean writes and then reads the buffer back (L2 is left full of
+ * CLEAN foreign lines). */
 int emo_l2_flush(void* buf, long long bytes, void* stream);
+int emo_l2_flush_clean(void* buf, long long bytes, void* stream);
 
 #ifdef __cplusplus
 }

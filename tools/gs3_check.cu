@@ -1,12 +1,13 @@
-// Native (no Python) check of the two channels-last grid_sample_3d kernels behind the C-ABI:
-// the brick kernel (default) against the balanced persistent variant (EMO_GS3_BALANCED), bit for bit, plus timings.
+// Native (no Python) check of the channels-last grid_sample_3d kernel behind the C-ABI: the brick shape the library picks
+// ("auto") and forced shapes (EMO_GS3_BRICK="bw,bh,bd[,threads]", instrumented build) against the round-1 brick of
+// 8 x 8 x 4 voxels, bit for bit, plus timings.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/gs3_check tools/gs3_check.cu -ldl
 //   tools/gs3_check [path/to/libemoport_dbg.so]    (default: emoportraits_b200/csrc/libemoport_dbg.so, the instrumented build:
 //                                                   `python -m emoportraits_b200.csrc.build --debug`; the product library has no switches)
 //
-// For every case: run both kernels on the same seeded input, count differing output words on the device (must be 0:
-// the two kernels share the per-voxel and per-item arithmetic), then time each over REPS launches with an L2 flush
+// For every case: run every shape on the same seeded input, count differing output words on the device (must be 0:
+// the brick shape only changes which CTA computes a voxel), then time each over REPS launches with an L2 flush
 // (emo_l2_flush, 256 MB) before every launch and CUDA events around the launch only.  Prints one line per case and
 // variant: median microseconds and algorithmic GB/s ((2*C*D*H*W [+ 3*D*H*W for a grid tensor]) * 4 B * N).
 #include <cuda_runtime.h>
@@ -74,7 +75,7 @@ struct Case {
 };
 
 int main(int argc, char** argv) {
-  const char* libpath = argc > 1 ? argv[1] : "emoportraits_b200/csrc/libemoport_dbg.so";  // the instrumented build honours EMO_GS3_BALANCED
+  const char* libpath = argc > 1 ? argv[1] : "emoportraits_b200/csrc/libemoport_dbg.so";  // the instrumented build honours EMO_GS3_BRICK
   void* h = dlopen(libpath, RTLD_NOW);
   if (!h) { fprintf(stderr, "dlopen(%s): %s\n", libpath, dlerror()); return 2; }
   gs3_fn gs3 = (gs3_fn)dlsym(h, "emo_grid_sample3d");
@@ -153,10 +154,11 @@ int main(int argc, char** argv) {
       d.os_w = c.C; d.os_h = (long long)c.Wo * c.C; d.os_d = d.os_h * c.Ho; d.os_n = d.os_d * c.Do;
     }
     const double bytes = ((double)2 * c.C + (c.affine ? 0 : 3)) * 4.0 * (double)vox;
-    const char* variants[] = {"brick", "balanced", "balanced_5perSM", "balanced_8perSM"};
-    const char* envs[] = {"0", "1", "740", "1184"};
-    for (int v = 0; v < 4; ++v) {
-      setenv("EMO_GS3_BALANCED", envs[v], 1);
+    const char* variants[] = {"brick_8x8x4", "auto", "brick_8x8x2", "brick_8x8x1", "brick_8x8x1_128thr", "brick_4x4x4"};
+    const char* envs[] = {"8,8,4", nullptr, "8,8,2", "8,8,1", "8,8,1,128", "4,4,4"};
+    for (int v = 0; v < 6; ++v) {
+      if (envs[v]) setenv("EMO_GS3_BRICK", envs[v], 1);
+      else unsetenv("EMO_GS3_BRICK");
       const int slot = v == 0 ? 0 : 1;
       d.out = out[slot];
       d.out_hi = planes[slot][0]; d.out_lo = planes[slot][1];
@@ -186,7 +188,7 @@ int main(int argc, char** argv) {
         CK(cudaMemsetAsync(out[1], 0xff, out_n * 4, st));  // the next variant must write everything again
         if (c.split) for (int k = 0; k < 2; ++k) CK(cudaMemsetAsync(planes[1][k], 0xff, out_n * 2, st));
       }
-      printf("%-22s %-20s median %8.2f us  min %8.2f us  %8.1f GB/s algorithmic  diff_words_vs_brick %llu\n", c.name,
+      printf("%-22s %-20s median %8.2f us  min %8.2f us  %8.1f GB/s algorithmic  diff_words_vs_8x8x4 %llu\n", c.name,
              variants[v], med * 1e3, ms[0] * 1e3, bytes / (med * 1e-3) * 1e-9, diff);
       fflush(stdout);
     }
@@ -198,7 +200,7 @@ int main(int argc, char** argv) {
       for (int k = 0; k < 2; ++k) if (planes[v][k]) CK(cudaFree(planes[v][k]));
     }
   }
-  unsetenv("EMO_GS3_BALANCED");
-  printf(bad ? "FAIL: %d variant runs differ from the brick kernel\n" : "OK: all variants bit-identical to the brick kernel\n", bad);
+  unsetenv("EMO_GS3_BRICK");
+  printf(bad ? "FAIL: %d variant runs differ from the 8x8x4 brick\n" : "OK: all brick shapes bit-identical\n", bad);
   return bad ? 1 : 0;
 }

@@ -14,6 +14,209 @@
 
 #include "../emoportraits_b200/csrc/grid_sample.cu"
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernels that were product code until the processing-order study (sweep_main below) replaced them by the brick kernel with
+// flat bricks: the two phases of the brick kernel as device functions, the balanced persistent kernel (one contiguous share
+// of the brick-ordered enumeration per CTA) and the sweep kernel (persistent, the enumeration cut into waves).  Kept here so
+// that the study stays reproducible.
+// ---------------------------------------------------------------------------------------------------------------
+namespace emo {
+struct LabParams : GS3Params {
+  int rounds;                // sweep kernel: number of consecutive waves the enumeration is cut into
+  int hint_in;               // 1: volume loads carry L2::evict_last, 0: evict_normal
+  long long prefetch_bytes;  // > 0: the CTAs first prefetch this many bytes of `in` into L2 (bulk prefetch, one slice per CTA)
+};
+// The two device functions below restate the brick kernel's two phases for the balanced variant further down (the
+// brick kernel keeps its own inline copy: routing it through these functions changed its register allocation, 40 -> 44,
+// i.e. 6 -> 5 resident CTAs per SM).
+// phase 1 for one output voxel: sample position -> eight clamped corner offsets (in float4 units) and trilinear
+// weights (0 for corners outside the volume: zeros padding) -> shared memory slot `vox`
+__device__ __forceinline__ void gs3_setup_voxel(const GS3Params& p, int n, int od, int oh, int ow, int vox,
+                                                int (*s_off)[8], float (*s_wgt)[8], long long* s_out) {
+  const int c4n = p.C >> 2;
+  long long o = -1;
+  if (ow < p.Wout && oh < p.Hout && od < p.Dout) {
+    float gx, gy, gz;
+    sample_coord(p, n, od, oh, ow, gx, gy, gz);
+    const Corner8 k = corners(p, gx, gy, gz);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+      const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+      const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
+      const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
+      s_wgt[vox][j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+      s_off[vox][j] = ((zc * p.Hin + yc) * p.Win + xc) * c4n;
+    }
+    o = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
+  }
+  s_out[vox] = o;
+}
+
+// phase 2: the CTA's threads sweep (voxel, float4-of-channels) items of `nvox` voxels set up in shared memory
+template <bool SPLIT>
+__device__ __forceinline__ void gs3_gather_items(const GS3Params& p, int n, int nvox, const int (*s_off)[8],
+                                                 const float (*s_wgt)[8], const long long* s_out, uint64_t pol_in, uint64_t pol_out) {
+  const int c4n = p.C >> 2;
+  const int work = nvox * c4n;
+  const float4* in4 = (const float4*)p.in + (long long)n * p.Din * p.Hin * p.Win * c4n;
+  for (int t = threadIdx.x; t < work; t += blockDim.x) {
+    const int vox = t / c4n, c4 = t - vox * c4n;
+    const long long ob = s_out[vox];
+    if (ob < 0) continue;
+    const int4 o0 = *(const int4*)&s_off[vox][0], o1 = *(const int4*)&s_off[vox][4];
+    const float4 w0 = *(const float4*)&s_wgt[vox][0], w1 = *(const float4*)&s_wgt[vox][4];
+    const float4* base = in4 + c4;
+    const float4 v0 = ldg_hint(base + o0.x, pol_in), v1 = ldg_hint(base + o0.y, pol_in), v2 = ldg_hint(base + o0.z, pol_in), v3 = ldg_hint(base + o0.w, pol_in);
+    const float4 v4 = ldg_hint(base + o1.x, pol_in), v5 = ldg_hint(base + o1.y, pol_in), v6 = ldg_hint(base + o1.z, pol_in), v7 = ldg_hint(base + o1.w, pol_in);
+    float4 acc;
+#define EMO_GS_ACC(f) \
+  acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
+          fmaf(v3.f, w0.w, fmaf(v2.f, w0.z, fmaf(v1.f, w0.y, v0.f * w0.x)))))));
+    EMO_GS_ACC(x) EMO_GS_ACC(y) EMO_GS_ACC(z) EMO_GS_ACC(w)
+#undef EMO_GS_ACC
+    const long long o = ob + (long long)(c4 * 4) * p.os_c;
+    if (p.os_c == 1) {
+      if (p.out) stg_hint((float4*)(p.out + o), acc, pol_out);  // the output is not re-read by this kernel
+      if (SPLIT) {
+        uint2 hi, lo, lo2;
+        if (p.out_lo2) {
+          split4x3(acc, hi, lo, lo2);
+          *(uint2*)(p.out_lo2 + o) = lo2;
+        } else {
+          split4(acc, hi, lo);
+        }
+        *(uint2*)(p.out_hi + o) = hi;
+        *(uint2*)(p.out_lo + o) = lo;
+      }
+    } else {
+      const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (p.out) p.out[o + j * p.os_c] = a[j];
+        if (SPLIT) {
+          __nv_bfloat16 h, l, l2;
+          split_bf16x3(a[j], h, l, l2);
+          if (!p.out_lo2) split_bf16(a[j], h, l);
+          p.out_hi[o + j * p.os_c] = h;
+          p.out_lo[o + j * p.os_c] = l;
+          if (p.out_lo2) p.out_lo2[o + j * p.os_c] = l2;
+        }
+      }
+    }
+  }
+}
+
+
+// Balanced variant (the product's choice for single-sample 64^3 lattices until the brick-order study below replaced it;
+// profiles/gs3_check_r1.txt).  The brick kernel above launches one CTA
+// per 256-voxel brick: 1024 CTAs for a 64^3 lattice against 148 SMs x 6 resident CTAs = 888 slots, so 136 bricks run
+// in a second, nearly empty wave whose lone CTA per SM is latency-bound (24 dependent gather rounds).  Here the grid
+// is exactly (SMs x resident CTAs) and every CTA takes an equal contiguous share of the brick-ordered voxel
+// enumeration, processed in chunks of <= 256 voxels; a chunk never straddles two samples.  Same per-voxel and per-item
+// arithmetic as the brick kernel (shared device functions), so the outputs are bit-identical.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 6) gs3_cl_balanced_kernel(const LabParams p) {
+  __shared__ __align__(16) int s_off[kBrickVox][8];
+  __shared__ __align__(16) float s_wgt[kBrickVox][8];
+  __shared__ long long s_out[kBrickVox];
+  const int brick_vox = p.bw * p.bh * p.bd;
+  const int per_sample = p.bricks_w * p.bricks_h * p.bricks_d * brick_vox;  // padded lattice; N * per_sample < 2^31 (host)
+  const long long total = (long long)per_sample * p.N;
+  const int v_begin = (int)(total * blockIdx.x / gridDim.x), v_end = (int)(total * (blockIdx.x + 1) / gridDim.x);
+  for (int base = v_begin; base < v_end;) {
+    const int n = base / per_sample;
+    const int stop = min(min(base + kBrickVox, v_end), (n + 1) * per_sample);
+    const int nvox = stop - base;
+    if ((int)threadIdx.x < nvox) {
+      const int v = base + (int)threadIdx.x - n * per_sample;
+      int b = v / brick_vox;
+      const int l = v - b * brick_vox;
+      const int bwi = b % p.bricks_w; b /= p.bricks_w;
+      const int bhi = b % p.bricks_h; b /= p.bricks_h;
+      const int bdi = b;
+      const int lw = l % p.bw, lh = (l / p.bw) % p.bh, ld = l / (p.bw * p.bh);
+      gs3_setup_voxel(p, n, bdi * p.bd + ld, bhi * p.bh + lh, bwi * p.bw + lw, threadIdx.x, s_off, s_wgt, s_out);
+    }
+    __syncthreads();
+    gs3_gather_items<SPLIT>(p, n, nvox, s_off, s_wgt, s_out, l2_policy_evict_last(), l2_policy_evict_first());
+    __syncthreads();  // the next chunk overwrites the shared-memory slots
+    base = stop;
+  }
+}
+
+// Sweep variant: persistent CTAs like the balanced kernel, but the voxel enumeration is cut into `rounds` consecutive waves
+// and every wave is shared equally by all CTAs, so that at any moment the whole grid works inside ONE thin slab of the
+// lattice.  Why: with one contiguous share per CTA (balanced kernel) or one brick per CTA (brick kernel, 1024 bricks
+// against 888 resident CTAs) the whole 64^3 lattice is in flight at once; a warp-field tensor with sigma = 3 voxels of
+// jitter re-uses every input line from ~8 output voxels spread over +-10 slices, i.e. from other SMs at other times, and
+// the 100 MB volume does not survive in L2 between those uses: ncu counts 256 MB of DRAM reads for a 100 MB volume
+// (profiles/prof_gs3_r2.txt).  A slab of (wave + jitter) slices is 30-45 MB and stays resident.  Chunks are staged
+// through double-buffered shared-memory slots (one __syncthreads per chunk); per-voxel and per-item arithmetic is the
+// brick kernel's (shared device functions): bit-identical outputs.  With prefetch_bytes > 0 (volumes that fit L2) each
+// CTA first issues one bulk L2 prefetch of its slice of the volume, so that the cold DRAM fetch of the volume streams at
+// full rate beside the first gathers instead of trickling in miss by miss.
+static constexpr int kSweepVox = 64;
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 6) gs3_cl_sweep_kernel(const LabParams p) {
+  __shared__ __align__(16) int s_off[2][kSweepVox][8];
+  __shared__ __align__(16) float s_wgt[2][kSweepVox][8];
+  __shared__ long long s_out[2][kSweepVox];
+  if (p.prefetch_bytes > 0 && threadIdx.x == 0) {
+    const long long per = ((p.prefetch_bytes / gridDim.x) + 15) & ~15ll;
+    const long long off = per * blockIdx.x;
+    if (off < p.prefetch_bytes) {
+      const unsigned size = (unsigned)min(per, p.prefetch_bytes - off);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const char*)p.in + off), "r"(size) : "memory");
+    }
+  }
+  const int brick_vox = p.bw * p.bh * p.bd;
+  const int per_sample = p.bricks_w * p.bricks_h * p.bricks_d * brick_vox;  // padded lattice; N * per_sample < 2^31 (host)
+  const long long total = (long long)per_sample * p.N;
+  const uint64_t pol_in = p.hint_in ? l2_policy_evict_last() : l2_policy_evict_normal(), pol_out = l2_policy_evict_first();
+  int r = -1, b = 0, e = 0;  // current wave, remaining range of this CTA's share of it
+  // next chunk: sample n, first voxel v0 (inside the sample's enumeration), nvox voxels; false when the CTA is done
+  auto next = [&](int& n, int& v0, int& nvox) -> bool {
+    while (b >= e) {
+      if (++r >= p.rounds) return false;
+      const long long lo = total * r / p.rounds, w = total * (r + 1) / p.rounds - lo;
+      b = (int)(lo + w * blockIdx.x / gridDim.x);
+      e = (int)(lo + w * (blockIdx.x + 1) / gridDim.x);
+    }
+    n = b / per_sample;
+    const int stop = min(min(b + kSweepVox, e), (n + 1) * per_sample);
+    v0 = b - n * per_sample; nvox = stop - b; b = stop;
+    return true;
+  };
+  auto setup = [&](int n, int v0, int nvox, int buf) {
+    if ((int)threadIdx.x < nvox) {
+      const int v = v0 + (int)threadIdx.x;
+      int bk = v / brick_vox;
+      const int l = v - bk * brick_vox;
+      const int bwi = bk % p.bricks_w; bk /= p.bricks_w;
+      const int bhi = bk % p.bricks_h; bk /= p.bricks_h;
+      const int lw = l % p.bw, lh = (l / p.bw) % p.bh, ld = l / (p.bw * p.bh);
+      gs3_setup_voxel(p, n, bk * p.bd + ld, bhi * p.bh + lh, bwi * p.bw + lw, threadIdx.x, s_off[buf], s_wgt[buf], s_out[buf]);
+    }
+  };
+  int n, v0, nvox, buf = 0;
+  bool have = next(n, v0, nvox);
+  if (have) setup(n, v0, nvox, 0);
+  __syncthreads();
+  while (have) {
+    int n2 = 0, v2 = 0, nvox2 = 0;
+    const bool have2 = next(n2, v2, nvox2);
+    if (have2) setup(n2, v2, nvox2, buf ^ 1);  // its readers (previous iteration) are behind the barrier below
+    gs3_gather_items<SPLIT>(p, n, nvox, s_off[buf], s_wgt[buf], s_out[buf], pol_in, pol_out);
+    __syncthreads();
+    n = n2; v0 = v2; nvox = nvox2; buf ^= 1; have = have2;
+  }
+}
+
+
+}  // namespace emo
+
 namespace emo {
 static char g_err[512];
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
@@ -275,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) gs3_staged_kernel(const __grid_constan
 
 struct Case { const char* name; int N, C, D, S; bool affine; };
 
-int main() {
+static int legacy_main() {
   cudaStream_t st;
   CK(cudaStreamCreate(&st));
   cudaEvent_t e0, e1;
@@ -327,7 +530,7 @@ int main() {
       CK(cudaMalloc(&grid, vox * 3 * 4));
       fill_grid<<<592, 256, 0, st>>>(grid, c.N, c.D, c.S, c.S, 0.1f, 99u);
     }
-    GS3Params p;
+    LabParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.grid = grid; p.theta = theta; p.N = c.N; p.C = c.C; p.Din = c.D; p.Hin = c.S; p.Win = c.S; p.Dout = c.D; p.Hout = c.S; p.Wout = c.S;
     p.os_c = 1; p.os_w = c.C; p.os_h = (long long)c.S * c.C; p.os_d = p.os_h * c.S; p.os_n = p.os_d * c.D;
@@ -409,4 +612,144 @@ int main() {
   }
   printf(bad ? "FAIL: %d variants differ\n" : "OK: all variants bit-identical to the product kernel\n", bad);
   return bad ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sweep study (round 2, second half): processing ORDER.  Variants: the brick kernel with its standard 8x8x4 bricks (reference
+// output) and with small flat bricks in plain blockIdx order (the hardware's CTA dispatch is the sweep), the balanced kernel,
+// and the sweep kernel over several enumerations (brick shapes), chunk targets (voxels per CTA and wave), L2 hint on/off,
+// bulk L2 prefetch (volumes that fit L2).  Timed after a DIRTY flush (256 MB of zeros written: what bench.py does) and, for
+// selected variants, after a CLEAN flush (the same buffer read back afterwards: L2 full of clean lines).
+// ---------------------------------------------------------------------------------------------------------------
+struct Variant {
+  const char* kind;   // "brick", "balanced", "sweep"
+  int bw, bh, bd;     // enumeration / brick shape
+  int chunk;          // sweep: target voxels per CTA per wave (0: one wave)
+  int hint, prefetch, clean;
+  int threads;        // brick kernel: threads per CTA (0 = 256)
+};
+
+static int sweep_main(int quick) {
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const long long flush_bytes = 256ll << 20;
+  float4* flush_buf; CK(cudaMalloc(&flush_buf, flush_bytes));
+  float* sink; CK(cudaMalloc(&sink, 4));
+  unsigned long long* d_cnt; CK(cudaMalloc(&d_cnt, 8));
+  int sms = 0, occ = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_cl_sweep_kernel<false>, 256, 0));
+  printf("SMs %d, resident sweep CTAs per SM %d\n", sms, occ);
+  const int slots = sms * occ;
+  const Case cases[] = {{"d64_grid", 1, 96, 64, 64, false}, {"d64_affine", 1, 96, 64, 64, true}, {"d16_grid", 1, 96, 16, 64, false},
+                        {"d16_affine", 1, 96, 16, 64, true},  {"d64_b8_grid", 8, 96, 64, 64, false}, {"d64_b8_affine", 8, 96, 64, 64, true}};
+  std::vector<Variant> vars = {
+      {"brick", 8, 8, 4, 0, 1, 0, 0, 0},     // reference output (round-1 brick)
+      {"brick", 8, 8, 4, 0, 1, 0, 1, 0},
+      {"balanced", 8, 8, 4, 0, 1, 0, 0, 0},
+      {"balanced", 8, 8, 4, 0, 1, 0, 1, 0},
+      {"brick", 8, 8, 2, 0, 1, 0, 0, 0},
+      {"brick", 8, 8, 2, 0, 1, 0, 1, 0},
+      {"brick", 8, 8, 2, 0, 1, 0, 0, 128},
+      {"brick", 8, 8, 1, 0, 1, 0, 0, 0},
+      {"brick", 8, 8, 1, 0, 1, 0, 1, 0},
+      {"brick", 8, 8, 1, 0, 1, 0, 0, 128},
+      {"brick", 8, 8, 1, 0, 1, 0, 0, 64},
+      {"brick", 8, 4, 1, 0, 1, 0, 0, 0},
+      {"brick", 8, 4, 1, 0, 1, 0, 0, 128},
+      {"brick", 8, 4, 1, 0, 1, 0, 0, 64},
+      {"brick", 16, 4, 1, 0, 1, 0, 0, 0},
+      {"brick", 16, 8, 1, 0, 1, 0, 0, 0},
+      {"brick", 16, 16, 1, 0, 1, 0, 0, 0},
+      {"brick", 4, 4, 4, 0, 1, 0, 0, 0},
+      {"sweep", 8, 8, 4, 0, 1, 0, 0, 0},
+      {"sweep", 8, 8, 1, 64, 1, 0, 0, 0},
+      {"sweep", 16, 16, 1, 64, 1, 0, 0, 0},
+      {"sweep", 16, 16, 1, 32, 1, 0, 0, 0},
+      {"sweep", 16, 16, 1, 32, 0, 0, 0, 0},
+      {"sweep", 16, 16, 1, 32, 1, 1, 0, 0},
+  };
+  int bad = 0;
+  for (const Case& c : cases) {
+    const long long vox = (long long)c.N * c.D * c.S * c.S, n = vox * c.C;
+    float *in, *grid = nullptr, *theta = nullptr, *out[2];
+    CK(cudaMalloc(&in, n * 4)); CK(cudaMalloc(&out[0], n * 4)); CK(cudaMalloc(&out[1], n * 4));
+    fill_uniform<<<592, 256, 0, st>>>(in, n, 17u, -1.f, 1.f);
+    if (c.affine) {
+      std::vector<float> t(12 * c.N);
+      for (int k = 0; k < c.N; ++k) {
+        const float a = 0.5236f;
+        const float m[12] = {cosf(a), -sinf(a), 0, 0.2f, sinf(a), cosf(a), 0, 0.2f, 0, 0, 1.f, 0.2f};
+        for (int i = 0; i < 12; ++i) t[k * 12 + i] = m[i];
+      }
+      CK(cudaMalloc(&theta, t.size() * 4));
+      CK(cudaMemcpy(theta, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    } else {
+      CK(cudaMalloc(&grid, vox * 3 * 4));
+      fill_grid<<<592, 256, 0, st>>>(grid, c.N, c.D, c.S, c.S, 0.1f, 99u);
+    }
+    const double bytes = ((double)2 * c.C + (c.affine ? 0 : 3)) * 4.0 * (double)vox;
+    const int reps = c.N > 1 ? 7 : 15;
+    for (size_t vi = 0; vi < vars.size(); ++vi) {
+      const Variant& v = vars[vi];
+      if (v.prefetch && (long long)c.D * c.S * c.S * c.C * 4 * c.N > (48ll << 20)) continue;  // prefetch only for volumes that fit L2
+      if (quick && !strcmp(v.kind, "sweep")) continue;
+      LabParams p;
+      memset(&p, 0, sizeof(p));
+      p.in = in; p.grid = grid; p.theta = theta; p.N = c.N; p.C = c.C; p.Din = c.D; p.Hin = c.S; p.Win = c.S; p.Dout = c.D; p.Hout = c.S; p.Wout = c.S;
+      p.os_c = 1; p.os_w = c.C; p.os_h = (long long)c.S * c.C; p.os_d = p.os_h * c.S; p.os_n = p.os_d * c.D;
+      p.bw = v.bw; p.bh = v.bh; p.bd = v.bd; p.bricks_w = c.S / v.bw; p.bricks_h = c.S / v.bh; p.bricks_d = c.D / v.bd;
+      p.rounds = 1; p.hint_in = v.hint;
+      p.prefetch_bytes = v.prefetch ? (long long)c.N * c.D * c.S * c.S * c.C * 4 : 0;
+      p.out = out[vi == 0 ? 0 : 1];
+      const long long total = vox;
+      unsigned ctas = 0;
+      if (!strcmp(v.kind, "brick")) ctas = (unsigned)(c.N * p.bricks_w * p.bricks_h * p.bricks_d);
+      else {
+        ctas = (unsigned)std::min<long long>(slots, (total + 31) / 32);
+        if (v.chunk > 0) p.rounds = (int)std::max<long long>(1, (total + (long long)ctas * v.chunk / 2) / ((long long)ctas * v.chunk));
+      }
+      std::vector<float> ms;
+      for (int r = 0; r < reps; ++r) {
+        flush_k<<<148 * 8, 256, 0, st>>>(flush_buf, flush_bytes / 16);
+        if (v.clean) read_stream_kernel<<<148 * 8, 256, 0, st>>>(flush_buf, flush_bytes / 16, 1, sink);
+        CK(cudaEventRecord(e0, st));
+        if (!strcmp(v.kind, "brick")) gs3_cl_kernel<false><<<ctas, v.threads ? v.threads : 256, 0, st>>>(p);
+        else if (!strcmp(v.kind, "balanced")) gs3_cl_balanced_kernel<false><<<ctas, 256, 0, st>>>(p);
+        else gs3_cl_sweep_kernel<false><<<ctas, 256, 0, st>>>(p);
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        float t; CK(cudaEventElapsedTime(&t, e0, e1));
+        ms.push_back(t);
+      }
+      std::sort(ms.begin(), ms.end());
+      unsigned long long diff = 0;
+      if (vi > 0) {
+        CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+        count_diff<<<592, 256, 0, st>>>((const unsigned*)out[0], (const unsigned*)out[1], n, d_cnt);
+        CK(cudaMemcpyAsync(&diff, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (diff) ++bad;
+        CK(cudaMemsetAsync(out[1], 0xff, n * 4, st));
+      }
+      const double med = ms[reps / 2];
+      printf("%-13s %-8s enum %2dx%2dx%d thr %3d chunk %3d rounds %3d hint %d prefetch %d %s  median %8.2f us  min %8.2f us  %7.1f GB/s algorithmic  frac(6480) %.3f  diff_words %llu\n",
+             c.name, v.kind, v.bw, v.bh, v.bd, v.threads ? v.threads : 256, v.chunk, p.rounds, v.hint, v.prefetch, v.clean ? "clean-flush" : "dirty-flush", med * 1e3, ms[0] * 1e3,
+             bytes / (med * 1e-3) * 1e-9, bytes / (med * 1e-3) * 1e-9 / 6480.0, diff);
+      fflush(stdout);
+    }
+    CK(cudaFree(in)); CK(cudaFree(out[0])); CK(cudaFree(out[1]));
+    if (grid) CK(cudaFree(grid));
+    if (theta) CK(cudaFree(theta));
+  }
+  printf(bad ? "FAIL: %d variants differ\n" : "OK: all variants bit-identical to the brick kernel\n", bad);
+  return bad ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && !strcmp(argv[1], "--legacy")) return legacy_main();
+  return sweep_main(argc > 1 && !strcmp(argv[1], "--quick"));
 }

@@ -5,7 +5,7 @@
    splitk_post_kernel  the fused finalize + GroupNorm + ReLU + plane split behind that split-K layer
    apply_kernel        GroupNorm-apply + ReLU + plane split @512^2 x 128
    gn_head_kernel      image head @512^2 x 128 -> 3
-   gs3_cl_balanced_kernel  96ch 64^3 volume through a warp-field tensor / through the fused affine lattice; 16x64x64 (model-true)"""
+   gs3_cl_kernel       96ch 64^3 volume through a warp-field tensor / through the fused affine lattice; 16x64x64 (model-true)"""
 import math, sys, pathlib
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parents[1]))
 import torch
