@@ -15,7 +15,7 @@ import sys
 
 HERE = pathlib.Path(__file__).resolve().parent
 LIB = HERE / "libemoport.so"
-SOURCES = ["conv_igemm.cu", "grid_sample.cu", "norm.cu", "misc.cu"]
+SOURCES = ["conv_igemm.cu", "grid_sample.cu", "norm.cu", "misc.cu", "masks.cu"]
 HEADERS = ["common.cuh", "pose_math.cuh", "conv_igemm_kernel.inc", "apply_kernel.inc", "../../include/emoportraits_b200.h"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

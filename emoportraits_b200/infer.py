@@ -5,9 +5,11 @@ Same constructor and `forward` signature, same `args.txt` / checkpoint layout (`
 `(list[PIL.Image], img Tensor (B,3,H,W) fp32 on device)`.  The hot path underneath is emoportraits_b200's sm_100a
 kernels; there is no torch/CPU fallback — without a B200 and the built libemoport.so this module raises.
 
-Out of scope here: the external face detector (crop=True), MODNet and BiSeNet mask
-networks.  `crop=True`/`modnet_mask=True` raise NotImplementedError; when `source_mask` is not given the mask is all
-ones (what the stubbed reference oracle uses too).
+Out of scope here: the external face detector (`crop=True` raises) and the WEIGHTS / model
+code of the external mask networks (MODNet, BiSeNet: separate checkouts, not in the reference tree).  The processing the
+reference does around them is here (`masks.py`, csrc/masks.cu): plug the networks in with `wrapper.face_idt =
+masks.FaceParsing(None, net=...)` / `wrapper.modnet = ...`; without them the source mask is `source_mask` or all ones (what the
+stubbed reference oracle uses too) and `modnet_mask=True` raises.
 """
 from __future__ import annotations
 
@@ -282,6 +284,18 @@ class InferenceWrapper(torch.nn.Module):
         self.use_seg = getattr(self.args, 'use_seg', True)
         self._state = None
         self._pipeline = self._pipeline_key = None
+        # external mask networks (separate checkouts in the reference: repos/face_par_off behind model.face_idt, infer.py:410;
+        # repos/MODNet, infer.py:140-149): None until the caller plugs them in (masks.FaceParsing(None, net=...), any MODNet module)
+        self.face_idt = None
+        self.modnet = None
+
+    def get_mask(self, img):
+        """notebooks/infer.py:649-684: MODNet matte of img (N,3,h,w) in [0,1]; normalisation and both 'area' resizes on the device."""
+        from .masks import modnet_get_mask
+
+        if self.modnet is None:
+            raise NotImplementedError("get_mask needs the external MODNet network: set wrapper.modnet = <module>")
+        return modnet_get_mask(self.modnet, img.to(self.device))
 
     # -- notebooks/infer.py:229-243
     def convert_to_tensor(self, image):
@@ -315,8 +329,9 @@ class InferenceWrapper(torch.nn.Module):
         if crop:
             raise NotImplementedError("crop=True needs the external mediapipe face detector (out of scope); pass crop=False "
                                       "with pre-cropped images, as notebooks/E_emo_infer_video.ipynb does")
-        if modnet_mask:
-            raise NotImplementedError("modnet_mask=True needs the external MODNet (out of scope)")
+        if modnet_mask and self.modnet is None:
+            raise NotImplementedError("modnet_mask=True needs the external MODNet network: set wrapper.modnet = <module> "
+                                      "(repos/MODNet is a separate checkout, not part of the reference tree)")
         # hard_normalize, soft_normalize, cloth, thetas_pass, theta_n are accepted and unused, exactly as in the reference
         # (infer.py:355-357 declares them; nothing in :358-647 reads them).  driver_mask only travels in the reference's
         # data_dict: the expression embedder is called with use_seg=False (:597) and never multiplies by it.
@@ -334,11 +349,19 @@ class InferenceWrapper(torch.nn.Module):
             if src.shape[0] != 1:
                 raise ValueError("one source image per call (the reference reshapes the latents with view(1, c, d, s, s), infer.py:483)")
             self.source_image = self.source_image_crop = src
-            mask = None
-            if source_mask is not None:
-                mask = source_mask.to(self.device).float()
-                if source_mask_add:
-                    mask = mask.clamp_(max=1, min=0)
+            # infer.py:408-426.  face_idt (the external BiSeNet behind masks.FaceParsing) is optional here: without it the face
+            # mask is all ones, which is what the reference computes for a frame the parser labels 'face' everywhere
+            face_mask = None
+            if self.face_idt is not None:
+                face_mask = (self.face_idt.forward(src)[0] > 0.6).float()             # :410-411 (trashhold 0.6)
+            modnet_matte = self.get_mask(src) if modnet_mask else None               # :413, before the face mask is applied
+            if face_mask is not None:
+                src = (src * face_mask).float().contiguous()                          # :417
+            mask = source_mask.to(self.device).float() if source_mask is not None else face_mask   # :421
+            if modnet_mask:
+                mask = modnet_matte                                                   # :422
+            if mask is not None and source_mask_add:
+                mask = mask.clamp_(max=1, min=0)                                      # :423-424
             self.source_img_mask = mask if mask is not None else torch.ones_like(src[:, :1])
             self.source_img = self.source_img_crop_m = src
             st = self.model.source_pass(src, mask=mask, c_source_latent_volume=c_source_latent_volume,

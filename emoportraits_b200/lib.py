@@ -121,6 +121,9 @@ SYMBOLS = {
     "emo_composite": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "emo_l2_flush": (c_int, [c_void_p, c_ll, c_void_p]),
     "emo_l2_flush_clean": (c_int, [c_void_p, c_ll, c_void_p]),
+    "emo_parsing_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emo_parsing_masks": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "emo_resize_area": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
 }
 
 # EMO_DRY_RUN=1: host-logic test mode for the GPU-less CI box — every C-ABI call is validated for presence in the

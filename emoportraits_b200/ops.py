@@ -638,3 +638,37 @@ def l2_flush(buf: torch.Tensor, clean: bool = False):
     """Benchmark helper: evict L2 by writing `buf` (>= 2x the L2 size).  clean=True also reads it back, so that L2 holds clean
     foreign lines and the kernel under test does not pay for the write-back of the flush's own dirty lines."""
     L.call("emo_l2_flush_clean" if clean else "emo_l2_flush", _p(buf), buf.numel() * buf.element_size(), _stream())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mask pre/post-processing around the external mask networks (csrc/masks.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def parsing_prepare(img_nchw: torch.Tensor, mean: torch.Tensor, std: torch.Tensor, out_hw=(512, 512)) -> torch.Tensor:
+    """(x - mean) / std per channel, then F.interpolate(size=out_hw, mode='bilinear')  (face_parcing.py:57-58)"""
+    _chk(img_nchw); _chk(mean); _chk(std)
+    N, Cc, Hi, Wi = img_nchw.shape
+    out = torch.empty((N, Cc, out_hw[0], out_hw[1]), dtype=torch.float32, device=img_nchw.device)
+    L.call("emo_parsing_prepare", _p(img_nchw), N, Cc, Hi, Wi, out_hw[0], out_hw[1], _p(mean), _p(std), _p(out), _stream())
+    return out
+
+
+def parsing_masks(logits_nchw: torch.Tensor, out_hw, label_sets, want_labels: bool = False):
+    """F.interpolate(logits, size=out_hw, 'bilinear') -> argmax over classes -> membership in the four label sets
+    (face_parcing.py:60-80) in one pass.  label_sets: four iterables of class ids.  Returns uint8 (4, N, 1, H, W) [, labels (N,1,H,W)]."""
+    _chk(logits_nchw)
+    N, K, Hi, Wi = logits_nchw.shape
+    assert len(label_sets) == 4 and K <= 32
+    bits = (C.c_uint * 4)(*[sum(1 << int(i) for i in set(ls)) for ls in label_sets])
+    out = torch.empty((4, N, 1, out_hw[0], out_hw[1]), dtype=torch.uint8, device=logits_nchw.device)
+    labels = torch.empty((N, 1, out_hw[0], out_hw[1]), dtype=torch.uint8, device=logits_nchw.device) if want_labels else None
+    L.call("emo_parsing_masks", _p(logits_nchw), N, K, Hi, Wi, out_hw[0], out_hw[1], bits, _p(out), _p(labels), _stream())
+    return (out, labels) if want_labels else out
+
+
+def resize_area(img_nchw: torch.Tensor, out_hw, scale: float = 1.0, shift: float = 0.0) -> torch.Tensor:
+    """F.interpolate(x * scale + shift, size=out_hw, mode='area') (adaptive average pooling; notebooks/infer.py:676, 682)"""
+    _chk(img_nchw)
+    N, Cc, Hi, Wi = img_nchw.shape
+    out = torch.empty((N, Cc, out_hw[0], out_hw[1]), dtype=torch.float32, device=img_nchw.device)
+    L.call("emo_resize_area", _p(img_nchw), N, Cc, Hi, Wi, out_hw[0], out_hw[1], float(scale), float(shift), _p(out), _stream())
+    return out

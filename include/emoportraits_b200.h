@@ -345,6 +345,24 @@ int emo_resize_bicubic(const float* in, int N, int C, int Hin, int Win, int Hout
  *   m' = (mask > threshold ? mask : 0)^8;  out = m' * img + (1 - m') * bg
  * img, out fp32 [N][C][H][W]; mask fp32 [N][1][H][W]; bg fp32 [C][H][W] (one background for the whole clip). */
 int emo_composite(const float* img, const float* mask, const float* bg, int N, int C, int H, int W, float threshold, float* out, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Mask pre/post-processing around the EXTERNAL mask networks (BiSeNet face parsing, MODNet matting: separate checkouts that
+ * are not part of the reference tree).  All tensors fp32 NCHW on the device unless noted.
+ *   emo_parsing_prepare  out[n][c] = bilinear_resize((in[n][c] - mean[c]) / std[c], Hout x Wout), align_corners=False
+ *                        replaces networks/volumetric_avatar/face_parcing.py:57-58 (normalise, F.interpolate to 512 x 512)
+ *   emo_parsing_masks    logits [N][K][Hin][Win] -> bilinear resize to Hout x Wout -> argmax over K -> membership of the label
+ *                        in four class sets; out uint8 [4][N][Hout][Wout] (0/1), labels uint8 [N][Hout][Wout] or NULL.
+ *                        label_sets: HOST array of four 32-bit sets (bit k = class k).  K <= 32.
+ *                        replaces face_parcing.py:60-80 (F.interpolate, argmax, the four `mask += labels == i` loops)
+ *   emo_resize_area      out = adaptive_average_pool(in * scale + shift, Hout x Wout) = F.interpolate(mode='area')
+ *                        replaces notebooks/infer.py:651-657 + :676 (Normalize(0.5, 0.5) then area resize) and :682
+ * ------------------------------------------------------------------------------------------------ */
+int emo_parsing_prepare(const float* in, int N, int C, int Hin, int Win, int Hout, int Wout, const float* mean, const float* std,
+                        float* out, void* stream);
+int emo_parsing_masks(const float* logits, int N, int K, int Hin, int Win, int Hout, int Wout, const unsigned* label_sets,
+                      unsigned char* out, unsigned char* labels, void* stream);
+int emo_resize_area(const float* in, int N, int C, int Hin, int Win, int Hout, int Wout, float scale, float shift, float* out,
+                    void* stream);
 /* L2 flush helpers for benchmarks: emo_l2_flush writes `bytes` of `buf` (L2 is left full of DIRTY foreign lines: the next
  * kernel also pays for their write-back); emo_l2_flush_clean writes and then reads the buffer back (L2 is left full of
  * CLEAN foreign lines). */

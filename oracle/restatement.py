@@ -604,3 +604,64 @@ def stage2_forward(sd, img, output_size):
     add = stage2_decoder(sd, vol)
     ffhq = (resized + add).clamp(min=0, max=1)
     return resized, add, ffhq
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mask pre/post-processing around the external mask networks.  `net` / `modnet` are callables with the
+# signatures the reference uses; pinned against the unmodified reference code by oracle/make_golden_masks.py ->
+# tests/golden/masks.pt (tests/test_masks.py)
+# ------------------------------------------------------------------------------------------------------------------
+PARSING_MEAN = (0.485, 0.456, 0.406)   # face_parcing.py:31
+PARSING_STD = (0.229, 0.224, 0.225)    # face_parcing.py:32
+
+
+def parsing_label_sets(mask_type=None):
+    """face_parcing.py:34-53: the label lists of (mask, face_body, mask_body, mask_cloth)."""
+    if mask_type is None:
+        return ([1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 7, 8, 9, 14, 17, 18], [1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 7, 8, 9, 17, 18], [18], [16])
+    mask = []
+    for key, labs in (("face", [1, 2, 3, 4, 5, 6, 10, 11, 12, 13]), ("ears", [7, 8, 9]), ("neck", [14, 15]), ("hair", [17]), ("hat", [18]),
+                      ("cloth", [16])):
+        if key in mask_type:
+            mask += labs
+    return (mask, None, None, None)  # face_labels / body_labels / cloth_labels only exist for mask_type None (:40-42)
+
+
+def face_parsing_forward(net, x, mask_type=None):
+    """face_parcing.py:55-81 (FaceParsing.forward).  x (N,3,h,w) in [0,1] -> four int64 (N,1,h,w) masks."""
+    h, w = x.shape[2:]
+    mean = torch.tensor(PARSING_MEAN, dtype=x.dtype)[None, :, None, None]
+    std = torch.tensor(PARSING_STD, dtype=x.dtype)[None, :, None, None]
+    x = (x - mean) / std                                                   # :57
+    x = F.interpolate(x, size=(512, 512), mode="bilinear")                 # :58
+    y = net(x)[0]                                                          # :59
+    y = F.interpolate(y, size=(h, w), mode="bilinear")                     # :60
+    labels = y.argmax(1, keepdim=True)                                     # :62
+    outs = []
+    for labs in parsing_label_sets(mask_type):                             # :64-79
+        m = torch.zeros_like(labels)
+        for i in labs or []:
+            m += labels == i
+        outs.append(m)
+    return tuple(outs), y, labels
+
+
+def modnet_get_mask(modnet, img):
+    """notebooks/infer.py:649-684 (InferenceWrapper.get_mask).  img (N,3,h,w) in [0,1] -> matte (N,1,h,w)."""
+    im = (img - 0.5) / 0.5                                                 # :651-657 Normalize((0.5,)*3, (0.5,)*3)
+    ref_size = 512
+    im_b, im_c, im_h, im_w = im.shape
+    if max(im_h, im_w) < ref_size or min(im_h, im_w) > ref_size:           # :663-669
+        if im_w >= im_h:
+            im_rh = ref_size
+            im_rw = int(im_w / im_h * ref_size)
+        else:
+            im_rw = ref_size
+            im_rh = int(im_h / im_w * ref_size)
+    else:
+        im_rh, im_rw = im_h, im_w
+    im_rw = im_rw - im_rw % 32                                             # :674-675
+    im_rh = im_rh - im_rh % 32
+    im = F.interpolate(im, size=(im_rh, im_rw), mode="area")               # :676
+    _, _, matte = modnet(im, True)                                         # :679
+    return F.interpolate(matte, size=(im_h, im_w), mode="area")            # :682

@@ -7,6 +7,8 @@ timeout 200 tools/gs3_lab --quick > "$out/gs3_lab.txt" 2>&1; echo "lab rc=$?" | 
 timeout 200 tools/gs3_check > "$out/gs3_check.txt" 2>&1; echo "check rc=$?" | tee -a "$out/summary.txt"
 timeout 600 python -m pytest tests/test_ops_gpu.py -q -m gpu -k "grid_sample" -rA > "$out/pytest_gs.txt" 2>&1; echo "pytest gs rc=$?" | tee -a "$out/summary.txt"
 tail -3 "$out/pytest_gs.txt" >> "$out/summary.txt"
+timeout 600 python -m pytest tests/test_masks.py -q -m gpu -rA > "$out/pytest_masks.txt" 2>&1; echo "pytest masks rc=$?" | tee -a "$out/summary.txt"
+grep -E "^(FAILED|ERROR)|passed|failed" "$out/pytest_masks.txt" | tail -12 >> "$out/summary.txt"
 timeout 900 python bench.py > "$out/bench_full.json" 2> "$out/bench_full.err"; echo "bench rc=$?" | tee -a "$out/summary.txt"
 python - <<'P' | tee -a "$out/summary.txt"
 import json
