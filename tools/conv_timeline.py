@@ -10,7 +10,8 @@ import torch
 from emoportraits_b200 import lib as L, ops
 
 NAMES = ["entry", "prologue done", "producer starts", "producer done", "first operands landed", "last MMA issued",
-         "last chunk consumed", "final-phase stores issued", "statistics done", "teardown barrier", "TMEM freed"]
+         "last chunk consumed", "final-phase stores issued", "statistics done", "teardown barrier", "TMEM freed",
+         "TMA epilogue: staging tile written", "TMA epilogue: stores issued", "TMA epilogue: statistics done", "TMA epilogue: staging tile read by the store"]
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
 
@@ -47,7 +48,7 @@ def run(Cin, Cout, sp, k, planes, residual=True):
     s = s[live]
     t0 = s[:, 0].min()
     print(f"--- {Cin}->{Cout} {sp} k{k} planes {planes} EMO_CONV_EPI={os.environ.get('EMO_CONV_EPI', 'default')}: {int(live.sum())} CTAs, "
-          f"launch {e0.elapsed_time(e1) * 1000:.1f} us (events), last stamp {(s[:, :11].max() - t0) / 1000:.1f} us after the first entry")
+          f"launch {e0.elapsed_time(e1) * 1000:.1f} us (events), last stamp {(s[:, :15].max() - t0) / 1000:.1f} us after the first entry")
     for k_, name in enumerate(NAMES):
         col = s[:, k_]
         col = col[col > 0]

@@ -476,6 +476,121 @@ __global__ void __launch_bounds__(256, 1) gs3_staged_kernel(const __grid_constan
   if (tid == 0 && s_bad) p.out[0] = __int_as_float(0x7fc00000);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk-copy gather ("TMA-staged feature tiles" in gather form).  The LSU path of the product kernel pays one L1tex wavefront per
+// 128-byte line and ~2 clk per additional line inside one LDG.128: ~50 clk per voxel and SM at C = 96, i.e. 46 us for a 64^3
+// lattice however the loads are arranged.  Here the eight corner rows of a voxel (C x 4 bytes each, contiguous in a channels-last
+// volume) are fetched by cp.async.bulk (1-D bulk copies, global -> shared memory, completion on an mbarrier): the async proxy
+// does not go through the L1tex wavefront path.  One producer warp per CTA sets up BV voxels per stage (sample position ->
+// clamped corner offsets + trilinear weights -> shared memory) and issues the 8 x BV row copies; BV x C/4 consumer threads
+// (one float4 of one voxel each) wait for the stage, blend the eight rows from shared memory in the product kernel's FMA
+// order (bit-identical output) and store; NST stages ring.  Chunks of BV voxels go round-robin over the persistent CTAs in
+// raster order (x fastest ... z slowest): the grid sweeps the lattice as one thin slab (see the order study).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mb_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src), "r"(bytes),
+               "r"(s_u32(bar)) : "memory");
+}
+
+template <int BV, int NST>
+__global__ void __launch_bounds__(32 + BV * 24, 1) gs3_bulk_kernel(const GS3Params p) {
+  extern __shared__ __align__(128) uint8_t sraw[];
+  const int c4n = p.C >> 2;                       // 24
+  const uint32_t row_bytes = (uint32_t)p.C * 4u;  // 384
+  float* ring = (float*)sraw;                     // [NST][BV][8][C]
+  __shared__ __align__(16) float s_wgt[NST][BV][8];
+  __shared__ long long s_out[NST][BV];
+  __shared__ int s_offb[BV][8];
+  __shared__ uint64_t full_bar[NST], empty_bar[NST];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncw = (BV * c4n + 31) / 32;  // consumer warps
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { mb_init(&full_bar[i], 1); mb_init(&empty_bar[i], ncw); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long per_sample = (long long)p.Dout * p.Hout * p.Wout;
+  const long long total = per_sample * p.N;  // chunks never straddle samples when per_sample % BV == 0 (host checks)
+  const long long nchunks = total / BV;
+  const size_t stage_floats = (size_t)BV * 8 * p.C;
+  if (warp == 0) {
+    // ---------------- producer ----------------
+    int it = 0;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    long long chunk = blockIdx.x;
+    auto coords = [&](long long ch) {  // lanes < BV: sample position of voxel ch * BV + lane (issued one stage ahead of its use)
+      if (lane < BV && ch < nchunks) {
+        const long long v = ch * BV + lane;
+        const int n = (int)(v / per_sample);
+        long long r = v - (long long)n * per_sample;
+        const int ow = (int)(r % p.Wout); r /= p.Wout;
+        const int oh = (int)(r % p.Hout);
+        const int od = (int)(r / p.Hout);
+        sample_coord(p, n, od, oh, ow, gx, gy, gz);
+      }
+    };
+    coords(chunk);
+    for (; chunk < nchunks; chunk += gridDim.x, ++it) {
+      const int slot = it % NST;
+      const float cx = gx, cy = gy, cz = gz;
+      coords(chunk + gridDim.x);  // next stage's grid loads fly during this stage's set-up
+      if (it >= NST) mb_wait(&empty_bar[slot], ((it / NST) - 1) & 1);
+      const long long v0 = chunk * BV;
+      const int n = (int)(v0 / per_sample);
+      if (lane < BV) {
+        const long long v = v0 + lane;
+        long long r = v - (long long)n * per_sample;
+        const int ow = (int)(r % p.Wout); r /= p.Wout;
+        const int oh = (int)(r % p.Hout);
+        const int od = (int)(r / p.Hout);
+        const Corner8 k = corners(p, cx, cy, cz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+          const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+          const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
+          const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
+          s_wgt[slot][lane][j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+          s_offb[lane][j] = ((zc * p.Hin + yc) * p.Win + xc);
+        }
+        s_out[slot][lane] = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
+      }
+      __syncwarp();
+      if (lane == 0) mb_expect(&full_bar[slot], (uint32_t)(BV * 8) * row_bytes);
+      __syncwarp();
+      const char* vol = (const char*)(p.in + (long long)n * p.Din * p.Hin * p.Win * p.C);
+      float* dst = ring + (size_t)slot * stage_floats;
+      for (int q = lane; q < BV * 8; q += 32)
+        bulk_g2s(dst + (size_t)q * p.C, vol + (long long)(&s_offb[0][0])[q] * row_bytes, row_bytes, &full_bar[slot]);
+      __syncwarp();  // s_offb is rewritten by the next stage
+    }
+  } else if (warp - 1 < ncw) {
+    // ---------------- consumers ----------------
+    const int t = threadIdx.x - 32;
+    const int vox = t / c4n, c4 = t - vox * c4n;
+    const bool active = t < BV * c4n;
+    uint64_t pol_out;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_out));
+    int it = 0;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+      const int slot = it % NST;
+      mb_wait(&full_bar[slot], (it / NST) & 1);
+      if (active) {
+        const float4 w0 = *(const float4*)&s_wgt[slot][vox][0], w1 = *(const float4*)&s_wgt[slot][vox][4];
+        const float4* src = (const float4*)(ring + (size_t)slot * stage_floats + (size_t)vox * 8 * p.C) + c4;
+        const float4 v0 = src[0 * c4n], v1 = src[1 * c4n], v2 = src[2 * c4n], v3 = src[3 * c4n];
+        const float4 v4 = src[4 * c4n], v5 = src[5 * c4n], v6 = src[6 * c4n], v7 = src[7 * c4n];
+        float4 acc;
+        GS_ACC(x) GS_ACC(y) GS_ACC(z) GS_ACC(w)
+        st_hint((float4*)(p.out + s_out[slot][vox] + (long long)(c4 * 4)), acc, pol_out);
+      }
+      __syncwarp();
+      if (lane == 0) mb_arrive(&empty_bar[slot]);
+    }
+  }
+}
+
 struct Case { const char* name; int N, C, D, S; bool affine; };
 
 static int legacy_main() {
@@ -664,6 +779,15 @@ static int sweep_main(int quick) {
       {"brick", 16, 8, 1, 0, 1, 0, 0, 0},
       {"brick", 16, 16, 1, 0, 1, 0, 0, 0},
       {"brick", 4, 4, 4, 0, 1, 0, 0, 0},
+      {"bulk", 8, 4, 1, 0, 1, 0, 0, 0},      // bulk-copy gather: bw = voxels per stage, bh = ring stages, chunk = CTAs per SM (0 = as many as fit)
+      {"bulk", 8, 4, 1, 0, 1, 0, 1, 0},
+      {"bulk", 8, 4, 1, 1, 1, 0, 0, 0},
+      {"bulk", 8, 3, 1, 0, 1, 0, 0, 0},
+      {"bulk", 16, 2, 1, 0, 1, 0, 0, 0},
+      {"bulk", 16, 3, 1, 0, 1, 0, 0, 0},
+      {"bulk", 16, 4, 1, 0, 1, 0, 0, 0},
+      {"bulk", 4, 8, 1, 0, 1, 0, 0, 0},
+      {"bulk", 4, 4, 1, 0, 1, 0, 0, 0},
       {"sweep", 8, 8, 4, 0, 1, 0, 0, 0},
       {"sweep", 8, 8, 1, 64, 1, 0, 0, 0},
       {"sweep", 16, 16, 1, 64, 1, 0, 0, 0},
@@ -700,13 +824,36 @@ static int sweep_main(int quick) {
       memset(&p, 0, sizeof(p));
       p.in = in; p.grid = grid; p.theta = theta; p.N = c.N; p.C = c.C; p.Din = c.D; p.Hin = c.S; p.Win = c.S; p.Dout = c.D; p.Hout = c.S; p.Wout = c.S;
       p.os_c = 1; p.os_w = c.C; p.os_h = (long long)c.S * c.C; p.os_d = p.os_h * c.S; p.os_n = p.os_d * c.D;
-      p.bw = v.bw; p.bh = v.bh; p.bd = v.bd; p.bricks_w = c.S / v.bw; p.bricks_h = c.S / v.bh; p.bricks_d = c.D / v.bd;
+      const bool bulk = !strcmp(v.kind, "bulk");
+      if (!bulk) { p.bw = v.bw; p.bh = v.bh; p.bd = v.bd; p.bricks_w = c.S / v.bw; p.bricks_h = c.S / v.bh; p.bricks_d = c.D / v.bd; }
       p.rounds = 1; p.hint_in = v.hint;
       p.prefetch_bytes = v.prefetch ? (long long)c.N * c.D * c.S * c.S * c.C * 4 : 0;
       p.out = out[vi == 0 ? 0 : 1];
       const long long total = vox;
       unsigned ctas = 0;
-      if (!strcmp(v.kind, "brick")) ctas = (unsigned)(c.N * p.bricks_w * p.bricks_h * p.bricks_d);
+      size_t bulk_smem = 0;
+      int bulk_threads = 0;
+      void (*bulk_fn)(const GS3Params) = nullptr;
+      if (bulk) {
+        if (v.bw == 8 && v.bh == 4) bulk_fn = gs3_bulk_kernel<8, 4>;
+        else if (v.bw == 8 && v.bh == 3) bulk_fn = gs3_bulk_kernel<8, 3>;
+        else if (v.bw == 16 && v.bh == 2) bulk_fn = gs3_bulk_kernel<16, 2>;
+        else if (v.bw == 16 && v.bh == 3) bulk_fn = gs3_bulk_kernel<16, 3>;
+        else if (v.bw == 16 && v.bh == 4) bulk_fn = gs3_bulk_kernel<16, 4>;
+        else if (v.bw == 4 && v.bh == 8) bulk_fn = gs3_bulk_kernel<4, 8>;
+        else if (v.bw == 4 && v.bh == 4) bulk_fn = gs3_bulk_kernel<4, 4>;
+        else { fprintf(stderr, "no bulk instantiation %d %d\n", v.bw, v.bh); return 2; }
+        bulk_smem = (size_t)v.bh * v.bw * 8 * c.C * 4;
+        bulk_threads = 32 + v.bw * (c.C / 4);
+        bulk_threads = (bulk_threads + 31) / 32 * 32;
+        CK(cudaFuncSetAttribute(bulk_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem));
+        int bocc = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bocc, bulk_fn, bulk_threads, bulk_smem));
+        if (v.chunk > 0 && v.chunk < bocc) bocc = v.chunk;
+        ctas = (unsigned)(sms * bocc);
+        p.rounds = bocc;  // printed in the rounds column: resident CTAs per SM
+        if ((vox / c.N) % v.bw) { fprintf(stderr, "lattice not a multiple of the stage\n"); return 2; }
+      } else if (!strcmp(v.kind, "brick")) ctas = (unsigned)(c.N * p.bricks_w * p.bricks_h * p.bricks_d);
       else {
         ctas = (unsigned)std::min<long long>(slots, (total + 31) / 32);
         if (v.chunk > 0) p.rounds = (int)std::max<long long>(1, (total + (long long)ctas * v.chunk / 2) / ((long long)ctas * v.chunk));
@@ -716,7 +863,8 @@ static int sweep_main(int quick) {
         flush_k<<<148 * 8, 256, 0, st>>>(flush_buf, flush_bytes / 16);
         if (v.clean) read_stream_kernel<<<148 * 8, 256, 0, st>>>(flush_buf, flush_bytes / 16, 1, sink);
         CK(cudaEventRecord(e0, st));
-        if (!strcmp(v.kind, "brick")) gs3_cl_kernel<false><<<ctas, v.threads ? v.threads : 256, 0, st>>>(p);
+        if (bulk) bulk_fn<<<ctas, bulk_threads, bulk_smem, st>>>(p);
+        else if (!strcmp(v.kind, "brick")) gs3_cl_kernel<false><<<ctas, v.threads ? v.threads : 256, 0, st>>>(p);
         else if (!strcmp(v.kind, "balanced")) gs3_cl_balanced_kernel<false><<<ctas, 256, 0, st>>>(p);
         else gs3_cl_sweep_kernel<false><<<ctas, 256, 0, st>>>(p);
         CK(cudaEventRecord(e1, st));
