@@ -195,6 +195,139 @@ __global__ void __launch_bounds__(256) gs3_cl_kernel(const GS3Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Bulk-copy gather variant of the channels-last kernel ("TMA-staged feature tiles" in gather form; instrumented build only until
+// measured: EMO_GS3_BULK=1, tools/gs3_check and tools/gs3_lab).  The eight corner rows of a voxel (C x 4 bytes each, contiguous in a
+// channels-last volume) are fetched with cp.async.bulk (1-D bulk copies global -> shared memory, completion counted on an
+// mbarrier) instead of LDG.128: the async proxy does not pay the L1tex wavefront cost that bounds the LSU path (~50 clk per voxel
+// and SM at C = 96).  Warp 0 is the producer: lanes < BV set up one voxel each (sample position -> clamped corner offsets +
+// trilinear weights -> shared memory; the grid coordinates of the NEXT stage are loaded before this stage's set-up), then all 32
+// lanes issue the 8 x BV row copies.  The other threads are consumers, one float4 of one voxel each: wait for the stage, blend the
+// eight rows from shared memory in the brick kernel's FMA order (bit-identical output), store.  NST stages ring; chunks of BV
+// voxels go round-robin over the persistent CTAs in raster order, so the grid sweeps the lattice as one thin slab.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gs_mbar_init(uint64_t* b, uint32_t c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gs_smem_u32(b)), "r"(c)); }
+__device__ __forceinline__ void gs_mbar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gs_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gs_mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gs_smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void gs_mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile("{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(gs_smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void gs_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gs_smem_u32(dst)), "l"(src), "r"(bytes),
+               "r"(gs_smem_u32(bar)) : "memory");
+}
+
+template <int BV, int NST, bool SPLIT>
+__global__ void __launch_bounds__(1024, 1) gs3_bulk_kernel(const GS3Params p) {
+  extern __shared__ __align__(128) uint8_t gs_sraw[];
+  const int c4n = p.C >> 2;
+  const uint32_t row_bytes = (uint32_t)p.C * 4u;
+  float* ring = (float*)gs_sraw;  // [NST][BV][8][C]
+  __shared__ __align__(16) float s_wgt[NST][BV][8];
+  __shared__ long long s_out[NST][BV];
+  __shared__ int s_row[BV * 8];
+  __shared__ uint64_t full_bar[NST], empty_bar[NST];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncw = (BV * c4n + 31) / 32;  // consumer warps (host launches exactly 1 + ncw warps)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { gs_mbar_init(&full_bar[i], 1); gs_mbar_init(&empty_bar[i], (uint32_t)ncw); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long per_sample = (long long)p.Dout * p.Hout * p.Wout;  // a multiple of BV (host): chunks never straddle samples
+  const long long nchunks = per_sample * p.N / BV;
+  const size_t stage_floats = (size_t)BV * 8 * p.C;
+  if (warp == 0) {
+    int it = 0;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    auto coords = [&](long long ch) {
+      if (lane < BV && ch < nchunks) {
+        const long long v = ch * BV + lane;
+        const int n = (int)(v / per_sample);
+        long long r = v - (long long)n * per_sample;
+        const int ow = (int)(r % p.Wout); r /= p.Wout;
+        const int oh = (int)(r % p.Hout);
+        const int od = (int)(r / p.Hout);
+        sample_coord(p, n, od, oh, ow, gx, gy, gz);
+      }
+    };
+    long long chunk = blockIdx.x;
+    coords(chunk);
+    for (; chunk < nchunks; chunk += gridDim.x, ++it) {
+      const int slot = it % NST;
+      const float cx = gx, cy = gy, cz = gz;
+      coords(chunk + gridDim.x);
+      if (it >= NST) gs_mbar_wait(&empty_bar[slot], (uint32_t)((it / NST) - 1) & 1u);
+      const long long v0 = chunk * BV;
+      const int n = (int)(v0 / per_sample);
+      if (lane < BV) {
+        long long r = v0 + lane - (long long)n * per_sample;
+        const int ow = (int)(r % p.Wout); r /= p.Wout;
+        const int oh = (int)(r % p.Hout);
+        const int od = (int)(r / p.Hout);
+        const Corner8 k = corners(p, cx, cy, cz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+          const int x = k.x0 + dx, y = k.y0 + dy, z = k.z0 + dz;
+          const bool ok = (unsigned)x < (unsigned)p.Win && (unsigned)y < (unsigned)p.Hin && (unsigned)z < (unsigned)p.Din;
+          const int xc = min(max(x, 0), p.Win - 1), yc = min(max(y, 0), p.Hin - 1), zc = min(max(z, 0), p.Din - 1);
+          s_wgt[slot][lane][j] = ok ? (dx ? k.fx : 1.f - k.fx) * (dy ? k.fy : 1.f - k.fy) * (dz ? k.fz : 1.f - k.fz) : 0.f;
+          s_row[lane * 8 + j] = (zc * p.Hin + yc) * p.Win + xc;
+        }
+        s_out[slot][lane] = (long long)n * p.os_n + (long long)od * p.os_d + (long long)oh * p.os_h + (long long)ow * p.os_w;
+      }
+      __syncwarp();
+      if (lane == 0) gs_mbar_expect(&full_bar[slot], (uint32_t)(BV * 8) * row_bytes);
+      __syncwarp();
+      const char* vol = (const char*)(p.in + (long long)n * p.Din * p.Hin * p.Win * p.C);
+      float* dst = ring + (size_t)slot * stage_floats;
+      for (int q = lane; q < BV * 8; q += 32) gs_bulk_g2s(dst + (size_t)q * p.C, vol + (long long)s_row[q] * row_bytes, row_bytes, &full_bar[slot]);
+      __syncwarp();  // s_row is rewritten by the next stage
+    }
+  } else {
+    const int t = (int)threadIdx.x - 32;
+    const int vox = t / c4n, c4 = t - vox * c4n;
+    const bool active = t < BV * c4n;
+    const uint64_t pol_out = l2_policy_evict_first();
+    int it = 0;
+    for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x, ++it) {
+      const int slot = it % NST;
+      gs_mbar_wait(&full_bar[slot], (uint32_t)(it / NST) & 1u);
+      if (active) {
+        const float4 w0 = *(const float4*)&s_wgt[slot][vox][0], w1 = *(const float4*)&s_wgt[slot][vox][4];
+        const float4* src = (const float4*)(ring + (size_t)slot * stage_floats + (size_t)vox * 8 * p.C) + c4;
+        const float4 v0 = src[0 * c4n], v1 = src[1 * c4n], v2 = src[2 * c4n], v3 = src[3 * c4n];
+        const float4 v4 = src[4 * c4n], v5 = src[5 * c4n], v6 = src[6 * c4n], v7 = src[7 * c4n];
+        float4 acc;
+#define EMO_GS_ACC(f) \
+  acc.f = fmaf(v7.f, w1.w, fmaf(v6.f, w1.z, fmaf(v5.f, w1.y, fmaf(v4.f, w1.x, \
+          fmaf(v3.f, w0.w, fmaf(v2.f, w0.z, fmaf(v1.f, w0.y, v0.f * w0.x)))))));
+        EMO_GS_ACC(x) EMO_GS_ACC(y) EMO_GS_ACC(z) EMO_GS_ACC(w)
+#undef EMO_GS_ACC
+        const long long o = s_out[slot][vox] + (long long)(c4 * 4);
+        if (p.out) stg_hint((float4*)(p.out + o), acc, pol_out);
+        if (SPLIT) {
+          uint2 hi, lo, lo2;
+          if (p.out_lo2) {
+            split4x3(acc, hi, lo, lo2);
+            *(uint2*)(p.out_lo2 + o) = lo2;
+          } else {
+            split4(acc, hi, lo);
+          }
+          *(uint2*)(p.out_hi + o) = hi;
+          *(uint2*)(p.out_lo + o) = lo;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) gs_mbar_arrive(&empty_bar[slot]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // NCDHW kernel (drop-in layout of F.grid_sample): one thread = one output voxel, loops over channels with the
 // corner offsets/weights held in registers; lanes run along W so both the gathers and the stores coalesce.
 // ------------------------------------------------------------------------------------------------
@@ -491,6 +624,29 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
       if (bs && sscanf(bs, "%d,%d,%d,%d", &fw, &fh, &fd, &ft) >= 3 && fw > 0 && fh > 0 && fd > 0 && fw * fh * fd <= kBrickVox) {
         p.bw = fw < d->Wout ? fw : d->Wout; p.bh = fh < d->Hout ? fh : d->Hout; p.bd = fd < d->Dout ? fd : d->Dout;
         if (ft >= p.bw * p.bh * p.bd && ft <= 256 && ft % 32 == 0) threads = (unsigned)ft;
+      }
+    }
+#endif
+#ifdef EMO_CONV_DEBUG
+    {  // EMO_GS3_BULK=1: the bulk-copy gather variant where its preconditions hold (vector stores, whole stages, rows >= 256 B)
+      const char* bk = getenv("EMO_GS3_BULK");
+      constexpr int BV = 8, NST = 4;
+      const long long per_sample = (long long)d->Dout * d->Hout * d->Wout;
+      if (bk && atoi(bk) > 0 && d->os_c == 1 && per_sample % BV == 0 && d->C >= 64 && BV * (d->C / 4) <= 992) {
+        const size_t smem = (size_t)NST * BV * 8 * d->C * 4;
+        const int threads = 32 + cdiv(BV * (d->C / 4), 32) * 32;
+        cudaError_t e = d->out_hi ? cudaFuncSetAttribute(gs3_bulk_kernel<BV, NST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                  : cudaFuncSetAttribute(gs3_bulk_kernel<BV, NST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0;
+        if (e == cudaSuccess)
+          e = d->out_hi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_bulk_kernel<BV, NST, true>, threads, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gs3_bulk_kernel<BV, NST, false>, threads, smem);
+        EMO_REQUIRE(e == cudaSuccess && occ > 0, "emo_grid_sample3d: bulk variant does not fit (%s)", cudaGetErrorString(e));
+        long long ctas = (long long)sms_dev[dev & 63] * occ;
+        if (ctas > per_sample * d->N / BV) ctas = per_sample * d->N / BV;
+        if (d->out_hi) launch_kernel(gs3_bulk_kernel<BV, NST, true>, (unsigned)ctas, (unsigned)threads, smem, stream, p);
+        else launch_kernel(gs3_bulk_kernel<BV, NST, false>, (unsigned)ctas, (unsigned)threads, smem, stream, p);
+        return check_launch("emo_grid_sample3d");
       }
     }
 #endif

@@ -152,3 +152,28 @@ def test_dry_run_fp16_two_plane_networks():
     env = dict(os.environ, EMO_DRY_RUN="1")
     r = subprocess.run([sys.executable, "-c", H2_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+MASK_SCRIPT = r"""
+import torch, sys
+sys.path.insert(0, %r)
+from emoportraits_b200 import lib as L
+assert L.DRY_RUN
+from emoportraits_b200.masks import FaceParsing, modnet_get_mask
+from oracle.stub_nets import StubBiSeNet, StubMODNet
+fp = FaceParsing(None, device="cpu", net=StubBiSeNet())
+n0 = L.launch_count
+m = fp.forward(torch.rand(2, 3, 300, 400))
+assert len(m) == 4 and all(t.shape == (2, 1, 300, 400) and t.dtype == torch.int64 for t in m)
+assert L.launch_count - n0 == 2                      # normalise + resize, resize + argmax + label sets
+matte = modnet_get_mask(StubMODNet(), torch.rand(1, 3, 300, 400))
+assert matte.shape == (1, 1, 300, 400)               # 300 x 400 -> 512 x 672 for the network -> back (infer.py:663-682)
+assert L.launch_count - n0 == 4
+print("ok")
+"""
+
+
+def test_dry_run_mask_processing_shapes():
+    env = dict(os.environ, EMO_DRY_RUN="1")
+    r = subprocess.run([sys.executable, "-c", MASK_SCRIPT % str(ROOT)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr

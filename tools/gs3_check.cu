@@ -154,11 +154,13 @@ int main(int argc, char** argv) {
       d.os_w = c.C; d.os_h = (long long)c.Wo * c.C; d.os_d = d.os_h * c.Ho; d.os_n = d.os_d * c.Do;
     }
     const double bytes = ((double)2 * c.C + (c.affine ? 0 : 3)) * 4.0 * (double)vox;
-    const char* variants[] = {"brick_8x8x4", "auto", "brick_8x8x2", "brick_8x8x1", "brick_8x8x1_128thr", "brick_4x4x4"};
-    const char* envs[] = {"8,8,4", nullptr, "8,8,2", "8,8,1", "8,8,1,128", "4,4,4"};
-    for (int v = 0; v < 6; ++v) {
+    const char* variants[] = {"brick_8x8x4", "auto", "brick_8x8x2", "brick_8x8x1", "brick_8x8x1_128thr", "brick_4x4x4", "bulk_copy_gather"};
+    const char* envs[] = {"8,8,4", nullptr, "8,8,2", "8,8,1", "8,8,1,128", "4,4,4", nullptr};
+    for (int v = 0; v < 7; ++v) {
       if (envs[v]) setenv("EMO_GS3_BRICK", envs[v], 1);
       else unsetenv("EMO_GS3_BRICK");
+      if (v == 6) setenv("EMO_GS3_BULK", "1", 1);  // falls back to the brick kernel where its preconditions do not hold (ragged cases)
+      else unsetenv("EMO_GS3_BULK");
       const int slot = v == 0 ? 0 : 1;
       d.out = out[slot];
       d.out_hi = planes[slot][0]; d.out_lo = planes[slot][1];
@@ -201,6 +203,7 @@ int main(int argc, char** argv) {
     }
   }
   unsetenv("EMO_GS3_BRICK");
+  unsetenv("EMO_GS3_BULK");
   printf(bad ? "FAIL: %d variant runs differ from the 8x8x4 brick\n" : "OK: all brick shapes bit-identical\n", bad);
   return bad ? 1 : 0;
 }
