@@ -17,8 +17,10 @@ namespace emo {
 // F.interpolate bilinear, align_corners=False: src = (dst + 0.5) * (in / out) - 0.5, clamped at 0; the upper neighbour is
 // clamped to the last index; lambda from the unclamped-at-the-top source coordinate (ATen area_pixel_compute_source_index)
 __device__ __forceinline__ void bilinear_taps(int o, int in, int out, int& i0, int& i1, float& l1) {
-  const float scale = (float)in / (float)out;
-  float s = ((float)o + 0.5f) * scale - 0.5f;
+  // two roundings, never contracted into an FMA: ATen's CPU path computes scale * (dst + 0.5) - 0.5 that way, and one ulp of the
+  // source coordinate (6e-5 at index 700) times a steep image gradient is far above fp32 noise
+  const float scale = __fdiv_rn((float)in, (float)out);
+  float s = __fsub_rn(__fmul_rn(scale, (float)o + 0.5f), 0.5f);
   if (s < 0.f) s = 0.f;
   i0 = (int)s;
   if (i0 > in - 1) i0 = in - 1;
