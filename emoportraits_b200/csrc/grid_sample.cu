@@ -606,15 +606,21 @@ extern "C" int emo_grid_sample3d(const emo_grid_sample3d_desc* d, void* stream_)
     // through the lattice along d.  With the round-1 brick of 8 x 8 x 4 = 256 voxels a 64^3 lattice is 1024 CTAs against 888
     // resident ones: the whole lattice is in flight at once, and a warp-field tensor whose samples scatter over +-10 slices
     // re-reads the 100 MB volume 2.5 times from DRAM (ncu, profiles/prof_gs3_r2.txt) because the lines do not survive in L2
-    // between their ~8 uses.  Flat bricks keep the in-flight slab thin (8 x 8 x 1: 4096 CTAs, ~14 slices in flight):
-    // 64^3 warp-field 90.2 -> 65.5 us, batch 8 474 -> 403 us (8 x 8 x 2).  A persistent kernel walking the same order with
+    // between their ~8 uses.  Small bricks keep the in-flight slab thin (64-voxel bricks: 4096 CTAs, ~14 slices in flight):
+    // 64^3 warp-field 90.2 -> 63.5 us, batch 8 474 -> 401 us (8 x 8 x 2).  A persistent kernel walking the same order with
     // a barrier per chunk was slower than letting the hardware dispatch small CTAs (96-131 us; tools/gs3_lab.cu keeps it).
-    //   depth 2 bricks (128 voxels) when that still gives >= 4 waves of CTAs, else depth 1 (64 voxels);
-    //   small lattices then halve the brick height until there are >= 4 CTAs per SM.
+    //   8 x 8 x 2 bricks (128 voxels) when that gives >= 4 waves of CTAs (batches: 474 -> 401 us for 8 x 64^3), else compact
+    //   4 x 4 x 4 bricks (64 voxels: 4096 CTAs for 64^3; second call of the study: 63.5 / 56.5 us warp-field / fused lattice
+    //   against 65.5 / 59.4 for 8 x 8 x 1 and 69.6 / 59.4 for 8 x 8 x 2; 16 x 64 x 64: 22.5 us, all shapes within noise),
+    //   8 x 8 x 1 when the lattice is shallower than 4; small lattices then halve the brick height until there are >= 4 CTAs
+    //   per SM.  (128- and 64-thread CTAs, tried for finer dispatch, lose 20-50 %: same study.)
     p.bw = d->Wout >= 8 ? 8 : d->Wout;
     p.bh = d->Hout >= 8 ? 8 : d->Hout;
     p.bd = d->Dout >= 2 ? 2 : d->Dout;
-    if ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4ll * slots[k]) p.bd = 1;
+    if ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4ll * slots[k]) {
+      if (d->Dout >= 4 && d->Hout >= 4 && d->Wout >= 4) { p.bw = 4; p.bh = 4; p.bd = 4; }
+      else p.bd = 1;
+    }
     while ((long long)d->N * cdiv(d->Wout, p.bw) * cdiv(d->Hout, p.bh) * cdiv(d->Dout, p.bd) < 4ll * sms_dev[dev & 63] && p.bh > 2) p.bh >>= 1;
     unsigned threads = 256;
 #ifdef EMO_CONV_DEBUG

@@ -19,4 +19,9 @@ for k,v in d['roofline_grid_sample3d'].items():
 P
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gs3_cl -c 8 -o /tmp/prof_gs3_r2b python tools/prof_kernels.py > "$out/prof_gs3.log" 2>&1
 ncu -i /tmp/prof_gs3_r2b.ncu-rep --page raw --csv > "$out/prof_gs3_r2b.raw.csv" 2>/dev/null
+for e in auto 1; do timeout 120 python tools/conv_timeline.py $e > "$out/timeline_$e.txt" 2>&1; done
+rm -f gpurun_out/stage_parity.txt gpurun_out/parity_*.txt
+timeout 1500 python -m pytest tests -q -m gpu -rA -s > "$out/pytest_gpu.txt" 2>&1; echo "pytest full rc=$?" | tee -a "$out/summary.txt"
+grep -E "^(FAILED|ERROR)|passed|failed" "$out/pytest_gpu.txt" | tail -30 >> "$out/summary.txt"
+cp gpurun_out/parity_*.txt gpurun_out/stage_parity.txt "$out/" 2>/dev/null
 ls -la "$out"; cat "$out/summary.txt"
