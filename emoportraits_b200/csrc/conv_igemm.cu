@@ -29,6 +29,8 @@
 //   the weight tile, which halves the weight ingest and brings the shared-memory operand reads per MMA under the
 //   tensor floor (measured in tools/mma_probe.cu).
 // Persistent CTAs walk tiles round-robin; the chunk ring lets the MMA of the next tile run ahead of the epilogue.
+#include <type_traits>
+
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
@@ -93,6 +95,14 @@ struct ConvKParams {
 // PTX wrappers
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -757,9 +767,10 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   const size_t smem_limit = 227 * 1024;
   // Final phase of a tile (template parameter EPI, see the kernel's header comment).  TMA epilogue when the layer qualifies
   // (pair mode, full K loop, channels-last output in whole 32-channel panels, no post-add) and pays: per-layer CUDA-graph timings
-  // of every shape of the driver frame (tools/conv_layer_bench.py, profiles/conv_layers_r2.md) put it ahead for N tiles of
-  // >= 96 channels when either a residual rides in through TMA or the CTA walks >= 2 tiles; narrow-N 3-D layers and
-  // single-wave layers without a residual stay with the in-warp form.
+  // of every shape of the driver frame (tools/conv_layer_bench.py, profiles/conv_layers_r2.md; re-measured after the staging
+  // loop was rewritten, profiles/conv_layers_r2b.md) put it ahead for N tiles of >= 96 channels, with or without a residual,
+  // except the single-wave layer with a half-resolution residual (128^2 320->320: 425 vs 450 TFLOP/s); narrow-N 3-D layers stay
+  // with the in-warp form.
   int epi = 0;
   int want_epi = -1;
 #ifdef EMO_CONV_DEBUG
@@ -771,7 +782,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     const bool eligible = p.cg == 2 && ksplit == 1 && !d->out_nchw && d->Cout == d->Cout_pad && d->Cout % 32 == 0 && BN % 32 == 0 && !d->post_add &&
                           ((uintptr_t)d->out % 16) == 0 && (!d->residual || ((uintptr_t)d->residual % 16) == 0) && (!ps || d->N * (long long)gH < (1ll << 31));
     const bool res_ok = !d->residual || d->res_shift == 0 || (d->res_shift == 1 && !ps && p.td == 1 && p.tw % 2 == 0 && p.th % 2 == 0 && p.tw * p.th == kTileM);
-    const bool pays = BN >= 96 && (d->residual || tiles >= 2ll * sm_count);
+    const bool pays = BN >= 96 && (!d->residual || d->res_shift == 0 || tiles >= 2ll * sm_count);
     if (eligible && res_ok && (want < 0 ? pays : want == 1)) epi = 1;
   }
   p.res_tma = (epi == 1 && d->residual && !ps) ? (d->res_shift == 0 ? 1 : 2) : 0;

@@ -10,7 +10,7 @@ import torch
 from emoportraits_b200 import lib as L, ops
 
 NAMES = ["entry", "prologue done", "producer starts", "producer done", "first operands landed", "last MMA issued",
-         "last chunk consumed", "final-phase stores issued", "statistics done", "teardown barrier", "TMEM freed",
+         "last chunk consumed", "final-phase stores issued (TMA epilogue: staging tile free)", "statistics done (TMA epilogue: staging loop done)", "teardown barrier", "TMEM freed",
          "TMA epilogue: staging tile written", "TMA epilogue: stores issued", "TMA epilogue: statistics done", "TMA epilogue: staging tile read by the store"]
 dev = "cuda"
 g = torch.Generator().manual_seed(0)
