@@ -18,6 +18,11 @@ for k,v in d['roofline_grid_sample3d'].items():
     if isinstance(v,dict) and 'ms' in v: print(k, round(v['ms']*1e3,1),'us', round(v['frac'],3), 'dirty', round(v['ms_dirty_flush']*1e3,1), round(v['frac_dirty_flush'],3))
 P
 timeout 300 python tools/conv_layer_bench.py > "$out/layers_auto.txt" 2>&1; tail -1 "$out/layers_auto.txt"
+DBG=$PWD/emoportraits_b200/csrc/libemoport_dbg.so
+for e in 0 1; do EMO_LIB=$DBG EMO_CONV_EPI=$e timeout 300 python tools/conv_layer_bench.py > "$out/layers_epi$e.txt" 2>&1; done
+for n in 1 2 4; do timeout 300 python bench.py --steps 40 --warmup 5 --quick --inflight $n > "$out/bench_inflight$n.json" 2>/dev/null; python -c "
+import json
+d=json.loads(open('$out/bench_inflight$n.json').read().strip().splitlines()[-1]); print('inflight $n', round(d['value'],1), round(d['e2e']['value'],1))" | tee -a "$out/summary.txt"; done
 for e in auto 0 1; do timeout 120 python tools/conv_timeline.py $e > "$out/timeline_$e.txt" 2>&1; done
 timeout 200 tools/gs3_lab > "$out/gs3_lab.txt" 2>&1
 timeout 200 tools/gs3_check > "$out/gs3_check.txt" 2>&1
