@@ -659,8 +659,8 @@ def main():
     ap.add_argument("--eager", action="store_true", help="do not capture the driver frame in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="A/B runs: skip the grid_sample microbench and the CPU baseline (not a bench record)")
-    ap.add_argument("--inflight", type=int, default=3, help="driver frames in flight per GPU (1 = strictly one after the other; measured "
-                    "round 2: 219 / 262 / 284 / 289 frames/s with 1 / 2 / 3 / 4)")
+    ap.add_argument("--inflight", type=int, default=4, help="driver frames in flight per GPU (1 = strictly one after the other; measured "
+                    "round 2, final tree: 239 / 291 / 304 / 312 frames/s with 1 / 2 / 3 / 4)")
     ap.add_argument("--workload", default="driver", choices=["driver", "stage2"],
                     help="driver = the headline metric (default); stage2 = BASELINE config 5, secondary")
     args = ap.parse_args()

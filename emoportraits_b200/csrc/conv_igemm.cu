@@ -764,10 +764,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
   EMO_REQUIRE(!ps || p.cg == 2, "emo_conv_igemm: upconv needs an even number of pixel tiles and BN %% 32 == 0 (pair mode)");
 
   const size_t tail_bytes = (2 * kMaxStages + 2 * kAccBufs + 2 + 2 * kMaxAStages) * 8 + 16 + 8 * kMaxBN * sizeof(float);
-  size_t smem_limit = 227 * 1024;
-#ifdef EMO_CONV_DEBUG
-  { const char* e = getenv("EMO_CONV_SMEM_KB"); if (e && atoi(e) >= 96 && atoi(e) <= 227) smem_limit = (size_t)atoi(e) * 1024; }  // co-residency experiments
-#endif
+  const size_t smem_limit = 227 * 1024;
   // Final phase of a tile (template parameter EPI, see the kernel's header comment).  TMA epilogue when the layer qualifies
   // (pair mode, full K loop, channels-last output in whole 32-channel panels, no post-add) and pays: per-layer CUDA-graph timings
   // of every shape of the driver frame (tools/conv_layer_bench.py, profiles/conv_layers_r2.md; re-measured after the staging

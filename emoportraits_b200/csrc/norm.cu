@@ -237,28 +237,21 @@ extern "C" int emo_apply(const emo_apply_desc* d, void* stream_) {
   const long long cap = (148ll * 32) / (d->N > 0 ? d->N : 1);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  unsigned threads = 256;
-#ifdef EMO_CONV_DEBUG
-  {  // instrumented build: CTA size of the apply kernels (co-residency experiments with the convolution's 1-CTA-per-SM grid)
-    const char* e = getenv("EMO_APPLY_THREADS");
-    if (e && (atoi(e) == 64 || atoi(e) == 128)) { threads = (unsigned)atoi(e); blocks = cdivll(per_n, threads); if (blocks > cap * (256 / threads)) blocks = cap * (256 / threads); }
-  }
-#endif
   const dim3 grid((unsigned)blocks, (unsigned)d->N);
   const size_t smem = d->stats ? 2 * (size_t)d->C * sizeof(float) : 0;
   EMO_REQUIRE(smem <= 48 * 1024, "emo_apply: C=%d too large for the fused finalisation", d->C);
   if (d->plane_fp16) {
     EMO_REQUIRE(!d->out_lo2 && d->plane_scale > 0.f, "emo_apply: fp16 planes come in pairs and need a positive plane_scale");
-    if (d->up == 1 && V == 2) launch_kernel(apply_f16_kernel<1, 2>, grid, threads, smem, stream, *d);
-    else if (d->up == 1) launch_kernel(apply_f16_kernel<1, 1>, grid, threads, smem, stream, *d);
-    else if (V == 2) launch_kernel(apply_f16_kernel<2, 2>, grid, threads, smem, stream, *d);
-    else launch_kernel(apply_f16_kernel<2, 1>, grid, threads, smem, stream, *d);
+    if (d->up == 1 && V == 2) launch_kernel(apply_f16_kernel<1, 2>, grid, 256, smem, stream, *d);
+    else if (d->up == 1) launch_kernel(apply_f16_kernel<1, 1>, grid, 256, smem, stream, *d);
+    else if (V == 2) launch_kernel(apply_f16_kernel<2, 2>, grid, 256, smem, stream, *d);
+    else launch_kernel(apply_f16_kernel<2, 1>, grid, 256, smem, stream, *d);
     return check_launch("emo_apply");
   }
-  if (d->up == 1 && V == 2) launch_kernel(apply_kernel<1, 2>, grid, threads, smem, stream, *d);
-  else if (d->up == 1) launch_kernel(apply_kernel<1, 1>, grid, threads, smem, stream, *d);
-  else if (V == 2) launch_kernel(apply_kernel<2, 2>, grid, threads, smem, stream, *d);
-  else launch_kernel(apply_kernel<2, 1>, grid, threads, smem, stream, *d);
+  if (d->up == 1 && V == 2) launch_kernel(apply_kernel<1, 2>, grid, 256, smem, stream, *d);
+  else if (d->up == 1) launch_kernel(apply_kernel<1, 1>, grid, 256, smem, stream, *d);
+  else if (V == 2) launch_kernel(apply_kernel<2, 2>, grid, 256, smem, stream, *d);
+  else launch_kernel(apply_kernel<2, 1>, grid, 256, smem, stream, *d);
   return check_launch("emo_apply");
 }
 

@@ -387,11 +387,11 @@ class InferenceWrapper(torch.nn.Module):
             custom_srt = torch.cat([torch.as_tensor(t).float().reshape(1, 3) for t in custome_target_theta_embed], 1)
         per_frame = smooth_pose or custom_srt is not None or custome_target_pose_embed is not None
         if not per_frame:
-            # captured driver frames (CUDA graphs), three in flight when a list of frames is given (DriverPipeline); same
+            # captured driver frames (CUDA graphs), four in flight when a list of frames is given (DriverPipeline); same
             # kernels as the eager pass below
             key = (bool(mix), bool(target_theta), bool(mix_old))
             if self._pipeline is None or self._pipeline.st is not self._state or self._pipeline_key != key:
-                self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=3, mix=mix,
+                self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=4, mix=mix,
                                                                     target_theta=target_theta, mix_old=mix_old), key
             img = torch.empty_like(drv)
             for i in range(drv.shape[0]):
