@@ -408,10 +408,10 @@ struct FinParams {
 };
 
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f) {
-  extern __shared__ float sstat[];
+  extern __shared__ double sstat[];  // fp64: sums of fp32 values are exact -> independent of the order of the atomics
   const int n = blockIdx.y;
   if (f.stats) {
-    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * f.G; i += blockDim.x) sstat[i] = 0.0;
     __syncthreads();
   }
   const long long per_n = f.S * f.C;
@@ -430,15 +430,15 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const FinParams f)
     if (f.out_nchw) f.out[((long long)n * f.C + c) * f.S + sp] = v;
     else f.out[i] = v;
     if (f.stats) {
-      atomicAdd(&sstat[c / cpg], v);
-      atomicAdd(&sstat[f.G + c / cpg], v * v);
+      atomicAdd(&sstat[c / cpg], (double)v);
+      atomicAdd(&sstat[f.G + c / cpg], (double)(v * v));
     }
   }
   if (f.stats) {
     __syncthreads();
     for (int g = threadIdx.x; g < f.G; g += blockDim.x) {
-      atomicAdd(&f.stats[((long long)n * f.G + g) * 2], (double)sstat[g]);
-      atomicAdd(&f.stats[((long long)n * f.G + g) * 2 + 1], (double)sstat[f.G + g]);
+      atomicAdd(&f.stats[((long long)n * f.G + g) * 2], sstat[g]);
+      atomicAdd(&f.stats[((long long)n * f.G + g) * 2 + 1], sstat[f.G + g]);
     }
   }
 }
@@ -1012,7 +1012,7 @@ extern "C" int emo_conv_igemm(const emo_conv_desc* d, void* stream_) {
     if (bx > 148 * 4) bx = 148 * 4;
     if (bx < 1) bx = 1;
     dim3 fg((unsigned)bx, (unsigned)d->N);
-    launch_kernel(splitk_finalize_kernel, fg, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, f);
+    launch_kernel(splitk_finalize_kernel, fg, 256, d->stats ? 2 * d->G * sizeof(double) : 0, stream, f);
   }
   if (post) {
     // every other layer: the post-op is the ordinary elementwise pass over the convolution's output

@@ -55,9 +55,9 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const emo_conv_direct_
   const int co4n = d.Cout >> 2;
   const long long total = (long long)d.N * d.Hout * d.Wout * co4n;
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  extern __shared__ float sstat[];  // [2][G] when stats requested
+  extern __shared__ double sstat[];  // [2][G] when stats requested
   if (d.stats) {
-    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.0;
     __syncthreads();
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -96,16 +96,16 @@ __global__ void __launch_bounds__(256) conv_direct_kernel(const emo_conv_direct_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = (co4 * 4 + j) / cpg;
-        atomicAdd(&sstat[g], a[j]);
-        atomicAdd(&sstat[d.G + g], a[j] * a[j]);
+        atomicAdd(&sstat[g], (double)a[j]);
+        atomicAdd(&sstat[d.G + g], (double)(a[j] * a[j]));
       }
     }
     __syncthreads();
     const long long first = (long long)blockIdx.x * blockDim.x;
     const int nb = (int)(first / ((long long)d.Hout * d.Wout * co4n));
     for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
-      atomicAdd(&d.stats[((long long)nb * d.G + g) * 2], (double)sstat[g]);
-      atomicAdd(&d.stats[((long long)nb * d.G + g) * 2 + 1], (double)sstat[d.G + g]);
+      atomicAdd(&d.stats[((long long)nb * d.G + g) * 2], sstat[g]);
+      atomicAdd(&d.stats[((long long)nb * d.G + g) * 2 + 1], sstat[d.G + g]);
     }
   }
 }
@@ -130,9 +130,9 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resam
   const long long per_n = So * c4n;
   // grid.y = sample index so that a CTA never straddles samples (needed for the stats reduction)
   const int n = blockIdx.y;
-  extern __shared__ float sstat[];
+  extern __shared__ double sstat[];
   if (d.stats) {
-    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.0;
     __syncthreads();
   }
   const float4* x4 = (const float4*)d.x + (long long)n * d.D * d.H * d.W * c4n;
@@ -180,8 +180,8 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resam
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int g = (c4 * 4 + j) / cpg;
-          atomicAdd(&sstat[g], a[j]);
-          atomicAdd(&sstat[d.G + g], a[j] * a[j]);
+          atomicAdd(&sstat[g], (double)a[j]);
+          atomicAdd(&sstat[d.G + g], (double)(a[j] * a[j]));
         }
       }
     }
@@ -193,14 +193,14 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resam
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = (c4 * 4 + j) / cpg;
-        atomicAdd(&sstat[g], rs[j]);
-        atomicAdd(&sstat[d.G + g], rq[j]);
+        atomicAdd(&sstat[g], (double)rs[j]);
+        atomicAdd(&sstat[d.G + g], (double)rq[j]);
       }
     }
     __syncthreads();
     for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
-      atomicAdd(&d.stats[((long long)n * d.G + g) * 2], (double)sstat[g]);
-      atomicAdd(&d.stats[((long long)n * d.G + g) * 2 + 1], (double)sstat[d.G + g]);
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2], sstat[g]);
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2 + 1], sstat[d.G + g]);
     }
   }
 }
@@ -211,9 +211,9 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d)
   const int Do = d.D / d.fd, Ho = d.H / d.fh, Wo = d.W / d.fw;
   const long long per_n = (long long)Do * Ho * Wo * c4n;
   const int n = blockIdx.y;
-  extern __shared__ float sstat[];
+  extern __shared__ double sstat[];
   if (d.stats) {
-    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * d.G; i += blockDim.x) sstat[i] = 0.0;
     __syncthreads();
   }
   const float4* x4 = (const float4*)d.x + (long long)n * d.D * d.H * d.W * c4n;
@@ -250,8 +250,8 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int g = (c4 * 4 + j) / cpg;
-          atomicAdd(&sstat[g], a[j]);
-          atomicAdd(&sstat[d.G + g], a[j] * a[j]);
+          atomicAdd(&sstat[g], (double)a[j]);
+          atomicAdd(&sstat[d.G + g], (double)(a[j] * a[j]));
         }
       }
     }
@@ -263,14 +263,14 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = (c4 * 4 + j) / cpg;
-        atomicAdd(&sstat[g], rs[j]);
-        atomicAdd(&sstat[d.G + g], rq[j]);
+        atomicAdd(&sstat[g], (double)rs[j]);
+        atomicAdd(&sstat[d.G + g], (double)rq[j]);
       }
     }
     __syncthreads();
     for (int g = threadIdx.x; g < d.G; g += blockDim.x) {
-      atomicAdd(&d.stats[((long long)n * d.G + g) * 2], (double)sstat[g]);
-      atomicAdd(&d.stats[((long long)n * d.G + g) * 2 + 1], (double)sstat[d.G + g]);
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2], sstat[g]);
+      atomicAdd(&d.stats[((long long)n * d.G + g) * 2 + 1], sstat[d.G + g]);
     }
   }
 }
@@ -385,7 +385,7 @@ extern "C" int emo_conv_direct(const emo_conv_direct_desc* d, void* stream_) {
   const long long per_n = (long long)d->Hout * d->Wout * (d->Cout / 4);
   if (d->stats) EMO_REQUIRE(per_n % 256 == 0 && d->G > 0 && d->Cout % d->G == 0, "emo_conv_direct: stats need Hout*Wout*Cout/4 %% 256 == 0");
   const long long total = per_n * d->N;
-  launch_kernel(conv_direct_kernel, (unsigned)cdivll(total, 256), 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, *d);
+  launch_kernel(conv_direct_kernel, (unsigned)cdivll(total, 256), 256, d->stats ? 2 * d->G * sizeof(double) : 0, stream, *d);
   return check_launch("emo_conv_direct");
 }
 
@@ -406,7 +406,7 @@ extern "C" int emo_upsample_trilinear(const emo_resample_desc* d, void* stream_)
   if (bx > 148 * 16) bx = 148 * 16;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)d->N);
-  launch_kernel(upsample_trilinear_kernel, grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, *d);
+  launch_kernel(upsample_trilinear_kernel, grid, 256, d->stats ? 2 * d->G * sizeof(double) : 0, stream, *d);
   return check_launch("emo_upsample_trilinear");
 }
 
@@ -420,7 +420,7 @@ extern "C" int emo_avgpool(const emo_resample_desc* d, void* stream_) {
   if (bx > 148 * 16) bx = 148 * 16;
   if (bx < 1) bx = 1;
   dim3 grid((unsigned)bx, (unsigned)d->N);
-  launch_kernel(avgpool_kernel, grid, 256, d->stats ? 2 * d->G * sizeof(float) : 0, stream, *d);
+  launch_kernel(avgpool_kernel, grid, 256, d->stats ? 2 * d->G * sizeof(double) : 0, stream, *d);
   return check_launch("emo_avgpool");
 }
 

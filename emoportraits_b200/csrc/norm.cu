@@ -20,8 +20,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
   const long long s0 = (long long)ch * s_per;
   const long long s1 = (s0 + s_per < S) ? s0 + s_per : S;
   const int cpg = C / G;
-  extern __shared__ float sh[];  // [2][G]
-  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.f;
+  extern __shared__ double sh[];  // [2][G]; fp64: sums of fp32 values are exact, so the result does not depend on the order of the atomics
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh[i] = 0.0;
   __syncthreads();
   const int c4n = C >> 2;
   const float4* x4 = (const float4*)(x + (long long)n * S * C);
@@ -42,15 +42,15 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int g = (c4 * 4 + j) / cpg;
-        atomicAdd(&sh[g], acc_s[j]);
-        atomicAdd(&sh[G + g], acc_q[j]);
+        atomicAdd(&sh[g], (double)acc_s[j]);
+        atomicAdd(&sh[G + g], (double)acc_q[j]);
       }
     }
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    atomicAdd(&stats[((long long)n * G + g) * 2], (double)sh[g]);
-    atomicAdd(&stats[((long long)n * G + g) * 2 + 1], (double)sh[G + g]);
+    atomicAdd(&stats[((long long)n * G + g) * 2], sh[g]);
+    atomicAdd(&stats[((long long)n * G + g) * 2 + 1], sh[G + g]);
   }
 }
 
@@ -207,7 +207,7 @@ extern "C" int emo_gn_stats(const float* x, int N, long long spatial, int C, int
   if (chunks < 1) chunks = 1;
   const int max_chunks = (148 * 8) / (N > 0 ? N : 1) > 0 ? (148 * 8) / N : 1;
   if (chunks > max_chunks) chunks = max_chunks;
-  launch_kernel(gn_stats_kernel, N * chunks, 256, 2 * G * sizeof(float), stream, x, N, spatial, C, G, stats, chunks);
+  launch_kernel(gn_stats_kernel, N * chunks, 256, 2 * G * sizeof(double), stream, x, N, spatial, C, G, stats, chunks);
   return check_launch("emo_gn_stats");
 }
 

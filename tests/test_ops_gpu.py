@@ -268,7 +268,7 @@ def test_conv_statistics_are_reproducible(ops):
     """GroupNorm statistics of a multi-tile layer: per-tile column sums go through per-quadrant slots (one writer each, fixed
     summation order), the per-tile group sums are added to the global fp64 sums with atomics - fp64 sums of fp32-sized terms,
     whose order can only move the last bits of a double: two runs agree to 1e-13 relative (the shared-memory fp32 atomics of
-    round 1 left 1e-7)."""
+    round 1 left 1e-7; see test_resampler_statistics_are_reproducible for the other producers of statistics)."""
     g = torch.Generator().manual_seed(11)
     x = torch.randn(1, 1, 128, 128, 128, generator=g).cuda()
     w = torch.randn(128, 128, 3, 3, generator=g) / math.sqrt(9 * 128)
@@ -495,3 +495,36 @@ def test_grid_sample3d_empty_and_invalid_inputs():
         ops.grid_sample3d(x, theta=torch.eye(4, device="cuda")[None, :3].contiguous(), out_size=(4, 4, 4), in_layout="cl")
 
 
+
+
+@pytest.mark.gpu
+def test_resampler_statistics_are_reproducible(ops):
+    """The GroupNorm statistics that are NOT produced by a convolution epilogue - trilinear up-sampling (+ add), average pooling,
+    the stand-alone statistics pass, the un-fused split-K finalize - accumulate per CTA in fp64 shared memory (sums of fp32 terms
+    are exact in fp64, whatever order the atomics arrive in) and then in the global fp64 sums: repeated runs agree to the last
+    bits of a double, and both match an fp64 torch reduction of the produced tensor."""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(1, 8, 16, 16, 128, generator=g).cuda() * 3 + 0.5
+    add = torch.randn(1, 16, 32, 32, 128, generator=g).cuda()
+
+    def ref(y):
+        t = y.double().reshape(1, -1, 32, 4)  # [N][spatial][G][C/G]
+        return torch.stack([t.sum((1, 3)), (t * t).sum((1, 3))], -1)
+
+    cases = {"upsample": lambda st: ops.upsample_trilinear(x, (2, 2, 2), add=add, stats=st),
+             "avgpool": lambda st: ops.avgpool(add, (1, 2, 2), stats=st),
+             "gn_stats": lambda st: (ops.gn_stats(add, 32, stats=st), add)[1]}
+    for name, fn in cases.items():
+        runs = []
+        for _ in range(3):
+            ops.begin_pass("cuda")
+            st = ops.new_stats(1, 32, "cuda")
+            y = fn(st)
+            torch.cuda.synchronize()
+            runs.append((y.clone(), st.clone()))
+        want = ref(runs[0][0])
+        for y, st in runs:
+            assert torch.equal(y, runs[0][0]), name
+            assert ((st - runs[0][1]).abs() / runs[0][1].abs().clamp_min(1.0)).max().item() < 1e-13, name
+            # per-thread partial sums are fp32 (a fixed order per thread), squares are rounded to fp32: ~1e-7 relative each
+            assert ((st.reshape(want.shape) - want).abs() / want.abs().clamp_min(1.0)).max().item() < 2e-6, name
