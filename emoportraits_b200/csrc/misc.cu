@@ -142,10 +142,12 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const emo_resam
   const bool fixed_c = ((long long)gridDim.x * blockDim.x) % c4n == 0;
   float rs[4] = {0.f, 0.f, 0.f, 0.f}, rq[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per_n; t += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % c4n);
-    long long s = t / c4n;
-    const int ow = (int)(s % Wo); s /= Wo;
-    const int oh = (int)(s % Ho); s /= Ho;
+    // 32-bit index arithmetic (the host requires per_n < 2^31): the 64-bit form is four emulated divisions per float4
+    const unsigned tu = (unsigned)t;
+    const int c4 = (int)(tu % (unsigned)c4n);
+    unsigned s = tu / (unsigned)c4n;
+    const int ow = (int)(s % (unsigned)Wo); s /= (unsigned)Wo;
+    const int oh = (int)(s % (unsigned)Ho); s /= (unsigned)Ho;
     const int od = (int)s;
     int z0, z1, y0, y1, x0, x1;
     float lz, ly, lx;
@@ -221,10 +223,12 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const emo_resample_desc d)
   const bool fixed_c = ((long long)gridDim.x * blockDim.x) % c4n == 0;  // see upsample_trilinear_kernel
   float rs[4] = {0.f, 0.f, 0.f, 0.f}, rq[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < per_n; t += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(t % c4n);
-    long long s = t / c4n;
-    const int ow = (int)(s % Wo); s /= Wo;
-    const int oh = (int)(s % Ho); s /= Ho;
+    // 32-bit index arithmetic (the host requires per_n < 2^31): the 64-bit form is four emulated divisions per float4
+    const unsigned tu = (unsigned)t;
+    const int c4 = (int)(tu % (unsigned)c4n);
+    unsigned s = tu / (unsigned)c4n;
+    const int ow = (int)(s % (unsigned)Wo); s /= (unsigned)Wo;
+    const int oh = (int)(s % (unsigned)Ho); s /= (unsigned)Ho;
     const int od = (int)s;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int a = 0; a < d.fd; ++a)
@@ -402,6 +406,7 @@ extern "C" int emo_upsample_trilinear(const emo_resample_desc* d, void* stream_)
   int rc = resample_check(d, "emo_upsample_trilinear");
   if (rc) return rc;
   const long long per_n = (long long)d->D * d->fd * d->H * d->fh * d->W * d->fw * (d->C / 4);
+  EMO_REQUIRE(per_n < (1ll << 31), "emo_upsample_trilinear: more than 2^31 output vectors per sample");
   long long bx = cdivll(per_n, 256 * 4);
   if (bx > 148 * 16) bx = 148 * 16;
   if (bx < 1) bx = 1;
@@ -416,6 +421,7 @@ extern "C" int emo_avgpool(const emo_resample_desc* d, void* stream_) {
   if (rc) return rc;
   EMO_REQUIRE(d->D % d->fd == 0 && d->H % d->fh == 0 && d->W % d->fw == 0, "emo_avgpool: size not divisible by the kernel");
   const long long per_n = (long long)(d->D / d->fd) * (d->H / d->fh) * (d->W / d->fw) * (d->C / 4);
+  EMO_REQUIRE(per_n < (1ll << 31), "emo_avgpool: more than 2^31 output vectors per sample");
   long long bx = cdivll(per_n, 256 * 4);
   if (bx > 148 * 16) bx = 148 * 16;
   if (bx < 1) bx = 1;

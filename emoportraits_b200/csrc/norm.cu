@@ -76,6 +76,11 @@ __global__ void gn_finalize_kernel(const emo_gn_finalize_desc d) {
   d.B[idx] = bet - (float)mean * A;
 }
 
+// resident CTAs per SM the apply kernels are compiled for (register cap 65536 / (256 * n)).  Measured round 2 (tools/apply_probe.py,
+// 512^2 x 128): 4 -> 56.1 us, 6 (40 registers, ~100 B of spills) -> 60.1 us; unconstrained (66 registers, 3 CTAs) was 1 % of the frame slower.
+#ifndef EMO_APPLY_MIN_CTAS
+#define EMO_APPLY_MIN_CTAS 4
+#endif
 #define EMO_APPLY_F16 0
 #define EMO_APPLY_KERNEL_NAME apply_kernel
 #include "apply_kernel.inc"
