@@ -653,8 +653,8 @@ def run_stage2(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)  # 0.65 s of device time at ~300 frames/s: ~130 NVML clock samples in the timed region
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="do not capture the driver frame in a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
