@@ -183,15 +183,18 @@ def wrapper_fps(sd, hsd, K):
         out, img = w.forward(None, pil[i % 8], **kw)
     torch.cuda.synchronize()
     per_call = K / (time.perf_counter() - t0)
-    batch = [pil[i % 8] for i in range(K)]
+    LIST = 32  # frames per call of the list form (a caller with a long clip hands it over in chunks: one call converts, copies
+    batch = [pil[i % 8] for i in range(LIST)]  # back and wraps ALL of its frames after the last one is computed)
     w.forward(None, batch[:4], **kw)
     torch.cuda.synchronize()
+    calls = max(1, K // LIST)
     t0 = time.perf_counter()
-    out, img = w.forward(None, batch, **kw)
+    for _ in range(calls):
+        out, img = w.forward(None, batch, **kw)
     torch.cuda.synchronize()
-    listed = K / (time.perf_counter() - t0)
-    assert len(out) == K and out[0].size == (SIZE, SIZE)
-    return {"one_frame_per_call": per_call, "list_of_frames_per_call": listed, "unit": "frames/s",
+    listed = calls * LIST / (time.perf_counter() - t0)
+    assert len(out) == LIST and out[0].size == (SIZE, SIZE)
+    return {"one_frame_per_call": per_call, "list_of_frames_per_call": listed, "frames_per_list_call": LIST, "unit": "frames/s",
             "what": "InferenceWrapper.forward(None, PIL...) -> (list[PIL], tensor): uint8 H2D 0.79 MB + D2H 0.79 MB per frame, wall clock"}
 
 
