@@ -297,6 +297,48 @@ class InferenceWrapper(torch.nn.Module):
             raise NotImplementedError("get_mask needs the external MODNet network: set wrapper.modnet = <module>")
         return modnet_get_mask(self.modnet, img.to(self.device))
 
+    def _driver_pipeline(self, mix, target_theta, mix_old):
+        key = (bool(mix), bool(target_theta), bool(mix_old))
+        if self._pipeline is None or self._pipeline.st is not self._state or self._pipeline_key != key:
+            self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=4, mix=mix,
+                                                                target_theta=target_theta, mix_old=mix_old), key
+        return self._pipeline
+
+    def _forward_list(self, frames, mix, target_theta, mix_old):
+        """A list of PIL / numpy driver frames: every frame is converted, uploaded and queued on its own (four captured frames in
+        flight), its uint8 image is produced and copied back on the frame's stream, so the host-side conversions of frame i + 1
+        overlap the device work of frame i; the PIL images are wrapped as their copies land.  Same results as one call per frame."""
+        from PIL import Image
+
+        pipe = self._driver_pipeline(mix, target_theta, mix_old)
+        n, s = len(frames), self.cfg.image_size
+        img = torch.empty((n, 3, s, s), dtype=torch.float32, device=self.device)
+        u8 = torch.empty((n, s, s, 3), dtype=torch.uint8, device=self.device)
+        host = torch.empty((n, s, s, 3), dtype=torch.uint8).pin_memory()
+        keep, done = [], []
+        for i, f in enumerate(frames):
+            t = self._prep(f)
+            keep.append(t)  # read by the slot's stream later: must not return to the allocator (of the current stream) before
+            sl = pipe.submit(t, dev_out=img[i:i + 1]).slot
+            with torch.cuda.stream(sl.stream):
+                ops.image_to_u8(img[i:i + 1], out=u8[i:i + 1])  # clamp(0, 1) + ToPILImage (mul(255).byte()) on the device
+                host[i].copy_(u8[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            done.append(ev)
+            if len(keep) > 2 * pipe.depth and done[i - 2 * pipe.depth].query():
+                keep[i - 2 * pipe.depth] = None
+        pred_target_img = []
+        for i in range(n):
+            done[i].synchronize()
+            pred_target_img.append(Image.fromarray(host[i].numpy()))
+        pipe.drain()
+        so = sl.run.static_state
+        self.pred_target_theta = so.pred_target_theta.clone()
+        self.pred_target_srt = (so.srt[:, :3].clone(), so.srt[:, 3:6].clone(), so.srt[:, 6:9].clone())
+        self.target_pose_embed = so.target_pose_embed.clone()
+        return pred_target_img, img
+
     # -- notebooks/infer.py:229-243
     def convert_to_tensor(self, image):
         """PIL image(s) / numpy uint8 (H,W,C) -> fp32 (N,C,H,W) in [0,1] on the device.  uint8 pixels cross the bus as bytes
@@ -381,18 +423,17 @@ class InferenceWrapper(torch.nn.Module):
             return None
         if self._state is None:
             raise RuntimeError("forward(driver_image=...) called before a source image was given")
-        drv = self._prep(driver_image)
         custom_srt = None
         if custome_target_theta_embed is not None:   # (scale, rotation, translation), each (1,3): infer.py:566-567
             custom_srt = torch.cat([torch.as_tensor(t).float().reshape(1, 3) for t in custome_target_theta_embed], 1)
         per_frame = smooth_pose or custom_srt is not None or custome_target_pose_embed is not None
+        if not per_frame and isinstance(driver_image, list) and len(driver_image) > 1 and not isinstance(driver_image[0], torch.Tensor):
+            return self._forward_list(driver_image, mix, target_theta, mix_old)
+        drv = self._prep(driver_image)
         if not per_frame:
             # captured driver frames (CUDA graphs), four in flight when a list of frames is given (DriverPipeline); same
             # kernels as the eager pass below
-            key = (bool(mix), bool(target_theta), bool(mix_old))
-            if self._pipeline is None or self._pipeline.st is not self._state or self._pipeline_key != key:
-                self._pipeline, self._pipeline_key = DriverPipeline(self.model, self._state, depth=4, mix=mix,
-                                                                    target_theta=target_theta, mix_old=mix_old), key
+            self._driver_pipeline(mix, target_theta, mix_old)
             img = torch.empty_like(drv)
             for i in range(drv.shape[0]):
                 sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1]).slot
