@@ -153,31 +153,40 @@ class Model:
         return img, deep_f, img_f, st_out
 
 
-    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True, slot: int = 0, mix_old: bool = False):
+    def make_driver_graph(self, st, mix: bool = True, target_theta: bool = True, slot: int = 0, mix_old: bool = False,
+                          smooth_state: Optional[torch.Tensor] = None, smooth_momentum: float = 0.5):
         """Capture one driver frame (all ~240 kernel launches) into a CUDA graph: removes the Python/ctypes launch
         overhead from the per-frame loop.  Returns replay(drv (1,3,H,W) on device) -> img (1,3,H,W) (static buffer).
         `slot` selects the scratch set (ops.set_slot) the captured frame uses; graphs that may replay concurrently on
-        different streams need different slots."""
+        different streams need different slots.  smooth_state (3,4): the captured frame also smooths its pose into this
+        tensor in place (smooth_pose=True, infer.py:571-581; the state must already be seeded by one eager frame) - frames of
+        such a graph are a recurrence and must replay one after the other on one stream."""
         prev = ops.set_slot(slot)
         try:
-            return self._make_driver_graph(st, mix, target_theta, mix_old)
+            return self._make_driver_graph(st, mix, target_theta, mix_old, smooth_state, smooth_momentum)
         finally:
             ops.set_slot(prev)
 
-    def _make_driver_graph(self, st, mix, target_theta, mix_old=False):
+    def _make_driver_graph(self, st, mix, target_theta, mix_old=False, smooth_state=None, smooth_momentum=0.5):
         s = self.cfg.image_size
         static_in = torch.zeros((1, 3, s, s), dtype=torch.float32, device=self.device)
+        kw = dict(mix=mix, target_theta=target_theta, mix_old=mix_old)
+        if smooth_state is not None:
+            kw.update(smooth_state=smooth_state, smooth_momentum=smooth_momentum, smooth_init=False)
+            saved = smooth_state.clone()  # the warm-up and capture passes smooth a dummy frame into the state: put it back after
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.driver_pass(st, static_in, mix=mix, target_theta=target_theta, mix_old=mix_old)
+                self.driver_pass(st, static_in, **kw)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            out = self.driver_pass(st, static_in, mix=mix, target_theta=target_theta, mix_old=mix_old)
+            out = self.driver_pass(st, static_in, **kw)
             static_out = out[0]
+        if smooth_state is not None:
+            smooth_state.copy_(saved)
 
         def replay(drv: torch.Tensor) -> torch.Tensor:
             static_in.copy_(drv, non_blocking=True)
@@ -284,6 +293,7 @@ class InferenceWrapper(torch.nn.Module):
         self.use_seg = getattr(self.args, 'use_seg', True)
         self._state = None
         self._pipeline = self._pipeline_key = None
+        self._smooth_graph = None
         # external mask networks (separate checkouts in the reference: repos/face_par_off behind model.face_idt, infer.py:410;
         # repos/MODNet, infer.py:140-149): None until the caller plugs them in (masks.FaceParsing(None, net=...), any MODNet module)
         self.face_idt = None
@@ -439,6 +449,30 @@ class InferenceWrapper(torch.nn.Module):
                 sl = self._pipeline.submit(drv[i:i + 1], dev_out=img[i:i + 1]).slot
             self._pipeline.drain()
             so = sl.run.static_state
+            self.pred_target_theta = so.pred_target_theta.clone()
+            self.pred_target_srt = (so.srt[:, :3].clone(), so.srt[:, 3:6].clone(), so.srt[:, 6:9].clone())
+            self.target_pose_embed = so.target_pose_embed.clone()
+        elif smooth_pose and custom_srt is None and custome_target_pose_embed is None:
+            # pose smoothing is a recurrence over the frames (infer.py:571-581): the first frame seeds self.theta eagerly, every
+            # further frame replays a captured graph that smooths into the same tensor, one after the other on this stream
+            imgs = []
+            for i in range(drv.shape[0]):
+                if self.theta is None:
+                    self.theta = torch.zeros((3, 4), dtype=torch.float32, device=self.device)
+                    im, _, _, so = self.model.driver_pass(self._state, drv[i:i + 1].contiguous(), mix=mix, target_theta=target_theta,
+                                                          mix_old=mix_old, smooth_state=self.theta, smooth_momentum=self.pose_momentum,
+                                                          smooth_init=True)
+                    self._smooth_graph = None
+                else:
+                    key = (bool(mix), bool(target_theta), bool(mix_old), float(self.pose_momentum))
+                    g = self._smooth_graph
+                    if g is None or g.st is not self._state or g.theta is not self.theta or g.key != key:
+                        run = self.model.make_driver_graph(self._state, mix=mix, target_theta=target_theta, mix_old=mix_old,
+                                                           smooth_state=self.theta, smooth_momentum=self.pose_momentum)
+                        g = self._smooth_graph = SimpleNamespace(run=run, st=self._state, theta=self.theta, key=key)
+                    im, so = g.run(drv[i:i + 1]).clone(), g.run.static_state
+                imgs.append(im)
+            img = imgs[0] if len(imgs) == 1 else torch.cat(imgs)
             self.pred_target_theta = so.pred_target_theta.clone()
             self.pred_target_srt = (so.srt[:, :3].clone(), so.srt[:, 3:6].clone(), so.srt[:, 6:9].clone())
             self.target_pose_embed = so.target_pose_embed.clone()
