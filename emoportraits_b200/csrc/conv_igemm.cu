@@ -318,10 +318,13 @@ __device__ __forceinline__ void tile_group_stats(const ConvKParams& p, const flo
   const int cpg = p.cpg;
   if (BN % cpg == 0 && (n0 % cpg) == 0) {
     const int ng = BN / cpg;
+    // tile_stats<R> leaves data only in the first column of every R-group (R = largest power of two <= 16 dividing cpg); the other
+    // slots hold zeros from the kernel's start, so skipping them changes neither the sums nor their order
+    const int rstep = (cpg & -cpg) < 16 ? (cpg & -cpg) : 16;
     for (int g = et; g < ng; g += nthreads) {
       float a = 0.f, b = 0.f;
       for (int q = 0; q < 4; ++q)
-        for (int j = 0; j < cpg; ++j) { a += cs[q * kMaxBN + g * cpg + j]; b += cq[q * kMaxBN + g * cpg + j]; }
+        for (int j = 0; j < cpg; j += rstep) { a += cs[q * kMaxBN + g * cpg + j]; b += cq[q * kMaxBN + g * cpg + j]; }
       const int gi = (n0 / cpg) + g;
       if (gi < p.G) {
         atomicAdd(&p.stats[((long long)n * p.G + gi) * 2], (double)a);
