@@ -50,3 +50,19 @@ def test_pose_theta_guards(L):
     _refused(L, "emo_pose_theta", P(FAKE, None, 0, 0, 0, FAKE, FAKE, FAKE, None, 0, 0, None, 0.5), "N must be positive")
     _refused(L, "emo_pose_theta", P(FAKE, None, 1, 1, 0, FAKE, FAKE, FAKE, None, 0, 0, None, 0.5), "mix needs source_theta")
     _refused(L, "emo_pose_theta", P(FAKE, None, 1, 0, 0, FAKE, FAKE, FAKE, None, 0, 0, FAKE, 1.5), "smooth_momentum")
+
+
+def test_mask_processing_guards(L):
+    lib = L.load()
+
+    def refused(rc, match):
+        assert rc == -1, rc
+        assert match in lib.emo_last_error().decode(), lib.emo_last_error().decode()
+
+    refused(lib.emo_parsing_prepare(None, 1, 3, 8, 8, 512, 512, None, None, FAKE, None), "emo_parsing_prepare: bad arguments")
+    refused(lib.emo_parsing_prepare(FAKE, 1, 3, 8, 0, 512, 512, None, None, FAKE, None), "emo_parsing_prepare: bad arguments")
+    sets = (C.c_uint * 4)(1, 2, 4, 8)
+    refused(lib.emo_parsing_masks(FAKE, 1, 33, 8, 8, 8, 8, sets, FAKE, None, None), "1..32 classes")
+    refused(lib.emo_parsing_masks(FAKE, 1, 19, 8, 8, 8, 8, None, FAKE, None, None), "emo_parsing_masks: bad arguments")
+    refused(lib.emo_resize_area(FAKE, 1, 3, 8, 8, 0, 4, 1.0, 0.0, FAKE, None), "emo_resize_area: bad arguments")
+    refused(lib.emo_l2_flush_clean(None, 1 << 20, None), "emo_l2_flush_clean: bad buffer")
